@@ -1,0 +1,190 @@
+/*
+ * csi_that.h -- C ABI of libcsi_that.so: the B200 (sm_100a) kernels behind the THAT train step.
+ *
+ * The reference (amirhosseinmhd/multi_modal_CSI) has no FFI of its own: its hot path is Python calling
+ * torch.nn modules.  Each entry point below therefore names the reference call(s) it replaces, with paths
+ * relative to the reference checkout (benchmark/wifi_csi/...).  The Python side of the boundary
+ * (multi_modal_csi_b200/ops.py) binds these symbols with ctypes; INTEGRATION.md shows the stub.
+ *
+ * Conventions
+ *   - every function returns 0 on success, a negative csi_status otherwise; csi_last_error() gives the text
+ *     (thread local).  Launches are asynchronous on `stream` (a cudaStream_t passed as void*); nothing here
+ *     allocates, frees or synchronises, so every call is CUDA-graph capturable.
+ *   - all buffers are device pointers owned by the caller (PyTorch's allocator).
+ *   - dtype arguments: CSI_F32 = 0, CSI_BF16 = 1.
+ *   - "token buffer": a [B*Lp, ld] row-major matrix holding B samples of L tokens with `halo` zero rows in
+ *     front of and behind every sample (Lp = L + 2*halo), ld >= Dp = round_up(d,16) and CSI_GUARD_ROWS
+ *     readable rows before row 0 and after the last row.  Token (b,l) lives in row b*Lp + halo + l.  The
+ *     halo/guard rows are what turn Conv1d(padding="same") into a GEMM over row-shifted views.
+ *   - dropout: element idx of site `drop_site` is kept iff philox(rng[0], rng[1], drop_site, idx) >= p and
+ *     then scaled by 1/(1-p).  `rng` points at two device uint64 {seed, step}; it is not read when p == 0.
+ */
+#ifndef CSI_THAT_H
+#define CSI_THAT_H
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define CSI_F32 0
+#define CSI_BF16 1
+#define CSI_GUARD_ROWS 16
+#define CSI_MAX_SEGS 32
+
+typedef enum {
+    CSI_OK = 0,
+    CSI_ERR_ARG = -1,      /* bad argument (null pointer, unsupported size or dtype) */
+    CSI_ERR_CUDA = -2,     /* a CUDA runtime / driver call failed */
+    CSI_ERR_ARCH = -3      /* device is not sm_100 */
+} csi_status;
+
+/* One K-segment of a row-shifted GEMM: A columns [a_col_off, a_col_off+klen) of row (m + a_row_shift)
+ * are contracted with B columns [b_col_off, b_col_off+klen).  klen must be a multiple of 16. */
+typedef struct { int a_row_shift, a_col_off, b_col_off, klen; } csi_seg;
+
+/* One output segment of the weight-gradient GEMM (see csi_gemm_tn). */
+typedef struct { int b_row_shift, b_col_off, c_off, nlen; } csi_seg_tn;
+
+/* Up to three per-branch parameter pointers (the three Conv1d->BatchNorm1d branches of an Encoder). */
+typedef struct { void* p[3]; } csi_ptr3;
+
+/* One tensor of the weight re-layout table (see csi_pack_weights). */
+typedef struct {
+    long long src_off;   /* element offset of the fp32 [N, C, k] source in the parameter arena        */
+    long long dst_off;   /* element offset of the destination matrix in the packed arena            */
+    int N, C, k;         /* source shape (k = 1 for Linear weights)                                  */
+    int ld;              /* destination leading dimension                                           */
+    int mode;            /* 0: dst[n*ld + j*P + c] = src[n,c,j]      (forward operand)               */
+                         /* 1: dst[c*ld + (seg_base+j)*P + n] = src[n,c,j]  (data-gradient operand)  */
+    int P;               /* padded channel pitch of one tap                                         */
+    int seg_base;        /* first segment index of this tensor in mode 1                            */
+    int reserved;
+} csi_pack_entry;
+
+const char* csi_last_error(void);
+/* Returns the library ABI version (bumped on any signature change). */
+int csi_abi_version(void);
+/* Compute capability (major*10+minor) of `device`, or a negative csi_status. */
+int csi_device_arch(int device);
+
+/* ---- a1-a5: load_data.py:66-72 (front zero-pad), train.py:65-73 (apply_augmentation),
+ *      that.py:257-259,279-280 (AvgPool1d(20,20) of both streams + permutes), that.py:88 (x + PE).
+ * x: fp32 [B,T,F] dense when offs == NULL; otherwise sample b is lens[b] <= T rows of F floats starting at
+ * element offs[b] of x and is FRONT-padded with zeros to T.  left/right: fp32 token buffers with
+ * (L,d) = (T/20, F) and (F, T/20).  pe: fp32 [T/20, ld_pe] added to the left stream (NULL = none).
+ * augment != 0 applies (x + 0.1*N(0,1)) * U[0.9,1.1)_b * Bernoulli(0.96) before pooling. */
+int csi_pool_dual(const float* x, const long long* offs, const int* lens, int B, int T, int F,
+                  const float* pe, int ld_pe, float* left, int ld_left, float* right, int ld_right,
+                  int halo, int augment, const unsigned long long* rng, void* stream);
+
+/* ---- a6: that.py:61-90 Gaussian_Position.  w: [L,K] softmax weights (saved for backward). */
+int csi_gauss_pe_fwd(const float* pos, const float* mu, const float* sigma, const float* emb,
+                     int L, int K, int F, float* w, float* pe, int ld_pe, void* stream);
+/* dleft: fp32 token-buffer gradient of the PE output; dpe_ws: fp32 scratch [L, ld_ws].
+ * demb [K,F], dmu [K], dsigma [K] are accumulated (caller zeroes). */
+int csi_gauss_pe_bwd(const float* dleft, int ld_dleft, int B, int halo, const float* w, const float* pos,
+                     const float* mu, const float* sigma, const float* emb, int L, int K, int F,
+                     float* dpe_ws, int ld_ws, float* demb, float* dmu, float* dsigma, void* stream);
+
+/* ---- a7: torch.nn.LayerNorm(d, eps=1e-6) at that.py:112,120,206,229.
+ * x: fp32 token buffer; y: token buffer of y_dtype (halo rows and pad columns are written as zero). */
+int csi_layernorm_fwd(const float* x, int ldx, const float* gamma, const float* beta, void* y, int ldy,
+                      int y_dtype, float* mean, float* rstd, int B, int L, int d, int halo, float eps,
+                      void* stream);
+/* dx = LN'(dy) + dres (dres nullable); optional second output dxm = dropout_mask(dx) in dxm_dtype (the
+ * gradient entering the out-projection, that.py:151).  dgamma/dbeta accumulated (caller zeroes). */
+int csi_layernorm_bwd(const void* dy, int lddy, int dy_dtype, const float* x, int ldx, const float* gamma,
+                      const float* mean, const float* rstd, const float* dres, int lddres, float* dx,
+                      int lddx, void* dxm, int lddxm, int dxm_dtype, float drop_p, unsigned drop_site,
+                      const unsigned long long* rng, float* dgamma, float* dbeta, int B, int L, int d,
+                      int halo, void* stream);
+
+/* ---- a8/a10/a11/a12 contractions: F.linear / Conv1d forward and data-gradient.
+ * C[m, n] = sum_s sum_{q<klen_s} A[(m + shift_s)*lda + a_col_off_s + q] * Bw[n*ldb + b_col_off_s + q]
+ *           (+ bias[n]) -> dropout(site) -> (+ residual[m*ldr + n]),   m < M, n < N.
+ * A and Bw have ab_dtype; C has c_dtype; bias/residual are fp32 and nullable.
+ * With ab_dtype == CSI_BF16 this is the tcgen05/TMA kernel; CSI_F32 is the FFMA "fp32 parity" kernel. */
+int csi_gemm_nt(const void* A, int lda, const void* Bw, int ldb, int ab_dtype, void* C, int ldc, int c_dtype,
+                int M, int N, const csi_seg* segs, int nseg, const float* bias, const float* residual,
+                int ldr, float drop_p, unsigned drop_site, const unsigned long long* rng, void* stream);
+
+/* ---- weight gradients (autograd of the same calls):
+ * C[i*ldc + c_off_s + q*c_col_stride] += sum_{m<M} A[m*lda + i] * Bv[(m + b_row_shift_s)*ldb + b_col_off_s + q]
+ * for i < Na, q < nlen_s.  C is fp32 and is accumulated with atomics (caller zeroes); with c_col_stride = k
+ * it writes Conv1d weight gradients straight into the reference [N, C, k] layout. */
+int csi_gemm_tn(const void* A, int lda, const void* Bv, int ldb, int ab_dtype, float* C, int ldc,
+                int c_col_stride, int M, int Na, const csi_seg_tn* segs, int nseg, void* stream);
+
+/* Column sums over the valid token rows: out[c] += sum_{b,l} A[row(b,l), c]  (bias gradients). */
+int csi_colsum_tokens(const void* A, int lda, int dtype, int B, int L, int halo, int ncols, float* out,
+                      void* stream);
+
+/* ---- a8: nn.MultiheadAttention core at that.py:149 (per head softmax(q k^T / sqrt(hd)) v).
+ * qkv: token buffer [rows, ld3] holding q | k | v in columns [0,d) [d,2d) [2d,3d).  lse: fp32 [B,H,L]. */
+int csi_attn_fwd(const void* qkv, int ld3, void* o, int ldo, int dtype, float* lse, int B, int L, int d,
+                 int H, int halo, void* stream);
+int csi_attn_bwd(const void* qkv, int ld3, const void* o, int ldo, const void* dout, int lddo, void* dqkv,
+                 int lddqkv, int dtype, const float* lse, int B, int L, int d, int H, int halo, void* stream);
+
+/* ---- a10: BatchNorm1d (train: batch statistics) -> Dropout(.1) -> LeakyReLU, mean of the 3 branches,
+ * Dropout(.1), residual (that.py:126-132,160-168).  z: token buffer [rows, ldz] with branch br in columns
+ * [br*Dp, br*Dp + d); it holds the convolution WITHOUT its bias (the bias only shifts the batch mean). */
+int csi_bn_stats(const void* z, int ldz, int dtype, int B, int L, int halo, int ncols, double* sums,
+                 void* stream);                                   /* sums: [2, ncols], accumulated */
+int csi_bn_finalize(const double* sums, int Dp, int d, int nbr, long long count, csi_ptr3 conv_bias,
+                    csi_ptr3 run_mean, csi_ptr3 run_var, csi_ptr3 num_batches, float momentum, float eps,
+                    float* mean, float* invstd, void* stream);
+/* eval mode: mean = running_mean - conv_bias, invstd = rsqrt(running_var + eps) */
+int csi_bn_eval_prepare(int Dp, int d, int nbr, csi_ptr3 conv_bias, csi_ptr3 run_mean, csi_ptr3 run_var,
+                        float eps, float* mean, float* invstd, void* stream);
+int csi_bn_act_fwd(const void* z, int ldz, int dtype, const float* mean, const float* invstd, csi_ptr3 gamma,
+                   csi_ptr3 beta, const float* t_res, int ldt, float* out, int ldo, int B, int L, int d,
+                   int halo, int nbr, float p_branch, unsigned site_branch, float p_out, unsigned site_out,
+                   const unsigned long long* rng, void* stream);
+/* red: [2, nbr*Dp] doubles (sum dy, sum dy*zhat), accumulated */
+int csi_bn_act_bwd_reduce(const float* dout, int lddo, const void* z, int ldz, int dtype, const float* mean,
+                          const float* invstd, csi_ptr3 gamma, csi_ptr3 beta, int B, int L, int d, int halo,
+                          int nbr, float p_branch, unsigned site_branch, float p_out, unsigned site_out,
+                          const unsigned long long* rng, double* red, void* stream);
+int csi_bn_act_bwd_dz(const float* dout, int lddo, const void* z, int ldz, int dtype, const float* mean,
+                      const float* invstd, csi_ptr3 gamma, csi_ptr3 beta, const double* red, int B, int L,
+                      int d, int halo, int nbr, float p_branch, unsigned site_branch, float p_out,
+                      unsigned site_out, const unsigned long long* rng, void* dz, int lddz, csi_ptr3 dgamma,
+                      csi_ptr3 dbeta, void* stream);
+
+/* ---- a11: head Conv1d (valid) + LeakyReLU + sum over time (that.py:268-272,287-291).
+ * p: token buffer [rows, ldp] of conv pre-activations; columns [0,n0) come from a kernel of size k0 and
+ * [n0,N) from size k1, so token t contributes iff t <= L - k.  feat: fp32 [B, ldf]. */
+int csi_head_reduce_fwd(const void* p, int ldp, int dtype, int B, int L, int halo, int N, int n0, int k0,
+                        int k1, float* feat, int ldf, void* stream);
+int csi_head_reduce_bwd(const float* dfeat, int ldf, const void* p, int ldp, int dtype, int B, int L, int halo,
+                        int N, int n0, int k0, int k1, void* dp, int lddp, void* stream);
+
+/* ---- a12: Dropout(0.5) on the concatenated features (that.py:274-275,293-294); out = mask(in). */
+int csi_dropout_rows(const float* in, int ldi, void* out, int ldo, int out_dtype, int rows, int cols, float p,
+                     unsigned site, const unsigned long long* rng, void* stream);
+
+/* ---- a13: BCEWithLogitsLoss(pos_weight) mean (that.py:401, train.py:97) and its gradient * grad_scale. */
+int csi_bce_logits(const float* z, int ldz, const float* y, int ldy, int rows, int cols, float pos_weight,
+                   float grad_scale, float* loss, float* dz, int lddz, void* stream);
+
+/* ---- a15: torch.optim.Adam with coupled L2 (that.py:395-397) over the flat arenas.
+ * step: device int64 holding the 1-based step of THIS update.  g is multiplied by grad_scale first. */
+int csi_adam_flat(float* p, const float* g, float* m, float* v, long long n, float lr, float beta1, float beta2,
+                  float eps, float weight_decay, const long long* step, float grad_scale, void* stream);
+/* rng[1] += 1; step[0] += 1 (one tiny launch so a captured graph advances its own counters) */
+int csi_advance_counters(unsigned long long* rng, long long* step, void* stream);
+
+/* ---- per-step re-layout of the fp32 master weights into the GEMM operand copies (table on device). */
+int csi_pack_weights(const float* params, void* packed, int dtype, const csi_pack_entry* table, int n_entries,
+                     int max_elems, void* stream);
+
+/* Generic helpers */
+int csi_fill_f32(float* p, long long n, float v, void* stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* CSI_THAT_H */

@@ -1,0 +1,334 @@
+"""THAT train-step engine: owns the token buffers and composes the C-ABI kernels into
+forward / backward / optimizer for one GPU.
+
+Reference path this replaces (benchmark/wifi_csi): model/that.py:249-302 (THAT.forward), autograd of the
+same (train.py:100), that.py:401 (BCEWithLogitsLoss), that.py:395-397 + train.py:99-101 (Adam step) and
+train.py:65-73 (augmentation).  Every arithmetic step is one call into ``libcsi_that.so`` through
+``ops`` (multi_modal_csi_b200/ops.py); this file only sequences them, so a whole train step is a fixed
+list of kernel launches that is captured into one CUDA graph (``capture_train_step``).
+
+The ``ops`` object is injectable so that the CPU test-suite can check this sequencing (in particular the
+hand-derived backward pass) against the oracle with a torch mirror of the kernels; the product always
+uses the native library and fails loudly without it.
+"""
+from __future__ import annotations
+
+from typing import Dict, Optional
+
+import torch
+
+from . import layout as LY
+from .layout import GUARD, HALO, ModelGeom, StreamGeom, site
+
+LN_EPS = 1e-6      # that.py:112,120,206,229
+BN_EPS = 1e-5      # torch.nn.BatchNorm1d default (that.py:130)
+BN_MOMENTUM = 0.1
+P_DROP = 0.1       # that.py:117,131,137
+P_FEAT = 0.5       # that.py:216,239
+
+
+class _TokBuf:
+    """[GUARD + rows + GUARD, ld] zero-initialised; ``.t`` is the [rows, ld] body."""
+
+    def __init__(self, rows, ld, dtype, device):
+        self.full = torch.zeros(rows + 2 * GUARD, ld, dtype=dtype, device=device)
+        self.t = self.full[GUARD:GUARD + rows]
+
+
+class THATEngine:
+    def __init__(self, geom: ModelGeom, max_batch: int, params: torch.Tensor, grads: torch.Tensor,
+                 arena: LY.Arena, buffers: Dict[str, torch.Tensor], frozen: Dict[str, torch.Tensor],
+                 act_dtype: torch.dtype = torch.bfloat16, ops=None, seed: int = 0):
+        self.g = geom
+        self.B = int(max_batch)
+        self.params = params              # flat fp32 arena (views of it are the nn.Parameters)
+        self.grads = grads                # flat fp32 arena of the same layout
+        self.arena = arena
+        self.frozen = frozen              # non-trainable parameters (var_position), not in the arena
+        self.bn = buffers                 # running_mean / running_var / num_batches_tracked by state_dict key
+        self.dev = params.device
+        self.adt = act_dtype
+        if ops is None:
+            from .ops import NativeOps    # raises if libcsi_that.so is missing or the device is not CUDA
+            ops = NativeOps(self.dev)
+        self.ops = ops
+        self.pack = LY.build_pack_plan(geom, arena)
+        self.packed = torch.zeros(self.pack.size, dtype=act_dtype, device=self.dev)
+        self.pack_table = ops.make_pack_table(self.pack.entries, self.dev)
+        self.rng = torch.tensor([seed, 0], dtype=torch.int64, device=self.dev)      # {seed, step}
+        self.opt_step = torch.ones(1, dtype=torch.int64, device=self.dev)           # 1-based Adam step
+        self._alloc()
+        self._graph = None
+        self.weights_dirty = True
+
+    # ------------------------------------------------------------------ views
+    def P(self, name):
+        if name in self.frozen:
+            return self.frozen[name]
+        off, shp = self.arena.offsets[name], self.arena.shapes[name]
+        return self.params[off:off + LY.numel(shp)]
+
+    def G(self, name):
+        off, shp = self.arena.offsets[name], self.arena.shapes[name]
+        return self.grads[off:off + LY.numel(shp)]
+
+    def W(self, key):
+        m = self.pack.mats[key]
+        return self.packed[m.off:m.off + m.rows * m.ld].view(m.rows, m.ld)
+
+    # ------------------------------------------------------------------ buffers
+    def _alloc(self):
+        dev, B, adt, f32 = self.dev, self.B, self.adt, torch.float32
+        self.s: Dict[str, dict] = {}
+        for sg in self.g.streams:
+            rows, Dp = sg.rows(B), sg.Dp
+            st = {"x0": _TokBuf(rows, Dp, f32, dev), "enc": []}
+            for _ in range(sg.n_enc):
+                st["enc"].append({
+                    "t0": _TokBuf(rows, Dp, adt, dev), "mean0": torch.zeros(rows, device=dev),
+                    "rstd0": torch.zeros(rows, device=dev),
+                    "qkv": _TokBuf(rows, sg.ld3, adt, dev), "o": _TokBuf(rows, Dp, adt, dev),
+                    "lse": torch.zeros(B * sg.H * sg.L, device=dev),
+                    "t": _TokBuf(rows, Dp, f32, dev),
+                    "s": _TokBuf(rows, Dp, adt, dev), "mean1": torch.zeros(rows, device=dev),
+                    "rstd1": torch.zeros(rows, device=dev),
+                    "z": _TokBuf(rows, 3 * Dp, adt, dev),
+                    "bn_mean": torch.zeros(3 * Dp, device=dev), "bn_invstd": torch.zeros(3 * Dp, device=dev),
+                    "bn_sums": torch.zeros(2 * 3 * Dp, dtype=torch.float64, device=dev),
+                    "out": _TokBuf(rows, Dp, f32, dev),
+                })
+            st["hn"] = _TokBuf(rows, Dp, adt, dev)
+            st["meanf"] = torch.zeros(rows, device=dev)
+            st["rstdf"] = torch.zeros(rows, device=dev)
+            st["p"] = _TokBuf(rows, 2 * sg.head_np, adt, dev)
+            # backward scratch (shared by the encoders of the stream)
+            st["dout"] = [_TokBuf(rows, Dp, f32, dev), _TokBuf(rows, Dp, f32, dev)]
+            st["dz"] = _TokBuf(rows, 3 * Dp, adt, dev)
+            st["ds"] = _TokBuf(rows, Dp, adt, dev)
+            st["dt"] = _TokBuf(rows, Dp, f32, dev)
+            st["dtm"] = _TokBuf(rows, Dp, adt, dev)
+            st["do"] = _TokBuf(rows, Dp, adt, dev)
+            st["dqkv"] = _TokBuf(rows, sg.ld3, adt, dev)
+            st["dt0"] = _TokBuf(rows, Dp, adt, dev)
+            st["dp"] = _TokBuf(rows, 2 * sg.head_np, adt, dev)
+            st["dhn"] = _TokBuf(rows, Dp, adt, dev)
+            st["red"] = torch.zeros(2 * 3 * Dp, dtype=torch.float64, device=dev)
+            self.s[sg.name] = st
+        L, F = self.g.left.L, self.g.F
+        self.pe = torch.zeros(L, self.g.left.Dp, device=dev)
+        self.pe_w = torch.zeros(L, LY.NUM_GAUSS, device=dev)
+        self.dpe_ws = torch.zeros(L, self.g.left.Dp, device=dev)
+        self.feat = torch.zeros(B, LY.FEAT, device=dev)
+        self.featd = torch.zeros(B, LY.FEAT, dtype=adt, device=dev)
+        self.dfeatd = torch.zeros(B, LY.FEAT, device=dev)
+        self.dfeat = torch.zeros(B, LY.FEAT, device=dev)
+        self.logits = torch.zeros(B, self.g.ld_out, device=dev)
+        self.dlogits = torch.zeros(B, self.g.ld_out, device=dev)
+        self.dlogits_a = torch.zeros(B, self.g.ld_out, dtype=adt, device=dev)
+        self.loss = torch.zeros(1, device=dev)
+        self.x_static: Optional[torch.Tensor] = None
+        self.y_static: Optional[torch.Tensor] = None
+
+    def activation_bytes(self) -> int:
+        n = 0
+        for st in self.s.values():
+            def walk(o):
+                nonlocal n
+                if isinstance(o, _TokBuf):
+                    n += o.full.numel() * o.full.element_size()
+                elif isinstance(o, torch.Tensor):
+                    n += o.numel() * o.element_size()
+                elif isinstance(o, dict):
+                    for v in o.values():
+                        walk(v)
+                elif isinstance(o, list):
+                    for v in o:
+                        walk(v)
+            walk(st)
+        return n
+
+    # ------------------------------------------------------------------ weights
+    def repack(self):
+        """fp32 master weights -> GEMM operand copies (forward + data-gradient layouts) in the act dtype."""
+        self.ops.pack_weights(self.params, self.packed, self.pack_table, len(self.pack.entries),
+                              self.pack.max_elems)
+        self.weights_dirty = False
+
+    def _bn3(self, sg: StreamGeom, e: int, leaf: str, grad=False, buf=False):
+        p = sg.prefix(e)
+        out = []
+        for j in range(len(sg.kernels)):
+            key = f"{p}layer_cnn.{j}.{leaf}"
+            out.append(self.bn[key] if buf else (self.G(key) if grad else self.P(key)))
+        return out
+
+    # ------------------------------------------------------------------ forward
+    def forward(self, x: torch.Tensor, B: int, training: bool, dropout: bool = True, augment: bool = False,
+                offs=None, lens=None) -> torch.Tensor:
+        """x: fp32 [B,T,F] (or a packed ragged arena with offs/lens).  Returns logits [B, out] (a view of
+        the engine's static logits buffer)."""
+        ops, g = self.ops, self.g
+        assert B <= self.B
+        if self.weights_dirty:
+            self.repack()
+        pd = P_DROP if (training and dropout) else 0.0
+        pf = P_FEAT if (training and dropout) else 0.0
+        gp = "layer_left_gaussian."
+        ops.gauss_pe_fwd(self.P(gp + "var_position"), self.P(gp + "var_mu"), self.P(gp + "var_sigma"),
+                         self.P(gp + "var_embedding"), g.left.L, LY.NUM_GAUSS, g.F, self.pe_w, self.pe)
+        ops.pool_dual(x, offs, lens, B, g.T, g.F, self.pe, self.s["left"]["x0"].t, self.s["right"]["x0"].t,
+                      HALO, 1 if (training and augment) else 0, self.rng)
+        for si, sg in enumerate(g.streams):
+            st = self.s[sg.name]
+            rows, d, Dp, L = sg.rows(B), sg.d, sg.Dp, sg.L
+            x_in = st["x0"]
+            one = [(0, 0, 0, Dp)]
+            for e in range(sg.n_enc):
+                a, p = st["enc"][e], sg.prefix(e)
+                ops.layernorm_fwd(x_in.t, self.P(p + "layer_norm_0.weight"), self.P(p + "layer_norm_0.bias"),
+                                  a["t0"].t, a["mean0"], a["rstd0"], B, L, d, HALO, LN_EPS)
+                ops.gemm_nt(a["t0"].t, self.W("f:" + p + "layer_attention.in_proj_weight"), a["qkv"].t, rows,
+                            3 * d, one, self.P(p + "layer_attention.in_proj_bias"), None, 0.0, 0, self.rng)
+                ops.attn_fwd(a["qkv"].t, a["o"].t, a["lse"], B, L, d, sg.H, HALO)
+                ops.gemm_nt(a["o"].t, self.W("f:" + p + "layer_attention.out_proj.weight"), a["t"].t, rows, d,
+                            one, self.P(p + "layer_attention.out_proj.bias"), x_in.t, pd,
+                            site(si, e, LY.SITE_ATTN), self.rng)
+                ops.layernorm_fwd(a["t"].t, self.P(p + "layer_norm_1.weight"), self.P(p + "layer_norm_1.bias"),
+                                  a["s"].t, a["mean1"], a["rstd1"], B, L, d, HALO, LN_EPS)
+                for j, k in enumerate(sg.kernels):
+                    pl = (k - 1) // 2
+                    segs = [(t - pl, 0, t * Dp, Dp) for t in range(k)]
+                    ops.gemm_nt(a["s"].t, self.W(f"f:{p}layer_cnn.{j}.0.weight"), a["z"].t[:, j * Dp:], rows, d,
+                                segs, None, None, 0.0, 0, self.rng)
+                cb = self._bn3(sg, e, "0.bias")
+                rm = self._bn3(sg, e, "1.running_mean", buf=True)
+                rv = self._bn3(sg, e, "1.running_var", buf=True)
+                if training:
+                    a["bn_sums"].zero_()
+                    ops.bn_stats(a["z"].t, B, L, HALO, 3 * Dp, a["bn_sums"])
+                    ops.bn_finalize(a["bn_sums"], Dp, d, 3, B * L, cb, rm, rv,
+                                    self._bn3(sg, e, "1.num_batches_tracked", buf=True), BN_MOMENTUM, BN_EPS,
+                                    a["bn_mean"], a["bn_invstd"])
+                else:
+                    ops.bn_eval_prepare(Dp, d, 3, cb, rm, rv, BN_EPS, a["bn_mean"], a["bn_invstd"])
+                ops.bn_act_fwd(a["z"].t, a["bn_mean"], a["bn_invstd"], self._bn3(sg, e, "1.weight"),
+                               self._bn3(sg, e, "1.bias"), a["t"].t, a["out"].t, B, L, d, HALO, 3,
+                               pd, site(si, e, LY.SITE_BRANCH), pd, site(si, e, LY.SITE_SUM), self.rng)
+                x_in = a["out"]
+            st["x_last"] = x_in
+            nm = f"layer_{sg.name}_norm."
+            ops.layernorm_fwd(x_in.t, self.P(nm + "weight"), self.P(nm + "bias"), st["hn"].t, st["meanf"],
+                              st["rstdf"], B, L, d, HALO, LN_EPS)
+            for j, k in enumerate(sg.head_k):
+                w = f"layer_{sg.name}_cnn_{j}"
+                segs = [(t, 0, t * Dp, Dp) for t in range(k)]
+                ops.gemm_nt(st["hn"].t, self.W("f:" + w + ".weight"), st["p"].t[:, j * sg.head_np:], rows,
+                            sg.head_n, segs, self.P(w + ".bias"), None, 0.0, 0, self.rng)
+            ops.head_reduce_fwd(st["p"].t, B, L, HALO, 2 * sg.head_n, sg.head_n, sg.head_k[0], sg.head_k[1],
+                                self.feat[:, sg.feat_off:])
+        ops.dropout_rows(self.feat, self.featd, B, LY.FEAT, pf, LY.SITE_FEAT, self.rng)
+        ops.gemm_nt(self.featd, self.W("f:layer_output.weight"), self.logits, B, g.out, [(0, 0, 0, LY.FEAT)],
+                    self.P("layer_output.bias"), None, 0.0, 0, self.rng)
+        return self.logits[:B, :g.out]
+
+    # ------------------------------------------------------------------ backward
+    def backward(self, dlogits: Optional[torch.Tensor], B: int, dropout: bool = True, zero_grads: bool = True):
+        """Gradient of every parameter into ``self.grads`` given dL/dlogits ([B,out] fp32; None = use the
+        engine's own ``dlogits`` buffer written by ``loss_fwd_bwd``)."""
+        ops, g = self.ops, self.g
+        pd = P_DROP if dropout else 0.0
+        pf = P_FEAT if dropout else 0.0
+        if zero_grads:
+            self.grads.zero_()
+        if dlogits is not None:
+            self.dlogits[:B, :g.out].copy_(dlogits)
+        ops.dropout_rows(self.dlogits, self.dlogits_a, B, g.ld_out, 0.0, 0, self.rng)      # cast to act dtype
+        ops.gemm_tn(self.dlogits_a, self.featd, self.G("layer_output.weight"), LY.FEAT, 1, B, g.out,
+                    [(0, 0, 0, LY.FEAT)])
+        ops.colsum_tokens(self.dlogits_a, B, 1, 0, g.out, self.G("layer_output.bias"))
+        ops.gemm_nt(self.dlogits_a, self.W("b:layer_output.weight"), self.dfeatd, B, LY.FEAT,
+                    [(0, 0, 0, g.ld_out)], None, None, 0.0, 0, self.rng)
+        ops.dropout_rows(self.dfeatd, self.dfeat, B, LY.FEAT, pf, LY.SITE_FEAT, self.rng)
+        for si, sg in enumerate(g.streams):
+            st = self.s[sg.name]
+            rows, d, Dp, L = sg.rows(B), sg.d, sg.Dp, sg.L
+            Np = sg.head_np
+            ops.head_reduce_bwd(self.dfeat[:, sg.feat_off:], st["p"].t, B, L, HALO, 2 * sg.head_n, sg.head_n,
+                                sg.head_k[0], sg.head_k[1], st["dp"].t)
+            dsegs, seg = [], 0
+            for j, k in enumerate(sg.head_k):
+                w = f"layer_{sg.name}_cnn_{j}"
+                ops.gemm_tn(st["dp"].t[:, j * Np:], st["hn"].t, self.G(w + ".weight"), d * k, k, rows, sg.head_n,
+                            [(t, 0, t, d) for t in range(k)])
+                ops.colsum_tokens(st["dp"].t[:, j * Np:], B, L, HALO, sg.head_n, self.G(w + ".bias"))
+                dsegs += [(-t, j * Np, (seg + t) * Np, Np) for t in range(k)]
+                seg += k
+            ops.gemm_nt(st["dp"].t, self.W(f"b:layer_{sg.name}_cnn"), st["dhn"].t, rows, d, dsegs, None, None,
+                        0.0, 0, self.rng)
+            nm = f"layer_{sg.name}_norm."
+            dout, dnext = st["dout"]
+            ops.layernorm_bwd(st["dhn"].t, st["x_last"].t, self.P(nm + "weight"), st["meanf"], st["rstdf"], None,
+                              dout.t, None, 0.0, 0, self.rng, self.G(nm + "weight"), self.G(nm + "bias"),
+                              B, L, d, HALO)
+            for e in reversed(range(sg.n_enc)):
+                a, p = st["enc"][e], sg.prefix(e)
+                x_in = st["enc"][e - 1]["out"] if e > 0 else st["x0"]
+                gam, bet = self._bn3(sg, e, "1.weight"), self._bn3(sg, e, "1.bias")
+                sb, so = site(si, e, LY.SITE_BRANCH), site(si, e, LY.SITE_SUM)
+                st["red"].zero_()
+                ops.bn_act_bwd_reduce(dout.t, a["z"].t, a["bn_mean"], a["bn_invstd"], gam, bet, B, L, d, HALO, 3,
+                                      pd, sb, pd, so, self.rng, st["red"])
+                ops.bn_act_bwd_dz(dout.t, a["z"].t, a["bn_mean"], a["bn_invstd"], gam, bet, st["red"], B, L, d,
+                                  HALO, 3, pd, sb, pd, so, self.rng, st["dz"].t,
+                                  self._bn3(sg, e, "1.weight", grad=True), self._bn3(sg, e, "1.bias", grad=True))
+                dsegs, seg = [], 0
+                for j, k in enumerate(sg.kernels):
+                    pl = (k - 1) // 2
+                    ops.gemm_tn(st["dz"].t[:, j * Dp:], a["s"].t, self.G(f"{p}layer_cnn.{j}.0.weight"), d * k, k,
+                                rows, d, [(t - pl, 0, t, d) for t in range(k)])
+                    dsegs += [(pl - t, j * Dp, (seg + t) * Dp, Dp) for t in range(k)]
+                    seg += k
+                # the Conv1d biases feed a train-mode BatchNorm: their gradient is identically zero
+                ops.gemm_nt(st["dz"].t, self.W("b:" + p + "layer_cnn"), st["ds"].t, rows, d, dsegs, None, None,
+                            0.0, 0, self.rng)
+                ops.layernorm_bwd(st["ds"].t, a["t"].t, self.P(p + "layer_norm_1.weight"), a["mean1"], a["rstd1"],
+                                  dout.t, st["dt"].t, st["dtm"].t, pd, site(si, e, LY.SITE_ATTN), self.rng,
+                                  self.G(p + "layer_norm_1.weight"), self.G(p + "layer_norm_1.bias"), B, L, d, HALO)
+                one = [(0, 0, 0, d)]
+                w = p + "layer_attention.out_proj."
+                ops.gemm_tn(st["dtm"].t, a["o"].t, self.G(w + "weight"), d, 1, rows, d, one)
+                ops.colsum_tokens(st["dtm"].t, B, L, HALO, d, self.G(w + "bias"))
+                ops.gemm_nt(st["dtm"].t, self.W("b:" + w + "weight"), st["do"].t, rows, d, [(0, 0, 0, Dp)], None,
+                            None, 0.0, 0, self.rng)
+                ops.attn_bwd(a["qkv"].t, a["o"].t, st["do"].t, st["dqkv"].t, a["lse"], B, L, d, sg.H, HALO)
+                w = p + "layer_attention.in_proj_"
+                ops.gemm_tn(st["dqkv"].t, a["t0"].t, self.G(w + "weight"), d, 1, rows, 3 * d, one)
+                ops.colsum_tokens(st["dqkv"].t, B, L, HALO, 3 * d, self.G(w + "bias"))
+                ops.gemm_nt(st["dqkv"].t, self.W("b:" + w + "weight"), st["dt0"].t, rows, d, [(0, 0, 0, sg.ld3)],
+                            None, None, 0.0, 0, self.rng)
+                ops.layernorm_bwd(st["dt0"].t, x_in.t, self.P(p + "layer_norm_0.weight"), a["mean0"], a["rstd0"],
+                                  st["dt"].t, dnext.t, None, 0.0, 0, self.rng,
+                                  self.G(p + "layer_norm_0.weight"), self.G(p + "layer_norm_0.bias"), B, L, d, HALO)
+                dout, dnext = dnext, dout
+            if sg.name == "left":
+                gp = "layer_left_gaussian."
+                ops.gauss_pe_bwd(dout.t, B, HALO, self.pe_w, self.P(gp + "var_position"), self.P(gp + "var_mu"),
+                                 self.P(gp + "var_sigma"), self.P(gp + "var_embedding"), L, LY.NUM_GAUSS, g.F,
+                                 self.dpe_ws, self.G(gp + "var_embedding"), self.G(gp + "var_mu"),
+                                 self.G(gp + "var_sigma"))
+
+    # ------------------------------------------------------------------ loss / optimizer
+    def loss_fwd_bwd(self, y: torch.Tensor, B: int, pos_weight: float = 4.0, grad_scale: float = 1.0,
+                     want_grad: bool = True) -> torch.Tensor:
+        """BCEWithLogitsLoss(pos_weight).mean() of the engine's logits against y [B,out] fp32; writes
+        dL/dlogits * grad_scale into the engine's dlogits buffer.  Returns the 1-element loss tensor."""
+        self.ops.bce_logits(self.logits, y, B, self.g.out, pos_weight, grad_scale, self.loss,
+                            self.dlogits if want_grad else None)
+        return self.loss
+
+    def adam(self, m: torch.Tensor, v: torch.Tensor, lr: float, betas=(0.9, 0.999), eps: float = 1e-8,
+             weight_decay: float = 0.0, grad_scale: float = 1.0):
+        self.ops.adam_flat(self.params, self.grads, m, v, self.params.numel(), lr, betas[0], betas[1], eps,
+                           weight_decay, self.opt_step, grad_scale)
+        self.ops.advance_counters(self.rng, self.opt_step)
+        self.weights_dirty = True

@@ -1,0 +1,280 @@
+"""Drop-in for benchmark/wifi_csi/model/that.py: ``THAT(var_x_shape, var_y_shape)`` and ``run_that(...)``.
+
+The module keeps the reference's parameter names, shapes, registration order and initialisation calls
+(that.py:31-56,100-139,180-245), so ``torch.random.manual_seed(r + 39)`` produces the same initial weights and
+``state_dict()`` / ``.pth`` files interchange with the reference in both directions.  All parameters are views of
+one flat fp32 arena (and their ``.grad`` of a second one): that is what lets the optimizer be one fused kernel
+and the data-parallel all-reduce run over a few contiguous buckets.
+
+``forward`` runs the hand-written sm_100a kernels of ``libcsi_that.so`` through ``THATEngine``; there is no
+PyTorch-operator or CPU fallback: on a non-CUDA device, or without the library, it raises.
+"""
+from __future__ import annotations
+
+import math
+import weakref
+from collections import OrderedDict
+from typing import Optional
+
+import torch
+
+from . import layout as LY
+from .engine import THATEngine
+
+
+class _Node(torch.nn.Module):
+    """Parameter container; the module tree only exists to reproduce the reference's state_dict keys."""
+
+
+def _kaiming_conv(shape):
+    """torch.nn.Conv1d / Linear.reset_parameters(): kaiming_uniform_(a=sqrt(5)) weight, U(+-1/sqrt(fan_in)) bias."""
+    w = torch.empty(*shape)
+    torch.nn.init.kaiming_uniform_(w, a=math.sqrt(5))
+    fan_in = LY.numel(shape[1:])
+    bound = 1.0 / math.sqrt(fan_in) if fan_in > 0 else 0.0
+    b = torch.empty(shape[0]).uniform_(-bound, bound)
+    return w, b
+
+
+def _initial_values(g: LY.ModelGeom):
+    """Initial tensors, drawn in the order the reference's constructors consume the CPU RNG."""
+    vals = OrderedDict()
+    bufs = OrderedDict()
+    L, F = g.left.L, g.F
+    K = LY.NUM_GAUSS
+    emb = torch.zeros(K, F)
+    torch.nn.init.xavier_uniform_(emb)                                               # that.py:43-45
+    vals["layer_left_gaussian.var_embedding"] = emb
+    vals["layer_left_gaussian.var_position"] = torch.arange(0.0, L).unsqueeze(1).repeat(1, K)   # that.py:48
+    vals["layer_left_gaussian.var_mu"] = torch.arange(0.0, L, L / K).unsqueeze(0)    # that.py:52
+    vals["layer_left_gaussian.var_sigma"] = torch.tensor([50.0] * K).unsqueeze(0)    # that.py:56
+
+    def enc(p, d, kernels):
+        vals[p + "layer_norm_0.weight"] = torch.ones(d)
+        vals[p + "layer_norm_0.bias"] = torch.zeros(d)
+        # nn.MultiheadAttention.__init__: out_proj Linear is reset first, then _reset_parameters()
+        ow, _ob = _kaiming_conv((d, d))
+        iw = torch.empty(3 * d, d)
+        torch.nn.init.xavier_uniform_(iw)
+        vals[p + "layer_attention.in_proj_weight"] = iw
+        vals[p + "layer_attention.in_proj_bias"] = torch.zeros(3 * d)
+        vals[p + "layer_attention.out_proj.weight"] = ow
+        vals[p + "layer_attention.out_proj.bias"] = torch.zeros(d)
+        vals[p + "layer_norm_1.weight"] = torch.ones(d)
+        vals[p + "layer_norm_1.bias"] = torch.zeros(d)
+        for j, k in enumerate(kernels):
+            w, b = _kaiming_conv((d, d, k))
+            vals[f"{p}layer_cnn.{j}.0.weight"] = w
+            vals[f"{p}layer_cnn.{j}.0.bias"] = b
+            vals[f"{p}layer_cnn.{j}.1.weight"] = torch.ones(d)
+            vals[f"{p}layer_cnn.{j}.1.bias"] = torch.zeros(d)
+            bufs[f"{p}layer_cnn.{j}.1.running_mean"] = torch.zeros(d)
+            bufs[f"{p}layer_cnn.{j}.1.running_var"] = torch.ones(d)
+            bufs[f"{p}layer_cnn.{j}.1.num_batches_tracked"] = torch.tensor(0, dtype=torch.long)
+
+    for s in g.streams:
+        for e in range(s.n_enc):
+            enc(s.prefix(e), s.d, s.kernels)
+        vals[f"layer_{s.name}_norm.weight"] = torch.ones(s.d)
+        vals[f"layer_{s.name}_norm.bias"] = torch.zeros(s.d)
+        for j, k in enumerate(s.head_k):
+            w, b = _kaiming_conv((s.head_n, s.d, k))
+            vals[f"layer_{s.name}_cnn_{j}.weight"] = w
+            vals[f"layer_{s.name}_cnn_{j}.bias"] = b
+    w, b = _kaiming_conv((g.out, LY.FEAT))
+    vals["layer_output.weight"] = w
+    vals["layer_output.bias"] = b
+    return vals, bufs
+
+
+class _THATFunction(torch.autograd.Function):
+    """Autograd bridge for the reference-style loop ``loss(model(x), y).backward()`` (train.py:96-100)."""
+
+    @staticmethod
+    def forward(ctx, x, flat, model):
+        B = x.shape[0]
+        eng = model._engine_for(B)
+        eng.repack()
+        logits = eng.forward(x, B, training=True, dropout=model.dropout_enabled, augment=False)
+        ctx.model, ctx.B = model, B
+        return logits.clone()
+
+    @staticmethod
+    def backward(ctx, dlogits):
+        model, B = ctx.model, ctx.B
+        eng = model._engine
+        params = [p for p in model.parameters() if p.requires_grad]
+        fresh = all(p.grad is None for p in params)
+        eng.backward(dlogits.contiguous().float(), B, dropout=model.dropout_enabled, zero_grads=fresh)
+        model._attach_grads()
+        return None, None, None
+
+
+class THAT(torch.nn.Module):
+    """``THAT(var_x_shape, var_y_shape)``: var_x_shape[-2:] = (T, F), var_y_shape[-1] = out (that.py:183-192)."""
+
+    def __init__(self, var_x_shape, var_y_shape, act_dtype: Optional[str] = None, max_batch: Optional[int] = None):
+        super().__init__()
+        F, T, out = int(var_x_shape[-1]), int(var_x_shape[-2]), int(var_y_shape[-1])
+        self.geom = LY.ModelGeom(T, F, out)
+        self.specs = LY.parameter_specs(self.geom)
+        self.arena = LY.build_arena(self.specs)
+        self.act_dtype = {None: torch.bfloat16, "bf16": torch.bfloat16, "bfloat16": torch.bfloat16,
+                          "fp32": torch.float32, "float32": torch.float32}[act_dtype]
+        self.max_batch = max_batch
+        self.dropout_enabled = True          # parity tests switch the Dropout layers off (p = 0)
+        self.rng_seed = int(torch.initial_seed() & 0x7FFFFFFF)
+        self._engine: Optional[THATEngine] = None
+        self._ops_override = None            # tests only: inject the torch mirror of the kernels
+        vals, bufs = _initial_values(self.geom)
+        flat = torch.zeros(self.arena.size)
+        object.__setattr__(self, "_flat", flat)
+        object.__setattr__(self, "_gflat", torch.zeros(self.arena.size))
+        for name, shape in self.specs.items():
+            frozen = name in LY.FROZEN
+            if frozen:
+                data = vals[name].clone()
+            else:
+                off = self.arena.offsets[name]
+                data = flat[off:off + LY.numel(shape)].view(shape)
+                data.copy_(vals[name])
+            p = torch.nn.Parameter(data, requires_grad=not frozen)
+            p._csi_owner = weakref.ref(self)
+            p._csi_name = name
+            self._register(name, p, is_buffer=False)
+        for name, val in bufs.items():
+            self._register(name, val, is_buffer=True)
+
+    # ------------------------------------------------------------------ module tree
+    def _register(self, name, tensor, is_buffer):
+        parts = name.split(".")
+        node = self
+        for i, part in enumerate(parts[:-1]):
+            nxt = parts[i + 1]
+            if part.isdigit():
+                idx = int(part)
+                assert isinstance(node, torch.nn.ModuleList)
+                while len(node) <= idx:
+                    node.append(torch.nn.ModuleList() if nxt.isdigit() else _Node())
+                node = node[idx]
+            else:
+                if part not in node._modules:
+                    node.add_module(part, torch.nn.ModuleList() if nxt.isdigit() else _Node())
+                node = node._modules[part]
+        if is_buffer:
+            node.register_buffer(parts[-1], tensor)
+        else:
+            node.register_parameter(parts[-1], tensor)
+
+    def _named(self):
+        return OrderedDict(self.named_parameters())
+
+    def _apply(self, fn, recurse=True):
+        """``.to(device)`` / ``.cuda()``: move the two flat arenas and re-create the parameter views."""
+        new_flat = fn(self._flat)
+        if new_flat.dtype != torch.float32:
+            raise TypeError("THAT master weights are fp32; choose the compute type with act_dtype")
+        new_g = fn(self._gflat)
+        object.__setattr__(self, "_flat", new_flat)
+        object.__setattr__(self, "_gflat", new_g)
+        for name, p in self._named().items():
+            had_grad = p.grad is not None
+            if name in LY.FROZEN:
+                p.data = fn(p.data)
+            else:
+                off, shape = self.arena.offsets[name], self.arena.shapes[name]
+                p.data = new_flat[off:off + LY.numel(shape)].view(shape)
+                p.grad = new_g[off:off + LY.numel(shape)].view(shape) if had_grad else None
+        for mod in self.modules():
+            for k, b in mod._buffers.items():
+                if b is not None:
+                    mod._buffers[k] = fn(b)
+        self._engine = None
+        return self
+
+    def _attach_grads(self):
+        for name, p in self.named_parameters():
+            if p.requires_grad and p.grad is None:
+                off, shape = self.arena.offsets[name], self.arena.shapes[name]
+                p.grad = self._gflat[off:off + LY.numel(shape)].view(shape)
+
+    @property
+    def flat_params(self) -> torch.Tensor:
+        return self._flat
+
+    @property
+    def flat_grads(self) -> torch.Tensor:
+        return self._gflat
+
+    # ------------------------------------------------------------------ engine
+    def configure(self, act_dtype: Optional[str] = None, max_batch: Optional[int] = None):
+        """Optional preset keys ``nn.dtype`` / batch size feed this; defaults reproduce the reference call."""
+        if act_dtype is not None:
+            self.act_dtype = {"bf16": torch.bfloat16, "fp32": torch.float32}[act_dtype]
+        if max_batch is not None:
+            self.max_batch = max_batch
+        self._engine = None
+        return self
+
+    def _engine_for(self, B: int) -> THATEngine:
+        eng = self._engine
+        if eng is None or eng.B < B:
+            if self._flat.device.type != "cuda" and self._ops_override is None:
+                raise RuntimeError("multi_modal_csi_b200.THAT runs only on a CUDA (sm_100a) device: "
+                                   "call .to('cuda') first; there is no CPU path")
+            mb = max(B, self.max_batch or 0)
+            bn = OrderedDict((k, v) for k, v in self.named_buffers())
+            frozen = {k: p.data.reshape(-1) for k, p in self.named_parameters() if k in LY.FROZEN}
+            eng = THATEngine(self.geom, mb, self._flat, self._gflat, self.arena, bn, frozen,
+                             act_dtype=self.act_dtype, ops=self._ops_override, seed=self.rng_seed)
+            self._engine = eng
+        return eng
+
+    # ------------------------------------------------------------------ forward
+    def forward(self, var_input: torch.Tensor) -> torch.Tensor:
+        """float32 [B, T, F] -> float32 logits [B, out]  (that.py:249-302)."""
+        x = var_input
+        if x.dim() != 3 or x.shape[1] != self.geom.T or x.shape[2] != self.geom.F:
+            raise ValueError(f"expected input [B,{self.geom.T},{self.geom.F}], got {tuple(x.shape)}")
+        if x.dtype != torch.float32:
+            x = x.float()
+        x = x.contiguous()
+        if x.device != self._flat.device:
+            raise RuntimeError(f"input on {x.device} but model on {self._flat.device}")
+        if self.training and torch.is_grad_enabled():
+            return _THATFunction.apply(x, self._flat.requires_grad_(True), self)
+        return self._forward_nograd(x, self.training)
+
+    def _forward_nograd(self, x, training):
+        N = x.shape[0]
+        eng = self._engine_for(min(N, self.max_batch or 256))
+        eng.repack()
+        outs = []
+        for i in range(0, N, eng.B):
+            xb = x[i:i + eng.B]
+            outs.append(eng.forward(xb, xb.shape[0], training=training, dropout=self.dropout_enabled).clone())
+        return outs[0] if len(outs) == 1 else torch.cat(outs, 0)
+
+    # ------------------------------------------------------------------ fused train step
+    def fused_train_step(self, x, y, optimizer, pos_weight: float = 4.0, augment: bool = True,
+                         grad_hook=None, offs=None, lens=None):
+        """augmentation + forward + BCE + backward + Adam as one launch sequence (train.py:84-101).
+
+        x: fp32 [B,T,F] on the device (or a packed ragged arena with offs/lens); y: [B, ...] labels.
+        ``grad_hook(engine)`` runs between backward and the optimizer (data-parallel all-reduce).
+        Returns (loss 1-element tensor, logits [B,out]); both are views of static buffers."""
+        B = y.shape[0]
+        eng = self._engine_for(B)
+        yf = y.reshape(B, -1)
+        if yf.dtype != torch.float32:
+            yf = yf.float()
+        eng.repack()
+        logits = eng.forward(x, B, training=True, dropout=self.dropout_enabled, augment=augment,
+                             offs=offs, lens=lens)
+        loss = eng.loss_fwd_bwd(yf.contiguous(), B, pos_weight)
+        eng.backward(None, B, dropout=self.dropout_enabled, zero_grads=True)
+        self._attach_grads()
+        if grad_hook is not None:
+            grad_hook(eng)
+        optimizer.fused_step(eng)
+        return loss, logits
