@@ -181,6 +181,9 @@ int csi_advance_counters(unsigned long long* rng, long long* step, void* stream)
 int csi_pack_weights(const float* params, void* packed, int dtype, const csi_pack_entry* table, int n_entries,
                      int max_elems, void* stream);
 
+/* Test hook: 1 = route every contraction/attention call to the FFMA kernels, 0 = tensor-core kernels where eligible. */
+int csi_set_force_simt(int on);
+
 /* Generic helpers */
 int csi_fill_f32(float* p, long long n, float v, void* stream);
 

@@ -1,0 +1,110 @@
+// Shared device/host helpers for libcsi_that.so (sm_100a).
+#pragma once
+#include <cuda_runtime.h>
+#include <cuda_bf16.h>
+#include <stdint.h>
+#include <stdio.h>
+#include "../../include/csi_that.h"
+
+typedef __nv_bfloat16 bf16;
+
+void csi_set_error(const char* fmt, ...);
+
+#define CSI_CHECK_ARG(cond, msg)                                                   \
+    do { if (!(cond)) { csi_set_error("%s: %s", __func__, msg); return CSI_ERR_ARG; } } while (0)
+
+#define CSI_LAUNCH_CHECK()                                                         \
+    do { cudaError_t e__ = cudaGetLastError();                                     \
+         if (e__ != cudaSuccess) { csi_set_error("%s: %s", __func__, cudaGetErrorString(e__)); \
+                                   return CSI_ERR_CUDA; } } while (0)
+
+#define CSI_CUDA(call)                                                             \
+    do { cudaError_t e__ = (call);                                                 \
+         if (e__ != cudaSuccess) { csi_set_error("%s: %s failed: %s", __func__, #call, cudaGetErrorString(e__)); \
+                                   return CSI_ERR_CUDA; } } while (0)
+
+#define LEAKY_SLOPE 0.01f
+
+// ---------------------------------------------------------------- dtype access
+template <typename T> __device__ __forceinline__ float ldv(const T* p);
+template <> __device__ __forceinline__ float ldv<float>(const float* p) { return *p; }
+template <> __device__ __forceinline__ float ldv<bf16>(const bf16* p) { return __bfloat162float(*p); }
+template <typename T> __device__ __forceinline__ void stf(T* p, float v);
+template <> __device__ __forceinline__ void stf<float>(float* p, float v) { *p = v; }
+template <> __device__ __forceinline__ void stf<bf16>(bf16* p, float v) { *p = __float2bfloat16_rn(v); }
+
+// two consecutive elements (p must be 2-element aligned)
+template <typename T> __device__ __forceinline__ float2 ld2(const T* p);
+template <> __device__ __forceinline__ float2 ld2<float>(const float* p) { return *reinterpret_cast<const float2*>(p); }
+template <> __device__ __forceinline__ float2 ld2<bf16>(const bf16* p) {
+    return __bfloat1622float2(*reinterpret_cast<const __nv_bfloat162*>(p));
+}
+template <typename T> __device__ __forceinline__ void st2(T* p, float2 v);
+template <> __device__ __forceinline__ void st2<float>(float* p, float2 v) { *reinterpret_cast<float2*>(p) = v; }
+template <> __device__ __forceinline__ void st2<bf16>(bf16* p, float2 v) {
+    *reinterpret_cast<__nv_bfloat162*>(p) = __float22bfloat162_rn(v);
+}
+
+// ---------------------------------------------------------------- reductions
+__device__ __forceinline__ float warp_sum(float v) {
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+    return v;
+}
+__device__ __forceinline__ float warp_max(float v) {
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) v = fmaxf(v, __shfl_xor_sync(0xffffffffu, v, o));
+    return v;
+}
+
+// ---------------------------------------------------------------- counter-based RNG (Philox4x32-10)
+__device__ __forceinline__ uint4 philox4x32_10(uint4 c, uint2 k) {
+#pragma unroll
+    for (int r = 0; r < 10; ++r) {
+        uint32_t hi0 = __umulhi(0xD2511F53u, c.x), lo0 = 0xD2511F53u * c.x;
+        uint32_t hi1 = __umulhi(0xCD9E8D57u, c.z), lo1 = 0xCD9E8D57u * c.z;
+        c = make_uint4(hi1 ^ c.y ^ k.x, lo1, hi0 ^ c.w ^ k.y, lo0);
+        k.x += 0x9E3779B9u; k.y += 0xBB67AE85u;
+    }
+    return c;
+}
+
+struct RngKey { uint2 key; uint32_t step; };
+
+__device__ __forceinline__ RngKey rng_load(const unsigned long long* rng) {
+    RngKey r;
+    unsigned long long seed = rng[0], step = rng[1];
+    r.key = make_uint2((uint32_t)seed ^ (uint32_t)(step >> 32) * 0x85EBCA6Bu, (uint32_t)(seed >> 32) ^ 0x1234567u);
+    r.step = (uint32_t)step;
+    return r;
+}
+
+// 4 random words for the aligned group of 4 consecutive elements containing idx (idx4 = idx >> 2)
+__device__ __forceinline__ uint4 rng_group(const RngKey& k, uint32_t site, unsigned long long idx4) {
+    return philox4x32_10(make_uint4((uint32_t)idx4, (uint32_t)(idx4 >> 32), site, k.step), k.key);
+}
+__device__ __forceinline__ uint32_t pick(const uint4& v, int i) {
+    return i == 0 ? v.x : (i == 1 ? v.y : (i == 2 ? v.z : v.w));
+}
+__device__ __forceinline__ uint32_t drop_threshold(float p) {
+    return (uint32_t)fminf(p * 4294967296.0f, 4294967040.0f);
+}
+// keep-scale (0 or 1/(1-p)) of element idx
+__device__ __forceinline__ float drop_scale(const RngKey& k, uint32_t site, unsigned long long idx, uint32_t thr,
+                                            float inv_keep) {
+    uint4 g = rng_group(k, site, idx >> 2);
+    return pick(g, (int)(idx & 3)) >= thr ? inv_keep : 0.f;
+}
+// keep-scales of the two consecutive elements idx, idx+1 (idx even)
+__device__ __forceinline__ float2 drop_scale2(const RngKey& k, uint32_t site, unsigned long long idx, uint32_t thr,
+                                              float inv_keep) {
+    uint4 g = rng_group(k, site, idx >> 2);
+    int i = (int)(idx & 2);
+    uint32_t a = i ? g.z : g.x, b = i ? g.w : g.y;
+    return make_float2(a >= thr ? inv_keep : 0.f, b >= thr ? inv_keep : 0.f);
+}
+
+__device__ __forceinline__ float leaky(float v) { return v > 0.f ? v : LEAKY_SLOPE * v; }
+__device__ __forceinline__ float leaky_grad(float v) { return v > 0.f ? 1.f : LEAKY_SLOPE; }
+
+static inline int cdiv(long long a, long long b) { return (int)((a + b - 1) / b); }

@@ -1,0 +1,48 @@
+// Entry points whose implementation depends on operand type / shape: bf16 contractions go to the tcgen05 kernels
+// (gemm_tc.cu) when the shape qualifies, everything else to the FFMA kernels (gemm_simt.cu).
+#include "common.cuh"
+#include <stdlib.h>
+
+extern "C" int csi_gemm_nt_simt(const void*, int, const void*, int, int, void*, int, int, int, int, const csi_seg*, int,
+                                const float*, const float*, int, float, unsigned, const unsigned long long*, void*);
+extern "C" int csi_gemm_tn_simt(const void*, int, const void*, int, int, float*, int, int, int, int, const csi_seg_tn*,
+                                int, void*);
+extern "C" int csi_attn_fwd_simt(const void*, int, void*, int, int, float*, int, int, int, int, int, void*);
+extern "C" int csi_attn_bwd_simt(const void*, int, const void*, int, const void*, int, void*, int, int, const float*, int,
+                                 int, int, int, int, void*);
+extern "C" int csi_gemm_nt_tc(const void*, int, const void*, int, void*, int, int, int, int, const csi_seg*, int,
+                              const float*, const float*, int, float, unsigned, const unsigned long long*, void*);
+extern "C" int csi_gemm_nt_tc_ok(int lda, int ldb, int ldc, int M, int N, const csi_seg* segs, int nseg);
+
+static int g_force_simt = -1;
+static bool force_simt() {
+    if (g_force_simt < 0) { const char* e = getenv("CSI_FORCE_SIMT"); g_force_simt = (e && e[0] == '1') ? 1 : 0; }
+    return g_force_simt == 1;
+}
+// tests flip this at run time (1 = FFMA kernels only, 0 = tensor-core kernels where eligible)
+extern "C" int csi_set_force_simt(int on) { g_force_simt = on ? 1 : 0; return CSI_OK; }
+
+extern "C" int csi_gemm_nt(const void* A, int lda, const void* Bw, int ldb, int ab_dtype, void* C, int ldc, int c_dtype,
+                           int M, int N, const csi_seg* segs, int nseg, const float* bias, const float* residual,
+                           int ldr, float drop_p, unsigned drop_site, const unsigned long long* rng, void* stream) {
+    if (ab_dtype == CSI_BF16 && !force_simt() && csi_gemm_nt_tc_ok(lda, ldb, ldc, M, N, segs, nseg))
+        return csi_gemm_nt_tc(A, lda, Bw, ldb, C, ldc, c_dtype, M, N, segs, nseg, bias, residual, ldr, drop_p,
+                              drop_site, rng, stream);
+    return csi_gemm_nt_simt(A, lda, Bw, ldb, ab_dtype, C, ldc, c_dtype, M, N, segs, nseg, bias, residual, ldr, drop_p,
+                            drop_site, rng, stream);
+}
+
+extern "C" int csi_gemm_tn(const void* A, int lda, const void* Bv, int ldb, int ab_dtype, float* C, int ldc,
+                           int c_col_stride, int M, int Na, const csi_seg_tn* segs, int nseg, void* stream) {
+    return csi_gemm_tn_simt(A, lda, Bv, ldb, ab_dtype, C, ldc, c_col_stride, M, Na, segs, nseg, stream);
+}
+
+extern "C" int csi_attn_fwd(const void* qkv, int ld3, void* o, int ldo, int dtype, float* lse, int B, int L, int d,
+                            int H, int halo, void* stream) {
+    return csi_attn_fwd_simt(qkv, ld3, o, ldo, dtype, lse, B, L, d, H, halo, stream);
+}
+
+extern "C" int csi_attn_bwd(const void* qkv, int ld3, const void* o, int ldo, const void* dout, int lddo, void* dqkv,
+                            int lddqkv, int dtype, const float* lse, int B, int L, int d, int H, int halo, void* stream) {
+    return csi_attn_bwd_simt(qkv, ld3, o, ldo, dout, lddo, dqkv, lddqkv, dtype, lse, B, L, d, H, halo, stream);
+}

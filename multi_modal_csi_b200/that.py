@@ -91,7 +91,7 @@ class _THATFunction(torch.autograd.Function):
     """Autograd bridge for the reference-style loop ``loss(model(x), y).backward()`` (train.py:96-100)."""
 
     @staticmethod
-    def forward(ctx, x, flat, model):
+    def forward(ctx, x, anchor, model):
         B = x.shape[0]
         eng = model._engine_for(B)
         eng.repack()
@@ -242,7 +242,8 @@ class THAT(torch.nn.Module):
         if x.device != self._flat.device:
             raise RuntimeError(f"input on {x.device} but model on {self._flat.device}")
         if self.training and torch.is_grad_enabled():
-            return _THATFunction.apply(x, self._flat.requires_grad_(True), self)
+            anchor = torch.zeros((), device=x.device, requires_grad=True)   # ties the graph to backward()
+            return _THATFunction.apply(x, anchor, self)
         return self._forward_nograd(x, self.training)
 
     def _forward_nograd(self, x, training):

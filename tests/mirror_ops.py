@@ -197,9 +197,11 @@ class MirrorOps:
         nc = nbr * Dp
         m = sums[:nc] / count
         var = (sums[nc:2 * nc] / count - m * m).clamp_min(0)
-        mean[:nc] = m.float()
-        invstd[:nc] = torch.rsqrt(var + eps).float()
+        mean[:nc] = 0
+        invstd[:nc] = 0
         for br in range(nbr):
+            mean[br * Dp:br * Dp + d] = m[br * Dp:br * Dp + d].float()
+            invstd[br * Dp:br * Dp + d] = torch.rsqrt(var[br * Dp:br * Dp + d] + eps).float()
             mb, vb = m[br * Dp:br * Dp + d].float(), var[br * Dp:br * Dp + d].float()
             run_mean[br].mul_(1 - momentum).add_(momentum * (mb + conv_bias[br]))
             run_var[br].mul_(1 - momentum).add_(momentum * vb * (count / max(count - 1, 1)))

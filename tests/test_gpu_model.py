@@ -1,0 +1,222 @@
+"""Whole-path GPU parity: THAT forward / backward / BCE / Adam through libcsi_that.so against (1) the golden
+fixtures generated from the unmodified reference and (2) the CPU oracle run on the same seeded inputs."""
+import copy
+
+import numpy as np
+import pytest
+import torch
+
+pytestmark = pytest.mark.gpu
+
+# Stated tolerances (normwise relative error  ||a-b|| / ||b||):
+#   fp32 mode : 1e-4 on logits and on the full gradient vector (north_star)
+#   bf16 mode : 2e-2 on logits, 5e-2 on the gradient vector; multi-label predictions must be identical wherever
+#               |logit_ref| exceeds the measured absolute logit error (SURVEY.md section 7 "hard parts")
+TOL = {"fp32": (1e-4, 1e-4), "bf16": (2e-2, 5e-2)}
+
+
+def nrel(a, b):
+    a, b = a.double().cpu(), b.double().cpu()
+    return ((a - b).norm() / (b.norm() + 1e-30)).item()
+
+
+def grad_err(model, ref_grads):
+    num = den = 0.0
+    worst = (0.0, None)
+    for k, p in model.named_parameters():
+        if k in ref_grads:
+            r = ref_grads[k].double()
+            e = (p.grad.double().cpu() - r).norm().item()
+            n = r.norm().item()
+            num += e * e
+            den += n * n
+            if n > 1e-3 * max(den, 1e-30) ** 0.5 and e / n > worst[0]:
+                worst = (e / n, k)
+    return (num / den) ** 0.5, worst
+
+
+def build(T, F, out, mode, sd=None, seed=39):
+    from multi_modal_csi_b200 import THAT
+    torch.manual_seed(seed)
+    m = THAT((T, F), (out,), act_dtype=mode)
+    if sd is not None:
+        m.load_state_dict(sd)
+    m.dropout_enabled = False
+    return m.to("cuda")
+
+
+def synth(B, T, F, out, seed=1234):
+    g = torch.Generator().manual_seed(seed)
+    x = torch.rand(B, T, F, generator=g) * 20
+    y = (torch.rand(B, out, generator=g) < 0.15).float()
+    return x, y
+
+
+@pytest.mark.parametrize("mode", ["fp32", "bf16"])
+def test_small_known_answer(gold, mode):
+    g = gold("that_small.npz")
+    T, F, out, B = [int(v) for v in g["dims"]]
+    sd = {k[2:]: torch.from_numpy(g[k]) for k in g.files if k.startswith("w/")}
+    m = build(T, F, out, mode, sd)
+    x, y = torch.from_numpy(g["x"]).cuda(), torch.from_numpy(g["y"]).cuda()
+    m.train()
+    logits = m(x)
+    loss = torch.nn.BCEWithLogitsLoss(pos_weight=torch.full((out,), 4.0, device="cuda"))(logits, y)
+    loss.backward()
+    tl, tg = TOL[mode]
+    assert nrel(logits, torch.from_numpy(g["logits_train"])) < tl
+    assert abs(loss.item() - float(g["loss"])) < tl * 10 * abs(float(g["loss"]))
+    ref_grads = {k[2:]: torch.from_numpy(g[k]) for k in g.files if k.startswith("g/")}
+    ge, worst = grad_err(m, ref_grads)
+    assert ge < tg, (ge, worst)
+    sdm = m.state_dict()
+    for k in g.files:
+        if k.startswith("bn/"):
+            assert nrel(sdm[k[3:]].float(), torch.from_numpy(g[k]).float()) < (1e-5 if mode == "fp32" else 1e-2), k
+    m.eval()
+    with torch.no_grad():
+        le = m(x)
+    assert nrel(le, torch.from_numpy(g["logits_eval"])) < tl
+
+
+@pytest.mark.parametrize("mode,F,out", [("fp32", 270, 54), ("bf16", 270, 54), ("bf16", 540, 90), ("fp32", 540, 90)])
+def test_full_size_anchor_and_oracle(gold, mode, F, out):
+    """Full-size [B=4, 3000, F] case: weights re-created from seed 39 (bit-identical to the reference's init),
+    compared with the committed reference outputs and with the CPU oracle's full gradient."""
+    from oracle import that_oracle as O
+    g = gold(f"that_anchor_{F}.npz")
+    T, B = 3000, 4
+    m = build(T, F, out, mode)
+    for k, v in m.state_dict().items():
+        assert abs(v.double().sum().item() - float(g["init_sum/" + k])) <= 1e-6 * max(1.0, float(g["init_abs/" + k])), k
+    sd_cpu = copy.deepcopy({k: v.cpu() for k, v in m.state_dict().items()})
+    x, y = synth(B, T, F, out)
+    m.train()
+    logits = m(x.cuda())
+    loss = torch.nn.BCEWithLogitsLoss(pos_weight=torch.full((out,), 4.0, device="cuda"))(logits, y.cuda())
+    loss.backward()
+    tl, tg = TOL[mode]
+    ref_logits = torch.from_numpy(g["logits_train"])
+    err_abs = (logits.cpu() - ref_logits).abs().max().item()
+    assert nrel(logits, ref_logits) < tl
+    assert abs(loss.item() - float(g["loss"])) < 10 * tl * float(g["loss"])
+    # oracle on the box's CPU, in fp64 (the fp32 reference itself is 3e-5 away from it):
+    # full gradient vector
+    sd64 = {k: (v.double() if v.is_floating_point() else v.clone()) for k, v in sd_cpu.items()}
+    _, _, og = O.loss_and_grads(sd64, x.double(), y.double())
+    ge, worst = grad_err(m, og)
+    assert ge < tg, (ge, worst)
+    gn = sum(p.grad.double().pow(2).sum().item() for p in m.parameters() if p.grad is not None) ** 0.5
+    assert abs(gn - float(g["grad_norm"])) < tg * float(g["grad_norm"])
+    for k in ("layer_output.weight", "layer_left_gaussian.var_mu", "layer_left_gaussian.var_sigma"):
+        assert nrel(dict(m.named_parameters())[k].grad, torch.from_numpy(g["g/" + k])) < 5 * tg, k
+    # equal multi-label predictions after the reference decision rule (utils.py:147-183,234-239)
+    m.eval()
+    with torch.no_grad():
+        le = m(x.cuda()).cpu()
+    ref_eval = torch.from_numpy(g["logits_eval"])
+    assert nrel(le, ref_eval) < tl
+    users = 6
+    if out % users == 0:
+        mine, ref = O.predict_counts(le, users), O.predict_counts(ref_eval, users)
+        margin = (le - ref_eval).abs().max().item()
+        p = torch.sigmoid(ref_eval.double()).reshape(B, users, -1)
+        top2 = p.topk(2, dim=2).values
+        decisive = ((top2[..., 0] - 0.5).abs() > margin) & ((top2[..., 0] - top2[..., 1]) > margin)
+        if bool(decisive.all()):
+            assert torch.equal(mine, ref)
+        else:                                   # only samples whose every user decision is outside the error band
+            ok = decisive.all(dim=1)
+            assert torch.equal(mine[ok], ref[ok])
+    assert err_abs < 1.0
+
+
+def test_fused_train_step_trajectory(gold):
+    """3 Adam steps (lr 5e-4, wd 2e-4) with the fused path vs the reference's torch.optim.Adam trajectory."""
+    from multi_modal_csi_b200 import FusedAdam
+    g = gold("that_small.npz")
+    T, F, out, B = [int(v) for v in g["dims"]]
+    sd = {k[2:]: torch.from_numpy(g[k]) for k in g.files if k.startswith("w/")}
+    m = build(T, F, out, "fp32", sd)
+    opt = FusedAdam(m.parameters(), lr=5e-4, weight_decay=2e-4)
+    m.train()
+    for s in range(3):
+        x, y = synth(B, T, F, out, seed=1234 + s)
+        loss, _ = m.fused_train_step(x.cuda(), y.cuda(), opt, augment=False)
+        assert abs(loss.item() - float(g["traj_losses"][s])) < 2e-4 * max(1.0, float(g["traj_losses"][s]))
+    sdm = m.state_dict()
+    for k in g.files:
+        if k.startswith("traj_w/") and not k.endswith(".0.bias"):
+            # conv biases under a train-mode BatchNorm have a zero true gradient: the reference moves them by
+            # Adam-normalised rounding noise, so they are excluded from the trajectory comparison
+            assert (sdm[k[7:]].float().cpu() - torch.from_numpy(g[k]).float()).abs().max().item() < 2e-4, k
+
+
+def test_autograd_path_equals_fused_path():
+    """The reference-style loop (torch loss + torch.optim.Adam on the parameter views) and the fused step agree."""
+    from multi_modal_csi_b200 import FusedAdam
+    T, F, out, B = 400, 30, 12, 5
+    x, y = synth(B, T, F, out)
+    ma, mf = build(T, F, out, "fp32"), build(T, F, out, "fp32")
+    oa = torch.optim.Adam(ma.parameters(), lr=5e-4, weight_decay=2e-4)
+    of = FusedAdam(mf.parameters(), lr=5e-4, weight_decay=2e-4)
+    lossf = torch.nn.BCEWithLogitsLoss(pos_weight=torch.full((out,), 4.0, device="cuda"))
+    for s in range(2):
+        ma.train()
+        pred = ma(x.cuda())
+        la = lossf(pred, y.cuda())
+        oa.zero_grad()
+        la.backward()
+        oa.step()
+        lf, _ = mf.fused_train_step(x.cuda(), y.cuda(), of, augment=False)
+        assert abs(la.item() - lf.item()) < 1e-5 * max(1.0, abs(la.item()))
+    for (k, a), (_, b) in zip(ma.state_dict().items(), mf.state_dict().items()):
+        if k.endswith("in_proj_bias") or k.endswith(".0.bias"):
+            continue    # (partly) zero true gradient: Adam normalises atomic-order rounding noise into +-lr steps
+        assert (a.float() - b.float()).abs().max().item() < 2e-5, k
+
+
+def test_dropout_and_augmentation_step_runs_and_is_reproducible():
+    from multi_modal_csi_b200 import FusedAdam
+    T, F, out, B = 3000, 270, 54, 8
+    x, y = synth(B, T, F, out)
+    losses = []
+    for rep in range(2):
+        m = build(T, F, out, "bf16")
+        m.dropout_enabled = True
+        opt = FusedAdam(m.parameters(), lr=5e-4, weight_decay=2e-4)
+        m.train()
+        ls = []
+        for s in range(3):
+            loss, logits = m.fused_train_step(x.cuda(), y.cuda(), opt, augment=True)
+            ls.append(loss.item())
+            assert torch.isfinite(logits).all()
+        assert all(np.isfinite(ls))
+        assert all(torch.isfinite(p).all() for p in m.parameters())
+        losses.append(ls)
+    # same seed -> same augmentation and dropout masks; later steps differ only by fp32 atomic summation order
+    assert abs(losses[0][0] - losses[1][0]) < 1e-4 * abs(losses[0][0])
+    assert all(abs(a - b) < 5e-3 * abs(a) for a, b in zip(losses[0], losses[1]))
+    assert losses[0][0] != losses[0][1]
+
+
+def test_state_dict_roundtrip_and_eval_chunking():
+    T, F, out = 400, 30, 12
+    m = build(T, F, out, "fp32")
+    sd = copy.deepcopy(m.state_dict())
+    m2 = build(T, F, out, "fp32", seed=7)
+    m2.load_state_dict({k: v.cpu() for k, v in sd.items()})
+    x, _ = synth(11, T, F, out)
+    m.eval(); m2.eval()
+    m.configure(max_batch=4)                            # 11 samples -> chunks of 4,4,3
+    with torch.no_grad():
+        a, b = m(x.cuda()), m2(x.cuda())
+    assert a.shape == (11, out)
+    assert (a - b).abs().max().item() < 1e-5
+
+
+def test_no_cpu_path():
+    from multi_modal_csi_b200 import THAT
+    m = THAT((400, 30), (12,))
+    with pytest.raises(RuntimeError):
+        m(torch.zeros(2, 400, 30))

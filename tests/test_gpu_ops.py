@@ -1,0 +1,444 @@
+"""GPU parity of every C-ABI kernel against the torch mirror (tests/mirror_ops.py) on the same inputs.
+Runs through multi_modal_csi_b200.ops.NativeOps, i.e. through the ctypes boundary of libcsi_that.so."""
+import math
+
+import numpy as np
+import pytest
+import torch
+
+from mirror_ops import MirrorOps
+
+pytestmark = pytest.mark.gpu
+
+GUARD = 16
+HALO = 2
+
+
+def ru(x, m):
+    return (x + m - 1) // m * m
+
+
+@pytest.fixture(scope="module")
+def ops():
+    from multi_modal_csi_b200.ops import NativeOps
+    return NativeOps(torch.device("cuda", 0))
+
+
+@pytest.fixture(scope="module")
+def mir():
+    return MirrorOps("cuda")
+
+
+def tokbuf(B, L, ld, dtype, fill=None, gen=None, ncols=None):
+    """Token buffer with zero halo/guard rows; valid rows filled with N(0,1)*fill in the first ncols columns."""
+    Lp = L + 2 * HALO
+    rows = B * Lp
+    full = torch.zeros(rows + 2 * GUARD, ld, dtype=dtype, device="cuda")
+    body = full[GUARD:GUARD + rows]
+    if fill is not None:
+        ncols = ld if ncols is None else ncols
+        v = torch.randn(B, L, ncols, device="cuda", generator=gen) * fill
+        body.view(B, Lp, ld)[:, HALO:HALO + L, :ncols] = v.to(dtype)
+    return full, body
+
+
+def valid(body, B, L, ncols):
+    Lp = L + 2 * HALO
+    return body.view(B, Lp, -1)[:, HALO:HALO + L, :ncols].float()
+
+
+def relerr(a, b):
+    a, b = a.double(), b.double()
+    return ((a - b).norm() / (b.norm() + 1e-30)).item()
+
+
+DT = [torch.float32, torch.bfloat16]
+TOL = {torch.float32: 2e-5, torch.bfloat16: 1e-2}
+SHAPES = [(3, 20, 30), (2, 150, 270), (2, 270, 150), (1, 540, 150)]
+
+
+def gen(seed=0):
+    return torch.Generator(device="cuda").manual_seed(seed)
+
+
+# ------------------------------------------------------------------------------------------------ input stage
+@pytest.mark.parametrize("B,T,F", [(3, 400, 30), (2, 3000, 270), (1, 3000, 540)])
+def test_pool_dual_dense(ops, mir, B, T, F):
+    g = gen(1)
+    L = T // 20
+    x = torch.rand(B, T, F, device="cuda", generator=g) * 20
+    pe = torch.randn(L, ru(F, 16), device="cuda", generator=g)
+    outs = []
+    for o in (ops, mir):
+        _, left = tokbuf(B, L, ru(F, 16), torch.float32)
+        _, right = tokbuf(B, F, ru(L, 16), torch.float32)
+        o.pool_dual(x, None, None, B, T, F, pe, left, right, HALO, 0, None)
+        outs.append((left, right))
+    assert relerr(outs[0][0], outs[1][0]) < 1e-6
+    assert relerr(outs[0][1], outs[1][1]) < 1e-6
+    ref = torch.nn.functional.avg_pool1d(x.transpose(1, 2), 20, 20)          # [B,F,L]
+    assert relerr(valid(outs[0][1], B, F, L), ref) < 1e-6
+
+
+def test_pool_dual_ragged_front_pad(ops, mir):
+    B, T, F = 4, 400, 30
+    L = T // 20
+    g = gen(2)
+    lens = torch.tensor([400, 371, 1, 260], dtype=torch.int32)
+    offs = torch.zeros(B, dtype=torch.int64)
+    offs[1:] = torch.cumsum(lens[:-1].long() * F, 0)
+    arena = torch.rand(int((lens.long() * F).sum()), device="cuda", generator=g) * 20
+    outs = []
+    for o in (ops, mir):
+        _, left = tokbuf(B, L, ru(F, 16), torch.float32)
+        _, right = tokbuf(B, F, ru(L, 16), torch.float32)
+        o.pool_dual(arena, offs.cuda(), lens.cuda(), B, T, F, None, left, right, HALO, 0, None)
+        outs.append((left, right))
+    assert relerr(outs[0][0], outs[1][0]) < 1e-6
+    assert relerr(outs[0][1], outs[1][1]) < 1e-6
+    # the front of short samples is zero (load_data.py:70-72 pads in FRONT)
+    lv = valid(outs[0][0], B, L, F)
+    assert float(lv[2, :L - 1].abs().max()) == 0.0 and float(lv[2, L - 1].abs().max()) > 0.0
+
+
+def test_pool_dual_augment_statistics(ops):
+    B, T, F = 8, 3000, 270
+    L = T // 20
+    x = torch.full((B, T, F), 10.0, device="cuda")
+    rng = torch.tensor([1234, 7], dtype=torch.int64, device="cuda")
+    _, left = tokbuf(B, L, ru(F, 16), torch.float32)
+    _, right = tokbuf(B, F, ru(L, 16), torch.float32)
+    ops.pool_dual(x, None, None, B, T, F, None, left, right, HALO, 1, rng)
+    lv = valid(left, B, L, F)                                           # mean over 20 of (10+.1n)*s*m
+    per_sample = lv.mean(dim=(1, 2)) / 10.0 / 0.96                      # ~ scale_b in [0.9, 1.1)
+    assert float(per_sample.min()) > 0.89 and float(per_sample.max()) < 1.11
+    assert float(per_sample.std()) > 0.01                               # scales differ per sample
+    # pooled variance: keep-mask Bernoulli(.96) on a constant 10*s dominates; noise adds 0.01*s^2/20
+    s = per_sample.view(B, 1, 1)
+    resid = lv / s
+    expect_var = (100.0 * 0.96 * 0.04 + 0.01 * 0.96) / 20.0
+    assert abs(float(resid.var()) / expect_var - 1.0) < 0.05
+    assert relerr(valid(right, B, F, L), lv.transpose(1, 2)) < 1e-6     # both streams see the same pooled tensor
+    # a different step gives a different draw, the same step the same draw
+    _, left2 = tokbuf(B, L, ru(F, 16), torch.float32)
+    ops.pool_dual(x, None, None, B, T, F, None, left2, right, HALO, 1, rng)
+    assert torch.equal(left, left2)
+    rng2 = torch.tensor([1234, 8], dtype=torch.int64, device="cuda")
+    ops.pool_dual(x, None, None, B, T, F, None, left2, right, HALO, 1, rng2)
+    assert not torch.equal(left, left2)
+
+
+def test_gauss_pe(ops, mir):
+    L, K, F = 150, 10, 270
+    g = gen(3)
+    pos = torch.arange(0.0, L, device="cuda").unsqueeze(1).repeat(1, K).contiguous()
+    mu = torch.arange(0.0, L, L / K, device="cuda") + torch.randn(K, device="cuda", generator=g)
+    sigma = 50 + 5 * torch.randn(K, device="cuda", generator=g)
+    emb = torch.randn(K, F, device="cuda", generator=g) * 0.1
+    res = []
+    for o in (ops, mir):
+        w = torch.zeros(L, K, device="cuda")
+        pe = torch.zeros(L, ru(F, 16), device="cuda")
+        o.gauss_pe_fwd(pos, mu, sigma, emb, L, K, F, w, pe)
+        B = 5
+        _, dleft = tokbuf(B, L, ru(F, 16), torch.float32, fill=1.0, gen=gen(4), ncols=F)
+        ws = torch.zeros(L, ru(F, 16), device="cuda")
+        demb, dmu, dsg = torch.zeros(K, F, device="cuda"), torch.zeros(K, device="cuda"), torch.zeros(K, device="cuda")
+        o.gauss_pe_bwd(dleft, B, HALO, w, pos, mu, sigma, emb, L, K, F, ws, demb, dmu, dsg)
+        res.append((w, pe, demb, dmu, dsg))
+    for a, b in zip(*res):
+        assert relerr(a, b) < 1e-4
+
+
+# ------------------------------------------------------------------------------------------------ layernorm
+@pytest.mark.parametrize("dt", DT)
+@pytest.mark.parametrize("B,L,d", SHAPES + [(2, 150, 540)])
+def test_layernorm(ops, mir, dt, B, L, d):
+    ld = ru(d, 16)
+    g = gen(5)
+    _, x = tokbuf(B, L, ld, torch.float32, fill=3.0, gen=g, ncols=d)
+    x += 1.5 * (x != 0)
+    gamma = 1 + 0.1 * torch.randn(d, device="cuda", generator=g)
+    beta = 0.1 * torch.randn(d, device="cuda", generator=g)
+    _, dy = tokbuf(B, L, ld, dt, fill=1.0, gen=g, ncols=d)
+    _, dres = tokbuf(B, L, ld, torch.float32, fill=1.0, gen=g, ncols=d)
+    res = []
+    for o in (ops, mir):
+        _, y = tokbuf(B, L, ld, dt)
+        rows = B * (L + 2 * HALO)
+        mean, rstd = torch.zeros(rows, device="cuda"), torch.zeros(rows, device="cuda")
+        o.layernorm_fwd(x, gamma, beta, y, mean, rstd, B, L, d, HALO, 1e-6)
+        _, dx = tokbuf(B, L, ld, torch.float32)
+        _, dxm = tokbuf(B, L, ld, dt)
+        dg, db = torch.zeros(d, device="cuda"), torch.zeros(d, device="cuda")
+        o.layernorm_bwd(dy, x, gamma, mean, rstd, dres, dx, dxm, 0.0, 0, None, dg, db, B, L, d, HALO)
+        res.append((y.float(), mean, rstd, dx, dxm.float(), dg, db))
+    tol = TOL[dt]
+    for i, (a, b) in enumerate(zip(*res)):
+        assert relerr(a, b) < tol, i
+    ref = torch.nn.functional.layer_norm(valid(x, B, L, d), (d,), gamma, beta, 1e-6)
+    assert relerr(valid(res[0][0], B, L, d), ref) < tol
+    assert float(res[0][0][:, d:].abs().max()) == 0.0          # pad columns stay zero
+
+
+# ------------------------------------------------------------------------------------------------ GEMMs
+@pytest.mark.parametrize("dt", DT)
+@pytest.mark.parametrize("simt", [True, False])
+def test_gemm_nt_linear_and_conv(ops, mir, dt, simt):
+    ops.set_force_simt(simt)
+    try:
+        B, L, d, N = 3, 150, 270, 270
+        Dp = ru(d, 16)
+        g = gen(6)
+        _, A = tokbuf(B, L, Dp, dt, fill=1.0, gen=g, ncols=d)
+        rows = B * (L + 2 * HALO)
+        bias = torch.randn(N, device="cuda", generator=g)
+        _, res = tokbuf(B, L, Dp, torch.float32, fill=1.0, gen=g, ncols=d)
+        for k, cdt in ((1, torch.float32), (3, dt), (5, dt)):
+            W = torch.zeros(N, k * Dp, dtype=dt, device="cuda")
+            for j in range(k):
+                W[:, j * Dp:j * Dp + d] = (torch.randn(N, d, device="cuda", generator=g) / math.sqrt(d * k)).to(dt)
+            pl = (k - 1) // 2
+            segs = [(j - pl, 0, j * Dp, Dp) for j in range(k)]
+            outs = []
+            for o in (ops, mir):
+                _, Cm = tokbuf(B, L, ru(N, 16), cdt)
+                o.gemm_nt(A, W, Cm, rows, N, segs, bias, res if k == 1 else None, 0.0, 0, None)
+                outs.append(Cm.float())
+            assert relerr(outs[0], outs[1]) < (3e-6 if dt == torch.float32 and cdt == torch.float32 else 6e-3), (k, cdt)
+            if k == 3:                                                     # against torch's own Conv1d
+                torch.backends.cudnn.allow_tf32 = False
+                xin = valid(A, B, L, d).transpose(1, 2)
+                w3 =torch.stack([W[:, j * Dp:j * Dp + d].float() for j in range(k)], dim=-1)
+                ref = torch.nn.functional.conv1d(xin, w3, bias, padding=1).transpose(1, 2)
+                assert relerr(valid(outs[0], B, L, N), ref) < (1e-5 if dt == torch.float32 else 1e-2)
+    finally:
+        ops.set_force_simt(False)
+
+
+@pytest.mark.parametrize("dt", DT)
+@pytest.mark.parametrize("M,N,K", [(256, 54, 288), (37, 12, 288), (1000, 810, 272), (300, 16, 160)])
+def test_gemm_nt_plain(ops, mir, dt, M, N, K):
+    g = gen(7)
+    A = torch.randn(M, K, device="cuda", generator=g).to(dt)
+    W = (torch.randn(N, K, device="cuda", generator=g) / math.sqrt(K)).to(dt)
+    bias = torch.randn(N, device="cuda", generator=g)
+    outs = []
+    for o in (ops, mir):
+        Cm = torch.zeros(M, ru(N, 16), device="cuda")
+        o.gemm_nt(A, W, Cm, M, N, [(0, 0, 0, K)], bias, None, 0.0, 0, None)
+        outs.append(Cm)
+    assert relerr(outs[0], outs[1]) < (3e-6 if dt == torch.float32 else 2e-5)
+    if outs[0].shape[1] > N:
+        assert float(outs[0][:, N:].abs().max()) == 0.0
+
+
+@pytest.mark.parametrize("dt", DT)
+def test_gemm_tn_weight_gradients(ops, mir, dt):
+    B, L, d, N, k = 3, 150, 270, 128, 8
+    Dp = ru(d, 16)
+    g = gen(8)
+    rows = B * (L + 2 * HALO)
+    _, dY = tokbuf(B, L, ru(N, 16), dt, fill=1.0, gen=g, ncols=N)
+    _, X = tokbuf(B, L, Dp, dt, fill=1.0, gen=g, ncols=d)
+    outs = []
+    for o in (ops, mir):
+        gw = torch.zeros(N * d * k, device="cuda")
+        o.gemm_tn(dY, X, gw, d * k, k, rows, N, [(t, 0, t, d) for t in range(k)])
+        gl = torch.zeros(N * d, device="cuda")
+        o.gemm_tn(dY, X, gl, d, 1, rows, N, [(0, 0, 0, d)])
+        outs.append((gw, gl))
+    tol = 2e-5 if dt == torch.float32 else 2e-5
+    assert relerr(outs[0][0], outs[1][0]) < tol
+    assert relerr(outs[0][1], outs[1][1]) < tol
+    # independent check of the conv layout: autograd of a valid Conv1d whose output gradient is dY
+    xin = valid(X, B, L, d).transpose(1, 2).clone().requires_grad_(False)
+    w = torch.zeros(N, d, k, device="cuda", requires_grad=True)
+    y = torch.nn.functional.conv1d(xin, w)                                    # [B,N,L-k+1]
+    gy = valid(dY, B, L, N).transpose(1, 2)[:, :, :L - k + 1]
+    y.backward(gy)
+    # rows t > L-k of dY also contribute in the kernel (they read the next rows); zero them for this check
+    _, dY2 = tokbuf(B, L, ru(N, 16), dt)
+    dY2.view(B, L + 2 * HALO, -1)[:, HALO:HALO + L - k + 1] = dY.view(B, L + 2 * HALO, -1)[:, HALO:HALO + L - k + 1]
+    gw2 = torch.zeros(N * d * k, device="cuda")
+    ops.gemm_tn(dY2, X, gw2, d * k, k, rows, N, [(t, 0, t, d) for t in range(k)])
+    assert relerr(gw2.view(N, d, k), w.grad) < (1e-5 if dt == torch.float32 else 1e-5)
+
+
+@pytest.mark.parametrize("dt", DT)
+def test_colsum(ops, mir, dt):
+    B, L, n = 3, 150, 810
+    g = gen(9)
+    _, A = tokbuf(B, L, ru(n, 16), dt, fill=1.0, gen=g, ncols=n)
+    A[0:2] = 7.0                                                # halo rows must be ignored
+    outs = []
+    for o in (ops, mir):
+        out = torch.zeros(n, device="cuda")
+        o.colsum_tokens(A, B, L, HALO, n, out)
+        outs.append(out)
+    assert relerr(outs[0], outs[1]) < 1e-5
+    x = torch.randn(37, 16, device="cuda", generator=g)
+    out = torch.zeros(13, device="cuda")
+    ops.colsum_tokens(x, 37, 1, 0, 13, out)
+    assert relerr(out, x[:, :13].sum(0)) < 1e-5
+
+
+# ------------------------------------------------------------------------------------------------ attention
+@pytest.mark.parametrize("dt", DT)
+@pytest.mark.parametrize("B,L,d", [(2, 20, 30), (2, 30, 20), (2, 150, 270), (2, 270, 150), (1, 150, 540), (1, 540, 150)])
+def test_attention(ops, mir, dt, B, L, d):
+    H = 10
+    g = gen(10)
+    ld3 = ru(3 * d, 16)
+    _, qkv = tokbuf(B, L, ld3, dt, fill=1.0, gen=g, ncols=3 * d)
+    _, do = tokbuf(B, L, ru(d, 16), dt, fill=1.0, gen=g, ncols=d)
+    res = []
+    for o in (ops, mir):
+        _, out = tokbuf(B, L, ru(d, 16), dt)
+        lse = torch.zeros(B * H * L, device="cuda")
+        o.attn_fwd(qkv, out, lse, B, L, d, H, HALO)
+        _, dqkv = tokbuf(B, L, ld3, dt)
+        o.attn_bwd(qkv, out, do, dqkv, lse, B, L, d, H, HALO)
+        res.append((out.float(), lse, dqkv.float()))
+    tol = 2e-5 if dt == torch.float32 else 1.5e-2
+    for i, (a, b) in enumerate(zip(*res)):
+        assert relerr(a, b) < tol, i
+    # against torch's scaled_dot_product_attention
+    t = valid(qkv, B, L, 3 * d)
+    hd = d // H
+    q, k, v = [u.reshape(B, L, H, hd).transpose(1, 2) for u in (t[..., :d], t[..., d:2 * d], t[..., 2 * d:])]
+    ref = torch.nn.functional.scaled_dot_product_attention(q, k, v).transpose(1, 2).reshape(B, L, d)
+    assert relerr(valid(res[0][0], B, L, d), ref) < (1e-5 if dt == torch.float32 else 1e-2)
+
+
+# ------------------------------------------------------------------------------------------------ batchnorm block
+@pytest.mark.parametrize("dt", DT)
+@pytest.mark.parametrize("B,L,d", SHAPES)
+def test_bn_block(ops, mir, dt, B, L, d):
+    Dp = ru(d, 16)
+    g = gen(11)
+    _, z = tokbuf(B, L, 3 * Dp, dt)
+    zb = z.view(B, L + 2 * HALO, 3 * Dp)
+    for br in range(3):
+        zb[:, HALO:HALO + L, br * Dp:br * Dp + d] = (torch.randn(B, L, d, device="cuda", generator=g) * (br + 1) + 0.3 * br).to(dt)
+    _, t = tokbuf(B, L, Dp, torch.float32, fill=1.0, gen=g, ncols=d)
+    _, dout = tokbuf(B, L, Dp, torch.float32, fill=1.0, gen=g, ncols=d)
+    gam = [1 + 0.1 * torch.randn(d, device="cuda", generator=g) for _ in range(3)]
+    bet = [0.1 * torch.randn(d, device="cuda", generator=g) for _ in range(3)]
+    cb = [0.1 * torch.randn(d, device="cuda", generator=g) for _ in range(3)]
+    res = []
+    for o in (ops, mir):
+        rm = [torch.zeros(d, device="cuda") for _ in range(3)]
+        rv = [torch.ones(d, device="cuda") for _ in range(3)]
+        nbt = [torch.zeros((), dtype=torch.long, device="cuda") for _ in range(3)]
+        sums = torch.zeros(2 * 3 * Dp, dtype=torch.float64, device="cuda")
+        mean, inv = torch.zeros(3 * Dp, device="cuda"), torch.zeros(3 * Dp, device="cuda")
+        o.bn_stats(z, B, L, HALO, 3 * Dp, sums)
+        o.bn_finalize(sums, Dp, d, 3, B * L, cb, rm, rv, nbt, 0.1, 1e-5, mean, inv)
+        _, out = tokbuf(B, L, Dp, torch.float32)
+        o.bn_act_fwd(z, mean, inv, gam, bet, t, out, B, L, d, HALO, 3, 0.0, 0, 0.0, 0, None)
+        red = torch.zeros(2 * 3 * Dp, dtype=torch.float64, device="cuda")
+        o.bn_act_bwd_reduce(dout, z, mean, inv, gam, bet, B, L, d, HALO, 3, 0.0, 0, 0.0, 0, None, red)
+        _, dz = tokbuf(B, L, 3 * Dp, dt)
+        dg = [torch.zeros(d, device="cuda") for _ in range(3)]
+        db = [torch.zeros(d, device="cuda") for _ in range(3)]
+        o.bn_act_bwd_dz(dout, z, mean, inv, gam, bet, red, B, L, d, HALO, 3, 0.0, 0, 0.0, 0, None, dz, dg, db)
+        me, ie = torch.zeros(3 * Dp, device="cuda"), torch.zeros(3 * Dp, device="cuda")
+        o.bn_eval_prepare(Dp, d, 3, cb, rm, rv, 1e-5, me, ie)
+        res.append((mean, inv, out, dz.float(), torch.cat(dg), torch.cat(db), torch.cat(rm), torch.cat(rv),
+                    torch.stack(nbt).float(), me, ie))
+    tol = 3e-5 if dt == torch.float32 else 1e-2
+    for i, (a, b) in enumerate(zip(*res)):
+        assert relerr(a, b) < tol, i
+    # against torch BatchNorm1d autograd
+    zz = [valid(z, B, L, 3 * Dp)[..., br * Dp:br * Dp + d].transpose(1, 2).clone().requires_grad_(True) for br in range(3)]
+    acc = 0
+    for br in range(3):
+        y = torch.nn.functional.batch_norm(zz[br], None, None, gam[br], bet[br], True, 0.1, 1e-5)
+        acc = acc + torch.nn.functional.leaky_relu(y, 0.01)
+    outr = (acc / 3).transpose(1, 2) + valid(t, B, L, d)
+    assert relerr(valid(res[0][2], B, L, d), outr) < tol
+    outr.backward(valid(dout, B, L, d))
+    for br in range(3):
+        got = valid(res[0][3], B, L, 3 * Dp)[..., br * Dp:br * Dp + d]
+        assert relerr(got, zz[br].grad.transpose(1, 2)) < (1e-4 if dt == torch.float32 else 2e-2)
+
+
+# ------------------------------------------------------------------------------------------------ heads / loss / adam / pack
+@pytest.mark.parametrize("dt", DT)
+@pytest.mark.parametrize("B,L,N,k0,k1", [(3, 150, 128, 8, 16), (3, 270, 16, 2, 4), (2, 20, 128, 8, 16)])
+def test_head_reduce(ops, mir, dt, B, L, N, k0, k1):
+    g = gen(12)
+    _, p = tokbuf(B, L, 2 * N, dt, fill=1.0, gen=g)
+    dfeat = torch.randn(B, 288, device="cuda", generator=g)
+    res = []
+    for o in (ops, mir):
+        feat = torch.zeros(B, 288, device="cuda")
+        o.head_reduce_fwd(p, B, L, HALO, 2 * N, N, k0, k1, feat[:, 32:])
+        _, dp = tokbuf(B, L, 2 * N, dt)
+        o.head_reduce_bwd(dfeat[:, 32:], p, B, L, HALO, 2 * N, N, k0, k1, dp)
+        res.append((feat, dp.float()))
+    for a, b in zip(*res):
+        assert relerr(a, b) < 1e-5
+    assert float(res[0][0][:, :32].abs().max()) == 0.0
+
+
+def test_bce_and_dropout_and_adam(ops, mir):
+    g = gen(13)
+    B, out = 37, 54
+    z = torch.zeros(B, 64, device="cuda")
+    z[:, :out] = torch.randn(B, out, device="cuda", generator=g) * 8
+    y = (torch.rand(B, out, device="cuda", generator=g) < 0.15).float()
+    loss, dz = torch.zeros(1, device="cuda"), torch.zeros(B, 64, device="cuda")
+    ops.bce_logits(z, y, B, out, 4.0, 1.0, loss, dz)
+    zr = z[:, :out].clone().requires_grad_(True)
+    lr_ = torch.nn.BCEWithLogitsLoss(pos_weight=torch.full((out,), 4.0, device="cuda"))(zr, y)
+    lr_.backward()
+    assert abs(loss.item() - lr_.item()) < 1e-5 * max(1, abs(lr_.item()))
+    assert relerr(dz[:, :out], zr.grad) < 1e-5
+    # dropout: keep rate, scaling, determinism per (seed, step, site)
+    rng = torch.tensor([99, 3], dtype=torch.int64, device="cuda")
+    x = torch.ones(512, 288, device="cuda")
+    o1, o2 = torch.zeros(512, 288, device="cuda"), torch.zeros(512, 288, dtype=torch.bfloat16, device="cuda")
+    ops.dropout_rows(x, o1, 512, 288, 0.5, 9000, rng)
+    ops.dropout_rows(x, o2, 512, 288, 0.5, 9000, rng)
+    assert torch.equal(o1, o2.float())
+    keep = (o1 != 0).float().mean().item()
+    assert abs(keep - 0.5) < 0.01 and set(o1.unique().tolist()) == {0.0, 2.0}
+    ops.dropout_rows(x, o2, 512, 288, 0.5, 9001, rng)
+    assert not torch.equal(o1, o2.float())
+    o3 = torch.zeros(512, 288, device="cuda")
+    ops.dropout_rows(x, o3, 512, 288, 0.1, 5, rng)
+    assert abs((o3 != 0).float().mean().item() - 0.9) < 0.01
+    assert abs(o3.max().item() - 1 / 0.9) < 1e-6
+    # adam vs torch.optim.Adam (coupled L2), 3 steps
+    n = 4096 + 4
+    p0 = torch.randn(n, device="cuda", generator=g)
+    pt = p0.clone().requires_grad_(True)
+    opt = torch.optim.Adam([pt], lr=5e-4, weight_decay=2e-4)
+    p, m, v = p0.clone(), torch.zeros(n, device="cuda"), torch.zeros(n, device="cuda")
+    step = torch.ones(1, dtype=torch.int64, device="cuda")
+    rngc = torch.zeros(2, dtype=torch.int64, device="cuda")
+    for s in range(3):
+        gr = torch.randn(n, device="cuda", generator=g) * (10.0 ** (s - 1))
+        pt.grad = gr.clone()
+        opt.step()
+        ops.adam_flat(p, gr, m, v, n, 5e-4, 0.9, 0.999, 1e-8, 2e-4, step, 1.0)
+        ops.advance_counters(rngc, step)
+    assert step.item() == 4 and rngc[1].item() == 3
+    assert relerr(p, pt.detach()) < 1e-6
+
+
+@pytest.mark.parametrize("dt", DT)
+def test_pack_weights(ops, mir, dt):
+    from multi_modal_csi_b200 import layout as LY
+    g = LY.ModelGeom(400, 30, 12)
+    arena = LY.build_arena(LY.parameter_specs(g))
+    plan = LY.build_pack_plan(g, arena)
+    params = torch.randn(arena.size, device="cuda", generator=gen(14))
+    outs = []
+    for o in (ops, mir):
+        packed = torch.zeros(plan.size, dtype=dt, device="cuda")
+        o.pack_weights(params, packed, o.make_pack_table(plan.entries, "cuda"), len(plan.entries), plan.max_elems)
+        outs.append(packed.float())
+    assert torch.equal(outs[0], outs[1])

@@ -1,0 +1,276 @@
+"""CPU suite: oracle vs golden vectors (and vs the live reference when /root/reference exists), host logic
+(labels, metrics, engine sequencing with the torch mirror, optimizer, loader), and the C-ABI symbol table."""
+import copy
+import ctypes
+import os
+import re
+
+import numpy as np
+import pytest
+import torch
+
+from mirror_ops import MirrorOps
+from oracle import that_oracle as O
+from oracle.ref_import import reference_available
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+def nrel(a, b):
+    a, b = torch.as_tensor(a).double(), torch.as_tensor(b).double()
+    return ((a - b).norm() / (b.norm() + 1e-30)).item()
+
+
+# ------------------------------------------------------------------------------------------------ oracle pinned
+def test_oracle_matches_golden_small(gold):
+    g = gold("that_small.npz")
+    T, F, out, B = [int(v) for v in g["dims"]]
+    sd = {k[2:]: torch.from_numpy(g[k]).clone() for k in g.files if k.startswith("w/")}
+    x, y = torch.from_numpy(g["x"]), torch.from_numpy(g["y"])
+    logits, loss, grads = O.loss_and_grads(sd, x, y)
+    assert nrel(logits, g["logits_train"]) < 1e-5
+    assert abs(loss.item() - float(g["loss"])) < 1e-5
+    num = sum((grads[k] - torch.from_numpy(g["g/" + k])).pow(2).sum().item() for k in grads)
+    den = sum(torch.from_numpy(g["g/" + k]).pow(2).sum().item() for k in grads)
+    assert (num / den) ** 0.5 < 1e-5
+    for k in g.files:
+        if k.startswith("bn/"):
+            assert nrel(sd[k[3:]].float(), torch.from_numpy(g[k]).float()) < 1e-6, k
+    assert nrel(O.that_forward(sd, x, training=False), g["logits_eval"]) < 1e-5
+
+
+def test_oracle_adam_trajectory_matches_golden(gold):
+    g = gold("that_small.npz")
+    T, F, out, B = [int(v) for v in g["dims"]]
+    sd = {k[2:]: torch.from_numpy(g[k]).clone() for k in g.files if k.startswith("w/")}
+    opt = {}
+    for s in range(3):
+        gg = torch.Generator().manual_seed(1234 + s)
+        x = torch.rand(B, T, F, generator=gg) * 20
+        y = (torch.rand(B, out, generator=gg) < 0.15).float()
+        _, loss = O.train_step(sd, opt, x, y)
+        assert abs(loss.item() - float(g["traj_losses"][s])) < 2e-5 * max(1, float(g["traj_losses"][s]))
+
+
+@pytest.mark.parametrize("F,out", [(270, 54)])
+def test_oracle_matches_full_size_anchor(gold, F, out):
+    from multi_modal_csi_b200 import THAT
+    g = gold(f"that_anchor_{F}.npz")
+    torch.manual_seed(39)
+    m = THAT((3000, F), (out,))
+    sd = {k: v.detach().clone() for k, v in m.state_dict().items()}
+    for k, v in sd.items():                       # our initialisation == the reference's, tensor by tensor
+        assert abs(v.double().sum().item() - float(g["init_sum/" + k])) <= 1e-6 * max(1.0, float(g["init_abs/" + k])), k
+    gen = torch.Generator().manual_seed(1234)
+    x = torch.rand(4, 3000, F, generator=gen) * 20
+    y = (torch.rand(4, out, generator=gen) < 0.15).float()
+    logits, loss, grads = O.loss_and_grads(sd, x, y)
+    assert nrel(logits, g["logits_train"]) < 1e-5
+    assert abs(loss.item() - float(g["loss"])) < 1e-4
+    gn = sum(v.double().pow(2).sum().item() for v in grads.values()) ** 0.5
+    assert abs(gn - float(g["grad_norm"])) < 1e-4 * float(g["grad_norm"])
+
+
+@pytest.mark.reference
+@pytest.mark.skipif(not reference_available(), reason="reference checkout not present")
+def test_oracle_and_init_match_live_reference():
+    from oracle.ref_import import load_reference
+    from multi_modal_csi_b200 import THAT
+    ns = load_reference()
+    T, F, out, B = 600, 40, 18, 3
+    torch.manual_seed(41)
+    ref = ns.that.THAT((T, F), (out,))
+    torch.manual_seed(41)
+    mine = THAT((T, F), (out,))
+    sr, sm = ref.state_dict(), mine.state_dict()
+    assert list(sr.keys()) == list(sm.keys())
+    assert [n for n, _ in ref.named_parameters()] == [n for n, _ in mine.named_parameters()]
+    assert all(torch.equal(sr[k], sm[k]) for k in sr)
+    for mod in ref.modules():
+        if isinstance(mod, torch.nn.Dropout):
+            mod.p = 0.0
+    gen = torch.Generator().manual_seed(5)
+    x = torch.rand(B, T, F, generator=gen) * 20
+    y = (torch.rand(B, out, generator=gen) < 0.2).float()
+    sd = copy.deepcopy(sr)
+    ref.train()
+    lo = ref(x)
+    l = torch.nn.BCEWithLogitsLoss(pos_weight=torch.tensor([4.0] * out))(lo, y)
+    l.backward()
+    ol, oloss, og = O.loss_and_grads(sd, x, y)
+    assert nrel(ol, lo.detach()) < 1e-5 and abs(oloss.item() - l.item()) < 1e-5
+    named = dict(ref.named_parameters())
+    num = sum((og[k] - named[k].grad).pow(2).sum().item() for k in og)
+    den = sum(named[k].grad.pow(2).sum().item() for k in og)
+    assert (num / den) ** 0.5 < 1e-5
+
+
+def test_oracle_front_pad_and_prediction_rule(gold):
+    a = torch.arange(12.0).reshape(3, 4)
+    p = O.front_pad(a, 5)
+    assert p.shape == (5, 4) and float(p[:2].abs().sum()) == 0 and torch.equal(p[2:], a)
+    with pytest.raises(ValueError):
+        O.front_pad(a, 2)
+    g = gold("metrics.npz")
+    counts = O.predict_counts(torch.from_numpy(g["logits"]), 6)
+    assert np.array_equal(counts.numpy(), g["counts_pred"])
+
+
+# ------------------------------------------------------------------------------------------------ host logic
+def test_metrics_match_reference_fixture(gold):
+    from multi_modal_csi_b200.utils import performance_metrics, NumpyEncoder
+    import json
+    g = gold("metrics.npz")
+    res = performance_metrics(g["y_true"], g["logits"], var_mode="baseline", var_threshold=0.5)
+    for k, v in res.items():
+        assert np.allclose(np.asarray(v, dtype=np.float64), g["m/" + k], rtol=1e-9, atol=1e-12, equal_nan=True), k
+    # train.py:105-109 quirk: last-batch metrics use int-truncated logits
+    resq = performance_metrics(g["y_true"].reshape(64, -1).astype(int), g["logits"].astype(int), var_mode="baseline")
+    for k, v in resq.items():
+        assert np.allclose(np.asarray(v, dtype=np.float64), g["mq/" + k], rtol=1e-9, atol=1e-12, equal_nan=True), k
+    json.dumps(res, cls=NumpyEncoder)
+    with pytest.raises(ValueError):
+        performance_metrics(g["y_true"], g["logits"], var_mode="multi_head")
+
+
+def test_label_encoders_match_reference_fixture(gold):
+    from multi_modal_csi_b200 import load_data as LD
+    g = gold("labels.npz")
+    csv = os.path.join(ROOT, "tests", "golden", "annotation_excerpt.csv")
+    sel = LD.load_data_y(csv, ["classroom", "empty_room"], ["2.4"], ["0", "1", "3", "5"])
+    assert sel["label"].to_list() == [str(s) for s in g["labels"]]
+    assert np.array_equal(LD.encode_data_y(sel, "identity"), g["identity"])
+    assert np.array_equal(LD.encode_data_y(sel, "activity"), g["activity"])
+    assert np.array_equal(LD.encode_data_y(sel, "location"), g["location"])
+    allsel = LD.load_data_y(csv)
+    assert len(allsel) == int(g["n_all"])
+    assert np.array_equal(LD.encode_data_y(allsel, "activity"), g["activity_all"])
+
+
+def test_loader_front_pads_and_packs(tmp_path):
+    from multi_modal_csi_b200 import load_data as LD
+    from multi_modal_csi_b200.preset import preset
+    rng = np.random.default_rng(0)
+    lens = [3000, 2871, 17]
+    for i, t in enumerate(lens):
+        np.save(tmp_path / f"s{i}.npy", rng.random((t, 3, 3, 30), dtype=np.float32))
+    x = LD.load_data_x(str(tmp_path), ["s0", "s1", "s2"])
+    assert x.shape == (3, preset["data"]["length"], 3, 3, 30) and x.dtype == np.float32
+    assert float(np.abs(x[1, :3000 - 2871]).sum()) == 0 and float(np.abs(x[2, :3000 - 17]).sum()) == 0
+    arena, offs, ln, F = LD.load_data_x_packed(str(tmp_path), ["s0", "s1", "s2"])
+    assert F == 270 and list(ln) == lens and arena.size == sum(lens) * 270
+    for i, t in enumerate(lens):                                   # pack + front pad == reference padded array
+        assert np.array_equal(arena[offs[i]:offs[i] + t * F].reshape(t, F), x[i, 3000 - t:].reshape(t, F))
+    np.save(tmp_path / "long.npy", np.zeros((3001, 3, 3, 30), np.float32))
+    with pytest.raises(ValueError):
+        LD.load_data_x(str(tmp_path), ["long"])
+
+
+def _mirror_model(T, F, out, sd=None):
+    from multi_modal_csi_b200 import THAT
+    m = THAT((T, F), (out,), act_dtype="fp32")
+    m._ops_override = MirrorOps()
+    m.dropout_enabled = False
+    if sd is not None:
+        m.load_state_dict(sd)
+    return m
+
+
+def test_engine_sequencing_matches_golden_with_mirror_kernels(gold):
+    """Host-side composition (token layouts, shifted-GEMM convolutions, hand-derived backward) on CPU."""
+    g = gold("that_small.npz")
+    T, F, out, B = [int(v) for v in g["dims"]]
+    sd = {k[2:]: torch.from_numpy(g[k]) for k in g.files if k.startswith("w/")}
+    m = _mirror_model(T, F, out, sd)
+    x, y = torch.from_numpy(g["x"]), torch.from_numpy(g["y"])
+    m.train()
+    logits = m(x)
+    assert nrel(logits, g["logits_train"]) < 1e-5
+    loss = torch.nn.BCEWithLogitsLoss(pos_weight=torch.tensor([4.0] * out))(logits, y)
+    loss.backward()
+    num = den = 0.0
+    for k, p in m.named_parameters():
+        if "g/" + k in g.files:
+            r = torch.from_numpy(g["g/" + k])
+            num += (p.grad - r).pow(2).sum().item()
+            den += r.pow(2).sum().item()
+    assert (num / den) ** 0.5 < 1e-5
+    m.eval()
+    with torch.no_grad():
+        assert nrel(m(x), g["logits_eval"]) < 1e-5
+
+
+def test_ragged_input_equals_front_padded_dense():
+    T, F, out, B = 400, 30, 12, 3
+    torch.manual_seed(1)
+    m = _mirror_model(T, F, out)
+    lens = torch.tensor([400, 333, 20], dtype=torch.int32)
+    offs = torch.zeros(B, dtype=torch.int64)
+    offs[1:] = torch.cumsum(lens[:-1].long() * F, 0)
+    arena = torch.rand(int((lens.long() * F).sum())) * 20
+    dense = torch.stack([O.front_pad(arena[offs[i]:offs[i] + int(lens[i]) * F].view(int(lens[i]), F), T) for i in range(B)])
+    eng = m._engine_for(B)
+    eng.repack()
+    a = eng.forward(dense, B, training=False).clone()
+    b = eng.forward(arena, B, training=False, offs=offs, lens=lens).clone()
+    assert torch.equal(a, b)
+
+
+def test_fused_adam_is_coupled_l2_and_skips_frozen():
+    from multi_modal_csi_b200 import FusedAdam
+    T, F, out, B = 400, 30, 12, 2
+    torch.manual_seed(3)
+    m = _mirror_model(T, F, out)
+    ref = copy.deepcopy({k: v.clone() for k, v in m.state_dict().items()})
+    opt = FusedAdam(m.parameters(), lr=5e-4, weight_decay=2e-4)
+    x = torch.rand(B, T, F) * 20
+    y = (torch.rand(B, out) < 0.2).float()
+    m.train()
+    opt_state = {}
+    for _ in range(2):
+        m.fused_train_step(x, y, opt, augment=False)
+        O.train_step(ref, opt_state, x, y)
+    sd = m.state_dict()
+    assert torch.equal(sd["layer_left_gaussian.var_position"], ref["layer_left_gaussian.var_position"])
+    for k in sd:
+        if k.endswith(".0.bias") or k.endswith("in_proj_bias"):
+            continue
+        assert (sd[k].float() - ref[k].float()).abs().max().item() < 5e-5, k
+    with pytest.raises(ValueError):
+        FusedAdam([torch.nn.Parameter(torch.zeros(3))])
+
+
+def test_module_contract():
+    from multi_modal_csi_b200 import THAT
+    m = THAT((3000, 270), (54,))
+    sd = m.state_dict()
+    assert len(sd) == 163 and sum(p.numel() for p in m.parameters()) == 4901504
+    assert len(list(m.parameters())) == 118 and sum(p.requires_grad for p in m.parameters()) == 117
+    assert m.layer_left_encoder[3].layer_cnn[2][0].weight.shape == (270, 270, 5)
+    assert m.layer_right_encoder[0].layer_attention.out_proj.weight.shape == (150, 150)
+    m2 = THAT((3000, 270), (54,))
+    m2.load_state_dict(copy.deepcopy(sd))
+    assert all(torch.equal(a, b) for a, b in zip(m.state_dict().values(), m2.state_dict().values()))
+    # parameters alias the flat arena
+    m.layer_output.bias.data.fill_(3.0)
+    off = m.arena.offsets["layer_output.bias"]
+    assert float(m.flat_params[off]) == 3.0
+    for bad in ((3001, 270), (3000, 275), (200, 270)):
+        with pytest.raises(ValueError):
+            THAT(bad, (54,))
+    with pytest.raises(RuntimeError):                       # no CPU path in the product
+        m(torch.zeros(1, 3000, 270))
+
+
+# ------------------------------------------------------------------------------------------------ C ABI
+def test_library_exports_every_declared_symbol():
+    from multi_modal_csi_b200 import ops
+    hdr = open(os.path.join(ROOT, "include", "csi_that.h")).read()
+    declared = set(re.findall(r"\b(csi_[a-z0-9_]+)\s*\(", hdr))
+    assert declared, "no declarations parsed"
+    lib = ops.load_library()
+    missing = [s for s in sorted(declared) if not hasattr(lib, s)]
+    assert not missing, missing
+    assert set(ops.EXPORTS) <= declared
+    assert lib.csi_abi_version() == ops.ABI_VERSION
+    assert ctypes.sizeof(ops.PackEntry) == 48 and ctypes.sizeof(ops.Seg) == 16 and ctypes.sizeof(ops.Ptr3) == 24
