@@ -1,8 +1,317 @@
-// tcgen05 / TMEM / TMA contraction kernels (placeholder until the kernel lands: reports "not eligible").
+// tcgen05 / TMEM / TMA contraction kernels for sm_100a (bf16 operands, fp32 accumulation in tensor memory).
+//
+//   csi_gemm_nt_tc : C[m,n] = sum_seg A[(m+shift)*lda + aoff + q] * B[n*ldb + boff + q]  (+bias, dropout, +residual)
+//                    Linear layers, Conv1d forward and Conv1d data-gradient of the THAT encoder: every convolution
+//                    tap is a K-segment whose A tile is fetched by TMA at a row-shifted coordinate of the same
+//                    token buffer, so no im2col matrix ever exists.
+//
+// Structure (one 128 x BN output tile per CTA, 2 CTAs resident per SM so one CTA's epilogue overlaps the other's
+// main loop):
+//   warp 0   : TMA producer  -- cp.async.bulk.tensor.2d into a 128B-swizzled K-major smem ring (mbarrier tx-count)
+//   warp 1   : TMEM allocator + single-thread tcgen05.mma issuer (UMMA 128 x BN x 16, kind::f16, fp32 accumulate)
+//   warps 2-5: epilogue -- tcgen05.ld 32x32b, bias / dropout / residual, direct vectorised global stores
 #include "common.cuh"
-extern "C" int csi_gemm_nt_tc_ok(int lda, int ldb, int ldc, int M, int N, const csi_seg* segs, int nseg) { return 0; }
-extern "C" int csi_gemm_nt_tc(const void*, int, const void*, int, void*, int, int, int, int, const csi_seg*, int,
-                              const float*, const float*, int, float, unsigned, const unsigned long long*, void*) {
-    csi_set_error("csi_gemm_nt_tc: not built");
-    return CSI_ERR_ARG;
+#include <cuda.h>
+#include <mutex>
+
+#define ST(s) ((cudaStream_t)(s))
+#define TC_BM 128
+#define TC_BK 64
+#define TC_STAGES 3
+#define TC_THREADS 192
+
+struct SegList { csi_seg s[CSI_MAX_SEGS]; int n; };
+
+// ------------------------------------------------------------------------------------------------ PTX wrappers
+__device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+
+__device__ __forceinline__ void mbar_init(uint64_t* bar, uint32_t count) {
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count));
+}
+__device__ __forceinline__ void mbar_expect_tx(uint64_t* bar, uint32_t bytes) {
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
+    asm volatile(
+        "{\n"
+        ".reg .pred P1;\n"
+        "LAB_WAIT:\n"
+        "mbarrier.try_wait.parity.shared::cta.b64 P1, [%0], %1;\n"
+        "@P1 bra DONE;\n"
+        "bra LAB_WAIT;\n"
+        "DONE:\n"
+        "}\n" ::"r"(smem_u32(bar)), "r"(parity) : "memory");
+}
+__device__ __forceinline__ void fence_barrier_init() { asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory"); }
+__device__ __forceinline__ void fence_proxy_async() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
+
+__device__ __forceinline__ void tma_load_2d(const CUtensorMap* tm, uint64_t* bar, void* dst, int c0, int c1) {
+    asm volatile(
+        "cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4}], [%2];"
+        ::"r"(smem_u32(dst)), "l"(reinterpret_cast<uint64_t>(tm)), "r"(smem_u32(bar)), "r"(c0), "r"(c1) : "memory");
+}
+__device__ __forceinline__ void tma_prefetch_desc(const CUtensorMap* tm) {
+    asm volatile("prefetch.tensormap [%0];" ::"l"(reinterpret_cast<uint64_t>(tm)) : "memory");
+}
+
+__device__ __forceinline__ void tmem_alloc(uint32_t* dst_smem, uint32_t ncols) {
+    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(dst_smem)), "r"(ncols) : "memory");
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+}
+__device__ __forceinline__ void tmem_dealloc(uint32_t taddr, uint32_t ncols) {
+    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(taddr), "r"(ncols) : "memory");
+}
+__device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
+__device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
+
+__device__ __forceinline__ void umma_bf16(uint32_t tmem_d, uint64_t adesc, uint64_t bdesc, uint32_t idesc, uint32_t accumulate) {
+    asm volatile(
+        "{\n"
+        ".reg .pred p;\n"
+        "setp.ne.b32 p, %4, 0;\n"
+        "tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n"
+        "}\n" ::"r"(tmem_d), "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accumulate) : "memory");
+}
+__device__ __forceinline__ void umma_commit(uint64_t* bar) {
+    asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(smem_u32(bar)) : "memory");
+}
+__device__ __forceinline__ void tmem_ld16(uint32_t taddr, uint32_t* r) {
+    asm volatile(
+        "tcgen05.ld.sync.aligned.32x32b.x16.b32 {%0,%1,%2,%3,%4,%5,%6,%7,%8,%9,%10,%11,%12,%13,%14,%15}, [%16];"
+        : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]), "=r"(r[8]),
+          "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15])
+        : "r"(taddr));
+}
+__device__ __forceinline__ void tmem_ld_wait() { asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory"); }
+
+// K-major, 128B-swizzled operand tile ([rows][64 bf16], 8-row groups 1024 B apart): cute::UMMA::SmemDescriptor
+//   bits [0,14) start>>4 | [16,30) LBO>>4 (=1, ignored) | [32,46) SBO>>4 (=64) | [46,48) version=1 | [61,64) layout=2 (SW128)
+__device__ __forceinline__ uint64_t make_kmajor_desc(uint32_t saddr) {
+    uint64_t d = 0;
+    d |= (uint64_t)((saddr >> 4) & 0x3FFF);
+    d |= (uint64_t)1 << 16;
+    d |= (uint64_t)(1024 >> 4) << 32;
+    d |= (uint64_t)1 << 46;
+    d |= (uint64_t)2 << 61;
+    return d;
+}
+// cute::UMMA::InstrDescriptor: c_format F32 (1<<4), a/b format BF16 (1<<7, 1<<10), K-major A and B, N>>3 at 17, M>>4 at 24
+__device__ __forceinline__ uint32_t make_idesc(int m, int n) {
+    return (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(n >> 3) << 17) | ((uint32_t)(m >> 4) << 24);
+}
+
+struct NtParams {
+    void* C; int ldc; int M, N, BN;
+    const float* bias; const float* residual; int ldr;
+    float drop_p; unsigned drop_site; const unsigned long long* rng;
+    int row_base;                 // added to (m0 + shift) to form the TMA row coordinate (tensor map starts at the lowest row read)
+    uint32_t tmem_cols;
+};
+
+template <typename TC>
+__global__ void __launch_bounds__(TC_THREADS) gemm_nt_tc_kernel(const __grid_constant__ CUtensorMap tmA,
+                                                                const __grid_constant__ CUtensorMap tmB, NtParams p,
+                                                                SegList segs) {
+    extern __shared__ __align__(1024) uint8_t smem_raw[];
+    __shared__ __align__(8) uint64_t full_bar[TC_STAGES];
+    __shared__ __align__(8) uint64_t empty_bar[TC_STAGES];
+    __shared__ __align__(8) uint64_t tmem_full_bar;
+    __shared__ uint32_t tmem_base_smem;
+
+    uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int m0 = blockIdx.x * TC_BM, n0 = blockIdx.y * p.BN;
+    const uint32_t a_bytes = TC_BM * TC_BK * 2, b_bytes = (uint32_t)p.BN * TC_BK * 2;
+    const uint32_t stage_bytes = a_bytes + b_bytes;
+
+    if (threadIdx.x == 0) {
+        tma_prefetch_desc(&tmA);
+        tma_prefetch_desc(&tmB);
+        for (int s = 0; s < TC_STAGES; ++s) { mbar_init(&full_bar[s], 1); mbar_init(&empty_bar[s], 1); }
+        mbar_init(&tmem_full_bar, 1);
+        fence_barrier_init();
+    }
+    if (warp == 1) tmem_alloc(&tmem_base_smem, p.tmem_cols);
+    tc_fence_before();
+    __syncthreads();
+    tc_fence_after();
+    const uint32_t tmem_base = tmem_base_smem;
+
+    if (warp == 0) {
+        if (lane == 0) {
+            int it = 0;
+            for (int s = 0; s < segs.n; ++s) {
+                const csi_seg sg = segs.s[s];
+                for (int k0 = 0; k0 < sg.klen; k0 += TC_BK, ++it) {
+                    const int stage = it % TC_STAGES;
+                    const uint32_t ph = (uint32_t)(it / TC_STAGES) & 1u;
+                    mbar_wait(&empty_bar[stage], ph ^ 1u);
+                    uint8_t* sa = smem + (size_t)stage * stage_bytes;
+                    mbar_expect_tx(&full_bar[stage], stage_bytes);
+                    tma_load_2d(&tmA, &full_bar[stage], sa, sg.a_col_off + k0, m0 + sg.a_row_shift + p.row_base);
+                    tma_load_2d(&tmB, &full_bar[stage], sa + a_bytes, sg.b_col_off + k0, n0);
+                }
+            }
+        }
+    } else if (warp == 1) {
+        if (lane == 0) {
+            const uint32_t idesc = make_idesc(TC_BM, p.BN);
+            int it = 0;
+            uint32_t first = 1;
+            for (int s = 0; s < segs.n; ++s) {
+                const csi_seg sg = segs.s[s];
+                for (int k0 = 0; k0 < sg.klen; k0 += TC_BK, ++it) {
+                    const int stage = it % TC_STAGES;
+                    const uint32_t ph = (uint32_t)(it / TC_STAGES) & 1u;
+                    mbar_wait(&full_bar[stage], ph);
+                    tc_fence_after();
+                    const uint32_t sa = smem_u32(smem + (size_t)stage * stage_bytes);
+                    const uint64_t adesc = make_kmajor_desc(sa), bdesc = make_kmajor_desc(sa + a_bytes);
+                    const int ksteps = min(TC_BK, sg.klen - k0) >> 4;
+                    for (int k = 0; k < ksteps; ++k) {
+                        // +32 B per 16-element K step inside the 128 B swizzle row: start-address field += 2
+                        umma_bf16(tmem_base, adesc + (uint64_t)(2 * k), bdesc + (uint64_t)(2 * k), idesc, first ? 0u : 1u);
+                        first = 0;
+                    }
+                    umma_commit(&empty_bar[stage]);        // frees the smem slot once these MMAs have read it
+                }
+            }
+            umma_commit(&tmem_full_bar);                   // accumulator complete
+        }
+    } else {
+        // ---------------- epilogue: TMEM lane quarter (warp % 4) -> 32 rows of the tile, one row per thread
+        const int q = warp & 3;
+        const int m = m0 + q * 32 + lane;
+        mbar_wait(&tmem_full_bar, 0);
+        tc_fence_after();
+        const bool drop = p.drop_p > 0.f;
+        RngKey rk;
+        uint32_t thr = 0;
+        float inv_keep = 1.f;
+        if (drop) { rk = rng_load(p.rng); thr = drop_threshold(p.drop_p); inv_keep = 1.f / (1.f - p.drop_p); }
+        TC* crow = reinterpret_cast<TC*>(p.C) + (size_t)m * p.ldc;
+        const float* rrow = p.residual ? p.residual + (size_t)m * p.ldr : nullptr;
+        for (int c0 = 0; c0 < p.BN; c0 += 16) {
+            uint32_t r[16];
+            tmem_ld16(tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)c0, r);
+            tmem_ld_wait();
+            if (m < p.M) {
+                const int nb = n0 + c0;
+#pragma unroll
+                for (int j = 0; j < 16; j += 2) {
+                    const int n = nb + j;
+                    if (n >= p.N) break;
+                    float v0 = __uint_as_float(r[j]), v1 = __uint_as_float(r[j + 1]);
+                    const bool two = (n + 1) < p.N;
+                    if (p.bias) { v0 += p.bias[n]; if (two) v1 += p.bias[n + 1]; }
+                    if (drop) {
+                        v0 *= drop_scale(rk, p.drop_site, (unsigned long long)m * p.N + n, thr, inv_keep);
+                        if (two) v1 *= drop_scale(rk, p.drop_site, (unsigned long long)m * p.N + n + 1, thr, inv_keep);
+                    }
+                    if (rrow) { v0 += rrow[n]; if (two) v1 += rrow[n + 1]; }
+                    if (two) st2<TC>(crow + n, make_float2(v0, v1));
+                    else stf<TC>(crow + n, v0);
+                }
+            }
+        }
+    }
+    tc_fence_before();
+    __syncthreads();
+    if (warp == 1) {
+        tc_fence_after();
+        tmem_dealloc(tmem_base, p.tmem_cols);
+    }
+}
+
+// ------------------------------------------------------------------------------------------------ host side
+typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*, const cuuint64_t*,
+                                  const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave, CUtensorMapSwizzle,
+                                  CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+static EncodeTiledFn g_encode = nullptr;
+static std::once_flag g_encode_once;
+
+static EncodeTiledFn get_encode() {
+    std::call_once(g_encode_once, [] {
+        void* fn = nullptr;
+        cudaDriverEntryPointQueryResult qres;
+        if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &fn, cudaEnableDefault, &qres) == cudaSuccess &&
+            qres == cudaDriverEntryPointSuccess)
+            g_encode = (EncodeTiledFn)fn;
+    });
+    return g_encode;
+}
+
+// 2D bf16 row-major [rows, cols] with row pitch ld elements; box = box_rows x 64 columns, 128B swizzle
+static int make_map(CUtensorMap* tm, const void* base, long long rows, long long cols, long long ld, int box_rows) {
+    EncodeTiledFn enc = get_encode();
+    if (!enc) { csi_set_error("cuTensorMapEncodeTiled not available"); return CSI_ERR_CUDA; }
+    cuuint64_t dims[2] = {(cuuint64_t)cols, (cuuint64_t)rows};
+    cuuint64_t strides[1] = {(cuuint64_t)ld * 2};
+    cuuint32_t box[2] = {TC_BK, (cuuint32_t)box_rows};
+    cuuint32_t estr[2] = {1, 1};
+    CUresult r = enc(tm, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, const_cast<void*>(base), dims, strides, box, estr,
+                     CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                     CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    if (r != CUDA_SUCCESS) { csi_set_error("cuTensorMapEncodeTiled failed (%d)", (int)r); return CSI_ERR_CUDA; }
+    return CSI_OK;
+}
+
+static int pick_bn(int N) {
+    const int tiles = (N + 127) / 128;
+    int bn = ((N + tiles - 1) / tiles + 15) & ~15;
+    if (bn < 16) bn = 16;
+    return bn;
+}
+
+extern "C" int csi_gemm_nt_tc_ok(int lda, int ldb, int ldc, int M, int N, const csi_seg* segs, int nseg) {
+    if (M < 1 || N < 1 || nseg < 1 || nseg > CSI_MAX_SEGS) return 0;
+    if (lda % 8 || ldb % 8 || ldc % 2) return 0;               // 16-byte TMA row pitch; paired epilogue stores
+    for (int i = 0; i < nseg; ++i)
+        if (segs[i].klen % 16 || segs[i].klen <= 0 || segs[i].a_col_off % 8 || segs[i].b_col_off % 8) return 0;
+    return get_encode() != nullptr;
+}
+
+extern "C" int csi_gemm_nt_tc(const void* A, int lda, const void* Bw, int ldb, void* C, int ldc, int c_dtype, int M, int N,
+                              const csi_seg* segs, int nseg, const float* bias, const float* residual, int ldr,
+                              float drop_p, unsigned drop_site, const unsigned long long* rng, void* stream) {
+    CSI_CHECK_ARG(A && Bw && C && segs, "null pointer");
+    CSI_CHECK_ARG(csi_gemm_nt_tc_ok(lda, ldb, ldc, M, N, segs, nseg), "shape not eligible for the tcgen05 kernel");
+    CSI_CHECK_ARG(!(drop_p > 0.f) || rng, "dropout needs rng");
+    SegList sl;
+    sl.n = nseg;
+    int min_shift = 0, max_shift = 0, a_cols = 0, b_cols = 0;
+    for (int i = 0; i < nseg; ++i) {
+        sl.s[i] = segs[i];
+        if (segs[i].a_row_shift < min_shift) min_shift = segs[i].a_row_shift;
+        if (segs[i].a_row_shift > max_shift) max_shift = segs[i].a_row_shift;
+        if (segs[i].a_col_off + segs[i].klen > a_cols) a_cols = segs[i].a_col_off + segs[i].klen;
+        if (segs[i].b_col_off + segs[i].klen > b_cols) b_cols = segs[i].b_col_off + segs[i].klen;
+    }
+    CSI_CHECK_ARG(a_cols <= lda && b_cols <= ldb, "segment exceeds the row pitch");
+    const int BN = pick_bn(N);
+    CUtensorMap tmA, tmB;
+    const bf16* a_base = reinterpret_cast<const bf16*>(A) + (long long)min_shift * lda;
+    int rc = make_map(&tmA, a_base, (long long)M + (max_shift - min_shift), a_cols, lda, TC_BM);
+    if (rc) return rc;
+    rc = make_map(&tmB, Bw, N, b_cols, ldb, BN);
+    if (rc) return rc;
+    NtParams p;
+    p.C = C; p.ldc = ldc; p.M = M; p.N = N; p.BN = BN;
+    p.bias = bias; p.residual = residual; p.ldr = ldr;
+    p.drop_p = drop_p; p.drop_site = drop_site; p.rng = rng;
+    p.row_base = -min_shift;
+    uint32_t cols = 32;
+    while ((int)cols < BN) cols <<= 1;
+    p.tmem_cols = cols;
+    const size_t smem = (size_t)TC_STAGES * (TC_BM * TC_BK * 2 + (size_t)BN * TC_BK * 2) + 1024;
+    dim3 grid((M + TC_BM - 1) / TC_BM, (N + BN - 1) / BN);
+    if (c_dtype == CSI_BF16) {
+        CSI_CUDA(cudaFuncSetAttribute(gemm_nt_tc_kernel<bf16>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        gemm_nt_tc_kernel<bf16><<<grid, TC_THREADS, smem, ST(stream)>>>(tmA, tmB, p, sl);
+    } else {
+        CSI_CUDA(cudaFuncSetAttribute(gemm_nt_tc_kernel<float>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        gemm_nt_tc_kernel<float><<<grid, TC_THREADS, smem, ST(stream)>>>(tmA, tmB, p, sl);
+    }
+    CSI_LAUNCH_CHECK();
+    return CSI_OK;
 }
