@@ -13,6 +13,8 @@ extern "C" int csi_attn_bwd_simt(const void*, int, const void*, int, const void*
 extern "C" int csi_gemm_nt_tc(const void*, int, const void*, int, void*, int, int, int, int, const csi_seg*, int,
                               const float*, const float*, int, float, unsigned, const unsigned long long*, void*);
 extern "C" int csi_gemm_nt_tc_ok(int lda, int ldb, int ldc, int M, int N, const csi_seg* segs, int nseg);
+extern "C" int csi_gemm_tn_tc(const void*, int, const void*, int, float*, int, int, int, int, const csi_seg_tn*, int, void*);
+extern "C" int csi_gemm_tn_tc_ok(int lda, int ldb, int M, int Na, const csi_seg_tn* segs, int nseg);
 
 static int g_force_simt = -1;
 static bool force_simt() {
@@ -34,6 +36,8 @@ extern "C" int csi_gemm_nt(const void* A, int lda, const void* Bw, int ldb, int 
 
 extern "C" int csi_gemm_tn(const void* A, int lda, const void* Bv, int ldb, int ab_dtype, float* C, int ldc,
                            int c_col_stride, int M, int Na, const csi_seg_tn* segs, int nseg, void* stream) {
+    if (ab_dtype == CSI_BF16 && !force_simt() && csi_gemm_tn_tc_ok(lda, ldb, M, Na, segs, nseg))
+        return csi_gemm_tn_tc(A, lda, Bv, ldb, C, ldc, c_col_stride, M, Na, segs, nseg, stream);
     return csi_gemm_tn_simt(A, lda, Bv, ldb, ab_dtype, C, ldc, c_col_stride, M, Na, segs, nseg, stream);
 }
 

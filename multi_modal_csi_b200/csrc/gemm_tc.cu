@@ -315,3 +315,188 @@ extern "C" int csi_gemm_nt_tc(const void* A, int lda, const void* Bw, int ldb, v
     CSI_LAUNCH_CHECK();
     return CSI_OK;
 }
+
+// =================================================================================================================
+//   csi_gemm_tn_tc : C[i*ldc + coff + q*cs] += sum_{m in chunk} A[m*lda + i] * Bv[(m+shift)*ldb + boff + q]
+//                    Weight gradients (Linear and every Conv1d tap).  Both operands are read in their natural
+//                    [tokens, channels] layout: the contraction runs over the row index, i.e. both UMMA operands are
+//                    "MN-major" (a_major = b_major = 1) 128B-swizzled tiles filled by TMA boxes of 64 channels x 64 rows.
+//                    The token range is split over blockIdx.z; partial tiles are reduced with fp32 atomics.
+// =================================================================================================================
+#define TN_STAGES 4
+#define TN_BKM 64                 // token rows per pipeline stage (4 UMMA K-steps of 16)
+#define TN_BOX_BYTES (TN_BKM * 128)
+
+struct SegListTN { csi_seg_tn s[CSI_MAX_SEGS]; int n; };
+
+// MN-major 128B-swizzled operand: 64 channels contiguous per 128 B row, rows = K; 8-row groups SBO = 1024 B apart;
+// successive 64-channel chunks LBO = one TMA box (64 rows x 128 B) apart.
+__device__ __forceinline__ uint64_t make_mnmajor_desc(uint32_t saddr) {
+    uint64_t d = 0;
+    d |= (uint64_t)((saddr >> 4) & 0x3FFF);
+    d |= (uint64_t)(TN_BOX_BYTES >> 4) << 16;
+    d |= (uint64_t)(1024 >> 4) << 32;
+    d |= (uint64_t)1 << 46;
+    d |= (uint64_t)2 << 61;
+    return d;
+}
+
+struct TnParams {
+    float* C; int ldc; int cs; int M, Na, BN, chunk, qtiles;
+    int row_base;
+    uint32_t tmem_cols;
+};
+
+__global__ void __launch_bounds__(TC_THREADS) gemm_tn_tc_kernel(const __grid_constant__ CUtensorMap tmA,
+                                                                const __grid_constant__ CUtensorMap tmB, TnParams p,
+                                                                SegListTN segs) {
+    extern __shared__ __align__(1024) uint8_t smem_raw[];
+    __shared__ __align__(8) uint64_t full_bar[TN_STAGES];
+    __shared__ __align__(8) uint64_t empty_bar[TN_STAGES];
+    __shared__ __align__(8) uint64_t tmem_full_bar;
+    __shared__ uint32_t tmem_base_smem;
+
+    uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int seg_i = blockIdx.y / p.qtiles, qt = blockIdx.y % p.qtiles;
+    const csi_seg_tn sg = segs.s[seg_i];
+    const int i0 = blockIdx.x * TC_BM, q0 = qt * p.BN;
+    if (q0 >= sg.nlen) return;                                     // uniform per CTA
+    const int mbeg = blockIdx.z * p.chunk, mend = min(p.M, mbeg + p.chunk);
+    const int nkb = (mend - mbeg + TN_BKM - 1) / TN_BKM;
+    const int nbox_b = (p.BN + 63) / 64;
+    const uint32_t a_bytes = 2 * TN_BOX_BYTES, b_bytes = (uint32_t)nbox_b * TN_BOX_BYTES;
+    const uint32_t stage_bytes = a_bytes + b_bytes;
+
+    if (threadIdx.x == 0) {
+        tma_prefetch_desc(&tmA);
+        tma_prefetch_desc(&tmB);
+        for (int s = 0; s < TN_STAGES; ++s) { mbar_init(&full_bar[s], 1); mbar_init(&empty_bar[s], 1); }
+        mbar_init(&tmem_full_bar, 1);
+        fence_barrier_init();
+    }
+    if (warp == 1) tmem_alloc(&tmem_base_smem, p.tmem_cols);
+    tc_fence_before();
+    __syncthreads();
+    tc_fence_after();
+    const uint32_t tmem_base = tmem_base_smem;
+
+    if (warp == 0) {
+        if (lane == 0) {
+            for (int it = 0; it < nkb; ++it) {
+                const int stage = it % TN_STAGES;
+                const uint32_t ph = (uint32_t)(it / TN_STAGES) & 1u;
+                mbar_wait(&empty_bar[stage], ph ^ 1u);
+                uint8_t* sa = smem + (size_t)stage * stage_bytes;
+                const int m = mbeg + it * TN_BKM;
+                mbar_expect_tx(&full_bar[stage], stage_bytes);
+                tma_load_2d(&tmA, &full_bar[stage], sa, i0, m);
+                tma_load_2d(&tmA, &full_bar[stage], sa + TN_BOX_BYTES, i0 + 64, m);
+                for (int bx = 0; bx < nbox_b; ++bx)
+                    tma_load_2d(&tmB, &full_bar[stage], sa + a_bytes + (size_t)bx * TN_BOX_BYTES,
+                                sg.b_col_off + q0 + bx * 64, m + sg.b_row_shift + p.row_base);
+            }
+        }
+    } else if (warp == 1) {
+        if (lane == 0) {
+            const uint32_t idesc = make_idesc(TC_BM, p.BN) | (1u << 15) | (1u << 16);      // A and B MN-major
+            for (int it = 0; it < nkb; ++it) {
+                const int stage = it % TN_STAGES;
+                const uint32_t ph = (uint32_t)(it / TN_STAGES) & 1u;
+                mbar_wait(&full_bar[stage], ph);
+                tc_fence_after();
+                const uint32_t sa = smem_u32(smem + (size_t)stage * stage_bytes);
+                const uint64_t adesc = make_mnmajor_desc(sa), bdesc = make_mnmajor_desc(sa + a_bytes);
+                const int rows = min(TN_BKM, mend - (mbeg + it * TN_BKM));
+                const int ksteps = (rows + 15) >> 4;           // rows past mend inside a 16-row step are real data of the
+                for (int k = 0; k < ksteps; ++k)               // next chunk only if mend < M: chunk is a multiple of 16
+                    umma_bf16(tmem_base, adesc + (uint64_t)(k * (16 * 128 >> 4)), bdesc + (uint64_t)(k * (16 * 128 >> 4)),
+                              idesc, (it | k) ? 1u : 0u);
+                umma_commit(&empty_bar[stage]);
+            }
+            umma_commit(&tmem_full_bar);
+        }
+    } else {
+        const int q = warp & 3;
+        const int i = i0 + q * 32 + lane;
+        mbar_wait(&tmem_full_bar, 0);
+        tc_fence_after();
+        float* crow = p.C + (size_t)i * p.ldc + sg.c_off;
+        for (int c0 = 0; c0 < p.BN; c0 += 16) {
+            uint32_t r[16];
+            tmem_ld16(tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)c0, r);
+            tmem_ld_wait();
+            if (i < p.Na) {
+#pragma unroll
+                for (int j = 0; j < 16; ++j) {
+                    const int qq = q0 + c0 + j;
+                    if (qq < sg.nlen) atomicAdd(crow + (size_t)qq * p.cs, __uint_as_float(r[j]));
+                }
+            }
+        }
+    }
+    tc_fence_before();
+    __syncthreads();
+    if (warp == 1) {
+        tc_fence_after();
+        tmem_dealloc(tmem_base, p.tmem_cols);
+    }
+}
+
+extern "C" int csi_gemm_tn_tc_ok(int lda, int ldb, int M, int Na, const csi_seg_tn* segs, int nseg) {
+    if (M < 64 || Na < 1 || nseg < 1 || nseg > CSI_MAX_SEGS) return 0;
+    if (lda % 8 || ldb % 8) return 0;
+    for (int i = 0; i < nseg; ++i)
+        if (segs[i].nlen <= 0 || segs[i].b_col_off % 8) return 0;
+    return get_encode() != nullptr;
+}
+
+extern "C" int csi_gemm_tn_tc(const void* A, int lda, const void* Bv, int ldb, float* C, int ldc, int c_col_stride, int M,
+                              int Na, const csi_seg_tn* segs, int nseg, void* stream) {
+    CSI_CHECK_ARG(A && Bv && C && segs, "null pointer");
+    CSI_CHECK_ARG(csi_gemm_tn_tc_ok(lda, ldb, M, Na, segs, nseg), "shape not eligible for the tcgen05 kernel");
+    SegListTN sl;
+    sl.n = nseg;
+    int min_shift = 0, max_shift = 0, b_cols = 0, maxn = 0;
+    for (int i = 0; i < nseg; ++i) {
+        sl.s[i] = segs[i];
+        if (segs[i].b_row_shift < min_shift) min_shift = segs[i].b_row_shift;
+        if (segs[i].b_row_shift > max_shift) max_shift = segs[i].b_row_shift;
+        if (segs[i].b_col_off + segs[i].nlen > b_cols) b_cols = segs[i].b_col_off + segs[i].nlen;
+        if (segs[i].nlen > maxn) maxn = segs[i].nlen;
+    }
+    CSI_CHECK_ARG(b_cols <= ldb && Na <= lda, "segment exceeds the row pitch");
+    // N tile: split the widest segment evenly into <= 256-wide tiles (multiples of 16)
+    const int ntile = (maxn + 255) / 256;
+    int BN = ((maxn + ntile - 1) / ntile + 15) & ~15;
+    if (BN < 16) BN = 16;
+    const int qtiles = (maxn + BN - 1) / BN;
+    const int itiles = (Na + TC_BM - 1) / TC_BM;
+    // token split: about two waves of CTAs, chunks a multiple of 64 rows and at least 512 rows
+    const long long tiles = (long long)itiles * qtiles * nseg;
+    int zs = (int)((2 * 148 + tiles - 1) / tiles);
+    const int max_z = (M + 511) / 512;
+    if (zs > max_z) zs = max_z;
+    if (zs < 1) zs = 1;
+    int chunk = ((M + zs - 1) / zs + TN_BKM - 1) / TN_BKM * TN_BKM;
+    zs = (M + chunk - 1) / chunk;
+    CUtensorMap tmA, tmB;
+    int rc = make_map(&tmA, A, M, Na, lda, TN_BKM);
+    if (rc) return rc;
+    const bf16* b_base = reinterpret_cast<const bf16*>(Bv) + (long long)min_shift * ldb;
+    rc = make_map(&tmB, b_base, (long long)M + (max_shift - min_shift), b_cols, ldb, TN_BKM);
+    if (rc) return rc;
+    TnParams p;
+    p.C = C; p.ldc = ldc; p.cs = c_col_stride; p.M = M; p.Na = Na; p.BN = BN; p.chunk = chunk; p.qtiles = qtiles;
+    p.row_base = -min_shift;
+    uint32_t cols = 32;
+    while ((int)cols < BN) cols <<= 1;
+    p.tmem_cols = cols;
+    const int nbox_b = (BN + 63) / 64;
+    const size_t smem = (size_t)TN_STAGES * (2 + nbox_b) * TN_BOX_BYTES + 1024;
+    CSI_CUDA(cudaFuncSetAttribute(gemm_tn_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    dim3 grid(itiles, qtiles * nseg, zs);
+    gemm_tn_tc_kernel<<<grid, TC_THREADS, smem, ST(stream)>>>(tmA, tmB, p, sl);
+    CSI_LAUNCH_CHECK();
+    return CSI_OK;
+}
