@@ -1,0 +1,375 @@
+// Tensor-core attention core for bf16 activations (that.py:149, nn.MultiheadAttention with need_weights discarded):
+// one CTA per (sample, head); the head's Q, K, V (and dO in backward) live in shared memory as zero-padded
+// [tokens][head_dim] tiles, scores/probabilities only ever exist in registers.  Matrix products use
+// mma.sync.m16n8k16 (bf16 in, fp32 accumulate) fed by ldmatrix; head dims 27/15/54 are zero-padded to 32/16/64.
+//   forward : flash-style online softmax over 64-key blocks, one 16-query tile per warp iteration
+//   backward: pass A (per 16-query tile)  S, dP -> dS -> dQ = dS K
+//             pass B (per 16-key tile)    S^T, dP^T -> dV = P^T dO, dK = dS^T Q     (no atomics, no cross-warp sums)
+#include "common.cuh"
+
+#define ST(s) ((cudaStream_t)(s))
+#define AM_WARPS 4
+#define LOG2E 1.4426950408889634f
+
+__device__ __forceinline__ void ldsm_x4(uint32_t (&r)[4], const bf16* p) {
+    const uint32_t a = (uint32_t)__cvta_generic_to_shared(p);
+    asm volatile("ldmatrix.sync.aligned.m8n8.x4.shared.b16 {%0,%1,%2,%3}, [%4];" : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]) : "r"(a));
+}
+__device__ __forceinline__ void ldsm_x4_t(uint32_t (&r)[4], const bf16* p) {
+    const uint32_t a = (uint32_t)__cvta_generic_to_shared(p);
+    asm volatile("ldmatrix.sync.aligned.m8n8.x4.trans.shared.b16 {%0,%1,%2,%3}, [%4];" : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]) : "r"(a));
+}
+__device__ __forceinline__ void mma16816(float (&c)[4], const uint32_t (&a)[4], uint32_t b0, uint32_t b1) {
+    asm volatile("mma.sync.aligned.m16n8k16.row.col.f32.bf16.bf16.f32 {%0,%1,%2,%3}, {%4,%5,%6,%7}, {%8,%9}, {%0,%1,%2,%3};"
+                 : "+f"(c[0]), "+f"(c[1]), "+f"(c[2]), "+f"(c[3])
+                 : "r"(a[0]), "r"(a[1]), "r"(a[2]), "r"(a[3]), "r"(b0), "r"(b1));
+}
+__device__ __forceinline__ uint32_t pack_bf16(float lo, float hi) {
+    __nv_bfloat162 v = __floats2bfloat162_rn(lo, hi);
+    return *reinterpret_cast<uint32_t*>(&v);
+}
+
+// per-lane smem addresses of the three fragment kinds (LDS = row stride in elements)
+template <int LDS> __device__ __forceinline__ const bf16* a_frag_ptr(const bf16* s, int row0, int col0, int lane) {
+    return s + (row0 + (lane & 7) + ((lane >> 3) & 1) * 8) * LDS + col0 + (lane >> 4) * 8;
+}
+// B operand stored [n][k] (k contiguous): two n-tiles (n0..n0+15) x one k-step -> {b0,b1 | b0,b1}
+template <int LDS> __device__ __forceinline__ const bf16* b_frag_ptr(const bf16* s, int n0, int k0, int lane) {
+    return s + (n0 + (lane & 7) + ((lane >> 4) & 1) * 8) * LDS + k0 + ((lane >> 3) & 1) * 8;
+}
+// B operand stored [k][n] (n contiguous), read transposed: one k-step (k0..k0+15) x two n-tiles (n0..n0+15)
+template <int LDS> __device__ __forceinline__ const bf16* bt_frag_ptr(const bf16* s, int k0, int n0, int lane) {
+    return s + (k0 + (lane & 7) + ((lane >> 3) & 1) * 8) * LDS + n0 + (lane >> 4) * 8;
+}
+
+// global [L rows of one head, hd valid columns at arbitrary 2-byte alignment] -> smem [LP][LDS], zero padded
+template <int LDS>
+__device__ __forceinline__ void load_head_tile(const bf16* __restrict__ src, int ld, int L, int LP, int hd, bf16* __restrict__ dst) {
+    const bf16 z = __float2bfloat16_rn(0.f);
+    for (int i = threadIdx.x; i < LP * LDS; i += blockDim.x) {
+        const int l = i / LDS, e = i % LDS;
+        dst[i] = (l < L && e < hd) ? src[(size_t)l * ld + e] : z;
+    }
+}
+
+template <int HDP>
+__global__ void __launch_bounds__(AM_WARPS * 32) attn_fwd_mma_kernel(const bf16* __restrict__ qkv, int ld3, bf16* __restrict__ o,
+                                                                     int ldo, float* __restrict__ lse, int L, int d, int H, int halo) {
+    constexpr int LDS = HDP + 8, KS = HDP / 16, NTO = HDP / 8;
+    extern __shared__ __align__(16) uint8_t sm_raw[];
+    const int hd = d / H, b = blockIdx.x / H, h = blockIdx.x % H, Lp = L + 2 * halo;
+    const int LP = (L + 15) & ~15;
+    bf16* Qs = reinterpret_cast<bf16*>(sm_raw);
+    bf16* Ks = Qs + LP * LDS;
+    bf16* Vs = Ks + LP * LDS;
+    const size_t row0 = (size_t)b * Lp + halo;
+    const bf16* base = qkv + row0 * ld3 + h * hd;
+    load_head_tile<LDS>(base, ld3, L, LP, hd, Qs);
+    load_head_tile<LDS>(base + d, ld3, L, LP, hd, Ks);
+    load_head_tile<LDS>(base + 2 * d, ld3, L, LP, hd, Vs);
+    __syncthreads();
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, g = lane >> 2, t = lane & 3;
+    const float c = rsqrtf((float)hd) * LOG2E;
+    const int npair = LP / 16;
+    for (int qt = warp; qt < LP / 16; qt += AM_WARPS) {
+        uint32_t qa[KS][4];
+#pragma unroll
+        for (int ks = 0; ks < KS; ++ks) ldsm_x4(qa[ks], a_frag_ptr<LDS>(Qs, qt * 16, ks * 16, lane));
+        float m0 = -INFINITY, m1 = -INFINITY, l0 = 0.f, l1 = 0.f;
+        float oacc[NTO][4];
+#pragma unroll
+        for (int i = 0; i < NTO; ++i) oacc[i][0] = oacc[i][1] = oacc[i][2] = oacc[i][3] = 0.f;
+        for (int pb = 0; pb < npair; pb += 4) {                  // 64-key block = up to 4 pairs of n-tiles
+            const int np = min(4, npair - pb);
+            float s[8][4];
+#pragma unroll
+            for (int i = 0; i < 8; ++i) s[i][0] = s[i][1] = s[i][2] = s[i][3] = 0.f;
+#pragma unroll
+            for (int pp = 0; pp < 4; ++pp) {
+                if (pp < np) {
+#pragma unroll
+                    for (int ks = 0; ks < KS; ++ks) {
+                        uint32_t kb[4];
+                        ldsm_x4(kb, b_frag_ptr<LDS>(Ks, (pb + pp) * 16, ks * 16, lane));
+                        mma16816(s[2 * pp], qa[ks], kb[0], kb[1]);
+                        mma16816(s[2 * pp + 1], qa[ks], kb[2], kb[3]);
+                    }
+                }
+            }
+            float mx0 = -INFINITY, mx1 = -INFINITY;
+#pragma unroll
+            for (int nt = 0; nt < 8; ++nt) {
+                const int col = pb * 16 + nt * 8 + 2 * t;
+                if (col >= L) s[nt][0] = s[nt][2] = -INFINITY;
+                if (col + 1 >= L) s[nt][1] = s[nt][3] = -INFINITY;
+                mx0 = fmaxf(mx0, fmaxf(s[nt][0], s[nt][1]));
+                mx1 = fmaxf(mx1, fmaxf(s[nt][2], s[nt][3]));
+            }
+            mx0 = fmaxf(mx0, __shfl_xor_sync(0xffffffffu, mx0, 1)); mx0 = fmaxf(mx0, __shfl_xor_sync(0xffffffffu, mx0, 2));
+            mx1 = fmaxf(mx1, __shfl_xor_sync(0xffffffffu, mx1, 1)); mx1 = fmaxf(mx1, __shfl_xor_sync(0xffffffffu, mx1, 2));
+            const float mn0 = fmaxf(m0, mx0), mn1 = fmaxf(m1, mx1);
+            const float al0 = exp2f((m0 - mn0) * c), al1 = exp2f((m1 - mn1) * c);
+            m0 = mn0; m1 = mn1;
+            l0 *= al0; l1 *= al1;
+#pragma unroll
+            for (int i = 0; i < NTO; ++i) { oacc[i][0] *= al0; oacc[i][1] *= al0; oacc[i][2] *= al1; oacc[i][3] *= al1; }
+            const float mc0 = mn0 * c, mc1 = mn1 * c;
+#pragma unroll
+            for (int nt = 0; nt < 8; ++nt) {
+                s[nt][0] = exp2f(s[nt][0] * c - mc0); s[nt][1] = exp2f(s[nt][1] * c - mc0);
+                s[nt][2] = exp2f(s[nt][2] * c - mc1); s[nt][3] = exp2f(s[nt][3] * c - mc1);
+                l0 += s[nt][0] + s[nt][1];
+                l1 += s[nt][2] + s[nt][3];
+            }
+#pragma unroll
+            for (int pp = 0; pp < 4; ++pp) {
+                if (pp < np) {
+                    uint32_t pa[4];
+                    pa[0] = pack_bf16(s[2 * pp][0], s[2 * pp][1]);
+                    pa[1] = pack_bf16(s[2 * pp][2], s[2 * pp][3]);
+                    pa[2] = pack_bf16(s[2 * pp + 1][0], s[2 * pp + 1][1]);
+                    pa[3] = pack_bf16(s[2 * pp + 1][2], s[2 * pp + 1][3]);
+#pragma unroll
+                    for (int no = 0; no < NTO; no += 2) {
+                        uint32_t vb[4];
+                        ldsm_x4_t(vb, bt_frag_ptr<LDS>(Vs, (pb + pp) * 16, no * 8, lane));
+                        mma16816(oacc[no], pa, vb[0], vb[1]);
+                        mma16816(oacc[no + 1], pa, vb[2], vb[3]);
+                    }
+                }
+            }
+        }
+        l0 += __shfl_xor_sync(0xffffffffu, l0, 1); l0 += __shfl_xor_sync(0xffffffffu, l0, 2);
+        l1 += __shfl_xor_sync(0xffffffffu, l1, 1); l1 += __shfl_xor_sync(0xffffffffu, l1, 2);
+        const float i0 = 1.f / l0, i1 = 1.f / l1;
+        const int r0 = qt * 16 + g, r1 = r0 + 8;
+        const float sc = rsqrtf((float)hd);
+#pragma unroll
+        for (int no = 0; no < NTO; ++no) {
+            const int col = no * 8 + 2 * t;
+            if (r0 < L) {
+                bf16* dst = o + (row0 + r0) * ldo + h * hd + col;
+                if (col < hd) dst[0] = __float2bfloat16_rn(oacc[no][0] * i0);
+                if (col + 1 < hd) dst[1] = __float2bfloat16_rn(oacc[no][1] * i0);
+            }
+            if (r1 < L) {
+                bf16* dst = o + (row0 + r1) * ldo + h * hd + col;
+                if (col < hd) dst[0] = __float2bfloat16_rn(oacc[no][2] * i1);
+                if (col + 1 < hd) dst[1] = __float2bfloat16_rn(oacc[no][3] * i1);
+            }
+        }
+        if (t == 0) {
+            if (r0 < L) lse[((size_t)b * H + h) * L + r0] = m0 * sc + __logf(l0);
+            if (r1 < L) lse[((size_t)b * H + h) * L + r1] = m1 * sc + __logf(l1);
+        }
+    }
+}
+
+template <int HDP>
+__global__ void __launch_bounds__(AM_WARPS * 32) attn_bwd_mma_kernel(const bf16* __restrict__ qkv, int ld3, const bf16* __restrict__ o,
+                                                                     int ldo, const bf16* __restrict__ dout, int lddo,
+                                                                     bf16* __restrict__ dqkv, int lddqkv, const float* __restrict__ lse,
+                                                                     int L, int d, int H, int halo) {
+    constexpr int LDS = HDP + 8, KS = HDP / 16, NTO = HDP / 8;
+    extern __shared__ __align__(16) uint8_t sm_raw[];
+    const int hd = d / H, b = blockIdx.x / H, h = blockIdx.x % H, Lp = L + 2 * halo;
+    const int LP = (L + 15) & ~15;
+    bf16* Qs = reinterpret_cast<bf16*>(sm_raw);
+    bf16* Ks = Qs + LP * LDS;
+    bf16* Vs = Ks + LP * LDS;
+    bf16* Gs = Vs + LP * LDS;
+    float* Ls = reinterpret_cast<float*>(Gs + LP * LDS);      // lse * log2(e)
+    float* Ds = Ls + LP;                                      // rowsum(dO * O)
+    const size_t row0 = (size_t)b * Lp + halo;
+    const bf16* base = qkv + row0 * ld3 + h * hd;
+    load_head_tile<LDS>(base, ld3, L, LP, hd, Qs);
+    load_head_tile<LDS>(base + d, ld3, L, LP, hd, Ks);
+    load_head_tile<LDS>(base + 2 * d, ld3, L, LP, hd, Vs);
+    load_head_tile<LDS>(dout + row0 * lddo + h * hd, lddo, L, LP, hd, Gs);
+    for (int i = threadIdx.x; i < LP; i += blockDim.x) Ls[i] = i < L ? lse[((size_t)b * H + h) * L + i] * LOG2E : 0.f;
+    __syncthreads();
+    for (int i = threadIdx.x; i < LP; i += blockDim.x) {
+        float a = 0.f;
+        if (i < L) {
+            const bf16* orow = o + (row0 + i) * ldo + h * hd;
+            for (int e = 0; e < hd; ++e) a = fmaf(__bfloat162float(Gs[i * LDS + e]), __bfloat162float(orow[e]), a);
+        }
+        Ds[i] = a;
+    }
+    __syncthreads();
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, g = lane >> 2, t = lane & 3;
+    const float sc = rsqrtf((float)hd), c = sc * LOG2E;
+    const int ntile = LP / 16;
+    // ---------------- pass A: dQ
+    for (int qt = warp; qt < ntile; qt += AM_WARPS) {
+        uint32_t qa[KS][4], ga[KS][4];
+#pragma unroll
+        for (int ks = 0; ks < KS; ++ks) {
+            ldsm_x4(qa[ks], a_frag_ptr<LDS>(Qs, qt * 16, ks * 16, lane));
+            ldsm_x4(ga[ks], a_frag_ptr<LDS>(Gs, qt * 16, ks * 16, lane));
+        }
+        const int r0 = qt * 16 + g, r1 = r0 + 8;
+        const float ls0 = Ls[r0], ls1 = Ls[r1], d0 = Ds[r0], d1 = Ds[r1];
+        float dq[NTO][4];
+#pragma unroll
+        for (int i = 0; i < NTO; ++i) dq[i][0] = dq[i][1] = dq[i][2] = dq[i][3] = 0.f;
+        for (int kp = 0; kp < ntile; ++kp) {                    // 16 keys per iteration
+            float s[2][4] = {{0.f, 0.f, 0.f, 0.f}, {0.f, 0.f, 0.f, 0.f}}, dp[2][4] = {{0.f, 0.f, 0.f, 0.f}, {0.f, 0.f, 0.f, 0.f}};
+#pragma unroll
+            for (int ks = 0; ks < KS; ++ks) {
+                uint32_t kb[4], vb[4];
+                ldsm_x4(kb, b_frag_ptr<LDS>(Ks, kp * 16, ks * 16, lane));
+                ldsm_x4(vb, b_frag_ptr<LDS>(Vs, kp * 16, ks * 16, lane));
+                mma16816(s[0], qa[ks], kb[0], kb[1]);
+                mma16816(s[1], qa[ks], kb[2], kb[3]);
+                mma16816(dp[0], ga[ks], vb[0], vb[1]);
+                mma16816(dp[1], ga[ks], vb[2], vb[3]);
+            }
+            float ds[2][4];
+#pragma unroll
+            for (int nt = 0; nt < 2; ++nt) {
+                const int col = kp * 16 + nt * 8 + 2 * t;
+                const bool v0 = col < L, v1 = (col + 1) < L;
+                const float p0 = v0 ? exp2f(s[nt][0] * c - ls0) : 0.f, p1 = v1 ? exp2f(s[nt][1] * c - ls0) : 0.f;
+                const float p2 = v0 ? exp2f(s[nt][2] * c - ls1) : 0.f, p3 = v1 ? exp2f(s[nt][3] * c - ls1) : 0.f;
+                ds[nt][0] = p0 * (dp[nt][0] - d0) * sc; ds[nt][1] = p1 * (dp[nt][1] - d0) * sc;
+                ds[nt][2] = p2 * (dp[nt][2] - d1) * sc; ds[nt][3] = p3 * (dp[nt][3] - d1) * sc;
+            }
+            uint32_t da[4] = {pack_bf16(ds[0][0], ds[0][1]), pack_bf16(ds[0][2], ds[0][3]), pack_bf16(ds[1][0], ds[1][1]),
+                              pack_bf16(ds[1][2], ds[1][3])};
+#pragma unroll
+            for (int no = 0; no < NTO; no += 2) {
+                uint32_t kb[4];
+                ldsm_x4_t(kb, bt_frag_ptr<LDS>(Ks, kp * 16, no * 8, lane));
+                mma16816(dq[no], da, kb[0], kb[1]);
+                mma16816(dq[no + 1], da, kb[2], kb[3]);
+            }
+        }
+#pragma unroll
+        for (int no = 0; no < NTO; ++no) {
+            const int col = no * 8 + 2 * t;
+            if (r0 < L) {
+                bf16* dst = dqkv + (row0 + r0) * lddqkv + h * hd + col;
+                if (col < hd) dst[0] = __float2bfloat16_rn(dq[no][0]);
+                if (col + 1 < hd) dst[1] = __float2bfloat16_rn(dq[no][1]);
+            }
+            if (r1 < L) {
+                bf16* dst = dqkv + (row0 + r1) * lddqkv + h * hd + col;
+                if (col < hd) dst[0] = __float2bfloat16_rn(dq[no][2]);
+                if (col + 1 < hd) dst[1] = __float2bfloat16_rn(dq[no][3]);
+            }
+        }
+    }
+    // ---------------- pass B: dK, dV (rows of the accumulators are keys, columns of S^T are queries)
+    for (int kt = warp; kt < ntile; kt += AM_WARPS) {
+        uint32_t ka[KS][4], va[KS][4];
+#pragma unroll
+        for (int ks = 0; ks < KS; ++ks) {
+            ldsm_x4(ka[ks], a_frag_ptr<LDS>(Ks, kt * 16, ks * 16, lane));
+            ldsm_x4(va[ks], a_frag_ptr<LDS>(Vs, kt * 16, ks * 16, lane));
+        }
+        float dk[NTO][4], dv[NTO][4];
+#pragma unroll
+        for (int i = 0; i < NTO; ++i) { dk[i][0] = dk[i][1] = dk[i][2] = dk[i][3] = 0.f; dv[i][0] = dv[i][1] = dv[i][2] = dv[i][3] = 0.f; }
+        for (int qp = 0; qp < ntile; ++qp) {                    // 16 queries per iteration
+            float st[2][4] = {{0.f, 0.f, 0.f, 0.f}, {0.f, 0.f, 0.f, 0.f}}, dpt[2][4] = {{0.f, 0.f, 0.f, 0.f}, {0.f, 0.f, 0.f, 0.f}};
+#pragma unroll
+            for (int ks = 0; ks < KS; ++ks) {
+                uint32_t qb[4], gb[4];
+                ldsm_x4(qb, b_frag_ptr<LDS>(Qs, qp * 16, ks * 16, lane));
+                ldsm_x4(gb, b_frag_ptr<LDS>(Gs, qp * 16, ks * 16, lane));
+                mma16816(st[0], ka[ks], qb[0], qb[1]);
+                mma16816(st[1], ka[ks], qb[2], qb[3]);
+                mma16816(dpt[0], va[ks], gb[0], gb[1]);
+                mma16816(dpt[1], va[ks], gb[2], gb[3]);
+            }
+            float pt[2][4], dst_[2][4];
+#pragma unroll
+            for (int nt = 0; nt < 2; ++nt) {
+                const int q0 = qp * 16 + nt * 8 + 2 * t, q1 = q0 + 1;
+                const bool v0 = q0 < L, v1 = q1 < L;
+                const float lq0 = Ls[q0], lq1 = Ls[q1], dd0 = Ds[q0], dd1 = Ds[q1];
+                pt[nt][0] = v0 ? exp2f(st[nt][0] * c - lq0) : 0.f; pt[nt][1] = v1 ? exp2f(st[nt][1] * c - lq1) : 0.f;
+                pt[nt][2] = v0 ? exp2f(st[nt][2] * c - lq0) : 0.f; pt[nt][3] = v1 ? exp2f(st[nt][3] * c - lq1) : 0.f;
+                dst_[nt][0] = pt[nt][0] * (dpt[nt][0] - dd0) * sc; dst_[nt][1] = pt[nt][1] * (dpt[nt][1] - dd1) * sc;
+                dst_[nt][2] = pt[nt][2] * (dpt[nt][2] - dd0) * sc; dst_[nt][3] = pt[nt][3] * (dpt[nt][3] - dd1) * sc;
+            }
+            uint32_t pa[4] = {pack_bf16(pt[0][0], pt[0][1]), pack_bf16(pt[0][2], pt[0][3]), pack_bf16(pt[1][0], pt[1][1]),
+                              pack_bf16(pt[1][2], pt[1][3])};
+            uint32_t sa[4] = {pack_bf16(dst_[0][0], dst_[0][1]), pack_bf16(dst_[0][2], dst_[0][3]), pack_bf16(dst_[1][0], dst_[1][1]),
+                              pack_bf16(dst_[1][2], dst_[1][3])};
+#pragma unroll
+            for (int no = 0; no < NTO; no += 2) {
+                uint32_t gb[4], qb[4];
+                ldsm_x4_t(gb, bt_frag_ptr<LDS>(Gs, qp * 16, no * 8, lane));
+                ldsm_x4_t(qb, bt_frag_ptr<LDS>(Qs, qp * 16, no * 8, lane));
+                mma16816(dv[no], pa, gb[0], gb[1]);
+                mma16816(dv[no + 1], pa, gb[2], gb[3]);
+                mma16816(dk[no], sa, qb[0], qb[1]);
+                mma16816(dk[no + 1], sa, qb[2], qb[3]);
+            }
+        }
+        const int r0 = kt * 16 + g, r1 = r0 + 8;
+#pragma unroll
+        for (int no = 0; no < NTO; ++no) {
+            const int col = no * 8 + 2 * t;
+#pragma unroll
+            for (int half = 0; half < 2; ++half) {
+                const int r = half ? r1 : r0;
+                if (r < L) {
+                    bf16* pk = dqkv + (row0 + r) * lddqkv + d + h * hd + col;
+                    bf16* pv = dqkv + (row0 + r) * lddqkv + 2 * d + h * hd + col;
+                    if (col < hd) { pk[0] = __float2bfloat16_rn(dk[no][2 * half]); pv[0] = __float2bfloat16_rn(dv[no][2 * half]); }
+                    if (col + 1 < hd) { pk[1] = __float2bfloat16_rn(dk[no][2 * half + 1]); pv[1] = __float2bfloat16_rn(dv[no][2 * half + 1]); }
+                }
+            }
+        }
+    }
+}
+
+static int pad_hd(int hd) { return hd <= 16 ? 16 : (hd <= 32 ? 32 : 64); }
+
+extern "C" int csi_attn_mma_ok(int L, int d, int H) {
+    if (H <= 0 || d % H) return 0;
+    const int hd = d / H;
+    if (hd > 64) return 0;
+    const int LP = (L + 15) & ~15, LDS = pad_hd(hd) + 8;
+    return ((size_t)4 * LP * LDS * 2 + 2 * (size_t)LP * 4) <= 200 * 1024;
+}
+
+extern "C" int csi_attn_fwd_mma(const void* qkv, int ld3, void* o, int ldo, float* lse, int B, int L, int d, int H, int halo,
+                                void* stream) {
+    CSI_CHECK_ARG(qkv && o && lse, "null pointer");
+    CSI_CHECK_ARG(csi_attn_mma_ok(L, d, H), "shape not eligible");
+    if (B == 0) return CSI_OK;
+    const int hdp = pad_hd(d / H), LP = (L + 15) & ~15;
+    const size_t smem = (size_t)3 * LP * (hdp + 8) * 2;
+#define GO(HDP)                                                                                                        \
+    do {                                                                                                               \
+        CSI_CUDA(cudaFuncSetAttribute(attn_fwd_mma_kernel<HDP>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem)); \
+        attn_fwd_mma_kernel<HDP><<<B * H, AM_WARPS * 32, smem, ST(stream)>>>((const bf16*)qkv, ld3, (bf16*)o, ldo, lse, L, d, H, halo); \
+    } while (0)
+    if (hdp == 16) GO(16); else if (hdp == 32) GO(32); else GO(64);
+#undef GO
+    CSI_LAUNCH_CHECK();
+    return CSI_OK;
+}
+
+extern "C" int csi_attn_bwd_mma(const void* qkv, int ld3, const void* o, int ldo, const void* dout, int lddo, void* dqkv,
+                                int lddqkv, const float* lse, int B, int L, int d, int H, int halo, void* stream) {
+    CSI_CHECK_ARG(qkv && o && dout && dqkv && lse, "null pointer");
+    CSI_CHECK_ARG(csi_attn_mma_ok(L, d, H), "shape not eligible");
+    if (B == 0) return CSI_OK;
+    const int hdp = pad_hd(d / H), LP = (L + 15) & ~15;
+    const size_t smem = (size_t)4 * LP * (hdp + 8) * 2 + 2 * (size_t)LP * 4;
+#define GO(HDP)                                                                                                        \
+    do {                                                                                                               \
+        CSI_CUDA(cudaFuncSetAttribute(attn_bwd_mma_kernel<HDP>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem)); \
+        attn_bwd_mma_kernel<HDP><<<B * H, AM_WARPS * 32, smem, ST(stream)>>>((const bf16*)qkv, ld3, (const bf16*)o, ldo,   \
+                                                                            (const bf16*)dout, lddo, (bf16*)dqkv, lddqkv, lse, L, d, H, halo); \
+    } while (0)
+    if (hdp == 16) GO(16); else if (hdp == 32) GO(32); else GO(64);
+#undef GO
+    CSI_LAUNCH_CHECK();
+    return CSI_OK;
+}

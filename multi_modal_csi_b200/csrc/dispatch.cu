@@ -16,6 +16,11 @@ extern "C" int csi_gemm_nt_tc_ok(int lda, int ldb, int ldc, int M, int N, const 
 extern "C" int csi_gemm_tn_tc(const void*, int, const void*, int, float*, int, int, int, int, const csi_seg_tn*, int, void*);
 extern "C" int csi_gemm_tn_tc_ok(int lda, int ldb, int M, int Na, const csi_seg_tn* segs, int nseg);
 
+extern "C" int csi_attn_mma_ok(int L, int d, int H);
+extern "C" int csi_attn_fwd_mma(const void*, int, void*, int, float*, int, int, int, int, int, void*);
+extern "C" int csi_attn_bwd_mma(const void*, int, const void*, int, const void*, int, void*, int, const float*, int, int, int,
+                                int, int, void*);
+
 static int g_force_simt = -1;
 static bool force_simt() {
     if (g_force_simt < 0) { const char* e = getenv("CSI_FORCE_SIMT"); g_force_simt = (e && e[0] == '1') ? 1 : 0; }
@@ -43,10 +48,14 @@ extern "C" int csi_gemm_tn(const void* A, int lda, const void* Bv, int ldb, int 
 
 extern "C" int csi_attn_fwd(const void* qkv, int ld3, void* o, int ldo, int dtype, float* lse, int B, int L, int d,
                             int H, int halo, void* stream) {
+    if (dtype == CSI_BF16 && !force_simt() && csi_attn_mma_ok(L, d, H))
+        return csi_attn_fwd_mma(qkv, ld3, o, ldo, lse, B, L, d, H, halo, stream);
     return csi_attn_fwd_simt(qkv, ld3, o, ldo, dtype, lse, B, L, d, H, halo, stream);
 }
 
 extern "C" int csi_attn_bwd(const void* qkv, int ld3, const void* o, int ldo, const void* dout, int lddo, void* dqkv,
                             int lddqkv, int dtype, const float* lse, int B, int L, int d, int H, int halo, void* stream) {
+    if (dtype == CSI_BF16 && !force_simt() && csi_attn_mma_ok(L, d, H))
+        return csi_attn_bwd_mma(qkv, ld3, o, ldo, dout, lddo, dqkv, lddqkv, lse, B, L, d, H, halo, stream);
     return csi_attn_bwd_simt(qkv, ld3, o, ldo, dout, lddo, dqkv, lddqkv, dtype, lse, B, L, d, H, halo, stream);
 }
