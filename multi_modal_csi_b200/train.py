@@ -1,0 +1,153 @@
+"""``train(...)`` with the signature and semantics of benchmark/wifi_csi/train.py:36-176.
+
+Kept from the reference: shuffled DataLoader with pinned memory (:48), the LAST batch of every epoch is skipped
+(:81-82), augmentation only while ``model.training`` (:88-89), ``baseline`` labels flattened to [B, -1] (:93-94), the
+once-per-epoch metrics of the last train batch on int-truncated logits (:105-109), whole-validation-set evaluation
+in one batch (:49,111-127), the wandb keys (:130-144), the selection rule f1 AND perfect-prediction-percentage
+(:159-166) and early stopping after ``patience`` non-improving epochs (:167-174).
+
+Changed underneath: when the model is a multi_modal_csi_b200.THAT on a CUDA device, the optimizer a FusedAdam and the
+loss a uniform-pos_weight BCEWithLogitsLoss, one step is ``model.fused_train_step`` (augmentation, forward, loss,
+backward and Adam in hand-written sm_100a kernels); otherwise the same loop runs through autograd on the model's
+kernels with torch's loss/optimizer.  Under ``torch.distributed`` the batches are sharded over ranks and gradients are
+all-reduced before the update.
+"""
+from __future__ import annotations
+
+import time
+from copy import deepcopy
+
+import torch
+import torch.distributed as dist
+from torch.utils.data import DataLoader, TensorDataset
+from torch.utils.data.distributed import DistributedSampler
+
+from .optim import FusedAdam
+from .parallel import GradSync
+from .that import THAT
+from .utils import performance_metrics
+
+try:                                    # wandb is optional; WANDB_MODE=disabled also works as in the reference
+    import wandb as _wandb
+except Exception:                       # pragma: no cover
+    _wandb = None
+
+
+def _log(payload):
+    if _wandb is not None and getattr(_wandb, "run", None) is not None:
+        _wandb.log(payload)
+
+
+def apply_augmentation(x_batch: torch.Tensor) -> torch.Tensor:
+    """train.py:65-73 with torch ops (used on the generic path; the fused path does this inside csi_pool_dual)."""
+    x_batch = x_batch + torch.randn_like(x_batch) * 0.1
+    scale = torch.rand(x_batch.size(0), 1, device=x_batch.device) * 0.2 + 0.9
+    x_batch = x_batch * scale.unsqueeze(-1)
+    return x_batch * torch.bernoulli(torch.ones_like(x_batch) * 0.96)
+
+
+def _uniform_pos_weight(loss):
+    if not isinstance(loss, torch.nn.BCEWithLogitsLoss) or loss.reduction != "mean" or loss.weight is not None:
+        return None
+    pw = loss.pos_weight
+    if pw is None:
+        return 1.0
+    v = float(pw.flatten()[0])
+    return v if bool((pw == v).all()) else None
+
+
+def train(model, optimizer, loss, data_train_set: TensorDataset, data_test_set: TensorDataset, var_threshold: float,
+          var_batch_size: int, var_epochs: int, device, var_mode: str, patience: int = 150):
+    device = torch.device(device)
+    distributed = dist.is_available() and dist.is_initialized() and dist.get_world_size() > 1
+    sampler = DistributedSampler(data_train_set, shuffle=True, drop_last=False) if distributed else None
+    data_train_loader = DataLoader(data_train_set, var_batch_size, shuffle=sampler is None, sampler=sampler, pin_memory=True)
+    data_test_loader = DataLoader(data_test_set, len(data_test_set))
+    pos_weight = _uniform_pos_weight(loss)
+    fused = (isinstance(model, THAT) and isinstance(optimizer, FusedAdam) and pos_weight is not None
+             and var_mode == "baseline" and device.type == "cuda")
+    sync = GradSync(model, dist.get_world_size()) if distributed and isinstance(model, THAT) else None
+
+    var_best_f1_score, var_best_PPP, var_best_weight, counter = 0, 0, None, 0
+    var_epoch_saved = None
+    for var_epoch in range(var_epochs):
+        var_time_e0 = time.time()
+        model.train()
+        if sampler is not None:
+            sampler.set_epoch(var_epoch)
+        total_batches = len(data_train_loader)
+        predict_train_y = data_batch_y = var_loss_train = None
+        for batch_idx, data_batch in enumerate(data_train_loader):
+            if batch_idx == total_batches - 1:
+                continue
+            data_batch_x, data_batch_y = data_batch
+            data_batch_x = data_batch_x.to(device, non_blocking=True)
+            data_batch_y = data_batch_y.to(device, non_blocking=True)
+            if var_mode == "baseline":
+                data_batch_y = data_batch_y.reshape(data_batch_y.shape[0], -1)
+            if fused:
+                x = data_batch_x.reshape(data_batch_x.shape[0], data_batch_x.shape[1], -1).float()
+                var_loss_train, predict_train_y = model.fused_train_step(
+                    x, data_batch_y, optimizer, pos_weight=pos_weight, augment=True, grad_hook=sync.hook if sync else None)
+                var_loss_train, predict_train_y = var_loss_train.clone(), predict_train_y.clone()
+            else:
+                if model.training:
+                    data_batch_x = apply_augmentation(data_batch_x)
+                predict_train_y = model(data_batch_x)
+                var_loss_train = loss(predict_train_y, data_batch_y.float())
+                optimizer.zero_grad()
+                var_loss_train.backward()
+                if sync is not None:
+                    sync.hook(model._engine)
+                optimizer.step()
+        if predict_train_y is None:
+            raise ValueError("training set smaller than two batches: the reference loop skips the last batch (train.py:81)")
+        data_batch_y = data_batch_y.detach().cpu().numpy()
+        predict_train_y = predict_train_y.detach().cpu().numpy()
+        dict_error_train = performance_metrics(data_batch_y.astype(int), predict_train_y.astype(int), var_mode=var_mode,
+                                               var_threshold=var_threshold)
+        model.eval()
+        with torch.no_grad():
+            data_test_x, data_test_y = next(iter(data_test_loader))
+            data_test_x, data_test_y = data_test_x.to(device), data_test_y.to(device)
+            if var_mode == "baseline":
+                data_test_y = data_test_y.reshape(data_test_y.shape[0], -1)
+            predict_test_y = model(data_test_x)
+            var_loss_test = loss(predict_test_y, data_test_y.float())
+            data_test_y = data_test_y.detach().cpu().numpy()
+            predict_test_y = predict_test_y.detach().cpu().numpy()
+            dict_error_test = performance_metrics(data_test_y, predict_test_y, var_mode, var_threshold)
+        _log({
+            "epoch": var_epoch, "train_loss": var_loss_train.item(), "test_loss": var_loss_test.item(),
+            "total_error_train": dict_error_train["total_error"], "total_error_test": dict_error_test["total_error"],
+            "perfect_prediction_percentage_test": dict_error_test["perfect_prediction_percentage"],
+            "perfect_prediction_percentage_train": dict_error_train["perfect_prediction_percentage"],
+            "accuracy_test": dict_error_test["accuracy"], "accuracy_train": dict_error_train["accuracy"],
+            "learning_rate": optimizer.param_groups[0]["lr"], "precision": dict_error_test["precision"],
+            "recall": dict_error_test["recall"], "f1_score": dict_error_test["f1_score"],
+        })
+        print(f"Epoch {var_epoch}/{var_epochs}", "- %.6fs" % (time.time() - var_time_e0),
+              "- Loss %.6f" % float(var_loss_train), "- Test Loss %.6f" % float(var_loss_test),
+              "- Total Error %.6f" % dict_error_test["total_error"],
+              "- Perfect Prediction Percentage Train %.6f" % dict_error_train["perfect_prediction_percentage"],
+              "- Perfect Prediction Percentage Test %.6f" % dict_error_test["perfect_prediction_percentage"],
+              "- Accuracy Test %.6f" % dict_error_test["accuracy"], "- Accuracy Train %.6f" % dict_error_train["accuracy"],
+              "- Precision %.6f" % dict_error_test["precision"], "- Recall %.6f" % dict_error_test["recall"],
+              "- F1 Score %.6f" % dict_error_test["f1_score"])
+        if (dict_error_test["f1_score"] > var_best_f1_score
+                and dict_error_test["perfect_prediction_percentage"] > var_best_PPP):
+            var_best_PPP = dict_error_test["perfect_prediction_percentage"]
+            var_best_f1_score = dict_error_test["f1_score"]
+            var_best_weight = deepcopy(model.state_dict())
+            var_epoch_saved = var_epoch
+            counter = 0
+        else:
+            counter += 1
+        if counter >= patience:
+            print(f"Early stopping triggered at epoch {var_epoch}")
+            break
+    if var_best_weight is None:
+        # the reference raises UnboundLocalError here (train.py:175); keep the last weights instead of crashing
+        var_best_weight = deepcopy(model.state_dict())
+    print(f"Epoch that the model was saved {var_epoch_saved}")
+    return var_best_weight

@@ -220,3 +220,30 @@ def test_no_cpu_path():
     m = THAT((400, 30), (12,))
     with pytest.raises(RuntimeError):
         m(torch.zeros(2, 400, 30))
+
+
+def test_train_and_run_that_end_to_end(tmp_path, monkeypatch):
+    """The reference-facing entry points on the GPU: train(...) (fused path) and run_that(...) on toy CSI data."""
+    import os
+    os.environ["WANDB_MODE"] = "disabled"
+    from multi_modal_csi_b200 import run as RUN
+    from multi_modal_csi_b200.preset import preset
+    rng = np.random.default_rng(0)
+
+    def mk(n):
+        x = (rng.random((n, 400, 3, 10), dtype=np.float32) * 20)
+        y = np.zeros((n, 6, 9), dtype=np.int64)
+        for i in range(n):
+            for u in range(6):
+                if rng.random() > 0.5:
+                    y[i, u, rng.integers(0, 9)] = 1
+        return x, y
+    xtr, ytr = mk(21)
+    xte, yte = mk(8)
+    monkeypatch.setitem(preset["nn"], "epoch", 2)
+    monkeypatch.setitem(preset["nn"], "batch_size", 4)
+    res = RUN.run_that(xtr, ytr, xte, yte, var_repeat=1)
+    for k in ("total_error", "perfect_prediction_percentage", "accuracy", "error_per_person", "mean_count_error",
+              "counting_error_perPerson", "precision", "recall", "f1_score"):
+        assert k in res
+    assert np.isfinite(res["total_error"]) and len(res["error_per_person"]) == 5

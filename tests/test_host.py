@@ -274,3 +274,45 @@ def test_library_exports_every_declared_symbol():
     assert set(ops.EXPORTS) <= declared
     assert lib.csi_abi_version() == ops.ABI_VERSION
     assert ctypes.sizeof(ops.PackEntry) == 48 and ctypes.sizeof(ops.Seg) == 16 and ctypes.sizeof(ops.Ptr3) == 24
+
+
+# ------------------------------------------------------------------------------------------------ train loop
+def _toy_sets(n_train=10, n_valid=6, T=400, F=30, seed=0):
+    g = torch.Generator().manual_seed(seed)
+    from torch.utils.data import TensorDataset
+
+    def mk(n):
+        x = torch.rand(n, T, F, generator=g) * 20
+        y = torch.zeros(n, 6, 9, dtype=torch.int64)
+        for i in range(n):
+            for u in range(6):
+                if torch.rand((), generator=g) > 0.5:
+                    y[i, u, int(torch.randint(0, 9, (), generator=g))] = 1
+        return TensorDataset(x, y)
+    return mk(n_train), mk(n_valid)
+
+
+def test_train_loop_semantics_on_cpu_with_mirror(monkeypatch):
+    """Reference loop semantics (train.py:75-176): last batch skipped, eval on the whole validation set, best weights
+    returned as a state_dict with the reference's keys."""
+    from multi_modal_csi_b200 import train as TR
+    os.environ["WANDB_MODE"] = "disabled"
+    tr, va = _toy_sets()
+    torch.manual_seed(39)
+    m = _mirror_model(400, 30, 54)
+    calls = {"train": 0, "eval": 0}
+    orig = m.forward
+
+    def counting(x):
+        calls["train" if m.training else "eval"] += 1
+        return orig(x)
+    monkeypatch.setattr(m, "forward", counting)
+    monkeypatch.setattr(TR, "apply_augmentation", lambda x: x)
+    opt = torch.optim.Adam(m.parameters(), lr=5e-4, weight_decay=2e-4)
+    loss = torch.nn.BCEWithLogitsLoss(pos_weight=torch.tensor([4.0] * 54))
+    before = {k: v.clone() for k, v in m.state_dict().items()}
+    best = TR.train(m, opt, loss, tr, va, 0.5, 4, 2, torch.device("cpu"), "baseline", patience=150)
+    assert calls == {"train": 2 * 2, "eval": 2}            # 3 batches per epoch, the last one skipped
+    assert list(best.keys()) == list(before.keys())
+    assert any(not torch.equal(best[k], before[k]) for k in best if k.endswith("weight"))
+    assert int(m.state_dict()["layer_left_encoder.0.layer_cnn.0.1.num_batches_tracked"]) == 4
