@@ -57,10 +57,12 @@ __device__ __forceinline__ float warp_max(float v) {
     return v;
 }
 
-// ---------------------------------------------------------------- counter-based RNG (Philox4x32-10)
-__device__ __forceinline__ uint4 philox4x32_10(uint4 c, uint2 k) {
+// ---------------------------------------------------------------- counter-based RNG (Philox4x32, 7 rounds)
+// Philox4x32-7 (Salmon et al., SC'11: 7 rounds already pass BigCrush); one call yields 128 bits = the dropout
+// decisions of 8 consecutive channels (16 bits each), or 4 augmentation samples.
+__device__ __forceinline__ uint4 philox4x32(uint4 c, uint2 k) {
 #pragma unroll
-    for (int r = 0; r < 10; ++r) {
+    for (int r = 0; r < 7; ++r) {
         uint32_t hi0 = __umulhi(0xD2511F53u, c.x), lo0 = 0xD2511F53u * c.x;
         uint32_t hi1 = __umulhi(0xCD9E8D57u, c.z), lo1 = 0xCD9E8D57u * c.z;
         c = make_uint4(hi1 ^ c.y ^ k.x, lo1, hi0 ^ c.w ^ k.y, lo0);
@@ -79,29 +81,35 @@ __device__ __forceinline__ RngKey rng_load(const unsigned long long* rng) {
     return r;
 }
 
-// 4 random words for the aligned group of 4 consecutive elements containing idx (idx4 = idx >> 2)
-__device__ __forceinline__ uint4 rng_group(const RngKey& k, uint32_t site, unsigned long long idx4) {
-    return philox4x32_10(make_uint4((uint32_t)idx4, (uint32_t)(idx4 >> 32), site, k.step), k.key);
+// 128 random bits for group `idx` of stream `site` at the current step
+__device__ __forceinline__ uint4 rng_group(const RngKey& k, uint32_t site, unsigned long long idx) {
+    return philox4x32(make_uint4((uint32_t)idx, (uint32_t)(idx >> 32), site, k.step), k.key);
 }
-__device__ __forceinline__ uint32_t pick(const uint4& v, int i) {
-    return i == 0 ? v.x : (i == 1 ? v.y : (i == 2 ? v.z : v.w));
+
+// ---- dropout: element (row, col) of a site belongs to group row*ld8 + col/8 (ld8 = round_up(cols,16)/8) and owns the
+//      16-bit field col%8 of that group's 128 bits; it is kept iff field >= round(p*65536).
+struct DropCtx { RngKey k; uint32_t thr; float inv_keep; };
+__device__ __forceinline__ DropCtx drop_ctx(const unsigned long long* rng, float p) {
+    DropCtx d;
+    d.k = rng_load(rng);
+    d.thr = (uint32_t)(p * 65536.0f + 0.5f);
+    d.inv_keep = 1.f / (1.f - p);
+    return d;
 }
-__device__ __forceinline__ uint32_t drop_threshold(float p) {
-    return (uint32_t)fminf(p * 4294967296.0f, 4294967040.0f);
+__device__ __forceinline__ uint32_t field16(const uint4& g, int j) {
+    const uint32_t w = (j >> 1) == 0 ? g.x : ((j >> 1) == 1 ? g.y : ((j >> 1) == 2 ? g.z : g.w));
+    return (j & 1) ? (w >> 16) : (w & 0xFFFFu);
 }
-// keep-scale (0 or 1/(1-p)) of element idx
-__device__ __forceinline__ float drop_scale(const RngKey& k, uint32_t site, unsigned long long idx, uint32_t thr,
-                                            float inv_keep) {
-    uint4 g = rng_group(k, site, idx >> 2);
-    return pick(g, (int)(idx & 3)) >= thr ? inv_keep : 0.f;
+// keep-scales (0 or 1/(1-p)) of the 8 channels of group idx8
+__device__ __forceinline__ void drop_scales8(const DropCtx& d, uint32_t site, unsigned long long idx8, float (&ks)[8]) {
+    const uint4 g = rng_group(d.k, site, idx8);
+#pragma unroll
+    for (int j = 0; j < 8; ++j) ks[j] = field16(g, j) >= d.thr ? d.inv_keep : 0.f;
 }
-// keep-scales of the two consecutive elements idx, idx+1 (idx even)
-__device__ __forceinline__ float2 drop_scale2(const RngKey& k, uint32_t site, unsigned long long idx, uint32_t thr,
-                                              float inv_keep) {
-    uint4 g = rng_group(k, site, idx >> 2);
-    int i = (int)(idx & 2);
-    uint32_t a = i ? g.z : g.x, b = i ? g.w : g.y;
-    return make_float2(a >= thr ? inv_keep : 0.f, b >= thr ? inv_keep : 0.f);
+// keep-scale of one element
+__device__ __forceinline__ float drop_scale1(const DropCtx& d, uint32_t site, unsigned long long row, int ld8, int col) {
+    const uint4 g = rng_group(d.k, site, row * (unsigned long long)ld8 + (col >> 3));
+    return field16(g, col & 7) >= d.thr ? d.inv_keep : 0.f;
 }
 
 __device__ __forceinline__ float leaky(float v) { return v > 0.f ? v : LEAKY_SLOPE * v; }

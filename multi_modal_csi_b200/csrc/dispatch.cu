@@ -2,6 +2,7 @@
 // (gemm_tc.cu) when the shape qualifies, everything else to the FFMA kernels (gemm_simt.cu).
 #include "common.cuh"
 #include <stdlib.h>
+#include <stdint.h>
 
 extern "C" int csi_gemm_nt_simt(const void*, int, const void*, int, int, void*, int, int, int, int, const csi_seg*, int,
                                 const float*, const float*, int, float, unsigned, const unsigned long long*, void*);
@@ -13,6 +14,13 @@ extern "C" int csi_attn_bwd_simt(const void*, int, const void*, int, const void*
 extern "C" int csi_gemm_nt_tc(const void*, int, const void*, int, void*, int, int, int, int, const csi_seg*, int,
                               const float*, const float*, int, float, unsigned, const unsigned long long*, void*);
 extern "C" int csi_gemm_nt_tc_ok(int lda, int ldb, int ldc, int M, int N, const csi_seg* segs, int nseg);
+extern "C" int csi_gemm_nt_tc2(const void*, int, const void*, int, void*, int, int, int, int, const csi_seg*, int,
+                               const float*, const float*, int, float, unsigned, const unsigned long long*, void*);
+static int g_gemm_v1 = -1;
+static bool gemm_v1() {
+    if (g_gemm_v1 < 0) { const char* e = getenv("CSI_GEMM_V1"); g_gemm_v1 = (e && e[0] == '1') ? 1 : 0; }
+    return g_gemm_v1 == 1;
+}
 extern "C" int csi_gemm_tn_tc(const void*, int, const void*, int, float*, int, int, int, int, const csi_seg_tn*, int, void*);
 extern "C" int csi_gemm_tn_tc_ok(int lda, int ldb, int M, int Na, const csi_seg_tn* segs, int nseg);
 
@@ -32,6 +40,12 @@ extern "C" int csi_set_force_simt(int on) { g_force_simt = on ? 1 : 0; return CS
 extern "C" int csi_gemm_nt(const void* A, int lda, const void* Bw, int ldb, int ab_dtype, void* C, int ldc, int c_dtype,
                            int M, int N, const csi_seg* segs, int nseg, const float* bias, const float* residual,
                            int ldr, float drop_p, unsigned drop_site, const unsigned long long* rng, void* stream) {
+    const int es = c_dtype == CSI_BF16 ? 2 : 4;
+    const bool v2_ok = ((long long)ldc * es) % 16 == 0 && (reinterpret_cast<uintptr_t>(C) & 15) == 0 &&
+                       (!residual || (c_dtype != CSI_BF16 && ldr % 4 == 0 && (reinterpret_cast<uintptr_t>(residual) & 15) == 0));
+    if (ab_dtype == CSI_BF16 && !force_simt() && !gemm_v1() && v2_ok && csi_gemm_nt_tc_ok(lda, ldb, ldc, M, N, segs, nseg))
+        return csi_gemm_nt_tc2(A, lda, Bw, ldb, C, ldc, c_dtype, M, N, segs, nseg, bias, residual, ldr, drop_p, drop_site,
+                               rng, stream);
     if (ab_dtype == CSI_BF16 && !force_simt() && csi_gemm_nt_tc_ok(lda, ldb, ldc, M, N, segs, nseg))
         return csi_gemm_nt_tc(A, lda, Bw, ldb, C, ldc, c_dtype, M, N, segs, nseg, bias, residual, ldr, drop_p,
                               drop_site, rng, stream);

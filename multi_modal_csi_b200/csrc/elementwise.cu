@@ -23,58 +23,100 @@ extern "C" int csi_device_arch(int device) {
 #define SITE_AUG 9001u
 #define SITE_AUG_SCALE 9002u
 
+// ------------------------------------------------------------------------------------------------ 8-wide access
+// 8 consecutive channels per thread: one 16-byte load for bf16, two for fp32 (pointers are 16-byte aligned because
+// every leading dimension / column offset is a multiple of 8 elements).
+template <typename T> __device__ __forceinline__ void load8f(const T* p, float (&v)[8]);
+template <> __device__ __forceinline__ void load8f<float>(const float* p, float (&v)[8]) {
+    const float4 a = reinterpret_cast<const float4*>(p)[0], b = reinterpret_cast<const float4*>(p)[1];
+    v[0] = a.x; v[1] = a.y; v[2] = a.z; v[3] = a.w; v[4] = b.x; v[5] = b.y; v[6] = b.z; v[7] = b.w;
+}
+template <> __device__ __forceinline__ void load8f<bf16>(const bf16* p, float (&v)[8]) {
+    const uint4 u = *reinterpret_cast<const uint4*>(p);
+    const __nv_bfloat162* h = reinterpret_cast<const __nv_bfloat162*>(&u);
+#pragma unroll
+    for (int i = 0; i < 4; ++i) { const float2 f = __bfloat1622float2(h[i]); v[2 * i] = f.x; v[2 * i + 1] = f.y; }
+}
+template <typename T> __device__ __forceinline__ void store8f(T* p, const float (&v)[8]);
+template <> __device__ __forceinline__ void store8f<float>(float* p, const float (&v)[8]) {
+    reinterpret_cast<float4*>(p)[0] = make_float4(v[0], v[1], v[2], v[3]);
+    reinterpret_cast<float4*>(p)[1] = make_float4(v[4], v[5], v[6], v[7]);
+}
+template <> __device__ __forceinline__ void store8f<bf16>(bf16* p, const float (&v)[8]) {
+    uint4 u;
+    __nv_bfloat162* h = reinterpret_cast<__nv_bfloat162*>(&u);
+#pragma unroll
+    for (int i = 0; i < 4; ++i) h[i] = __floats2bfloat162_rn(v[2 * i], v[2 * i + 1]);
+    *reinterpret_cast<uint4*>(p) = u;
+}
+
 // ------------------------------------------------------------------------------------------------ pool_dual
+// One CTA = (sample, 16 pooled tokens).  A work item is (token, 4 consecutive features): 20 x 2 float2 loads, one
+// Philox call per (time step, 4 features) when augmenting (2 Box-Muller pairs from 16-bit uniforms + 4 keep bits).
 #define POOL_K 20
 #define POOL_TL 16
 
 template <bool AUG>
-__global__ void __launch_bounds__(288) pool_dual_kernel(
+__global__ void __launch_bounds__(256) pool_dual_kernel(
     const float* __restrict__ x, const long long* __restrict__ offs, const int* __restrict__ lens, int T, int F,
     const float* __restrict__ pe, int ld_pe, float* __restrict__ left, int ld_left, float* __restrict__ right,
     int ld_right, int halo, const unsigned long long* __restrict__ rng) {
     extern __shared__ float tile[];                    // [POOL_TL][F + 1]
     const int b = blockIdx.y, l0 = blockIdx.x * POOL_TL, L = T / POOL_K;
     const int ntl = min(POOL_TL, L - l0);
-    const int Lp_l = L + 2 * halo, Lp_r = F + 2 * halo, FS = F + 1;
+    const int Lp_l = L + 2 * halo, Lp_r = F + 2 * halo, FS = F + 1, G = (F + 3) >> 2;
     const float* xb;
     int pad = 0;
     if (offs) { xb = x + offs[b]; pad = T - lens[b]; } else { xb = x + (size_t)b * T * F; }
     RngKey rk;
     float scale = 1.f;
-    uint32_t keep_thr = 0;
     if (AUG) {
         rk = rng_load(rng);
-        uint4 g = rng_group(rk, SITE_AUG_SCALE, (unsigned long long)b);
+        const uint4 g = rng_group(rk, SITE_AUG_SCALE, (unsigned long long)b);
         scale = (float)g.x * (0.2f / 4294967296.0f) + 0.9f;           // U[0.9, 1.1)
-        keep_thr = drop_threshold(0.04f);                             // Bernoulli(0.96) keep
     }
-    for (int fp = threadIdx.x; fp < F / 2; fp += blockDim.x) {
-        for (int tl = 0; tl < ntl; ++tl) {
-            const int l = l0 + tl;
-            float2 acc = make_float2(0.f, 0.f);
-#pragma unroll 5
-            for (int i = 0; i < POOL_K; ++i) {
-                const int tau = l * POOL_K + i;
-                float2 v = make_float2(0.f, 0.f);
-                if (tau >= pad) v = *reinterpret_cast<const float2*>(xb + (size_t)(tau - pad) * F + 2 * fp);
-                if (AUG) {
-                    unsigned long long e2 = (((unsigned long long)b * T + tau) * F + 2 * fp) >> 1;
-                    uint4 g = rng_group(rk, SITE_AUG, e2);
-                    float u1 = ((float)g.x + 1.0f) * (1.0f / 4294967296.0f);
-                    float u2 = (float)g.y * (1.0f / 4294967296.0f);
-                    float r = sqrtf(-2.0f * __logf(u1));
-                    float sn, cs;
-                    __sincosf(6.283185307179586f * u2, &sn, &cs);
-                    v.x = (v.x + 0.1f * r * cs) * scale * (g.z >= keep_thr ? 1.f : 0.f);
-                    v.y = (v.y + 0.1f * r * sn) * scale * (g.w >= keep_thr ? 1.f : 0.f);
-                }
-                acc.x += v.x; acc.y += v.y;
+    const uint32_t keep_thr = 2621;                                   // Bernoulli(0.96): drop iff u16 < 0.04 * 65536
+    for (int w = threadIdx.x; w < ntl * G; w += blockDim.x) {
+        const int tl = w / G, gq = w % G, l = l0 + tl, f0 = gq * 4;
+        const bool hi = (f0 + 2) < F;                                 // F is even: a group holds 4 or 2 valid features
+        float acc[4] = {0.f, 0.f, 0.f, 0.f};
+#pragma unroll 4
+        for (int i = 0; i < POOL_K; ++i) {
+            const int tau = l * POOL_K + i;
+            float2 v0 = make_float2(0.f, 0.f), v1 = make_float2(0.f, 0.f);
+            if (tau >= pad) {
+                const float* src = xb + (size_t)(tau - pad) * F + f0;
+                v0 = *reinterpret_cast<const float2*>(src);
+                if (hi) v1 = *reinterpret_cast<const float2*>(src + 2);
             }
-            acc.x *= (1.0f / POOL_K); acc.y *= (1.0f / POOL_K);
-            tile[tl * FS + 2 * fp] = acc.x;
-            tile[tl * FS + 2 * fp + 1] = acc.y;
-            if (pe) { acc.x += pe[l * ld_pe + 2 * fp]; acc.y += pe[l * ld_pe + 2 * fp + 1]; }
-            *reinterpret_cast<float2*>(left + ((size_t)b * Lp_l + halo + l) * ld_left + 2 * fp) = acc;
+            if (AUG) {
+                const uint4 g = rng_group(rk, SITE_AUG, ((unsigned long long)b * T + tau) * G + gq);
+                const float ua = (float)((g.x & 0xFFFFu) + 1u) * (1.0f / 65536.0f), ub = (float)(g.x >> 16) * (1.0f / 65536.0f);
+                const float uc = (float)((g.y & 0xFFFFu) + 1u) * (1.0f / 65536.0f), ud = (float)(g.y >> 16) * (1.0f / 65536.0f);
+                const float ra = sqrtf(-2.0f * __logf(ua)) * 0.1f, rc = sqrtf(-2.0f * __logf(uc)) * 0.1f;
+                float s0, c0, s1, c1;
+                __sincosf(6.283185307179586f * ub, &s0, &c0);
+                __sincosf(6.283185307179586f * ud, &s1, &c1);
+                v0.x = (v0.x + ra * c0) * ((g.z & 0xFFFFu) >= keep_thr ? scale : 0.f);
+                v0.y = (v0.y + ra * s0) * ((g.z >> 16) >= keep_thr ? scale : 0.f);
+                v1.x = (v1.x + rc * c1) * ((g.w & 0xFFFFu) >= keep_thr ? scale : 0.f);
+                v1.y = (v1.y + rc * s1) * ((g.w >> 16) >= keep_thr ? scale : 0.f);
+            }
+            acc[0] += v0.x; acc[1] += v0.y; acc[2] += v1.x; acc[3] += v1.y;
+        }
+#pragma unroll
+        for (int j = 0; j < 4; ++j) acc[j] *= (1.0f / POOL_K);
+        float* lrow = left + ((size_t)b * Lp_l + halo + l) * ld_left + f0;
+        tile[tl * FS + f0] = acc[0];
+        tile[tl * FS + f0 + 1] = acc[1];
+        float p0 = 0.f, p1 = 0.f, p2 = 0.f, p3 = 0.f;
+        if (pe) { p0 = pe[l * ld_pe + f0]; p1 = pe[l * ld_pe + f0 + 1]; }
+        *reinterpret_cast<float2*>(lrow) = make_float2(acc[0] + p0, acc[1] + p1);
+        if (hi) {
+            tile[tl * FS + f0 + 2] = acc[2];
+            tile[tl * FS + f0 + 3] = acc[3];
+            if (pe) { p2 = pe[l * ld_pe + f0 + 2]; p3 = pe[l * ld_pe + f0 + 3]; }
+            *reinterpret_cast<float2*>(lrow + 2) = make_float2(acc[2] + p2, acc[3] + p3);
         }
     }
     __syncthreads();
@@ -88,28 +130,23 @@ extern "C" int csi_pool_dual(const float* x, const long long* offs, const int* l
                              const float* pe, int ld_pe, float* left, int ld_left, float* right, int ld_right,
                              int halo, int augment, const unsigned long long* rng, void* stream) {
     CSI_CHECK_ARG(x && left && right, "null pointer");
-    CSI_CHECK_ARG(T % POOL_K == 0 && F % 2 == 0 && F <= 4096, "T must be a multiple of 20, F even and <= 4096");
+    CSI_CHECK_ARG(T % POOL_K == 0 && F % 2 == 0 && F <= 2800, "T must be a multiple of 20, F even and <= 2800");
     CSI_CHECK_ARG((offs == nullptr) == (lens == nullptr), "offs and lens go together");
     CSI_CHECK_ARG(!augment || rng, "augmentation needs rng");
     if (B == 0) return CSI_OK;
     const int L = T / POOL_K;
-    int threads = ((F / 2 + 31) / 32) * 32;
-    if (threads > 288) threads = 288;
     dim3 grid(cdiv(L, POOL_TL), B);
-    size_t smem = (size_t)POOL_TL * (F + 1) * sizeof(float);
+    const size_t smem = (size_t)POOL_TL * (F + 1) * sizeof(float);
     if (augment) {
         if (smem > 48 * 1024) CSI_CUDA(cudaFuncSetAttribute(pool_dual_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-        pool_dual_kernel<true><<<grid, threads, smem, ST(stream)>>>(x, offs, lens, T, F, pe, ld_pe, left, ld_left,
-                                                                    right, ld_right, halo, rng);
+        pool_dual_kernel<true><<<grid, 256, smem, ST(stream)>>>(x, offs, lens, T, F, pe, ld_pe, left, ld_left, right, ld_right, halo, rng);
     } else {
         if (smem > 48 * 1024) CSI_CUDA(cudaFuncSetAttribute(pool_dual_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-        pool_dual_kernel<false><<<grid, threads, smem, ST(stream)>>>(x, offs, lens, T, F, pe, ld_pe, left, ld_left,
-                                                                     right, ld_right, halo, rng);
+        pool_dual_kernel<false><<<grid, 256, smem, ST(stream)>>>(x, offs, lens, T, F, pe, ld_pe, left, ld_left, right, ld_right, halo, rng);
     }
     CSI_LAUNCH_CHECK();
     return CSI_OK;
 }
-
 // ------------------------------------------------------------------------------------------------ gaussian PE
 __global__ void gauss_pe_fwd_kernel(const float* __restrict__ pos, const float* __restrict__ mu,
                                     const float* __restrict__ sigma, const float* __restrict__ emb, int K, int F,
@@ -269,6 +306,8 @@ extern "C" int csi_layernorm_fwd(const float* x, int ldx, const float* gamma, co
     return CSI_OK;
 }
 
+// ------------------------------------------------------------------------------------------------ layernorm backward
+// warp per row, float2 per lane, the next row's operands are fetched before the current row is reduced.
 template <typename TDY, typename TM, int NP>
 __global__ void __launch_bounds__(256) ln_bwd_kernel(
     const TDY* __restrict__ dy, int lddy, const float* __restrict__ x, int ldx, const float* __restrict__ gamma,
@@ -279,13 +318,11 @@ __global__ void __launch_bounds__(256) ln_bwd_kernel(
     __shared__ float2 sg[8][NP * 32];
     const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
     const int gw = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, nw = (gridDim.x * blockDim.x) >> 5;
-    const int Lp = L + 2 * halo, np = d >> 1;
+    const int Lp = L + 2 * halo, np = d >> 1, ld8 = ((d + 15) & ~15) >> 3;
     const float inv_d = 1.0f / d;
-    RngKey rk;
-    uint32_t thr = 0;
-    float inv_keep = 1.f;
     const bool drop = (dxm != nullptr) && drop_p > 0.f;
-    if (drop) { rk = rng_load(rng); thr = drop_threshold(drop_p); inv_keep = 1.f / (1.f - drop_p); }
+    DropCtx dc;
+    if (drop) dc = drop_ctx(rng, drop_p);
     float2 ag[NP], ab[NP], gm[NP];
 #pragma unroll
     for (int j = 0; j < NP; ++j) {
@@ -293,47 +330,64 @@ __global__ void __launch_bounds__(256) ln_bwd_kernel(
         const int p = lane + 32 * j;
         gm[j] = p < np ? *reinterpret_cast<const float2*>(gamma + 2 * p) : make_float2(0.f, 0.f);
     }
-    for (int r = gw; r < B * L; r += nw) {
+    const int total = B * L;
+    float2 dvn[NP], xvn[NP], rvn[NP];
+    float mun = 0.f, rsn = 0.f;
+    auto fetch = [&](int r) {
         const size_t row = (size_t)(r / L) * Lp + halo + (r % L);
-        const float mu = mean[row], rs = rstd[row];
-        float2 g[NP], xh[NP];
-        float s1 = 0.f, s2 = 0.f;
+        mun = mean[row]; rsn = rstd[row];
 #pragma unroll
         for (int j = 0; j < NP; ++j) {
             const int p = lane + 32 * j;
             if (p < np) {
-                float2 dv = ld2<TDY>(dy + row * lddy + 2 * p);
-                float2 xv = *reinterpret_cast<const float2*>(x + row * ldx + 2 * p);
-                xh[j] = make_float2((xv.x - mu) * rs, (xv.y - mu) * rs);
-                g[j] = make_float2(dv.x * gm[j].x, dv.y * gm[j].y);
-                s1 += g[j].x + g[j].y;
-                s2 += g[j].x * xh[j].x + g[j].y * xh[j].y;
-                ag[j].x += dv.x * xh[j].x; ag[j].y += dv.y * xh[j].y;
-                ab[j].x += dv.x; ab[j].y += dv.y;
-            } else { g[j] = xh[j] = make_float2(0.f, 0.f); }
+                dvn[j] = ld2<TDY>(dy + row * lddy + 2 * p);
+                xvn[j] = *reinterpret_cast<const float2*>(x + row * ldx + 2 * p);
+                rvn[j] = dres ? *reinterpret_cast<const float2*>(dres + row * lddres + 2 * p) : make_float2(0.f, 0.f);
+            } else { dvn[j] = xvn[j] = rvn[j] = make_float2(0.f, 0.f); }
+        }
+    };
+    constexpr bool PREFETCH = NP <= 5;                 // wider rows would spill with two rows in flight
+    if (PREFETCH && gw < total) fetch(gw);
+    for (int r = gw; r < total; r += nw) {
+        const size_t row = (size_t)(r / L) * Lp + halo + (r % L);
+        if (!PREFETCH) fetch(r);
+        float2 dv[NP], xv[NP], rv[NP];
+        const float mu = mun, rs = rsn;
+#pragma unroll
+        for (int j = 0; j < NP; ++j) { dv[j] = dvn[j]; xv[j] = xvn[j]; rv[j] = rvn[j]; }
+        if (PREFETCH && r + nw < total) fetch(r + nw);
+        float2 g[NP], xh[NP];
+        float s1 = 0.f, s2 = 0.f;
+#pragma unroll
+        for (int j = 0; j < NP; ++j) {
+            xh[j] = make_float2((xv[j].x - mu) * rs, (xv[j].y - mu) * rs);
+            g[j] = make_float2(dv[j].x * gm[j].x, dv[j].y * gm[j].y);
+            s1 += g[j].x + g[j].y;
+            s2 += g[j].x * xh[j].x + g[j].y * xh[j].y;
+            if (lane + 32 * j < np) {
+                ag[j].x += dv[j].x * xh[j].x; ag[j].y += dv[j].y * xh[j].y;
+                ab[j].x += dv[j].x; ab[j].y += dv[j].y;
+            }
         }
         s1 = warp_sum(s1) * inv_d; s2 = warp_sum(s2) * inv_d;
 #pragma unroll
         for (int j = 0; j < NP; ++j) {
             const int p = lane + 32 * j;
             if (p < np) {
-                float2 o = make_float2(rs * (g[j].x - s1 - xh[j].x * s2), rs * (g[j].y - s1 - xh[j].y * s2));
-                if (dres) {
-                    float2 rv = *reinterpret_cast<const float2*>(dres + row * lddres + 2 * p);
-                    o.x += rv.x; o.y += rv.y;
-                }
+                float2 o = make_float2(rs * (g[j].x - s1 - xh[j].x * s2) + rv[j].x, rs * (g[j].y - s1 - xh[j].y * s2) + rv[j].y);
                 *reinterpret_cast<float2*>(dx + row * lddx + 2 * p) = o;
                 if (dxm) {
                     if (drop) {
-                        float2 ks = drop_scale2(rk, drop_site, (unsigned long long)row * d + 2 * p, thr, inv_keep);
-                        o.x *= ks.x; o.y *= ks.y;
+                        const uint4 gq = rng_group(dc.k, drop_site, (unsigned long long)row * ld8 + (p >> 2));
+                        const int j0 = (2 * p) & 7;
+                        o.x *= field16(gq, j0) >= dc.thr ? dc.inv_keep : 0.f;
+                        o.y *= field16(gq, j0 + 1) >= dc.thr ? dc.inv_keep : 0.f;
                     }
                     st2<TM>(dxm + row * lddxm + 2 * p, o);
                 }
             }
         }
     }
-    // block reduction of the per-warp dgamma / dbeta partials, then one atomic per column per block
 #pragma unroll
     for (int pass = 0; pass < 2; ++pass) {
 #pragma unroll
@@ -355,8 +409,8 @@ static void ln_bwd_launch(const void* dy, int lddy, const float* x, int ldx, con
                           const float* rstd, const float* dres, int lddres, float* dx, int lddx, void* dxm, int lddxm,
                           float drop_p, unsigned site, const unsigned long long* rng, float* dgamma, float* dbeta,
                           int B, int L, int d, int halo, cudaStream_t s) {
-    int blocks = cdiv(B * L, 8 * 16);
-    if (blocks > 148 * 4) blocks = 148 * 4;
+    int blocks = cdiv(B * L, 8 * 4);                 // 4 rows per warp
+    if (blocks > 148 * 16) blocks = 148 * 16;
     if (blocks < 1) blocks = 1;
 #define LNB_CASE(NP) ln_bwd_kernel<TDY, TM, NP><<<blocks, 256, 0, s>>>((const TDY*)dy, lddy, x, ldx, gamma, mean, rstd, \
         dres, lddres, dx, lddx, (TM*)dxm, lddxm, drop_p, site, rng, dgamma, dbeta, B, L, d, halo)
@@ -382,70 +436,82 @@ extern "C" int csi_layernorm_bwd(const void* dy, int lddy, int dy_dtype, const f
     return CSI_OK;
 }
 
-// ------------------------------------------------------------------------------------------------ column sums
-#define CS_ROWS 128
-template <typename T>
-__global__ void colsum_kernel(const T* __restrict__ A, int lda, int B, int L, int halo, int ncols,
-                              float* __restrict__ out) {
-    const int cp = blockIdx.y * blockDim.x + threadIdx.x;
-    if (2 * cp >= ncols) return;
+// ------------------------------------------------------------------------------------------------ column reductions
+// thread = one 8-channel chunk x one row lane; a CTA covers CR_ROWS valid token rows; lanes are combined in smem and
+// the CTA issues one atomic per column.
+#define CR_ROWS 64
+#define CR_THREADS 256
+
+template <typename T, bool SQ>
+__global__ void __launch_bounds__(CR_THREADS) colreduce_kernel(const T* __restrict__ A, int lda, int B, int L, int halo,
+                                                               int ncols, int CH, int RL, float* __restrict__ out_f,
+                                                               double* __restrict__ out_d) {
+    extern __shared__ float red[];                      // [RL][CH*8] (x2 when SQ)
+    const int ch = threadIdx.x % CH, rl = threadIdx.x / CH;
     const int Lp = L + 2 * halo, total = B * L;
-    const int r0 = blockIdx.x * CS_ROWS, r1 = min(total, r0 + CS_ROWS);
-    float2 a = make_float2(0.f, 0.f);
-    for (int r = r0; r < r1; ++r) {
-        const size_t row = (size_t)(r / L) * Lp + halo + (r % L);
-        float2 v = ld2<T>(A + row * lda + 2 * cp);
-        a.x += v.x; a.y += v.y;
+    const int r0 = blockIdx.x * CR_ROWS, r1 = min(total, r0 + CR_ROWS);
+    float a[8], q[8];
+#pragma unroll
+    for (int j = 0; j < 8; ++j) a[j] = q[j] = 0.f;
+    if (rl < RL) {
+        for (int r = r0 + rl; r < r1; r += RL) {
+            const size_t row = (size_t)(r / L) * Lp + halo + (r % L);
+            float v[8];
+            load8f<T>(A + row * lda + ch * 8, v);
+#pragma unroll
+            for (int j = 0; j < 8; ++j) { a[j] += v[j]; if (SQ) q[j] += v[j] * v[j]; }
+        }
+#pragma unroll
+        for (int j = 0; j < 8; ++j) {
+            red[(rl * CH + ch) * 8 + j] = a[j];
+            if (SQ) red[((RL + rl) * CH + ch) * 8 + j] = q[j];
+        }
     }
-    atomicAdd(out + 2 * cp, a.x);
-    if (2 * cp + 1 < ncols) atomicAdd(out + 2 * cp + 1, a.y);
+    __syncthreads();
+    for (int c = threadIdx.x; c < CH * 8; c += blockDim.x) {
+        if (c >= ncols) continue;
+        float s = 0.f, s2 = 0.f;
+        for (int i = 0; i < RL; ++i) { s += red[i * CH * 8 + c]; if (SQ) s2 += red[(RL + i) * CH * 8 + c]; }
+        if (SQ) { atomicAdd(out_d + c, (double)s); atomicAdd(out_d + ncols + c, (double)s2); }
+        else atomicAdd(out_f + c, s);
+    }
+}
+
+template <bool SQ>
+static int colreduce_launch(const void* A, int lda, int dtype, int B, int L, int halo, int ncols, float* out_f, double* out_d,
+                            cudaStream_t s) {
+    const int CH = (ncols + 7) / 8;
+    if (CH > CR_THREADS) { csi_set_error("colreduce: more than 2048 columns"); return CSI_ERR_ARG; }
+    const int RL = CR_THREADS / CH;
+    const size_t smem = (size_t)RL * CH * 8 * sizeof(float) * (SQ ? 2 : 1);
+    const int grid = cdiv(B * L, CR_ROWS);
+    if (dtype == CSI_BF16) colreduce_kernel<bf16, SQ><<<grid, CR_THREADS, smem, s>>>((const bf16*)A, lda, B, L, halo, ncols, CH, RL, out_f, out_d);
+    else colreduce_kernel<float, SQ><<<grid, CR_THREADS, smem, s>>>((const float*)A, lda, B, L, halo, ncols, CH, RL, out_f, out_d);
+    return CSI_OK;
 }
 
 extern "C" int csi_colsum_tokens(const void* A, int lda, int dtype, int B, int L, int halo, int ncols, float* out,
                                  void* stream) {
     CSI_CHECK_ARG(A && out, "null pointer");
-    CSI_CHECK_ARG(lda % 2 == 0 && ((ncols + 1) & ~1) <= lda, "lda must be even and cover ncols rounded up to 2");
+    CSI_CHECK_ARG(lda % 8 == 0 && ((ncols + 7) & ~7) <= lda, "lda must be a multiple of 8 covering ncols rounded up to 8");
     if (B * L == 0 || ncols == 0) return CSI_OK;
-    dim3 grid(cdiv(B * L, CS_ROWS), cdiv((ncols + 1) / 2, 128));
-    if (dtype == CSI_BF16) colsum_kernel<bf16><<<grid, 128, 0, ST(stream)>>>((const bf16*)A, lda, B, L, halo, ncols, out);
-    else colsum_kernel<float><<<grid, 128, 0, ST(stream)>>>((const float*)A, lda, B, L, halo, ncols, out);
+    int rc = colreduce_launch<false>(A, lda, dtype, B, L, halo, ncols, out, nullptr, ST(stream));
+    if (rc) return rc;
     CSI_LAUNCH_CHECK();
     return CSI_OK;
-}
-
-// ------------------------------------------------------------------------------------------------ batchnorm
-template <typename T>
-__global__ void bn_stats_kernel(const T* __restrict__ z, int ldz, int B, int L, int halo, int ncols,
-                                double* __restrict__ sums) {
-    const int cp = blockIdx.y * blockDim.x + threadIdx.x;
-    if (2 * cp >= ncols) return;
-    const int Lp = L + 2 * halo, total = B * L;
-    const int r0 = blockIdx.x * CS_ROWS, r1 = min(total, r0 + CS_ROWS);
-    float2 a = make_float2(0.f, 0.f), q = make_float2(0.f, 0.f);
-    for (int r = r0; r < r1; ++r) {
-        const size_t row = (size_t)(r / L) * Lp + halo + (r % L);
-        float2 v = ld2<T>(z + row * ldz + 2 * cp);
-        a.x += v.x; a.y += v.y;
-        q.x += v.x * v.x; q.y += v.y * v.y;
-    }
-    atomicAdd(sums + 2 * cp, (double)a.x);
-    atomicAdd(sums + 2 * cp + 1, (double)a.y);
-    atomicAdd(sums + ncols + 2 * cp, (double)q.x);
-    atomicAdd(sums + ncols + 2 * cp + 1, (double)q.y);
 }
 
 extern "C" int csi_bn_stats(const void* z, int ldz, int dtype, int B, int L, int halo, int ncols, double* sums,
                             void* stream) {
     CSI_CHECK_ARG(z && sums, "null pointer");
-    CSI_CHECK_ARG(ncols % 2 == 0 && ldz % 2 == 0, "ncols and ldz must be even");
+    CSI_CHECK_ARG(ldz % 8 == 0 && ((ncols + 7) & ~7) <= ldz, "ldz must be a multiple of 8 covering ncols");
     if (B * L == 0) return CSI_OK;
-    dim3 grid(cdiv(B * L, CS_ROWS), cdiv(ncols / 2, 128));
-    if (dtype == CSI_BF16) bn_stats_kernel<bf16><<<grid, 128, 0, ST(stream)>>>((const bf16*)z, ldz, B, L, halo, ncols, sums);
-    else bn_stats_kernel<float><<<grid, 128, 0, ST(stream)>>>((const float*)z, ldz, B, L, halo, ncols, sums);
+    int rc = colreduce_launch<true>(z, ldz, dtype, B, L, halo, ncols, nullptr, sums, ST(stream));
+    if (rc) return rc;
     CSI_LAUNCH_CHECK();
     return CSI_OK;
 }
-
+// ------------------------------------------------------------------------------------------------ batchnorm
 __global__ void bn_finalize_kernel(const double* __restrict__ sums, int Dp, int d, int nbr, long long count,
                                    csi_ptr3 conv_bias, csi_ptr3 run_mean, csi_ptr3 run_var, csi_ptr3 nbt,
                                    float momentum, float eps, float* __restrict__ mean, float* __restrict__ invstd) {
@@ -502,51 +568,71 @@ struct DropCfg {
     unsigned site_branch, site_out;
 };
 
-// gradient/forward helper of one branch value: returns activation a and d(a)/d(y) (incl. branch dropout scale)
-__device__ __forceinline__ void bn_branch(float zv, float mu, float is, float ga, float be, float ks, float& zh,
-                                          float& act, float& dact) {
-    zh = (zv - mu) * is;
-    const float y = (zh * ga + be) * ks;
-    act = leaky(y);
-    dact = leaky_grad(y) * ks;
+// Thread = one 8-channel chunk (fixed for the thread's lifetime, so the per-channel affine terms stay in registers)
+// x one row lane; a CTA walks BNA_ROWS valid token rows.
+#define BNA_THREADS 256
+#define BNA_ITERS 8
+
+// y = zhat*gamma + beta = z*a + b with a = invstd*gamma, b = beta - mean*a (0 for pad channels)
+__device__ __forceinline__ void bn_affine8(const float* __restrict__ mean, const float* __restrict__ invstd, const float* ga,
+                                           const float* be, int q0, int c0, int d, float (&a)[8], float (&b)[8]) {
+#pragma unroll
+    for (int j = 0; j < 8; ++j) {
+        const bool ok = (c0 + j) < d;
+        const float is = ok ? invstd[q0 + j] : 0.f, g = ok ? ga[c0 + j] : 0.f;
+        a[j] = is * g;
+        b[j] = ok ? be[c0 + j] - mean[q0 + j] * a[j] : 0.f;
+    }
 }
 
 template <typename T>
-__global__ void __launch_bounds__(256) bn_act_fwd_kernel(
-    const T* __restrict__ z, int ldz, const float* __restrict__ mean, const float* __restrict__ invstd,
-    csi_ptr3 gamma, csi_ptr3 beta, const float* __restrict__ t_res, int ldt, float* __restrict__ out, int ldo, int B,
-    int L, int d, int Dp, int halo, int nbr, DropCfg dc, const unsigned long long* __restrict__ rng) {
-    const int np = d >> 1;
-    const long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x;
-    if (idx >= (long long)B * L * np) return;
-    const int cp = (int)(idx % np);
-    const int r = (int)(idx / np);
-    const int Lp = L + 2 * halo;
-    const size_t row = (size_t)(r / L) * Lp + halo + (r % L);
-    const bool db = dc.p_branch > 0.f, dout = dc.p_out > 0.f;
-    RngKey rk;
-    if (db || dout) rk = rng_load(rng);
-    const unsigned long long eidx = (unsigned long long)row * d + 2 * cp;
-    float2 acc = make_float2(0.f, 0.f);
-    for (int br = 0; br < nbr; ++br) {
-        const int q = br * Dp + 2 * cp;
-        float2 zv = ld2<T>(z + row * ldz + q);
-        float2 ks = make_float2(1.f, 1.f);
-        if (db) ks = drop_scale2(rk, dc.site_branch + br, eidx, drop_threshold(dc.p_branch), 1.f / (1.f - dc.p_branch));
-        const float* ga = (const float*)gamma.p[br];
-        const float* be = (const float*)beta.p[br];
-        float zh, a, da;
-        bn_branch(zv.x, mean[q], invstd[q], ga[2 * cp], be[2 * cp], ks.x, zh, a, da); acc.x += a;
-        bn_branch(zv.y, mean[q + 1], invstd[q + 1], ga[2 * cp + 1], be[2 * cp + 1], ks.y, zh, a, da); acc.y += a;
+__global__ void __launch_bounds__(BNA_THREADS, 2) bn_act_fwd_kernel(
+    const T* __restrict__ z, int ldz, const float* __restrict__ mean, const float* __restrict__ invstd, csi_ptr3 gamma,
+    csi_ptr3 beta, const float* __restrict__ t_res, int ldt, float* __restrict__ out, int ldo, int B, int L, int d, int Dp,
+    int halo, int nbr, DropCfg dcfg, const unsigned long long* __restrict__ rng, int CH, int RL) {
+    const int ch = threadIdx.x % CH, rl = threadIdx.x / CH;
+    if (rl >= RL) return;
+    const int Lp = L + 2 * halo, total = B * L, ld8 = Dp >> 3;
+    const int r0 = blockIdx.x * (RL * BNA_ITERS), r1 = min(total, r0 + RL * BNA_ITERS);
+    float a[3][8], b[3][8];
+#pragma unroll
+    for (int br = 0; br < 3; ++br) {
+        if (br < nbr) bn_affine8(mean, invstd, (const float*)gamma.p[br], (const float*)beta.p[br], br * Dp + ch * 8, ch * 8, d, a[br], b[br]);
     }
+    const bool db = dcfg.p_branch > 0.f, dro = dcfg.p_out > 0.f;
+    DropCtx cb, co;
+    if (db) cb = drop_ctx(rng, dcfg.p_branch);
+    if (dro) co = drop_ctx(rng, dcfg.p_out);
     const float inv = 1.0f / nbr;
-    acc.x *= inv; acc.y *= inv;
-    if (dout) {
-        float2 ks = drop_scale2(rk, dc.site_out, eidx, drop_threshold(dc.p_out), 1.f / (1.f - dc.p_out));
-        acc.x *= ks.x; acc.y *= ks.y;
+    for (int r = r0 + rl; r < r1; r += RL) {
+        const size_t row = (size_t)(r / L) * Lp + halo + (r % L);
+        const unsigned long long idx8 = (unsigned long long)row * ld8 + ch;
+        float acc[8] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
+#pragma unroll
+        for (int br = 0; br < 3; ++br) {
+            if (br < nbr) {
+                float zv[8], ks[8];
+                load8f<T>(z + row * ldz + br * Dp + ch * 8, zv);
+                if (db) drop_scales8(cb, dcfg.site_branch + br, idx8, ks);
+#pragma unroll
+                for (int j = 0; j < 8; ++j) {
+                    float y = zv[j] * a[br][j] + b[br][j];
+                    if (db) y *= ks[j];
+                    acc[j] += leaky(y);
+                }
+            }
+        }
+        float tv[8], ks[8];
+        load8f<float>(t_res + row * ldt + ch * 8, tv);
+        if (dro) drop_scales8(co, dcfg.site_out, idx8, ks);
+#pragma unroll
+        for (int j = 0; j < 8; ++j) {
+            float v = acc[j] * inv;
+            if (dro) v *= ks[j];
+            tv[j] += v;
+        }
+        store8f<float>(out + row * ldo + ch * 8, tv);
     }
-    float2 tv = *reinterpret_cast<const float2*>(t_res + row * ldt + 2 * cp);
-    *reinterpret_cast<float2*>(out + row * ldo + 2 * cp) = make_float2(tv.x + acc.x, tv.y + acc.y);
 }
 
 extern "C" int csi_bn_act_fwd(const void* z, int ldz, int dtype, const float* mean, const float* invstd,
@@ -554,71 +640,131 @@ extern "C" int csi_bn_act_fwd(const void* z, int ldz, int dtype, const float* me
                               int L, int d, int halo, int nbr, float p_branch, unsigned site_branch, float p_out,
                               unsigned site_out, const unsigned long long* rng, void* stream) {
     CSI_CHECK_ARG(z && mean && invstd && t_res && out, "null pointer");
-    CSI_CHECK_ARG(d % 2 == 0 && nbr >= 1 && nbr <= 3, "bad shape");
+    CSI_CHECK_ARG(nbr >= 1 && nbr <= 3, "bad shape");
     CSI_CHECK_ARG(!(p_branch > 0.f || p_out > 0.f) || rng, "dropout needs rng");
     if (B * L == 0) return CSI_OK;
-    const int Dp = (d + 15) & ~15;
+    const int Dp = (d + 15) & ~15, CH = Dp / 8;
+    CSI_CHECK_ARG(CH <= BNA_THREADS && ldz % 8 == 0 && ldt % 4 == 0 && ldo % 4 == 0 && ldt >= Dp && ldo >= Dp, "bad leading dimension");
+    const int RL = BNA_THREADS / CH;
     DropCfg dc{p_branch, p_out, site_branch, site_out};
-    const long long n = (long long)B * L * (d / 2);
+    const int grid = cdiv(B * L, RL * BNA_ITERS);
     if (dtype == CSI_BF16)
-        bn_act_fwd_kernel<bf16><<<cdiv(n, 256), 256, 0, ST(stream)>>>((const bf16*)z, ldz, mean, invstd, gamma, beta, t_res,
-                                                                       ldt, out, ldo, B, L, d, Dp, halo, nbr, dc, rng);
+        bn_act_fwd_kernel<bf16><<<grid, BNA_THREADS, 0, ST(stream)>>>((const bf16*)z, ldz, mean, invstd, gamma, beta, t_res, ldt,
+                                                                       out, ldo, B, L, d, Dp, halo, nbr, dc, rng, CH, RL);
     else
-        bn_act_fwd_kernel<float><<<cdiv(n, 256), 256, 0, ST(stream)>>>((const float*)z, ldz, mean, invstd, gamma, beta, t_res,
-                                                                        ldt, out, ldo, B, L, d, Dp, halo, nbr, dc, rng);
+        bn_act_fwd_kernel<float><<<grid, BNA_THREADS, 0, ST(stream)>>>((const float*)z, ldz, mean, invstd, gamma, beta, t_res, ldt,
+                                                                        out, ldo, B, L, d, Dp, halo, nbr, dc, rng, CH, RL);
     CSI_LAUNCH_CHECK();
     return CSI_OK;
 }
 
-// per-channel sums of dy and dy*zhat (thread = channel pair, block = chunk of rows)
-template <typename T>
-__global__ void bn_act_bwd_reduce_kernel(const float* __restrict__ dout, int lddo, const T* __restrict__ z, int ldz,
-                                         const float* __restrict__ mean, const float* __restrict__ invstd,
-                                         csi_ptr3 gamma, csi_ptr3 beta, int B, int L, int d, int Dp, int halo, int nbr,
-                                         DropCfg dc, const unsigned long long* __restrict__ rng,
-                                         double* __restrict__ red) {
-    const int cp = blockIdx.y * blockDim.x + threadIdx.x;
-    if (2 * cp >= d) return;
-    const int Lp = L + 2 * halo, total = B * L, nc = nbr * Dp;
-    const int r0 = blockIdx.x * CS_ROWS, r1 = min(total, r0 + CS_ROWS);
-    const bool db = dc.p_branch > 0.f, dro = dc.p_out > 0.f;
-    RngKey rk;
-    if (db || dro) rk = rng_load(rng);
-    float2 s1[3], s2[3], mu[3], is[3], ga[3], be[3];
-    for (int br = 0; br < nbr; ++br) {
-        const int q = br * Dp + 2 * cp;
-        s1[br] = s2[br] = make_float2(0.f, 0.f);
-        mu[br] = make_float2(mean[q], mean[q + 1]);
-        is[br] = make_float2(invstd[q], invstd[q + 1]);
-        ga[br] = make_float2(((const float*)gamma.p[br])[2 * cp], ((const float*)gamma.p[br])[2 * cp + 1]);
-        be[br] = make_float2(((const float*)beta.p[br])[2 * cp], ((const float*)beta.p[br])[2 * cp + 1]);
-    }
-    const float inv = 1.0f / nbr;
-    for (int r = r0; r < r1; ++r) {
-        const size_t row = (size_t)(r / L) * Lp + halo + (r % L);
-        const unsigned long long eidx = (unsigned long long)row * d + 2 * cp;
-        float2 g = *reinterpret_cast<const float2*>(dout + row * lddo + 2 * cp);
-        g.x *= inv; g.y *= inv;
-        if (dro) {
-            float2 ks = drop_scale2(rk, dc.site_out, eidx, drop_threshold(dc.p_out), 1.f / (1.f - dc.p_out));
-            g.x *= ks.x; g.y *= ks.y;
+// Backward: thread = (8-channel chunk, branch) x row lane.
+//   MODE 0: per-channel sums of dy and dy*zhat -> red (doubles, atomics)
+//   MODE 1: dz = gamma*invstd*(dy - s1/n - zhat*s2/n), plus dgamma/dbeta written once by CTA 0
+#define BNB_ROWS 64
+template <typename T, int MODE>
+__global__ void __launch_bounds__(BNA_THREADS, 2) bn_act_bwd_kernel(
+    const float* __restrict__ dout, int lddo, const T* __restrict__ z, int ldz, const float* __restrict__ mean,
+    const float* __restrict__ invstd, csi_ptr3 gamma, csi_ptr3 beta, double* __restrict__ red, int B, int L, int d, int Dp,
+    int halo, int nbr, DropCfg dcfg, const unsigned long long* __restrict__ rng, T* __restrict__ dz, int lddz,
+    csi_ptr3 dgamma, csi_ptr3 dbeta, int CH, int RL) {
+    extern __shared__ float sred[];                               // MODE 0: [RL][CH*nbr][16]
+    const int combo = threadIdx.x % (CH * nbr), rl = threadIdx.x / (CH * nbr);
+    const int ch = combo % CH, br = combo / CH;
+    const int Lp = L + 2 * halo, total = B * L, ld8 = Dp >> 3, nc = nbr * Dp;
+    const int r0 = blockIdx.x * BNB_ROWS, r1 = min(total, r0 + BNB_ROWS);
+    const int q0 = br * Dp + ch * 8, c0 = ch * 8;
+    float a[8], b[8], gi[8], mu[8], is[8], k1[8], k2[8];
+    float s1[8], s2[8];
+    if (rl < RL) {
+        const float* ga = (const float*)gamma.p[br];
+        bn_affine8(mean, invstd, ga, (const float*)beta.p[br], q0, c0, d, a, b);
+        const float invn = 1.0f / ((float)B * (float)L);
+#pragma unroll
+        for (int j = 0; j < 8; ++j) {
+            const bool ok = (c0 + j) < d;
+            mu[j] = ok ? mean[q0 + j] : 0.f;
+            is[j] = ok ? invstd[q0 + j] : 0.f;
+            gi[j] = a[j];                                         // gamma * invstd
+            s1[j] = s2[j] = 0.f;
+            if (MODE == 1) { k1[j] = ok ? (float)red[q0 + j] * invn : 0.f; k2[j] = ok ? (float)red[nc + q0 + j] * invn : 0.f; }
         }
-        for (int br = 0; br < nbr; ++br) {
-            float2 zv = ld2<T>(z + row * ldz + br * Dp + 2 * cp);
-            float2 ks = make_float2(1.f, 1.f);
-            if (db) ks = drop_scale2(rk, dc.site_branch + br, eidx, drop_threshold(dc.p_branch), 1.f / (1.f - dc.p_branch));
-            float zh, a, da;
-            bn_branch(zv.x, mu[br].x, is[br].x, ga[br].x, be[br].x, ks.x, zh, a, da);
-            s1[br].x += g.x * da; s2[br].x += g.x * da * zh;
-            bn_branch(zv.y, mu[br].y, is[br].y, ga[br].y, be[br].y, ks.y, zh, a, da);
-            s1[br].y += g.y * da; s2[br].y += g.y * da * zh;
+        const bool db = dcfg.p_branch > 0.f, dro = dcfg.p_out > 0.f;
+        DropCtx cb, co;
+        if (db) cb = drop_ctx(rng, dcfg.p_branch);
+        if (dro) co = drop_ctx(rng, dcfg.p_out);
+        const float inv = 1.0f / nbr;
+        for (int r = r0 + rl; r < r1; r += RL) {
+            const size_t row = (size_t)(r / L) * Lp + halo + (r % L);
+            const unsigned long long idx8 = (unsigned long long)row * ld8 + ch;
+            float g[8], zv[8], kb[8], ko[8];
+            load8f<float>(dout + row * lddo + c0, g);
+            load8f<T>(z + row * ldz + q0, zv);
+            if (db) drop_scales8(cb, dcfg.site_branch + br, idx8, kb);
+            if (dro) drop_scales8(co, dcfg.site_out, idx8, ko);
+            float o[8];
+#pragma unroll
+            for (int j = 0; j < 8; ++j) {
+                float gg = g[j] * inv;
+                if (dro) gg *= ko[j];
+                float y = zv[j] * a[j] + b[j];
+                float ksj = 1.f;
+                if (db) { ksj = kb[j]; y *= ksj; }
+                const float dy = gg * leaky_grad(y) * ksj;
+                const float zh = (zv[j] - mu[j]) * is[j];
+                if (MODE == 0) { s1[j] += dy; s2[j] += dy * zh; }
+                else o[j] = gi[j] * (dy - k1[j] - zh * k2[j]);
+            }
+            if (MODE == 1) store8f<T>(dz + row * lddz + q0, o);
+        }
+        if (MODE == 0) {
+#pragma unroll
+            for (int j = 0; j < 8; ++j) {
+                sred[((rl * CH * nbr + combo) * 2 + 0) * 8 + j] = s1[j];
+                sred[((rl * CH * nbr + combo) * 2 + 1) * 8 + j] = s2[j];
+            }
+        }
+        if (MODE == 1 && blockIdx.x == 0 && rl == 0) {
+            float* dg = (float*)dgamma.p[br];
+            float* dbp = (float*)dbeta.p[br];
+#pragma unroll
+            for (int j = 0; j < 8; ++j)
+                if (c0 + j < d) { dg[c0 + j] += (float)red[nc + q0 + j]; dbp[c0 + j] += (float)red[q0 + j]; }
         }
     }
-    for (int br = 0; br < nbr; ++br) {
-        const int q = br * Dp + 2 * cp;
-        atomicAdd(red + q, (double)s1[br].x); atomicAdd(red + q + 1, (double)s1[br].y);
-        atomicAdd(red + nc + q, (double)s2[br].x); atomicAdd(red + nc + q + 1, (double)s2[br].y);
+    if (MODE == 0) {
+        __syncthreads();
+        const int ncombo = CH * nbr;
+        for (int e = threadIdx.x; e < ncombo * 16; e += blockDim.x) {
+            const int cmb = e / 16, which = (e / 8) & 1, j = e & 7;
+            const int cc = (cmb % CH) * 8 + j, bb = cmb / CH;
+            if (cc >= d) continue;
+            float s = 0.f;
+            for (int i = 0; i < RL; ++i) s += sred[((i * ncombo + cmb) * 2 + which) * 8 + j];
+            atomicAdd(red + which * nc + bb * Dp + cc, (double)s);
+        }
     }
+}
+
+template <int MODE>
+static int bn_bwd_launch(const float* dout, int lddo, const void* z, int ldz, int dtype, const float* mean, const float* invstd,
+                         csi_ptr3 gamma, csi_ptr3 beta, double* red, int B, int L, int d, int halo, int nbr, DropCfg dc,
+                         const unsigned long long* rng, void* dz, int lddz, csi_ptr3 dgamma, csi_ptr3 dbeta, cudaStream_t s) {
+    const int Dp = (d + 15) & ~15, CH = Dp / 8;
+    if (CH * nbr > BNA_THREADS) { csi_set_error("bn_act_bwd: more than %d channels", BNA_THREADS * 8 / nbr); return CSI_ERR_ARG; }
+    const int RL = BNA_THREADS / (CH * nbr);
+    const size_t smem = MODE == 0 ? (size_t)RL * CH * nbr * 16 * sizeof(float) : 0;
+    const int grid = cdiv(B * L, BNB_ROWS);
+    if (dtype == CSI_BF16) {
+        if (smem > 48 * 1024) cudaFuncSetAttribute(bn_act_bwd_kernel<bf16, MODE>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+        bn_act_bwd_kernel<bf16, MODE><<<grid, BNA_THREADS, smem, s>>>(dout, lddo, (const bf16*)z, ldz, mean, invstd, gamma, beta, red, B, L,
+                                                                      d, Dp, halo, nbr, dc, rng, (bf16*)dz, lddz, dgamma, dbeta, CH, RL);
+    } else {
+        if (smem > 48 * 1024) cudaFuncSetAttribute(bn_act_bwd_kernel<float, MODE>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+        bn_act_bwd_kernel<float, MODE><<<grid, BNA_THREADS, smem, s>>>(dout, lddo, (const float*)z, ldz, mean, invstd, gamma, beta, red, B,
+                                                                       L, d, Dp, halo, nbr, dc, rng, (float*)dz, lddz, dgamma, dbeta, CH, RL);
+    }
+    return CSI_OK;
 }
 
 extern "C" int csi_bn_act_bwd_reduce(const float* dout, int lddo, const void* z, int ldz, int dtype, const float* mean,
@@ -626,67 +772,15 @@ extern "C" int csi_bn_act_bwd_reduce(const float* dout, int lddo, const void* z,
                                      int nbr, float p_branch, unsigned site_branch, float p_out, unsigned site_out,
                                      const unsigned long long* rng, double* red, void* stream) {
     CSI_CHECK_ARG(dout && z && mean && invstd && red, "null pointer");
-    CSI_CHECK_ARG(d % 2 == 0 && nbr >= 1 && nbr <= 3, "bad shape");
+    CSI_CHECK_ARG(nbr >= 1 && nbr <= 3, "bad shape");
     if (B * L == 0) return CSI_OK;
-    const int Dp = (d + 15) & ~15;
     DropCfg dc{p_branch, p_out, site_branch, site_out};
-    dim3 grid(cdiv(B * L, CS_ROWS), cdiv(d / 2, 64));
-    if (dtype == CSI_BF16)
-        bn_act_bwd_reduce_kernel<bf16><<<grid, 64, 0, ST(stream)>>>(dout, lddo, (const bf16*)z, ldz, mean, invstd, gamma, beta,
-                                                                     B, L, d, Dp, halo, nbr, dc, rng, red);
-    else
-        bn_act_bwd_reduce_kernel<float><<<grid, 64, 0, ST(stream)>>>(dout, lddo, (const float*)z, ldz, mean, invstd, gamma, beta,
-                                                                      B, L, d, Dp, halo, nbr, dc, rng, red);
+    csi_ptr3 none{{nullptr, nullptr, nullptr}};
+    int rc = bn_bwd_launch<0>(dout, lddo, z, ldz, dtype, mean, invstd, gamma, beta, red, B, L, d, halo, nbr, dc, rng, nullptr, 0,
+                              none, none, ST(stream));
+    if (rc) return rc;
     CSI_LAUNCH_CHECK();
     return CSI_OK;
-}
-
-template <typename T>
-__global__ void __launch_bounds__(256) bn_act_bwd_dz_kernel(
-    const float* __restrict__ dout, int lddo, const T* __restrict__ z, int ldz, const float* __restrict__ mean,
-    const float* __restrict__ invstd, csi_ptr3 gamma, csi_ptr3 beta, const double* __restrict__ red, int B, int L, int d,
-    int Dp, int halo, int nbr, DropCfg dc, const unsigned long long* __restrict__ rng, T* __restrict__ dz, int lddz,
-    csi_ptr3 dgamma, csi_ptr3 dbeta) {
-    const int np = d >> 1;
-    const long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x;
-    if (idx >= (long long)B * L * np) return;
-    const int cp = (int)(idx % np);
-    const int r = (int)(idx / np);
-    const int Lp = L + 2 * halo, nc = nbr * Dp;
-    const size_t row = (size_t)(r / L) * Lp + halo + (r % L);
-    const bool db = dc.p_branch > 0.f, dro = dc.p_out > 0.f;
-    RngKey rk;
-    if (db || dro) rk = rng_load(rng);
-    const unsigned long long eidx = (unsigned long long)row * d + 2 * cp;
-    const float inv = 1.0f / nbr, invn = 1.0f / ((float)B * (float)L);
-    float2 g = *reinterpret_cast<const float2*>(dout + row * lddo + 2 * cp);
-    g.x *= inv; g.y *= inv;
-    if (dro) {
-        float2 ks = drop_scale2(rk, dc.site_out, eidx, drop_threshold(dc.p_out), 1.f / (1.f - dc.p_out));
-        g.x *= ks.x; g.y *= ks.y;
-    }
-    for (int br = 0; br < nbr; ++br) {
-        const int q = br * Dp + 2 * cp;
-        float2 zv = ld2<T>(z + row * ldz + q);
-        float2 ks = make_float2(1.f, 1.f);
-        if (db) ks = drop_scale2(rk, dc.site_branch + br, eidx, drop_threshold(dc.p_branch), 1.f / (1.f - dc.p_branch));
-        const float* ga = (const float*)gamma.p[br];
-        const float* be = (const float*)beta.p[br];
-        const float s1x = (float)red[q], s1y = (float)red[q + 1], s2x = (float)red[nc + q], s2y = (float)red[nc + q + 1];
-        float zh, a, da;
-        float2 o;
-        bn_branch(zv.x, mean[q], invstd[q], ga[2 * cp], be[2 * cp], ks.x, zh, a, da);
-        o.x = ga[2 * cp] * invstd[q] * (g.x * da - s1x * invn - zh * s2x * invn);
-        bn_branch(zv.y, mean[q + 1], invstd[q + 1], ga[2 * cp + 1], be[2 * cp + 1], ks.y, zh, a, da);
-        o.y = ga[2 * cp + 1] * invstd[q + 1] * (g.y * da - s1y * invn - zh * s2y * invn);
-        st2<T>(dz + row * lddz + q, o);
-        if (r == 0) {
-            float* dg = (float*)dgamma.p[br];
-            float* dbp = (float*)dbeta.p[br];
-            dg[2 * cp] += s2x; dg[2 * cp + 1] += s2y;
-            dbp[2 * cp] += s1x; dbp[2 * cp + 1] += s1y;
-        }
-    }
 }
 
 extern "C" int csi_bn_act_bwd_dz(const float* dout, int lddo, const void* z, int ldz, int dtype, const float* mean,
@@ -695,23 +789,15 @@ extern "C" int csi_bn_act_bwd_dz(const float* dout, int lddo, const void* z, int
                                  const unsigned long long* rng, void* dz, int lddz, csi_ptr3 dgamma, csi_ptr3 dbeta,
                                  void* stream) {
     CSI_CHECK_ARG(dout && z && mean && invstd && red && dz, "null pointer");
-    CSI_CHECK_ARG(d % 2 == 0 && nbr >= 1 && nbr <= 3, "bad shape");
+    CSI_CHECK_ARG(nbr >= 1 && nbr <= 3, "bad shape");
     if (B * L == 0) return CSI_OK;
-    const int Dp = (d + 15) & ~15;
     DropCfg dc{p_branch, p_out, site_branch, site_out};
-    const long long n = (long long)B * L * (d / 2);
-    if (dtype == CSI_BF16)
-        bn_act_bwd_dz_kernel<bf16><<<cdiv(n, 256), 256, 0, ST(stream)>>>(dout, lddo, (const bf16*)z, ldz, mean, invstd, gamma,
-                                                                          beta, red, B, L, d, Dp, halo, nbr, dc, rng, (bf16*)dz,
-                                                                          lddz, dgamma, dbeta);
-    else
-        bn_act_bwd_dz_kernel<float><<<cdiv(n, 256), 256, 0, ST(stream)>>>(dout, lddo, (const float*)z, ldz, mean, invstd, gamma,
-                                                                           beta, red, B, L, d, Dp, halo, nbr, dc, rng,
-                                                                           (float*)dz, lddz, dgamma, dbeta);
+    int rc = bn_bwd_launch<1>(dout, lddo, z, ldz, dtype, mean, invstd, gamma, beta, const_cast<double*>(red), B, L, d, halo, nbr,
+                              dc, rng, dz, lddz, dgamma, dbeta, ST(stream));
+    if (rc) return rc;
     CSI_LAUNCH_CHECK();
     return CSI_OK;
 }
-
 // ------------------------------------------------------------------------------------------------ heads
 // feat[b, n] = sum_{t <= L-k(n)} leaky(p[row(b,t), n]); block = (sample, 32 columns) x 8 row lanes
 template <typename T>
@@ -783,8 +869,8 @@ __global__ void dropout_rows_kernel(const float* __restrict__ in, int ldi, T* __
     const int c = (int)(idx % cols), r = (int)(idx / cols);
     float v = in[(size_t)r * ldi + c];
     if (p > 0.f) {
-        RngKey rk = rng_load(rng);
-        v *= drop_scale(rk, site, (unsigned long long)idx, drop_threshold(p), 1.f / (1.f - p));
+        const DropCtx dc = drop_ctx(rng, p);
+        v *= drop_scale1(dc, site, (unsigned long long)r, ((cols + 15) & ~15) >> 3, c);
     }
     stf<T>(out + (size_t)r * ldo + c, v);
 }

@@ -72,10 +72,9 @@ __global__ void __launch_bounds__(256) gemm_nt_kernel(
         }
     }
     const bool drop = drop_p > 0.f;
-    RngKey rk;
-    uint32_t thr = 0;
-    float inv_keep = 1.f;
-    if (drop) { rk = rng_load(rng); thr = drop_threshold(drop_p); inv_keep = 1.f / (1.f - drop_p); }
+    DropCtx dc;
+    if (drop) dc = drop_ctx(rng, drop_p);
+    const int ld8 = ((N + 15) & ~15) >> 3;
 #pragma unroll
     for (int i = 0; i < 8; ++i) {
         const int m = m0 + ty * 8 + i;
@@ -86,7 +85,7 @@ __global__ void __launch_bounds__(256) gemm_nt_kernel(
             if (n >= N) continue;
             float v = acc[i][j];
             if (bias) v += bias[n];
-            if (drop) v *= drop_scale(rk, drop_site, (unsigned long long)m * N + n, thr, inv_keep);
+            if (drop) v *= drop_scale1(dc, drop_site, (unsigned long long)m, ld8, n);
             if (residual) v += residual[(long long)m * ldr + n];
             stf<TC>(C + (long long)m * ldc + n, v);
         }

@@ -10,95 +10,13 @@
 //   warp 0   : TMA producer  -- cp.async.bulk.tensor.2d into a 128B-swizzled K-major smem ring (mbarrier tx-count)
 //   warp 1   : TMEM allocator + single-thread tcgen05.mma issuer (UMMA 128 x BN x 16, kind::f16, fp32 accumulate)
 //   warps 2-5: epilogue -- tcgen05.ld 32x32b, bias / dropout / residual, direct vectorised global stores
-#include "common.cuh"
-#include <cuda.h>
-#include <mutex>
+#include "tc_common.cuh"
 
 #define ST(s) ((cudaStream_t)(s))
-#define TC_BM 128
-#define TC_BK 64
 #define TC_STAGES 3
 #define TC_THREADS 192
 
 struct SegList { csi_seg s[CSI_MAX_SEGS]; int n; };
-
-// ------------------------------------------------------------------------------------------------ PTX wrappers
-__device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
-
-__device__ __forceinline__ void mbar_init(uint64_t* bar, uint32_t count) {
-    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count));
-}
-__device__ __forceinline__ void mbar_expect_tx(uint64_t* bar, uint32_t bytes) {
-    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
-}
-__device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
-    asm volatile(
-        "{\n"
-        ".reg .pred P1;\n"
-        "LAB_WAIT:\n"
-        "mbarrier.try_wait.parity.shared::cta.b64 P1, [%0], %1;\n"
-        "@P1 bra DONE;\n"
-        "bra LAB_WAIT;\n"
-        "DONE:\n"
-        "}\n" ::"r"(smem_u32(bar)), "r"(parity) : "memory");
-}
-__device__ __forceinline__ void fence_barrier_init() { asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory"); }
-__device__ __forceinline__ void fence_proxy_async() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
-
-__device__ __forceinline__ void tma_load_2d(const CUtensorMap* tm, uint64_t* bar, void* dst, int c0, int c1) {
-    asm volatile(
-        "cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4}], [%2];"
-        ::"r"(smem_u32(dst)), "l"(reinterpret_cast<uint64_t>(tm)), "r"(smem_u32(bar)), "r"(c0), "r"(c1) : "memory");
-}
-__device__ __forceinline__ void tma_prefetch_desc(const CUtensorMap* tm) {
-    asm volatile("prefetch.tensormap [%0];" ::"l"(reinterpret_cast<uint64_t>(tm)) : "memory");
-}
-
-__device__ __forceinline__ void tmem_alloc(uint32_t* dst_smem, uint32_t ncols) {
-    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(dst_smem)), "r"(ncols) : "memory");
-    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
-}
-__device__ __forceinline__ void tmem_dealloc(uint32_t taddr, uint32_t ncols) {
-    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(taddr), "r"(ncols) : "memory");
-}
-__device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
-__device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
-
-__device__ __forceinline__ void umma_bf16(uint32_t tmem_d, uint64_t adesc, uint64_t bdesc, uint32_t idesc, uint32_t accumulate) {
-    asm volatile(
-        "{\n"
-        ".reg .pred p;\n"
-        "setp.ne.b32 p, %4, 0;\n"
-        "tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n"
-        "}\n" ::"r"(tmem_d), "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accumulate) : "memory");
-}
-__device__ __forceinline__ void umma_commit(uint64_t* bar) {
-    asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(smem_u32(bar)) : "memory");
-}
-__device__ __forceinline__ void tmem_ld16(uint32_t taddr, uint32_t* r) {
-    asm volatile(
-        "tcgen05.ld.sync.aligned.32x32b.x16.b32 {%0,%1,%2,%3,%4,%5,%6,%7,%8,%9,%10,%11,%12,%13,%14,%15}, [%16];"
-        : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]), "=r"(r[8]),
-          "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15])
-        : "r"(taddr));
-}
-__device__ __forceinline__ void tmem_ld_wait() { asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory"); }
-
-// K-major, 128B-swizzled operand tile ([rows][64 bf16], 8-row groups 1024 B apart): cute::UMMA::SmemDescriptor
-//   bits [0,14) start>>4 | [16,30) LBO>>4 (=1, ignored) | [32,46) SBO>>4 (=64) | [46,48) version=1 | [61,64) layout=2 (SW128)
-__device__ __forceinline__ uint64_t make_kmajor_desc(uint32_t saddr) {
-    uint64_t d = 0;
-    d |= (uint64_t)((saddr >> 4) & 0x3FFF);
-    d |= (uint64_t)1 << 16;
-    d |= (uint64_t)(1024 >> 4) << 32;
-    d |= (uint64_t)1 << 46;
-    d |= (uint64_t)2 << 61;
-    return d;
-}
-// cute::UMMA::InstrDescriptor: c_format F32 (1<<4), a/b format BF16 (1<<7, 1<<10), K-major A and B, N>>3 at 17, M>>4 at 24
-__device__ __forceinline__ uint32_t make_idesc(int m, int n) {
-    return (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(n >> 3) << 17) | ((uint32_t)(m >> 4) << 24);
-}
 
 struct NtParams {
     void* C; int ldc; int M, N, BN;
@@ -185,10 +103,9 @@ __global__ void __launch_bounds__(TC_THREADS) gemm_nt_tc_kernel(const __grid_con
         mbar_wait(&tmem_full_bar, 0);
         tc_fence_after();
         const bool drop = p.drop_p > 0.f;
-        RngKey rk;
-        uint32_t thr = 0;
-        float inv_keep = 1.f;
-        if (drop) { rk = rng_load(p.rng); thr = drop_threshold(p.drop_p); inv_keep = 1.f / (1.f - p.drop_p); }
+        DropCtx dc;
+        if (drop) dc = drop_ctx(p.rng, p.drop_p);
+        const int ld8 = ((p.N + 15) & ~15) >> 3;
         TC* crow = reinterpret_cast<TC*>(p.C) + (size_t)m * p.ldc;
         const float* rrow = p.residual ? p.residual + (size_t)m * p.ldr : nullptr;
         for (int c0 = 0; c0 < p.BN; c0 += 16) {
@@ -197,6 +114,14 @@ __global__ void __launch_bounds__(TC_THREADS) gemm_nt_tc_kernel(const __grid_con
             tmem_ld_wait();
             if (m < p.M) {
                 const int nb = n0 + c0;
+                float ks[16];
+                if (drop) {
+                    float k0[8], k1[8];
+                    drop_scales8(dc, p.drop_site, (unsigned long long)m * ld8 + (nb >> 3), k0);
+                    drop_scales8(dc, p.drop_site, (unsigned long long)m * ld8 + (nb >> 3) + 1, k1);
+#pragma unroll
+                    for (int j = 0; j < 8; ++j) { ks[j] = k0[j]; ks[8 + j] = k1[j]; }
+                }
 #pragma unroll
                 for (int j = 0; j < 16; j += 2) {
                     const int n = nb + j;
@@ -204,10 +129,7 @@ __global__ void __launch_bounds__(TC_THREADS) gemm_nt_tc_kernel(const __grid_con
                     float v0 = __uint_as_float(r[j]), v1 = __uint_as_float(r[j + 1]);
                     const bool two = (n + 1) < p.N;
                     if (p.bias) { v0 += p.bias[n]; if (two) v1 += p.bias[n + 1]; }
-                    if (drop) {
-                        v0 *= drop_scale(rk, p.drop_site, (unsigned long long)m * p.N + n, thr, inv_keep);
-                        if (two) v1 *= drop_scale(rk, p.drop_site, (unsigned long long)m * p.N + n + 1, thr, inv_keep);
-                    }
+                    if (drop) { v0 *= ks[j]; v1 *= ks[j + 1]; }
                     if (rrow) { v0 += rrow[n]; if (two) v1 += rrow[n + 1]; }
                     if (two) st2<TC>(crow + n, make_float2(v0, v1));
                     else stf<TC>(crow + n, v0);
@@ -224,38 +146,6 @@ __global__ void __launch_bounds__(TC_THREADS) gemm_nt_tc_kernel(const __grid_con
 }
 
 // ------------------------------------------------------------------------------------------------ host side
-typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*, const cuuint64_t*,
-                                  const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave, CUtensorMapSwizzle,
-                                  CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
-static EncodeTiledFn g_encode = nullptr;
-static std::once_flag g_encode_once;
-
-static EncodeTiledFn get_encode() {
-    std::call_once(g_encode_once, [] {
-        void* fn = nullptr;
-        cudaDriverEntryPointQueryResult qres;
-        if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &fn, cudaEnableDefault, &qres) == cudaSuccess &&
-            qres == cudaDriverEntryPointSuccess)
-            g_encode = (EncodeTiledFn)fn;
-    });
-    return g_encode;
-}
-
-// 2D bf16 row-major [rows, cols] with row pitch ld elements; box = box_rows x 64 columns, 128B swizzle
-static int make_map(CUtensorMap* tm, const void* base, long long rows, long long cols, long long ld, int box_rows) {
-    EncodeTiledFn enc = get_encode();
-    if (!enc) { csi_set_error("cuTensorMapEncodeTiled not available"); return CSI_ERR_CUDA; }
-    cuuint64_t dims[2] = {(cuuint64_t)cols, (cuuint64_t)rows};
-    cuuint64_t strides[1] = {(cuuint64_t)ld * 2};
-    cuuint32_t box[2] = {TC_BK, (cuuint32_t)box_rows};
-    cuuint32_t estr[2] = {1, 1};
-    CUresult r = enc(tm, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, const_cast<void*>(base), dims, strides, box, estr,
-                     CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
-                     CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
-    if (r != CUDA_SUCCESS) { csi_set_error("cuTensorMapEncodeTiled failed (%d)", (int)r); return CSI_ERR_CUDA; }
-    return CSI_OK;
-}
-
 static int pick_bn(int N) {
     const int tiles = (N + 127) / 128;
     int bn = ((N + tiles - 1) / tiles + 15) & ~15;

@@ -105,7 +105,14 @@ def test_full_size_anchor_and_oracle(gold, mode, F, out):
     sd64 = {k: (v.double() if v.is_floating_point() else v.clone()) for k, v in sd_cpu.items()}
     _, _, og = O.loss_and_grads(sd64, x.double(), y.double())
     ge, worst = grad_err(m, og)
-    assert ge < tg, (ge, worst)
+    if ge >= tg:
+        # The gradient is discontinuous at the LeakyReLU kinks: with ~4e6 pre-activations a few lie within fp32
+        # rounding of zero, and flipping one of them moves the gradient vector by ~1e-4 (scripts/diag_parity.py:
+        # at F=540 the fp32 CPU reference itself is 1.14e-4 away from fp64 on exactly one such element).  The
+        # kernel path must then agree with the fp32 reference evaluation, which took the same side of the kink.
+        _, _, og32 = O.loss_and_grads(copy.deepcopy(sd_cpu), x, y)
+        ge32, worst32 = grad_err(m, og32)
+        assert ge32 < tg, (ge, worst, ge32, worst32)
     gn = sum(p.grad.double().pow(2).sum().item() for p in m.parameters() if p.grad is not None) ** 0.5
     assert abs(gn - float(g["grad_norm"])) < tg * float(g["grad_norm"])
     for k in ("layer_output.weight", "layer_left_gaussian.var_mu", "layer_left_gaussian.var_sigma"):
@@ -198,6 +205,45 @@ def test_dropout_and_augmentation_step_runs_and_is_reproducible():
     assert abs(losses[0][0] - losses[1][0]) < 1e-4 * abs(losses[0][0])
     assert all(abs(a - b) < 5e-3 * abs(a) for a, b in zip(losses[0], losses[1]))
     assert losses[0][0] != losses[0][1]
+
+
+@pytest.mark.parametrize("mode", ["fp32", "bf16"])
+def test_backward_uses_the_forward_dropout_masks(mode):
+    """Dropout on: the analytic gradient must equal the finite-difference directional derivative of the SAME masked
+    network (masks are regenerated in backward from (seed, step, site, element), never stored)."""
+    T, F, out, B = 400, 30, 12, 6
+    x, y = synth(B, T, F, out)
+    x, y = x.cuda(), y.cuda()
+    m = build(T, F, out, "fp32")
+    m.dropout_enabled = True
+    m.train()
+    if mode == "bf16":                      # exercise the tensor-core epilogue's mask on the analytic side only
+        m.configure(act_dtype="bf16")
+    lossf = torch.nn.BCEWithLogitsLoss(pos_weight=torch.full((out,), 4.0, device="cuda"))
+    loss = lossf(m(x), y)
+    loss.backward()
+    g = m.flat_grads.clone()
+    assert torch.isfinite(g).all()
+    eng = m._engine
+    step0 = int(eng.rng[1].item())
+    m.configure(act_dtype="fp32")           # finite differences always in fp32; same seed/step -> same masks
+    m._engine_for(B).rng.copy_(torch.tensor([m.rng_seed, step0], device="cuda"))
+    gen = torch.Generator(device="cuda").manual_seed(3)
+    worst = 0.0
+    for trial in range(3):
+        v = torch.randn(g.numel(), device="cuda", generator=gen)
+        v = v / v.norm()
+        analytic = float((g.double() * v.double()).sum())
+        eps = 2e-3
+        vals = []
+        for sgn in (1.0, -1.0):
+            with torch.no_grad():
+                m.flat_params.add_(v, alpha=sgn * eps)
+                vals.append(float(lossf(m._forward_nograd(x, True), y)))
+                m.flat_params.add_(v, alpha=-sgn * eps)
+        fd = (vals[0] - vals[1]) / (2 * eps)
+        worst = max(worst, abs(fd - analytic) / (abs(fd) + 1e-3))
+    assert worst < (3e-2 if mode == "fp32" else 8e-2), worst
 
 
 def test_state_dict_roundtrip_and_eval_chunking():
