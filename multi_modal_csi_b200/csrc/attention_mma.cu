@@ -42,13 +42,49 @@ template <int LDS> __device__ __forceinline__ const bf16* bt_frag_ptr(const bf16
     return s + (k0 + (lane & 7) + ((lane >> 3) & 1) * 8) * LDS + n0 + (lane >> 4) * 8;
 }
 
-// global [L rows of one head, hd valid columns at arbitrary 2-byte alignment] -> smem [LP][LDS], zero padded
+// global [L rows of one head, hd valid columns at arbitrary 2-byte alignment] -> smem [LP][LDS].  The tile must have been
+// zeroed (zero_tiles) before; 8 independent loads are issued per thread before any of them is consumed, so the copy is
+// bandwidth- rather than latency-bound.
 template <int LDS>
-__device__ __forceinline__ void load_head_tile(const bf16* __restrict__ src, int ld, int L, int LP, int hd, bf16* __restrict__ dst) {
-    const bf16 z = __float2bfloat16_rn(0.f);
-    for (int i = threadIdx.x; i < LP * LDS; i += blockDim.x) {
-        const int l = i / LDS, e = i % LDS;
-        dst[i] = (l < L && e < hd) ? src[(size_t)l * ld + e] : z;
+__device__ __forceinline__ void load_head_tile(const bf16* __restrict__ src, int ld, int L, int hd, bf16* __restrict__ dst) {
+    const int total = L * hd, stride = blockDim.x;
+    for (int base = threadIdx.x; base < total; base += 8 * stride) {
+        bf16 v[8];
+        int off[8];
+#pragma unroll
+        for (int u = 0; u < 8; ++u) {
+            const int i = base + u * stride;
+            const int l = i / hd, e = i - l * hd;
+            off[u] = l * LDS + e;
+            if (i < total) v[u] = src[(size_t)l * ld + e];
+        }
+#pragma unroll
+        for (int u = 0; u < 8; ++u)
+            if (base + u * stride < total) dst[off[u]] = v[u];
+    }
+}
+__device__ __forceinline__ void zero_tiles(void* p, int bytes) {
+    uint4* q = reinterpret_cast<uint4*>(p);
+    for (int i = threadIdx.x; i < bytes / 16; i += blockDim.x) q[i] = make_uint4(0u, 0u, 0u, 0u);
+}
+
+// accumulator tile (16 rows x NTO*8 cols, mma C layout) -> bf16 smem rows [row0, row0+16)
+template <int LDS, int NTO>
+__device__ __forceinline__ void stage_tile(bf16* __restrict__ dst, int row0, const float (&acc)[NTO][4], float s0, float s1, int g, int t) {
+#pragma unroll
+    for (int no = 0; no < NTO; ++no) {
+        const int col = no * 8 + 2 * t;
+        *reinterpret_cast<__nv_bfloat162*>(dst + (row0 + g) * LDS + col) = __floats2bfloat162_rn(acc[no][0] * s0, acc[no][1] * s0);
+        *reinterpret_cast<__nv_bfloat162*>(dst + (row0 + g + 8) * LDS + col) = __floats2bfloat162_rn(acc[no][2] * s1, acc[no][3] * s1);
+    }
+}
+// smem [L][LDS] -> global rows of one head (hd valid columns): consecutive threads write consecutive elements, so a warp
+// store fills whole 32-byte sectors instead of one sector per 2-byte element
+template <int LDS>
+__device__ __forceinline__ void flush_head_tile(const bf16* __restrict__ src, bf16* __restrict__ dst, int ld, int L, int hd) {
+    for (int i = threadIdx.x; i < L * hd; i += blockDim.x) {
+        const int l = i / hd, e = i - l * hd;
+        dst[(size_t)l * ld + e] = src[l * LDS + e];
     }
 }
 
@@ -64,9 +100,11 @@ __global__ void __launch_bounds__(AM_WARPS * 32) attn_fwd_mma_kernel(const bf16*
     bf16* Vs = Ks + LP * LDS;
     const size_t row0 = (size_t)b * Lp + halo;
     const bf16* base = qkv + row0 * ld3 + h * hd;
-    load_head_tile<LDS>(base, ld3, L, LP, hd, Qs);
-    load_head_tile<LDS>(base + d, ld3, L, LP, hd, Ks);
-    load_head_tile<LDS>(base + 2 * d, ld3, L, LP, hd, Vs);
+    zero_tiles(Qs, 3 * LP * LDS * 2);
+    __syncthreads();
+    load_head_tile<LDS>(base, ld3, L, hd, Qs);
+    load_head_tile<LDS>(base + d, ld3, L, hd, Ks);
+    load_head_tile<LDS>(base + 2 * d, ld3, L, hd, Vs);
     __syncthreads();
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, g = lane >> 2, t = lane & 3;
     const float c = rsqrtf((float)hd) * LOG2E;
@@ -144,25 +182,15 @@ __global__ void __launch_bounds__(AM_WARPS * 32) attn_fwd_mma_kernel(const bf16*
         const float i0 = 1.f / l0, i1 = 1.f / l1;
         const int r0 = qt * 16 + g, r1 = r0 + 8;
         const float sc = rsqrtf((float)hd);
-#pragma unroll
-        for (int no = 0; no < NTO; ++no) {
-            const int col = no * 8 + 2 * t;
-            if (r0 < L) {
-                bf16* dst = o + (row0 + r0) * ldo + h * hd + col;
-                if (col < hd) dst[0] = __float2bfloat16_rn(oacc[no][0] * i0);
-                if (col + 1 < hd) dst[1] = __float2bfloat16_rn(oacc[no][1] * i0);
-            }
-            if (r1 < L) {
-                bf16* dst = o + (row0 + r1) * ldo + h * hd + col;
-                if (col < hd) dst[0] = __float2bfloat16_rn(oacc[no][2] * i1);
-                if (col + 1 < hd) dst[1] = __float2bfloat16_rn(oacc[no][3] * i1);
-            }
-        }
+        __syncwarp();                                              // all lanes hold their Q fragments of this tile
+        stage_tile<LDS, NTO>(Qs, qt * 16, oacc, i0, i1, g, t);    // O overwrites the (now dead) Q rows of this tile
         if (t == 0) {
             if (r0 < L) lse[((size_t)b * H + h) * L + r0] = m0 * sc + __logf(l0);
             if (r1 < L) lse[((size_t)b * H + h) * L + r1] = m1 * sc + __logf(l1);
         }
     }
+    __syncthreads();
+    flush_head_tile<LDS>(Qs, o + row0 * ldo + h * hd, ldo, L, hd);
 }
 
 template <int HDP>
@@ -182,19 +210,28 @@ __global__ void __launch_bounds__(AM_WARPS * 32) attn_bwd_mma_kernel(const bf16*
     float* Ds = Ls + LP;                                      // rowsum(dO * O)
     const size_t row0 = (size_t)b * Lp + halo;
     const bf16* base = qkv + row0 * ld3 + h * hd;
-    load_head_tile<LDS>(base, ld3, L, LP, hd, Qs);
-    load_head_tile<LDS>(base + d, ld3, L, LP, hd, Ks);
-    load_head_tile<LDS>(base + 2 * d, ld3, L, LP, hd, Vs);
-    load_head_tile<LDS>(dout + row0 * lddo + h * hd, lddo, L, LP, hd, Gs);
+    zero_tiles(Qs, 4 * LP * LDS * 2);
+    __syncthreads();
+    load_head_tile<LDS>(base, ld3, L, hd, Qs);
+    load_head_tile<LDS>(base + d, ld3, L, hd, Ks);
+    load_head_tile<LDS>(base + 2 * d, ld3, L, hd, Vs);
+    load_head_tile<LDS>(dout + row0 * lddo + h * hd, lddo, L, hd, Gs);
     for (int i = threadIdx.x; i < LP; i += blockDim.x) Ls[i] = i < L ? lse[((size_t)b * H + h) * L + i] * LOG2E : 0.f;
     __syncthreads();
-    for (int i = threadIdx.x; i < LP; i += blockDim.x) {
+    // D_i = rowsum(dO_i * O_i): 8 lanes per row, each with its O loads issued together
+    for (int i = threadIdx.x >> 3; i < LP; i += blockDim.x >> 3) {
+        const int sub = threadIdx.x & 7;
         float a = 0.f;
         if (i < L) {
             const bf16* orow = o + (row0 + i) * ldo + h * hd;
-            for (int e = 0; e < hd; ++e) a = fmaf(__bfloat162float(Gs[i * LDS + e]), __bfloat162float(orow[e]), a);
+            bf16 ov[8];
+#pragma unroll
+            for (int u = 0; u < 8; ++u) { const int e = sub + 8 * u; if (e < hd) ov[u] = orow[e]; }
+#pragma unroll
+            for (int u = 0; u < 8; ++u) { const int e = sub + 8 * u; if (e < hd) a = fmaf(__bfloat162float(Gs[i * LDS + e]), __bfloat162float(ov[u]), a); }
         }
-        Ds[i] = a;
+        a += __shfl_xor_sync(0xffffffffu, a, 1); a += __shfl_xor_sync(0xffffffffu, a, 2); a += __shfl_xor_sync(0xffffffffu, a, 4);
+        if (sub == 0) Ds[i] = a;
     }
     __syncthreads();
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, g = lane >> 2, t = lane & 3;
@@ -309,22 +346,13 @@ __global__ void __launch_bounds__(AM_WARPS * 32) attn_bwd_mma_kernel(const bf16*
                 mma16816(dk[no + 1], sa, qb[2], qb[3]);
             }
         }
-        const int r0 = kt * 16 + g, r1 = r0 + 8;
-#pragma unroll
-        for (int no = 0; no < NTO; ++no) {
-            const int col = no * 8 + 2 * t;
-#pragma unroll
-            for (int half = 0; half < 2; ++half) {
-                const int r = half ? r1 : r0;
-                if (r < L) {
-                    bf16* pk = dqkv + (row0 + r) * lddqkv + d + h * hd + col;
-                    bf16* pv = dqkv + (row0 + r) * lddqkv + 2 * d + h * hd + col;
-                    if (col < hd) { pk[0] = __float2bfloat16_rn(dk[no][2 * half]); pv[0] = __float2bfloat16_rn(dv[no][2 * half]); }
-                    if (col + 1 < hd) { pk[1] = __float2bfloat16_rn(dk[no][2 * half + 1]); pv[1] = __float2bfloat16_rn(dv[no][2 * half + 1]); }
-                }
-            }
-        }
+        __syncwarp();                                              // K/V rows of this tile are only read as its own A fragments
+        stage_tile<LDS, NTO>(Ks, kt * 16, dk, 1.f, 1.f, g, t);
+        stage_tile<LDS, NTO>(Vs, kt * 16, dv, 1.f, 1.f, g, t);
     }
+    __syncthreads();
+    flush_head_tile<LDS>(Ks, dqkv + row0 * lddqkv + d + h * hd, lddqkv, L, hd);
+    flush_head_tile<LDS>(Vs, dqkv + row0 * lddqkv + 2 * d + h * hd, lddqkv, L, hd);
 }
 
 static int pad_hd(int hd) { return hd <= 16 ? 16 : (hd <= 32 ? 32 : 64); }
