@@ -50,6 +50,25 @@ template <> __device__ __forceinline__ void store8f<bf16>(bf16* p, const float (
     *reinterpret_cast<uint4*>(p) = u;
 }
 
+// raw (unconverted) 8-channel chunk: lets a loop issue the next row's loads before converting the current one
+template <typename T> struct Raw8;
+template <> struct Raw8<bf16> {
+    uint4 v;
+    __device__ __forceinline__ void load(const bf16* p) { v = *reinterpret_cast<const uint4*>(p); }
+    __device__ __forceinline__ void get(float (&f)[8]) const {
+        const __nv_bfloat162* h = reinterpret_cast<const __nv_bfloat162*>(&v);
+#pragma unroll
+        for (int i = 0; i < 4; ++i) { const float2 x = __bfloat1622float2(h[i]); f[2 * i] = x.x; f[2 * i + 1] = x.y; }
+    }
+};
+template <> struct Raw8<float> {
+    float4 a, b;
+    __device__ __forceinline__ void load(const float* p) { a = reinterpret_cast<const float4*>(p)[0]; b = reinterpret_cast<const float4*>(p)[1]; }
+    __device__ __forceinline__ void get(float (&f)[8]) const {
+        f[0] = a.x; f[1] = a.y; f[2] = a.z; f[3] = a.w; f[4] = b.x; f[5] = b.y; f[6] = b.z; f[7] = b.w;
+    }
+};
+
 // ------------------------------------------------------------------------------------------------ pool_dual
 // One CTA = (sample, 16 pooled tokens).  A work item is (token, 4 consecutive features): 20 x 2 float2 loads, one
 // Philox call per (time step, 4 features) when augmenting (2 Box-Muller pairs from 16-bit uniforms + 4 keep bits).
@@ -80,29 +99,53 @@ __global__ void __launch_bounds__(256) pool_dual_kernel(
         const int tl = w / G, gq = w % G, l = l0 + tl, f0 = gq * 4;
         const bool hi = (f0 + 2) < F;                                 // F is even: a group holds 4 or 2 valid features
         float acc[4] = {0.f, 0.f, 0.f, 0.f};
+        if (!AUG) {
 #pragma unroll 4
-        for (int i = 0; i < POOL_K; ++i) {
-            const int tau = l * POOL_K + i;
-            float2 v0 = make_float2(0.f, 0.f), v1 = make_float2(0.f, 0.f);
-            if (tau >= pad) {
-                const float* src = xb + (size_t)(tau - pad) * F + f0;
-                v0 = *reinterpret_cast<const float2*>(src);
-                if (hi) v1 = *reinterpret_cast<const float2*>(src + 2);
+            for (int i = 0; i < POOL_K; ++i) {
+                const int tau = l * POOL_K + i;
+                if (tau >= pad) {
+                    const float* src = xb + (size_t)(tau - pad) * F + f0;
+                    const float2 v0 = *reinterpret_cast<const float2*>(src);
+                    acc[0] += v0.x; acc[1] += v0.y;
+                    if (hi) { const float2 v1 = *reinterpret_cast<const float2*>(src + 2); acc[2] += v1.x; acc[3] += v1.y; }
+                }
             }
-            if (AUG) {
-                const uint4 g = rng_group(rk, SITE_AUG, ((unsigned long long)b * T + tau) * G + gq);
-                const float ua = (float)((g.x & 0xFFFFu) + 1u) * (1.0f / 65536.0f), ub = (float)(g.x >> 16) * (1.0f / 65536.0f);
-                const float uc = (float)((g.y & 0xFFFFu) + 1u) * (1.0f / 65536.0f), ud = (float)(g.y >> 16) * (1.0f / 65536.0f);
-                const float ra = sqrtf(-2.0f * __logf(ua)) * 0.1f, rc = sqrtf(-2.0f * __logf(uc)) * 0.1f;
-                float s0, c0, s1, c1;
-                __sincosf(6.283185307179586f * ub, &s0, &c0);
-                __sincosf(6.283185307179586f * ud, &s1, &c1);
-                v0.x = (v0.x + ra * c0) * ((g.z & 0xFFFFu) >= keep_thr ? scale : 0.f);
-                v0.y = (v0.y + ra * s0) * ((g.z >> 16) >= keep_thr ? scale : 0.f);
-                v1.x = (v1.x + rc * c1) * ((g.w & 0xFFFFu) >= keep_thr ? scale : 0.f);
-                v1.y = (v1.y + rc * s1) * ((g.w >> 16) >= keep_thr ? scale : 0.f);
+        } else {
+            // train.py:65-73 fused with the pooling that consumes it:  mean_i[(x_i + 0.1 n_i) * s * m_i]
+            //   = (s/20) * sum_i m_i x_i  +  (0.1 s/20) * sum_i m_i n_i,   and  sum_i m_i n_i | m  ~  N(0, #kept)
+            // so one normal per pooled output (scaled by sqrt(#kept)) is exactly equal in distribution to 20 of them.
+            // Keep masks: one Philox call = 8 x 16-bit fields = 2 time steps x 4 features.
+            const unsigned long long cbase = (((unsigned long long)b * L + l) * G + gq) * 16;
+            float kept[4] = {0.f, 0.f, 0.f, 0.f};
+#pragma unroll 2
+            for (int c = 0; c < POOL_K / 2; ++c) {
+                const uint4 g = rng_group(rk, SITE_AUG, cbase + c);
+#pragma unroll
+                for (int hstep = 0; hstep < 2; ++hstep) {
+                    const int tau = l * POOL_K + 2 * c + hstep;
+                    const uint32_t w0 = hstep ? g.z : g.x, w1 = hstep ? g.w : g.y;
+                    const float m0 = (w0 & 0xFFFFu) >= keep_thr ? 1.f : 0.f, m1 = (w0 >> 16) >= keep_thr ? 1.f : 0.f;
+                    const float m2 = (w1 & 0xFFFFu) >= keep_thr ? 1.f : 0.f, m3 = (w1 >> 16) >= keep_thr ? 1.f : 0.f;
+                    kept[0] += m0; kept[1] += m1; kept[2] += m2; kept[3] += m3;
+                    if (tau >= pad) {
+                        const float* src = xb + (size_t)(tau - pad) * F + f0;
+                        const float2 v0 = *reinterpret_cast<const float2*>(src);
+                        acc[0] += v0.x * m0; acc[1] += v0.y * m1;
+                        if (hi) { const float2 v1 = *reinterpret_cast<const float2*>(src + 2); acc[2] += v1.x * m2; acc[3] += v1.y * m3; }
+                    }
+                }
             }
-            acc[0] += v0.x; acc[1] += v0.y; acc[2] += v1.x; acc[3] += v1.y;
+            const uint4 g = rng_group(rk, SITE_AUG, cbase + 15);
+            const float ua = ((float)(g.x >> 8) + 1.0f) * (1.0f / 16777216.0f), ub = (float)(g.y >> 8) * (1.0f / 16777216.0f);
+            const float uc = ((float)(g.z >> 8) + 1.0f) * (1.0f / 16777216.0f), ud = (float)(g.w >> 8) * (1.0f / 16777216.0f);
+            const float ra = sqrtf(-2.0f * __logf(ua)) * 0.1f, rc = sqrtf(-2.0f * __logf(uc)) * 0.1f;
+            float s0, c0, s1, c1;
+            __sincosf(6.283185307179586f * ub, &s0, &c0);
+            __sincosf(6.283185307179586f * ud, &s1, &c1);
+            acc[0] = (acc[0] + ra * c0 * sqrtf(kept[0])) * scale;
+            acc[1] = (acc[1] + ra * s0 * sqrtf(kept[1])) * scale;
+            acc[2] = (acc[2] + rc * c1 * sqrtf(kept[2])) * scale;
+            acc[3] = (acc[3] + rc * s1 * sqrtf(kept[3])) * scale;
         }
 #pragma unroll
         for (int j = 0; j < 4; ++j) acc[j] *= (1.0f / POOL_K);
@@ -409,8 +452,8 @@ static void ln_bwd_launch(const void* dy, int lddy, const float* x, int ldx, con
                           const float* rstd, const float* dres, int lddres, float* dx, int lddx, void* dxm, int lddxm,
                           float drop_p, unsigned site, const unsigned long long* rng, float* dgamma, float* dbeta,
                           int B, int L, int d, int halo, cudaStream_t s) {
-    int blocks = cdiv(B * L, 8 * 4);                 // 4 rows per warp
-    if (blocks > 148 * 16) blocks = 148 * 16;
+    int blocks = cdiv(B * L, 8 * 2);                 // 2 rows per warp (measured: more CTAs beat fewer atomics)
+    if (blocks > 148 * 32) blocks = 148 * 32;
     if (blocks < 1) blocks = 1;
 #define LNB_CASE(NP) ln_bwd_kernel<TDY, TM, NP><<<blocks, 256, 0, s>>>((const TDY*)dy, lddy, x, ldx, gamma, mean, rstd, \
         dres, lddres, dx, lddx, (TM*)dxm, lddxm, drop_p, site, rng, dgamma, dbeta, B, L, d, halo)
@@ -604,15 +647,30 @@ __global__ void __launch_bounds__(BNA_THREADS, 2) bn_act_fwd_kernel(
     if (db) cb = drop_ctx(rng, dcfg.p_branch);
     if (dro) co = drop_ctx(rng, dcfg.p_out);
     const float inv = 1.0f / nbr;
+    Raw8<T> zn[3];
+    Raw8<float> tn;
+    auto fetch = [&](int r) {
+        const size_t row = (size_t)(r / L) * Lp + halo + (r % L);
+#pragma unroll
+        for (int br = 0; br < 3; ++br)
+            if (br < nbr) zn[br].load(z + row * ldz + br * Dp + ch * 8);
+        tn.load(t_res + row * ldt + ch * 8);
+    };
+    if (r0 + rl < r1) fetch(r0 + rl);
     for (int r = r0 + rl; r < r1; r += RL) {
         const size_t row = (size_t)(r / L) * Lp + halo + (r % L);
         const unsigned long long idx8 = (unsigned long long)row * ld8 + ch;
+        Raw8<T> zc[3];
+        Raw8<float> tc = tn;
+#pragma unroll
+        for (int br = 0; br < 3; ++br) zc[br] = zn[br];
+        if (r + RL < r1) fetch(r + RL);
         float acc[8] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
 #pragma unroll
         for (int br = 0; br < 3; ++br) {
             if (br < nbr) {
                 float zv[8], ks[8];
-                load8f<T>(z + row * ldz + br * Dp + ch * 8, zv);
+                zc[br].get(zv);
                 if (db) drop_scales8(cb, dcfg.site_branch + br, idx8, ks);
 #pragma unroll
                 for (int j = 0; j < 8; ++j) {
@@ -623,7 +681,7 @@ __global__ void __launch_bounds__(BNA_THREADS, 2) bn_act_fwd_kernel(
             }
         }
         float tv[8], ks[8];
-        load8f<float>(t_res + row * ldt + ch * 8, tv);
+        tc.get(tv);
         if (dro) drop_scales8(co, dcfg.site_out, idx8, ks);
 #pragma unroll
         for (int j = 0; j < 8; ++j) {
@@ -694,12 +752,21 @@ __global__ void __launch_bounds__(BNA_THREADS, 2) bn_act_bwd_kernel(
         if (db) cb = drop_ctx(rng, dcfg.p_branch);
         if (dro) co = drop_ctx(rng, dcfg.p_out);
         const float inv = 1.0f / nbr;
+        Raw8<float> gn;
+        Raw8<T> zn;
+        auto fetch = [&](int r) {
+            const size_t row = (size_t)(r / L) * Lp + halo + (r % L);
+            gn.load(dout + row * lddo + c0);
+            zn.load(z + row * ldz + q0);
+        };
+        if (r0 + rl < r1) fetch(r0 + rl);
         for (int r = r0 + rl; r < r1; r += RL) {
             const size_t row = (size_t)(r / L) * Lp + halo + (r % L);
             const unsigned long long idx8 = (unsigned long long)row * ld8 + ch;
             float g[8], zv[8], kb[8], ko[8];
-            load8f<float>(dout + row * lddo + c0, g);
-            load8f<T>(z + row * ldz + q0, zv);
+            gn.get(g);
+            zn.get(zv);
+            if (r + RL < r1) fetch(r + RL);
             if (db) drop_scales8(cb, dcfg.site_branch + br, idx8, kb);
             if (dro) drop_scales8(co, dcfg.site_out, idx8, ko);
             float o[8];
