@@ -15,13 +15,27 @@ __device__ __forceinline__ uint32_t pack_bf16x2(float lo, float hi) {
     __nv_bfloat162 v = __floats2bfloat162_rn(lo, hi);
     return *reinterpret_cast<uint32_t*>(&v);
 }
+__device__ __forceinline__ uint32_t cluster_ctarank() { uint32_t r; asm volatile("mov.u32 %0, %%cluster_ctarank;" : "=r"(r)); return r; }
+__device__ __forceinline__ void cluster_sync_all() {
+    asm volatile("barrier.cluster.arrive.release.aligned;" ::: "memory");
+    asm volatile("barrier.cluster.wait.acquire.aligned;" ::: "memory");
+}
+__device__ __forceinline__ void tma_load_2d_mc(const CUtensorMap* tm, uint64_t* bar, void* dst, int c0, int c1, uint16_t mask) {
+    asm volatile(
+        "cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes.multicast::cluster [%0], [%1, {%4, %5}], [%2], %3;"
+        ::"r"(smem_u32(dst)), "l"(reinterpret_cast<uint64_t>(tm)), "r"(smem_u32(bar)), "h"(mask), "r"(c0), "r"(c1) : "memory");
+}
+__device__ __forceinline__ void umma_commit_mc(uint64_t* bar, uint16_t mask) {
+    asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.multicast::cluster.b64 [%0], %1;"
+                 ::"r"(smem_u32(bar)), "h"(mask) : "memory");
+}
 #define T2_THREADS 192
 #define T2_MAX_STAGES 8
 
 struct SegList2 { csi_seg s[CSI_MAX_SEGS]; int n; };
 
 struct Nt2Params {
-    int M, N, BN, ntn, ntiles, nstages;
+    int M, N, BN, ntn, ntiles, nstages;          // ntiles = cluster work items (super m-tiles x n-tiles)
     void* C; int ldc;
     const float* bias; const float* residual; int ldr;
     float drop_p; unsigned drop_site; const unsigned long long* rng;
@@ -29,7 +43,7 @@ struct Nt2Params {
 };
 
 // PW = columns per epilogue panel (one 128-byte smem row): 64 for bf16 output, 32 for fp32 output
-template <typename TC, bool RES>
+template <typename TC, bool RES, int CL>
 __global__ void __launch_bounds__(T2_THREADS, 1) gemm_nt_tc2_kernel(const __grid_constant__ CUtensorMap tmA,
                                                                     const __grid_constant__ CUtensorMap tmB,
                                                                     const __grid_constant__ CUtensorMap tmC, Nt2Params p,
@@ -48,6 +62,10 @@ __global__ void __launch_bounds__(T2_THREADS, 1) gemm_nt_tc2_kernel(const __grid
     const uint32_t a_bytes = TC_BM * TC_BK * 2, b_bytes = (uint32_t)p.BN * TC_BK * 2;
     const uint32_t stage_bytes = a_bytes + b_bytes;
     const int NS = p.nstages;
+    const uint32_t crank = CL > 1 ? cluster_ctarank() : 0u;
+    const int cid = blockIdx.x / CL, ncl = gridDim.x / CL;
+    constexpr uint16_t cmask = (uint16_t)((1u << CL) - 1u);
+    const uint32_t bslice = b_bytes / CL;
     uint8_t* stage_base = smem;
     uint8_t* cstage = smem + (size_t)NS * stage_bytes;            // 4 warps x 2 buffers x (32 rows x 128 B)
 
@@ -55,21 +73,22 @@ __global__ void __launch_bounds__(T2_THREADS, 1) gemm_nt_tc2_kernel(const __grid
         tma_prefetch_desc(&tmA);
         tma_prefetch_desc(&tmB);
         tma_prefetch_desc(&tmC);
-        for (int s = 0; s < NS; ++s) { mbar_init(&full_bar[s], 1); mbar_init(&empty_bar[s], 1); }
+        for (int s = 0; s < NS; ++s) { mbar_init(&full_bar[s], 1); mbar_init(&empty_bar[s], CL); }
         for (int a = 0; a < 2; ++a) { mbar_init(&tmem_full_bar[a], 1); mbar_init(&tmem_empty_bar[a], 4); }
         fence_barrier_init();
     }
     if (warp == 1) tmem_alloc(&tmem_base_smem, 512);
     tc_fence_before();
     __syncthreads();
+    if (CL > 1) cluster_sync_all();                          // peers' barriers are initialised before any remote arrive
     tc_fence_after();
     const uint32_t tmem_base = tmem_base_smem;
 
     if (warp == 0) {
         if (lane == 0) {
             int it = 0;
-            for (int tile = blockIdx.x; tile < p.ntiles; tile += gridDim.x) {
-                const int m0 = (tile / p.ntn) * TC_BM, n0 = (tile % p.ntn) * p.BN;
+            for (int tile = cid; tile < p.ntiles; tile += ncl) {
+                const int m0 = ((tile / p.ntn) * CL + (int)crank) * TC_BM, n0 = (tile % p.ntn) * p.BN;
                 for (int s = 0; s < segs.n; ++s) {
                     const csi_seg sg = segs.s[s];
                     for (int k0 = 0; k0 < sg.klen; k0 += TC_BK, ++it) {
@@ -79,7 +98,11 @@ __global__ void __launch_bounds__(T2_THREADS, 1) gemm_nt_tc2_kernel(const __grid
                         uint8_t* sa = stage_base + (size_t)stage * stage_bytes;
                         mbar_expect_tx(&full_bar[stage], stage_bytes);
                         tma_load_2d(&tmA, &full_bar[stage], sa, sg.a_col_off + k0, m0 + sg.a_row_shift + p.row_base);
-                        tma_load_2d(&tmB, &full_bar[stage], sa + a_bytes, sg.b_col_off + k0, n0);
+                        if (CL > 1)
+                            tma_load_2d_mc(&tmB, &full_bar[stage], sa + a_bytes + crank * bslice, sg.b_col_off + k0,
+                                           n0 + (int)crank * (p.BN / CL), cmask);
+                        else
+                            tma_load_2d(&tmB, &full_bar[stage], sa + a_bytes, sg.b_col_off + k0, n0);
                     }
                 }
             }
@@ -88,7 +111,7 @@ __global__ void __launch_bounds__(T2_THREADS, 1) gemm_nt_tc2_kernel(const __grid
         if (lane == 0) {
             const uint32_t idesc = make_idesc(TC_BM, p.BN);
             int it = 0, ti = 0;
-            for (int tile = blockIdx.x; tile < p.ntiles; tile += gridDim.x, ++ti) {
+            for (int tile = cid; tile < p.ntiles; tile += ncl, ++ti) {
                 const int acc = ti & 1;
                 const uint32_t aph = (uint32_t)(ti >> 1) & 1u;
                 mbar_wait(&tmem_empty_bar[acc], aph ^ 1u);         // epilogue has drained this accumulator
@@ -109,7 +132,8 @@ __global__ void __launch_bounds__(T2_THREADS, 1) gemm_nt_tc2_kernel(const __grid
                             umma_bf16(tacc, adesc + (uint64_t)(2 * k), bdesc + (uint64_t)(2 * k), idesc, first ? 0u : 1u);
                             first = 0;
                         }
-                        umma_commit(&empty_bar[stage]);
+                        if (CL > 1) umma_commit_mc(&empty_bar[stage], cmask);   // frees this stage in every CTA of the cluster
+                        else umma_commit(&empty_bar[stage]);
                     }
                 }
                 umma_commit(&tmem_full_bar[acc]);
@@ -124,10 +148,10 @@ __global__ void __launch_bounds__(T2_THREADS, 1) gemm_nt_tc2_kernel(const __grid
         const int ld8 = ((p.N + 15) & ~15) >> 3;
         uint8_t* mybuf = cstage + (size_t)ew * 2 * 4096;
         int ti = 0, sbuf = 0;
-        for (int tile = blockIdx.x; tile < p.ntiles; tile += gridDim.x, ++ti) {
+        for (int tile = cid; tile < p.ntiles; tile += ncl, ++ti) {
             const int acc = ti & 1;
             const uint32_t aph = (uint32_t)(ti >> 1) & 1u;
-            const int m0 = (tile / p.ntn) * TC_BM, n0 = (tile % p.ntn) * p.BN;
+            const int m0 = ((tile / p.ntn) * CL + (int)crank) * TC_BM, n0 = (tile % p.ntn) * p.BN;
             const int m = m0 + q * 32 + lane;
             if (p.bias) {
                 for (int i = et; i < p.BN; i += 128) sbias[acc][i] = (n0 + i) < p.N ? p.bias[n0 + i] : 0.f;
@@ -233,6 +257,7 @@ __global__ void __launch_bounds__(T2_THREADS, 1) gemm_nt_tc2_kernel(const __grid
     }
     tc_fence_before();
     __syncthreads();
+    if (CL > 1) cluster_sync_all();                          // no CTA leaves while a peer may still multicast into it
     if (warp == 1) {
         tc_fence_after();
         tmem_dealloc(tmem_base, 512);
@@ -241,12 +266,14 @@ __global__ void __launch_bounds__(T2_THREADS, 1) gemm_nt_tc2_kernel(const __grid
 
 static int pick_bn2(int N) {
     const int tiles = (N + 255) / 256;
-    int bn = ((N + tiles - 1) / tiles + 15) & ~15;
+    int bn = ((N + tiles - 1) / tiles + 15) & ~15;      // multiple of 16: each of the 2 multicast slices is whole 8-row swizzle atoms
     if (bn < 16) bn = 16;
     return bn;
 }
 
 static int g_num_sms = 0;
+static int g_cluster2 = 0;     // measured: 2-CTA multicast does not cut L2 traffic on B200 (dedup window), lockstep costs 8%
+extern "C" int csi_set_gemm_cluster(int on) { g_cluster2 = on ? 1 : 0; return CSI_OK; }
 
 extern "C" int csi_gemm_nt_tc2(const void* A, int lda, const void* Bw, int ldb, void* C, int ldc, int c_dtype, int M, int N,
                                const csi_seg* segs, int nseg, const float* bias, const float* residual, int ldr,
@@ -277,14 +304,16 @@ extern "C" int csi_gemm_nt_tc2(const void* A, int lda, const void* Bw, int ldb, 
     const bf16* a_base = reinterpret_cast<const bf16*>(A) + (long long)min_shift * lda;
     int rc = make_map(&tmA, a_base, (long long)M + (max_shift - min_shift), a_cols, lda, TC_BM);
     if (rc) return rc;
-    rc = make_map(&tmB, Bw, N, b_cols, ldb, BN);
+    const int mtiles = (M + TC_BM - 1) / TC_BM;
+    const int CL = (g_cluster2 && mtiles >= 4) ? 2 : 1;     // CTA pairs share the weight tile through TMA multicast
+    rc = make_map(&tmB, Bw, N, b_cols, ldb, BN / CL);
     if (rc) return rc;
     rc = make_map_ex(&tmC, C, M, N, ldc, 32, 128 / es, es);
     if (rc) return rc;
     Nt2Params p;
     p.M = M; p.N = N; p.BN = BN; p.C = C; p.ldc = ldc;
     p.ntn = (N + BN - 1) / BN;
-    p.ntiles = p.ntn * ((M + TC_BM - 1) / TC_BM);
+    p.ntiles = p.ntn * ((mtiles + CL - 1) / CL);
     p.bias = bias; p.residual = residual; p.ldr = ldr;
     p.drop_p = drop_p; p.drop_site = drop_site; p.rng = rng;
     p.row_base = -min_shift;
@@ -295,16 +324,29 @@ extern "C" int csi_gemm_nt_tc2(const void* A, int lda, const void* Bw, int ldb, 
     if (ns < 2) ns = 2;
     p.nstages = ns;
     const size_t smem = fixed + (size_t)ns * stage_bytes;
-    const int grid = p.ntiles < g_num_sms ? p.ntiles : g_num_sms;
-#define LAUNCH(TC, RES)                                                                                                 \
+    int grid = (g_num_sms / CL) * CL;
+    if (p.ntiles * CL < grid) grid = p.ntiles * CL;
+#define LAUNCH(TC, RES, CLV)                                                                                            \
     do {                                                                                                                \
-        CSI_CUDA(cudaFuncSetAttribute(gemm_nt_tc2_kernel<TC, RES>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem)); \
-        gemm_nt_tc2_kernel<TC, RES><<<grid, T2_THREADS, smem, ST(stream)>>>(tmA, tmB, tmC, p, sl);                     \
+        CSI_CUDA(cudaFuncSetAttribute(gemm_nt_tc2_kernel<TC, RES, CLV>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem)); \
+        cudaLaunchConfig_t cfg = {};                                                                                    \
+        cfg.gridDim = dim3(grid); cfg.blockDim = dim3(T2_THREADS); cfg.dynamicSmemBytes = smem; cfg.stream = ST(stream); \
+        cudaLaunchAttribute at[1];                                                                                      \
+        at[0].id = cudaLaunchAttributeClusterDimension;                                                                 \
+        at[0].val.clusterDim.x = CLV; at[0].val.clusterDim.y = 1; at[0].val.clusterDim.z = 1;                           \
+        cfg.attrs = at; cfg.numAttrs = 1;                                                                               \
+        CSI_CUDA(cudaLaunchKernelEx(&cfg, gemm_nt_tc2_kernel<TC, RES, CLV>, tmA, tmB, tmC, p, sl));                     \
     } while (0)
     CSI_CHECK_ARG(!(residual && c_dtype == CSI_BF16), "residual is only fused for fp32 output");
-    if (c_dtype == CSI_BF16) LAUNCH(bf16, false);
-    else if (residual) LAUNCH(float, true);
-    else LAUNCH(float, false);
+    if (CL == 2) {
+        if (c_dtype == CSI_BF16) LAUNCH(bf16, false, 2);
+        else if (residual) LAUNCH(float, true, 2);
+        else LAUNCH(float, false, 2);
+    } else {
+        if (c_dtype == CSI_BF16) LAUNCH(bf16, false, 1);
+        else if (residual) LAUNCH(float, true, 1);
+        else LAUNCH(float, false, 1);
+    }
 #undef LAUNCH
     CSI_LAUNCH_CHECK();
     return CSI_OK;
