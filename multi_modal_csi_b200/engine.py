@@ -58,7 +58,8 @@ class THATEngine:
         self.rng = torch.tensor([seed, 0], dtype=torch.int64, device=self.dev)      # {seed, step}
         self.opt_step = torch.ones(1, dtype=torch.int64, device=self.dev)           # 1-based Adam step
         self._alloc()
-        self._graph = None
+        self._graphs = {}
+        self._graph_launches = {}
         self.weights_dirty = True
 
     # ------------------------------------------------------------------ views
@@ -126,8 +127,7 @@ class THATEngine:
         self.dlogits = torch.zeros(B, self.g.ld_out, device=dev)
         self.dlogits_a = torch.zeros(B, self.g.ld_out, dtype=adt, device=dev)
         self.loss = torch.zeros(1, device=dev)
-        self.x_static: Optional[torch.Tensor] = None
-        self.y_static: Optional[torch.Tensor] = None
+        self.y_static = torch.zeros(B, self.g.out, device=dev)
 
     def activation_bytes(self) -> int:
         n = 0
@@ -167,17 +167,26 @@ class THATEngine:
                 offs=None, lens=None) -> torch.Tensor:
         """x: fp32 [B,T,F] (or a packed ragged arena with offs/lens).  Returns logits [B, out] (a view of
         the engine's static logits buffer)."""
-        ops, g = self.ops, self.g
-        assert B <= self.B
         if self.weights_dirty:
             self.repack()
-        pd = P_DROP if (training and dropout) else 0.0
-        pf = P_FEAT if (training and dropout) else 0.0
+        self.forward_input(x, B, training, augment, offs, lens)
+        return self.forward_body(B, training, dropout)
+
+    def forward_input(self, x, B, training, augment=False, offs=None, lens=None):
+        """Input stage: Gaussian range encoding table + (augment, front-pad, pool, both stream layouts).  The only
+        part of a step that depends on the address of the input batch, so it stays outside the captured graph."""
+        ops, g = self.ops, self.g
+        assert B <= self.B
         gp = "layer_left_gaussian."
         ops.gauss_pe_fwd(self.P(gp + "var_position"), self.P(gp + "var_mu"), self.P(gp + "var_sigma"),
                          self.P(gp + "var_embedding"), g.left.L, LY.NUM_GAUSS, g.F, self.pe_w, self.pe)
         ops.pool_dual(x, offs, lens, B, g.T, g.F, self.pe, self.s["left"]["x0"].t, self.s["right"]["x0"].t,
                       HALO, 1 if (training and augment) else 0, self.rng)
+
+    def forward_body(self, B: int, training: bool, dropout: bool = True) -> torch.Tensor:
+        ops, g = self.ops, self.g
+        pd = P_DROP if (training and dropout) else 0.0
+        pf = P_FEAT if (training and dropout) else 0.0
         for si, sg in enumerate(g.streams):
             st = self.s[sg.name]
             rows, d, Dp, L = sg.rows(B), sg.d, sg.Dp, sg.L
@@ -316,6 +325,30 @@ class THATEngine:
                                  self.P(gp + "var_sigma"), self.P(gp + "var_embedding"), L, LY.NUM_GAUSS, g.F,
                                  self.dpe_ws, self.G(gp + "var_embedding"), self.G(gp + "var_mu"),
                                  self.G(gp + "var_sigma"))
+
+    # ------------------------------------------------------------------ CUDA-graph train body
+    def train_body(self, B: int, pos_weight: float, dropout: bool):
+        """repack + forward body + BCE + backward: a fixed launch sequence over static buffers."""
+        self.repack()
+        self.forward_body(B, True, dropout)
+        self.loss_fwd_bwd(self.y_static, B, pos_weight)
+        self.backward(None, B, dropout=dropout, zero_grads=True)
+
+    def train_body_graph(self, B: int, pos_weight: float, dropout: bool):
+        """Replays train_body as one CUDA graph (captured on first use for this (B, pos_weight, dropout))."""
+        key = (B, float(pos_weight), bool(dropout))
+        g = self._graphs.get(key)
+        if g is None:
+            torch.cuda.synchronize(self.dev)
+            g = torch.cuda.CUDAGraph()
+            n0 = self.ops.launches
+            with torch.cuda.graph(g):
+                self.train_body(B, pos_weight, dropout)
+            self._graph_launches[key] = self.ops.launches - n0
+            self._graphs[key] = g
+        else:
+            self.ops.launches += self._graph_launches[key]
+        g.replay()
 
     # ------------------------------------------------------------------ loss / optimizer
     def loss_fwd_bwd(self, y: torch.Tensor, B: int, pos_weight: float = 4.0, grad_scale: float = 1.0,

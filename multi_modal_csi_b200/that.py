@@ -126,6 +126,8 @@ class THAT(torch.nn.Module):
         self.rng_seed = int(torch.initial_seed() & 0x7FFFFFFF)
         self._engine: Optional[THATEngine] = None
         self._ops_override = None            # tests only: inject the torch mirror of the kernels
+        self.use_cuda_graph = True           # fused_train_step replays forward+loss+backward as one CUDA graph
+        self._eager_steps = 0
         vals, bufs = _initial_values(self.geom)
         flat = torch.zeros(self.arena.size)
         object.__setattr__(self, "_flat", flat)
@@ -228,6 +230,7 @@ class THAT(torch.nn.Module):
             eng = THATEngine(self.geom, mb, self._flat, self._gflat, self.arena, bn, frozen,
                              act_dtype=self.act_dtype, ops=self._ops_override, seed=self.rng_seed)
             self._engine = eng
+            self._eager_steps = 0
         return eng
 
     # ------------------------------------------------------------------ forward
@@ -258,7 +261,7 @@ class THAT(torch.nn.Module):
 
     # ------------------------------------------------------------------ fused train step
     def fused_train_step(self, x, y, optimizer, pos_weight: float = 4.0, augment: bool = True,
-                         grad_hook=None, offs=None, lens=None):
+                         grad_hook=None, offs=None, lens=None, use_graph=None):
         """augmentation + forward + BCE + backward + Adam as one launch sequence (train.py:84-101).
 
         x: fp32 [B,T,F] on the device (or a packed ragged arena with offs/lens); y: [B, ...] labels.
@@ -269,11 +272,15 @@ class THAT(torch.nn.Module):
         yf = y.reshape(B, -1)
         if yf.dtype != torch.float32:
             yf = yf.float()
-        eng.repack()
-        logits = eng.forward(x, B, training=True, dropout=self.dropout_enabled, augment=augment,
-                             offs=offs, lens=lens)
-        loss = eng.loss_fwd_bwd(yf.contiguous(), B, pos_weight)
-        eng.backward(None, B, dropout=self.dropout_enabled, zero_grads=True)
+        eng.forward_input(x, B, True, augment, offs, lens)
+        eng.y_static[:B].copy_(yf)
+        graph = self.use_cuda_graph if use_graph is None else use_graph
+        if graph and x.is_cuda and self._eager_steps >= 1:
+            eng.train_body_graph(B, pos_weight, self.dropout_enabled)
+        else:
+            eng.train_body(B, pos_weight, self.dropout_enabled)
+            self._eager_steps += 1
+        loss, logits = eng.loss, eng.logits[:B, :self.geom.out]
         self._attach_grads()
         if grad_hook is not None:
             grad_hook(eng)

@@ -293,3 +293,25 @@ def test_train_and_run_that_end_to_end(tmp_path, monkeypatch):
               "counting_error_perPerson", "precision", "recall", "f1_score"):
         assert k in res
     assert np.isfinite(res["total_error"]) and len(res["error_per_person"]) == 5
+
+
+def test_cuda_graph_step_equals_eager_step():
+    """The graph-replayed train body (forward + BCE + backward) follows the same trajectory as eager launches."""
+    from multi_modal_csi_b200 import FusedAdam
+    T, F, out, B = 400, 30, 12, 6
+    x, y = synth(B, T, F, out)
+    traj = []
+    for graph in (False, True):
+        m = build(T, F, out, "bf16")
+        m.dropout_enabled = True
+        m.use_cuda_graph = graph
+        opt = FusedAdam(m.parameters(), lr=5e-4, weight_decay=2e-4)
+        m.train()
+        ls = []
+        for s in range(5):
+            loss, logits = m.fused_train_step(x.cuda(), y.cuda(), opt, augment=True)
+            ls.append(loss.item())
+        traj.append(ls)
+        assert (len(m._engine._graphs) == 1) == graph
+    assert all(abs(a - b) < 5e-3 * max(1.0, abs(a)) for a, b in zip(*traj)), traj
+    assert traj[0][0] != traj[0][1]
