@@ -222,13 +222,14 @@ def run_b200(args):
     # ---- value: K steps, batch resident in HBM (forward+loss+backward replayed as one CUDA graph per step)
     launches0 = ops.launches
     ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-    with ClockSampler(local) as clk:
-        barrier()
-        ev0.record()
-        for i in range(K):
-            step_resident(i)
-        ev1.record()
-        barrier()
+    clk = ClockSampler(local)
+    clk.__enter__()
+    barrier()
+    ev0.record()
+    for i in range(K):
+        step_resident(i)
+    ev1.record()
+    barrier()
     gpu_launches = ops.launches - launches0
     # ---- roofline: the same K steps launched eagerly with a CUDA-event pair around every launch of the dominant
     #      kernel family (events cannot be placed inside a replayed graph)
@@ -291,6 +292,7 @@ def run_b200(args):
                "h2d_bytes_per_step": int(host[0][0].numel() * 4 + host[0][1].numel() * 4), "d2h_bytes_per_step": 4,
                "ms_per_step": ems}
 
+    clk.__exit__()
     if rank == 0:
         peaks = {}
         try:
@@ -321,6 +323,27 @@ def run_b200(args):
         dist.destroy_process_group()
 
 
+KERNEL_OF_OP = {"gemm_nt": "gemm_nt_tc2_kernel", "gemm_tn": "gemm_tn_tc_kernel", "attn_fwd": "attn_fwd_mma_kernel",
+                "attn_bwd": "attn_bwd_mma_kernel", "pool_dual": "pool_dual_kernel", "layernorm_bwd": "ln_bwd_kernel"}
+
+
+def dram_traffic(name):
+    """dram__bytes_read.sum + dram__bytes_write.sum per launch of the kernel family, from the committed ncu summary."""
+    import csv
+    import glob
+    files = sorted(glob.glob(os.path.join(ROOT, "profiles", "r*_kernel_metrics_step.csv")))
+    kern = KERNEL_OF_OP.get(name)
+    if not files or not kern:
+        return None
+    tot = n = 0.0
+    for row in csv.DictReader(open(files[-1])):
+        if row["kernel"].startswith(kern):
+            k = float(row["launches_in_window"])
+            tot += k * (float(row["dram__bytes_read.sum"]) + float(row["dram__bytes_write.sum"]))
+            n += k
+    return tot / n if n else None
+
+
 def roofline(name, dom, eng, B, peaks):
     """Live roofline of the dominant kernel family: algorithmic work per launch / mean launch time."""
     if not name or name not in dom:
@@ -332,10 +355,10 @@ def roofline(name, dom, eng, B, peaks):
     if work.get("flops", 0) > 0 and name in ("gemm_nt", "gemm_tn", "attn_fwd", "attn_bwd"):
         ach = work["flops"] / (total_ms * 1e-3) / 1e12
         return {"kernel": name, "bound": "tensor", "achieved": ach, "peak": tf, "unit": "TFLOP/s", "frac": ach / tf,
-                "traffic": None, "launches": calls, "ms_per_launch": total_ms / calls, "peak_source": src + " (sustained)"}
+                "traffic": dram_traffic(name), "launches": calls, "ms_per_launch": total_ms / calls, "peak_source": src + " (sustained)"}
     ach = work.get("bytes", 0) / (total_ms * 1e-3) / 1e9
     return {"kernel": name, "bound": "hbm", "achieved": ach, "peak": hbm, "unit": "GB/s", "frac": ach / hbm,
-            "traffic": None, "launches": calls, "ms_per_launch": total_ms / calls, "peak_source": src}
+            "traffic": dram_traffic(name), "launches": calls, "ms_per_launch": total_ms / calls, "peak_source": src}
 
 
 def main():

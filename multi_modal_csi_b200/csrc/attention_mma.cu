@@ -47,21 +47,28 @@ template <int LDS> __device__ __forceinline__ const bf16* bt_frag_ptr(const bf16
 // bandwidth- rather than latency-bound.
 template <int LDS>
 __device__ __forceinline__ void load_head_tile(const bf16* __restrict__ src, int ld, int L, int hd, bf16* __restrict__ dst) {
-    const int total = L * hd, stride = blockDim.x;
-    for (int base = threadIdx.x; base < total; base += 8 * stride) {
+    // EPR = lanes per row (power of two >= hd, <= HDP): no integer division, 8 rows in flight per thread
+    constexpr int EPR = LDS - 8;
+    const int e = threadIdx.x & (EPR - 1), r0 = threadIdx.x / EPR, rstep = blockDim.x / EPR;
+    if (e >= hd) return;
+    for (int base = r0; base < L; base += 8 * rstep) {
         bf16 v[8];
-        int off[8];
 #pragma unroll
         for (int u = 0; u < 8; ++u) {
-            const int i = base + u * stride;
-            const int l = i / hd, e = i - l * hd;
-            off[u] = l * LDS + e;
-            if (i < total) v[u] = src[(size_t)l * ld + e];
+            const int l = base + u * rstep;
+            if (l < L) v[u] = src[(size_t)l * ld + e];
         }
 #pragma unroll
-        for (int u = 0; u < 8; ++u)
-            if (base + u * stride < total) dst[off[u]] = v[u];
+        for (int u = 0; u < 8; ++u) {
+            const int l = base + u * rstep;
+            if (l < L) dst[l * LDS + e] = v[u];
+        }
     }
+}
+__device__ __forceinline__ float fast_exp2(float x) {
+    float y;
+    asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
+    return y;
 }
 __device__ __forceinline__ void zero_tiles(void* p, int bytes) {
     uint4* q = reinterpret_cast<uint4*>(p);
@@ -136,17 +143,23 @@ __global__ void __launch_bounds__(AM_WARPS * 32) attn_fwd_mma_kernel(const bf16*
             }
             float mx0 = -INFINITY, mx1 = -INFINITY;
 #pragma unroll
+            if (pb * 16 + 64 > L) {                             // only the last key block has columns >= L (warp-uniform)
+#pragma unroll
+                for (int nt = 0; nt < 8; ++nt) {
+                    const int col = pb * 16 + nt * 8 + 2 * t;
+                    if (col >= L) s[nt][0] = s[nt][2] = -INFINITY;
+                    if (col + 1 >= L) s[nt][1] = s[nt][3] = -INFINITY;
+                }
+            }
+#pragma unroll
             for (int nt = 0; nt < 8; ++nt) {
-                const int col = pb * 16 + nt * 8 + 2 * t;
-                if (col >= L) s[nt][0] = s[nt][2] = -INFINITY;
-                if (col + 1 >= L) s[nt][1] = s[nt][3] = -INFINITY;
                 mx0 = fmaxf(mx0, fmaxf(s[nt][0], s[nt][1]));
                 mx1 = fmaxf(mx1, fmaxf(s[nt][2], s[nt][3]));
             }
             mx0 = fmaxf(mx0, __shfl_xor_sync(0xffffffffu, mx0, 1)); mx0 = fmaxf(mx0, __shfl_xor_sync(0xffffffffu, mx0, 2));
             mx1 = fmaxf(mx1, __shfl_xor_sync(0xffffffffu, mx1, 1)); mx1 = fmaxf(mx1, __shfl_xor_sync(0xffffffffu, mx1, 2));
             const float mn0 = fmaxf(m0, mx0), mn1 = fmaxf(m1, mx1);
-            const float al0 = exp2f((m0 - mn0) * c), al1 = exp2f((m1 - mn1) * c);
+            const float al0 = fast_exp2((m0 - mn0) * c), al1 = fast_exp2((m1 - mn1) * c);
             m0 = mn0; m1 = mn1;
             l0 *= al0; l1 *= al1;
 #pragma unroll
@@ -154,8 +167,8 @@ __global__ void __launch_bounds__(AM_WARPS * 32) attn_fwd_mma_kernel(const bf16*
             const float mc0 = mn0 * c, mc1 = mn1 * c;
 #pragma unroll
             for (int nt = 0; nt < 8; ++nt) {
-                s[nt][0] = exp2f(s[nt][0] * c - mc0); s[nt][1] = exp2f(s[nt][1] * c - mc0);
-                s[nt][2] = exp2f(s[nt][2] * c - mc1); s[nt][3] = exp2f(s[nt][3] * c - mc1);
+                s[nt][0] = fast_exp2(s[nt][0] * c - mc0); s[nt][1] = fast_exp2(s[nt][1] * c - mc0);
+                s[nt][2] = fast_exp2(s[nt][2] * c - mc1); s[nt][3] = fast_exp2(s[nt][3] * c - mc1);
                 l0 += s[nt][0] + s[nt][1];
                 l1 += s[nt][2] + s[nt][3];
             }
@@ -267,8 +280,8 @@ __global__ void __launch_bounds__(AM_WARPS * 32) attn_bwd_mma_kernel(const bf16*
             for (int nt = 0; nt < 2; ++nt) {
                 const int col = kp * 16 + nt * 8 + 2 * t;
                 const bool v0 = col < L, v1 = (col + 1) < L;
-                const float p0 = v0 ? exp2f(s[nt][0] * c - ls0) : 0.f, p1 = v1 ? exp2f(s[nt][1] * c - ls0) : 0.f;
-                const float p2 = v0 ? exp2f(s[nt][2] * c - ls1) : 0.f, p3 = v1 ? exp2f(s[nt][3] * c - ls1) : 0.f;
+                const float p0 = v0 ? fast_exp2(s[nt][0] * c - ls0) : 0.f, p1 = v1 ? fast_exp2(s[nt][1] * c - ls0) : 0.f;
+                const float p2 = v0 ? fast_exp2(s[nt][2] * c - ls1) : 0.f, p3 = v1 ? fast_exp2(s[nt][3] * c - ls1) : 0.f;
                 ds[nt][0] = p0 * (dp[nt][0] - d0) * sc; ds[nt][1] = p1 * (dp[nt][1] - d0) * sc;
                 ds[nt][2] = p2 * (dp[nt][2] - d1) * sc; ds[nt][3] = p3 * (dp[nt][3] - d1) * sc;
             }
@@ -326,8 +339,8 @@ __global__ void __launch_bounds__(AM_WARPS * 32) attn_bwd_mma_kernel(const bf16*
                 const int q0 = qp * 16 + nt * 8 + 2 * t, q1 = q0 + 1;
                 const bool v0 = q0 < L, v1 = q1 < L;
                 const float lq0 = Ls[q0], lq1 = Ls[q1], dd0 = Ds[q0], dd1 = Ds[q1];
-                pt[nt][0] = v0 ? exp2f(st[nt][0] * c - lq0) : 0.f; pt[nt][1] = v1 ? exp2f(st[nt][1] * c - lq1) : 0.f;
-                pt[nt][2] = v0 ? exp2f(st[nt][2] * c - lq0) : 0.f; pt[nt][3] = v1 ? exp2f(st[nt][3] * c - lq1) : 0.f;
+                pt[nt][0] = v0 ? fast_exp2(st[nt][0] * c - lq0) : 0.f; pt[nt][1] = v1 ? fast_exp2(st[nt][1] * c - lq1) : 0.f;
+                pt[nt][2] = v0 ? fast_exp2(st[nt][2] * c - lq0) : 0.f; pt[nt][3] = v1 ? fast_exp2(st[nt][3] * c - lq1) : 0.f;
                 dst_[nt][0] = pt[nt][0] * (dpt[nt][0] - dd0) * sc; dst_[nt][1] = pt[nt][1] * (dpt[nt][1] - dd1) * sc;
                 dst_[nt][2] = pt[nt][2] * (dpt[nt][2] - dd0) * sc; dst_[nt][3] = pt[nt][3] * (dpt[nt][3] - dd1) * sc;
             }

@@ -190,6 +190,7 @@ class THATEngine:
         for si, sg in enumerate(g.streams):
             st = self.s[sg.name]
             rows, d, Dp, L = sg.rows(B), sg.d, sg.Dp, sg.L
+            ops.alg_scale = (L / sg.Lp) * (d / Dp)      # roofline numerators count valid tokens and true channels only
             x_in = st["x0"]
             one = [(0, 0, 0, Dp)]
             for e in range(sg.n_enc):
@@ -235,6 +236,7 @@ class THATEngine:
                             sg.head_n, segs, self.P(w + ".bias"), None, 0.0, 0, self.rng)
             ops.head_reduce_fwd(st["p"].t, B, L, HALO, 2 * sg.head_n, sg.head_n, sg.head_k[0], sg.head_k[1],
                                 self.feat[:, sg.feat_off:])
+        ops.alg_scale = 1.0
         ops.dropout_rows(self.feat, self.featd, B, LY.FEAT, pf, LY.SITE_FEAT, self.rng)
         ops.gemm_nt(self.featd, self.W("f:layer_output.weight"), self.logits, B, g.out, [(0, 0, 0, LY.FEAT)],
                     self.P("layer_output.bias"), None, 0.0, 0, self.rng)
@@ -251,6 +253,7 @@ class THATEngine:
             self.grads.zero_()
         if dlogits is not None:
             self.dlogits[:B, :g.out].copy_(dlogits)
+        ops.alg_scale = 1.0
         ops.dropout_rows(self.dlogits, self.dlogits_a, B, g.ld_out, 0.0, 0, self.rng)      # cast to act dtype
         ops.gemm_tn(self.dlogits_a, self.featd, self.G("layer_output.weight"), LY.FEAT, 1, B, g.out,
                     [(0, 0, 0, LY.FEAT)])
@@ -261,6 +264,7 @@ class THATEngine:
         for si, sg in enumerate(g.streams):
             st = self.s[sg.name]
             rows, d, Dp, L = sg.rows(B), sg.d, sg.Dp, sg.L
+            ops.alg_scale = (L / sg.Lp) * (d / Dp)
             Np = sg.head_np
             ops.head_reduce_bwd(self.dfeat[:, sg.feat_off:], st["p"].t, B, L, HALO, 2 * sg.head_n, sg.head_n,
                                 sg.head_k[0], sg.head_k[1], st["dp"].t)

@@ -157,17 +157,18 @@ class NativeOps:
 
 
     # -------------------------------------------------------------- algorithmic work per launch (roofline numerators)
-    @staticmethod
-    def _work(name, a):
+    alg_scale = 1.0     # set by the engine: (valid tokens / padded rows) * (true channels / padded channels)
+
+    def _work(self, name, a):
         """Algorithmic FLOPs / minimum HBM bytes of one launch (DESIGN.md lists the formulas)."""
         es = lambda t: 0 if t is None else t.element_size()
         if name == "gemm_nt":
             k = sum(s[3] for s in a["segs"])
-            return {"flops": 2 * a["M"] * a["N"] * k,
+            return {"flops": int(2 * a["M"] * a["N"] * k * self.alg_scale),
                     "nbytes": a["M"] * k // max(1, len(a["segs"])) * es(a["A"]) + a["N"] * k * es(a["Bw"]) + a["M"] * a["N"] * es(a["Cm"])}
         if name == "gemm_tn":
             n = sum(s[3] for s in a["segs"])
-            return {"flops": 2 * a["M"] * a["Na"] * n, "nbytes": a["M"] * (a["Na"] + n // max(1, len(a["segs"]))) * es(a["A"])}
+            return {"flops": int(2 * a["M"] * a["Na"] * n * (self.alg_scale if n > 16 else 1.0)), "nbytes": a["M"] * (a["Na"] + n // max(1, len(a["segs"]))) * es(a["A"])}
         if name == "attn_fwd":
             hd = a["d"] // a["H"]
             return {"flops": 4 * a["B"] * a["H"] * a["L"] * a["L"] * hd, "nbytes": a["B"] * a["L"] * a["d"] * 4 * es(a["qkv"])}
