@@ -243,12 +243,19 @@ class THATEngine:
         return self.logits[:B, :g.out]
 
     # ------------------------------------------------------------------ backward
-    def backward(self, dlogits: Optional[torch.Tensor], B: int, dropout: bool = True, zero_grads: bool = True):
+    def backward(self, dlogits: Optional[torch.Tensor], B: int, dropout: bool = True, zero_grads: bool = True,
+                 part: int = 0):
         """Gradient of every parameter into ``self.grads`` given dL/dlogits ([B,out] fp32; None = use the
-        engine's own ``dlogits`` buffer written by ``loss_fwd_bwd``)."""
+        engine's own ``dlogits`` buffer written by ``loss_fwd_bwd``).
+
+        part 0 = everything; part 1 = output layer + left stream (fills the first gradient bucket, see
+        ``bucket_split``); part 2 = right stream.  The split lets the data-parallel all-reduce of bucket 1 overlap
+        the right stream's backward."""
         ops, g = self.ops, self.g
         pd = P_DROP if dropout else 0.0
         pf = P_FEAT if dropout else 0.0
+        if part == 2:
+            return self._backward_streams(B, pd, ("right",))
         if zero_grads:
             self.grads.zero_()
         if dlogits is not None:
@@ -261,7 +268,18 @@ class THATEngine:
         ops.gemm_nt(self.dlogits_a, self.W("b:layer_output.weight"), self.dfeatd, B, LY.FEAT,
                     [(0, 0, 0, g.ld_out)], None, None, 0.0, 0, self.rng)
         ops.dropout_rows(self.dfeatd, self.dfeat, B, LY.FEAT, pf, LY.SITE_FEAT, self.rng)
+        self._backward_streams(B, pd, ("left",) if part == 1 else ("left", "right"))
+
+    @property
+    def bucket_split(self) -> int:
+        """Arena offset where the right stream's parameters start: gradients below it are final after part 1."""
+        return self.arena.offsets[self.g.right.prefix(0) + "layer_norm_0.weight"]
+
+    def _backward_streams(self, B: int, pd: float, which):
+        ops, g = self.ops, self.g
         for si, sg in enumerate(g.streams):
+            if sg.name not in which:
+                continue
             st = self.s[sg.name]
             rows, d, Dp, L = sg.rows(B), sg.d, sg.Dp, sg.L
             ops.alg_scale = (L / sg.Lp) * (d / Dp)
@@ -331,23 +349,25 @@ class THATEngine:
                                  self.G(gp + "var_sigma"))
 
     # ------------------------------------------------------------------ CUDA-graph train body
-    def train_body(self, B: int, pos_weight: float, dropout: bool):
-        """repack + forward body + BCE + backward: a fixed launch sequence over static buffers."""
-        self.repack()
-        self.forward_body(B, True, dropout)
-        self.loss_fwd_bwd(self.y_static, B, pos_weight)
-        self.backward(None, B, dropout=dropout, zero_grads=True)
+    def train_body(self, B: int, pos_weight: float, dropout: bool, part: int = 0):
+        """repack + forward body + BCE + backward: a fixed launch sequence over static buffers.
+        part 1 stops after the left stream's backward, part 2 is the right stream's backward (see ``backward``)."""
+        if part != 2:
+            self.repack()
+            self.forward_body(B, True, dropout)
+            self.loss_fwd_bwd(self.y_static, B, pos_weight)
+        self.backward(None, B, dropout=dropout, zero_grads=True, part=part)
 
-    def train_body_graph(self, B: int, pos_weight: float, dropout: bool):
-        """Replays train_body as one CUDA graph (captured on first use for this (B, pos_weight, dropout))."""
-        key = (B, float(pos_weight), bool(dropout))
+    def train_body_graph(self, B: int, pos_weight: float, dropout: bool, part: int = 0):
+        """Replays train_body as one CUDA graph (captured on first use for this (B, pos_weight, dropout, part))."""
+        key = (B, float(pos_weight), bool(dropout), part)
         g = self._graphs.get(key)
         if g is None:
             torch.cuda.synchronize(self.dev)
             g = torch.cuda.CUDAGraph()
             n0 = self.ops.launches
             with torch.cuda.graph(g):
-                self.train_body(B, pos_weight, dropout)
+                self.train_body(B, pos_weight, dropout, part)
             self._graph_launches[key] = self.ops.launches - n0
             self._graphs[key] = g
         else:

@@ -1,8 +1,13 @@
-"""Batch-sharded data parallelism: one process per GPU, replicated weights, gradients summed over ranks.
+"""Batch-sharded data parallelism: one process per GPU, replicated weights, gradients averaged over ranks.
 
 The reference is single-process (no collective anywhere); this is the one exchange the
 data-parallel path adds.  Gradients already live in ONE flat fp32 arena (multi_modal_csi_b200.that.THAT.flat_grads),
-so the exchange is a handful of large contiguous ``ncclAllReduce`` calls issued through ``torch.distributed``.
+so the exchange is two large contiguous ``ncclAllReduce`` calls issued through ``torch.distributed``:
+
+  bucket 1 = [0, bucket_split)   gaussian encoding + left stream (95 % of the bytes), final once the left stream's
+                                 backward is done -> reduced on a side stream WHILE the right stream's backward runs
+  bucket 2 = [bucket_split, n)   right stream + output layer, reduced after backward
+
 BatchNorm statistics stay per rank (DistributedDataParallel semantics).
 """
 from __future__ import annotations
@@ -12,23 +17,53 @@ import torch.distributed as dist
 
 
 class GradSync:
-    """Averages the flat gradient arena over the ranks between backward and the optimizer step."""
+    """Averages the flat gradient arena over the ranks between backward and the optimizer step.
 
-    def __init__(self, model, world_size: int, num_buckets: int = 1):
+    Usable as a plain hook (``sync(engine)``: one all-reduce after backward) or through ``start_bucket`` /
+    ``finish`` (what ``THAT.fused_train_step`` calls when it sees them) to overlap with backward."""
+
+    def __init__(self, model, world_size: int):
         self.model = model
         self.world = world_size
-        self.num_buckets = max(1, num_buckets)
+        self._side = None
+        self._work = None
+        self._event = None
+
+    def _reduce(self, t, async_op=False):
+        if t.is_cuda:
+            return dist.all_reduce(t, op=dist.ReduceOp.AVG, async_op=async_op)
+        w = dist.all_reduce(t, op=dist.ReduceOp.SUM, async_op=False)      # gloo (CPU tests): no AVG
+        t.div_(self.world)
+        return w
 
     def hook(self, engine):
-        g = engine.grads
+        if self.world > 1:
+            self._reduce(engine.grads)
+
+    __call__ = hook
+
+    def start_bucket(self, engine, lo: int, hi: int):
         if self.world <= 1:
             return
-        n = g.numel()
-        step = (n + self.num_buckets - 1) // self.num_buckets
-        for i in range(0, n, step):
-            dist.all_reduce(g[i:i + step], op=dist.ReduceOp.AVG if g.is_cuda else dist.ReduceOp.SUM)
+        g = engine.grads[lo:hi]
         if not g.is_cuda:
-            g.div_(self.world)
+            self._reduce(g)
+            return
+        if self._side is None:
+            self._side = torch.cuda.Stream(g.device)
+            self._event = torch.cuda.Event()
+        self._event.record(torch.cuda.current_stream(g.device))
+        with torch.cuda.stream(self._side):
+            self._side.wait_event(self._event)
+            self._work = self._reduce(g, async_op=True)
+
+    def finish(self, engine, lo: int, hi: int):
+        if self.world <= 1:
+            return
+        self._reduce(engine.grads[lo:hi])
+        if self._work is not None:
+            self._work.wait()                      # the compute stream waits for bucket 1's all-reduce
+            self._work = None
 
 
 def broadcast_parameters(model, src: int = 0):

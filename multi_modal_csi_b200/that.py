@@ -275,14 +275,22 @@ class THAT(torch.nn.Module):
         eng.forward_input(x, B, True, augment, offs, lens)
         eng.y_static[:B].copy_(yf)
         graph = self.use_cuda_graph if use_graph is None else use_graph
-        if graph and x.is_cuda and self._eager_steps >= 1:
-            eng.train_body_graph(B, pos_weight, self.dropout_enabled)
+        run = eng.train_body_graph if (graph and x.is_cuda and self._eager_steps >= 1) else eng.train_body
+        overlap = grad_hook is not None and hasattr(grad_hook, "start_bucket")
+        if overlap:
+            # data parallel: all-reduce the first gradient bucket (left stream, 95 % of the bytes) on a side stream
+            # while the right stream's backward runs
+            run(B, pos_weight, self.dropout_enabled, 1)
+            grad_hook.start_bucket(eng, 0, eng.bucket_split)
+            run(B, pos_weight, self.dropout_enabled, 2)
+            grad_hook.finish(eng, eng.bucket_split, eng.grads.numel())
         else:
-            eng.train_body(B, pos_weight, self.dropout_enabled)
+            run(B, pos_weight, self.dropout_enabled)
+        if run == eng.train_body:
             self._eager_steps += 1
         loss, logits = eng.loss, eng.logits[:B, :self.geom.out]
         self._attach_grads()
-        if grad_hook is not None:
+        if grad_hook is not None and not overlap:
             grad_hook(eng)
         optimizer.fused_step(eng)
         return loss, logits

@@ -88,7 +88,7 @@ def train(model, optimizer, loss, data_train_set: TensorDataset, data_test_set: 
             if fused:
                 x = data_batch_x.reshape(data_batch_x.shape[0], data_batch_x.shape[1], -1).float()
                 var_loss_train, predict_train_y = model.fused_train_step(
-                    x, data_batch_y, optimizer, pos_weight=pos_weight, augment=True, grad_hook=sync.hook if sync else None)
+                    x, data_batch_y, optimizer, pos_weight=pos_weight, augment=True, grad_hook=sync)
                 var_loss_train, predict_train_y = var_loss_train.clone(), predict_train_y.clone()
             else:
                 if model.training:

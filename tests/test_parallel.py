@@ -32,14 +32,19 @@ def _worker(rank, world, port, out_dir):
     y = (torch.rand(B, out, generator=g) < 0.2).float()
     m.train()
     opt = FusedAdam(m.parameters(), lr=5e-4, weight_decay=2e-4)
-    sync = GradSync(m, world, num_buckets=3)
-    captured = {}
+    sync = GradSync(m, world)
+    captured = {"local": torch.zeros_like(m.flat_grads)}
 
-    def hook(eng):
-        captured["local"] = eng.grads.clone()
-        sync.hook(eng)
-        captured["synced"] = eng.grads.clone()
-    m.fused_train_step(x, y, opt, augment=False, grad_hook=hook)
+    class Spy:                                       # records the local gradients of each bucket before it is reduced
+        def start_bucket(self, eng, lo, hi):
+            captured["local"][lo:hi] = eng.grads[lo:hi]
+            sync.start_bucket(eng, lo, hi)
+
+        def finish(self, eng, lo, hi):
+            captured["local"][lo:hi] = eng.grads[lo:hi]
+            sync.finish(eng, lo, hi)
+            captured["synced"] = eng.grads.clone()
+    m.fused_train_step(x, y, opt, augment=False, grad_hook=Spy())
     torch.save({"local": captured["local"], "synced": captured["synced"], "params": m.flat_params.clone()},
                os.path.join(out_dir, f"r{rank}.pt"))
     dist.barrier()
