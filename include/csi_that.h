@@ -184,6 +184,12 @@ int csi_pack_weights(const float* params, void* packed, int dtype, const csi_pac
 /* Test hook: 1 = route every contraction/attention call to the FFMA kernels, 0 = tensor-core kernels where eligible. */
 int csi_set_force_simt(int on);
 
+/* ---- a16: the reference decision rule (utils.py:147-183,234-239): sigmoid -> per user the arg-max class counts iff
+ * its probability exceeds `threshold` (the reference hard-codes 0.5) -> per-class counts.  logits: fp32 [rows, ldz]
+ * with users*classes valid columns; counts: int32 [rows, classes]. */
+int csi_predict_counts(const float* logits, int ldz, int rows, int users, int classes, float threshold, int* counts,
+                       void* stream);
+
 /* Generic helpers */
 int csi_fill_f32(float* p, long long n, float v, void* stream);
 

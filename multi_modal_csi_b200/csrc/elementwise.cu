@@ -1073,6 +1073,36 @@ extern "C" int csi_pack_weights(const float* params, void* packed, int dtype, co
     return CSI_OK;
 }
 
+// ------------------------------------------------------------------------------------------------ prediction rule
+__global__ void predict_counts_kernel(const float* __restrict__ z, int ldz, int rows, int users, int classes, float thr,
+                                      int* __restrict__ counts) {
+    const int r = blockIdx.x * blockDim.x + threadIdx.x;
+    if (r >= rows) return;
+    const float* zr = z + (size_t)r * ldz;
+    int* cr = counts + (size_t)r * classes;
+    for (int c = 0; c < classes; ++c) cr[c] = 0;
+    // sigmoid is monotone: arg-max of the probabilities = first arg-max of the logits (numpy argmax keeps the first)
+    const float zthr = logf(thr / (1.f - thr));
+    for (int u = 0; u < users; ++u) {
+        int best = 0;
+        float bv = zr[u * classes];
+        for (int c = 1; c < classes; ++c) {
+            const float v = zr[u * classes + c];
+            if (v > bv) { bv = v; best = c; }
+        }
+        if (bv > zthr) cr[best] += 1;
+    }
+}
+
+extern "C" int csi_predict_counts(const float* logits, int ldz, int rows, int users, int classes, float threshold, int* counts,
+                                  void* stream) {
+    CSI_CHECK_ARG(logits && counts && users > 0 && classes > 0 && threshold > 0.f && threshold < 1.f, "bad argument");
+    if (rows == 0) return CSI_OK;
+    predict_counts_kernel<<<cdiv(rows, 128), 128, 0, ST(stream)>>>(logits, ldz, rows, users, classes, threshold, counts);
+    CSI_LAUNCH_CHECK();
+    return CSI_OK;
+}
+
 __global__ void fill_kernel(float* p, long long n, float v) {
     for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x) p[i] = v;
 }

@@ -58,7 +58,7 @@ EXPORTS = [
     "csi_layernorm_fwd", "csi_layernorm_bwd", "csi_gemm_nt", "csi_gemm_tn", "csi_colsum_tokens", "csi_attn_fwd",
     "csi_attn_bwd", "csi_bn_stats", "csi_bn_finalize", "csi_bn_eval_prepare", "csi_bn_act_fwd",
     "csi_bn_act_bwd_reduce", "csi_bn_act_bwd_dz", "csi_head_reduce_fwd", "csi_head_reduce_bwd", "csi_dropout_rows",
-    "csi_bce_logits", "csi_adam_flat", "csi_advance_counters", "csi_pack_weights", "csi_fill_f32",
+    "csi_bce_logits", "csi_predict_counts", "csi_adam_flat", "csi_advance_counters", "csi_pack_weights", "csi_fill_f32",
 ]
 
 
@@ -314,6 +314,9 @@ class NativeOps:
         wk = self._work("bce_logits", locals())
         self._call("csi_bce_logits", _p(z), _ld(z), _p(y), _ld(y), rows, cols, C.c_float(pos_weight),
                                          C.c_float(grad_scale), _p(loss), _p(dz), _ld(dz), **wk)
+
+    def predict_counts(self, logits, rows, users, classes, threshold, counts):
+        self._call("csi_predict_counts", _p(logits), _ld(logits), rows, users, classes, C.c_float(threshold), _p(counts))
 
     def adam_flat(self, p, g, m, v, n, lr, b1, b2, eps, wd, step, grad_scale):
         wk = self._work("adam_flat", locals())

@@ -259,6 +259,16 @@ class THAT(torch.nn.Module):
             outs.append(eng.forward(xb, xb.shape[0], training=training, dropout=self.dropout_enabled).clone())
         return outs[0] if len(outs) == 1 else torch.cat(outs, 0)
 
+    # ------------------------------------------------------------------ prediction rule on the device
+    def predict_counts(self, logits: torch.Tensor, users: int = 6, threshold: float = 0.5) -> torch.Tensor:
+        """Per-class people counts [N, classes] (int32) from logits [N, users*classes] with the reference rule
+        (utils.py:147-183: per-user arg-max kept iff its sigmoid exceeds the threshold), computed on the GPU."""
+        z = logits.float().contiguous()
+        n, classes = z.shape[0], z.shape[1] // users
+        counts = torch.zeros(n, classes, dtype=torch.int32, device=z.device)
+        self._engine_for(1).ops.predict_counts(z, n, users, classes, threshold, counts)
+        return counts
+
     # ------------------------------------------------------------------ fused train step
     def fused_train_step(self, x, y, optimizer, pos_weight: float = 4.0, augment: bool = True,
                          grad_hook=None, offs=None, lens=None, use_graph=None):

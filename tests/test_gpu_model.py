@@ -315,3 +315,44 @@ def test_cuda_graph_step_equals_eager_step():
         assert (len(m._engine._graphs) == 1) == graph
     assert all(abs(a - b) < 5e-3 * max(1.0, abs(a)) for a, b in zip(*traj)), traj
     assert traj[0][0] != traj[0][1]
+
+
+def test_predict_counts_matches_reference_rule(gold):
+    """GPU decision rule == utils.process_predictions on the committed reference fixture (and the oracle)."""
+    from oracle import that_oracle as O
+    g = gold("metrics.npz")
+    m = build(400, 30, 54, "fp32")
+    logits = torch.from_numpy(g["logits"]).cuda()
+    counts = m.predict_counts(logits, users=6, threshold=0.5).cpu()
+    assert np.array_equal(counts.numpy(), g["counts_pred"].astype(np.int32))
+    assert torch.equal(counts.double(), O.predict_counts(torch.from_numpy(g["logits"]), 6))
+
+
+def test_full_batch_properties_b256():
+    """BASELINE-size batch (B=256, [3000, 270]): size-independent properties of the eval path -- sample-permutation
+    equivariance and invariance to how the batch is chunked -- plus a finite train step."""
+    from multi_modal_csi_b200 import FusedAdam
+    T, F, out, B = 3000, 270, 54, 256
+    g = torch.Generator(device="cuda").manual_seed(11)
+    x = torch.rand(B, T, F, device="cuda", generator=g) * 20
+    y = (torch.rand(B, out, device="cuda", generator=g) < 0.05).float()
+    m = build(T, F, out, "bf16")
+    m.configure(max_batch=B)
+    m.eval()
+    with torch.no_grad():
+        full = m(x)
+        perm = torch.randperm(B, device="cuda", generator=g)
+        assert torch.equal(m(x[perm]), full[perm])                       # samples are independent in eval mode
+    m.configure(max_batch=96)                                            # 256 -> chunks of 96, 96, 64
+    with torch.no_grad():
+        assert torch.equal(m(x), full)
+    m.configure(max_batch=B)
+    m.train()
+    m.dropout_enabled = True
+    opt = FusedAdam(m.parameters(), lr=5e-4, weight_decay=2e-4)
+    l0, _ = m.fused_train_step(x, y, opt, augment=True)
+    l0 = l0.item()
+    for _ in range(3):
+        l1, _ = m.fused_train_step(x, y, opt, augment=True)
+    assert np.isfinite(l0) and np.isfinite(l1.item()) and l1.item() < l0     # 4 Adam steps on one batch reduce its loss
+    assert int(m.state_dict()["layer_right_encoder.0.layer_cnn.2.1.num_batches_tracked"]) == 4
