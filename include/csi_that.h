@@ -50,6 +50,12 @@ typedef struct { int b_row_shift, b_col_off, c_off, nlen; } csi_seg_tn;
 /* Up to three per-branch parameter pointers (the three Conv1d->BatchNorm1d branches of an Encoder). */
 typedef struct { void* p[3]; } csi_ptr3;
 
+/* Head padding of a feature index: features come in groups (attention heads) of `valid` entries that are stored with
+ * a pitch of `pad` entries (27 -> 32, 15 -> 16, 54 -> 64) so that every head starts 16-byte aligned:
+ *   padded(i) = (i / valid) * pad + i % valid        compact(i') = (i' / pad) * valid + i' % pad  (if i' % pad < valid)
+ * {0, 0} means "no padding". */
+typedef struct { int valid, pad; } csi_grp;
+
 /* One tensor of the weight re-layout table (see csi_pack_weights). */
 typedef struct {
     long long src_off;   /* element offset of the fp32 [N, C, k] source in the parameter arena        */
@@ -60,6 +66,8 @@ typedef struct {
                          /* 1: dst[c*ld + (seg_base+j)*P + n] = src[n,c,j]  (data-gradient operand)  */
     int P;               /* padded channel pitch of one tap                                         */
     int seg_base;        /* first segment index of this tensor in mode 1                            */
+    csi_grp gn;          /* head padding of the n index (n -> n'), {0,0} = identity                  */
+    csi_grp gc;          /* head padding of the c index (c -> c')                                    */
     int reserved;
 } csi_pack_entry;
 
@@ -115,18 +123,23 @@ int csi_gemm_nt(const void* A, int lda, const void* Bw, int ldb, int ab_dtype, v
  * for i < Na, q < nlen_s.  C is fp32 and is accumulated with atomics (caller zeroes); with c_col_stride = k
  * it writes Conv1d weight gradients straight into the reference [N, C, k] layout. */
 int csi_gemm_tn(const void* A, int lda, const void* Bv, int ldb, int ab_dtype, float* C, int ldc,
-                int c_col_stride, int M, int Na, const csi_seg_tn* segs, int nseg, void* stream);
+                int c_col_stride, int M, int Na, const csi_seg_tn* segs, int nseg, csi_grp i_grp, csi_grp q_grp,
+                void* stream);
+/* i_grp / q_grp: A's columns (i) / Bv's columns (q) are head-padded; C is indexed with the compact indices and the
+ * padding entries are skipped (in-projection and out-projection weight gradients). */
 
-/* Column sums over the valid token rows: out[c] += sum_{b,l} A[row(b,l), c]  (bias gradients). */
-int csi_colsum_tokens(const void* A, int lda, int dtype, int B, int L, int halo, int ncols, float* out,
+/* Column sums over the valid token rows: out[compact(c)] += sum_{b,l} A[row(b,l), c]  (bias gradients). */
+int csi_colsum_tokens(const void* A, int lda, int dtype, int B, int L, int halo, int ncols, csi_grp grp, float* out,
                       void* stream);
 
 /* ---- a8: nn.MultiheadAttention core at that.py:149 (per head softmax(q k^T / sqrt(hd)) v).
- * qkv: token buffer [rows, ld3] holding q | k | v in columns [0,d) [d,2d) [2d,3d).  lse: fp32 [B,H,L]. */
+ * Head-padded layout: head h of q | k | v lives in columns [w*H*hp + h*hp, +hd) of the token buffer qkv (w = 0,1,2),
+ * head h of o / dout in columns [h*hp, +hd); hd = d/H, hp >= hd is the head pitch (padding columns are zero on input
+ * and written as zero).  lse: fp32 [B,H,L]. */
 int csi_attn_fwd(const void* qkv, int ld3, void* o, int ldo, int dtype, float* lse, int B, int L, int d,
-                 int H, int halo, void* stream);
+                 int H, int hp, int halo, void* stream);
 int csi_attn_bwd(const void* qkv, int ld3, const void* o, int ldo, const void* dout, int lddo, void* dqkv,
-                 int lddqkv, int dtype, const float* lse, int B, int L, int d, int H, int halo, void* stream);
+                 int lddqkv, int dtype, const float* lse, int B, int L, int d, int H, int hp, int halo, void* stream);
 
 /* ---- a10: BatchNorm1d (train: batch statistics) -> Dropout(.1) -> LeakyReLU, mean of the 3 branches,
  * Dropout(.1), residual (that.py:126-132,160-168).  z: token buffer [rows, ldz] with branch br in columns

@@ -38,7 +38,7 @@ __device__ __forceinline__ void row_times_matrix(const float* __restrict__ pw, c
 template <typename T>
 __global__ void __launch_bounds__(ATT_WARPS * 32) attn_fwd_kernel(const T* __restrict__ qkv, int ld3, T* __restrict__ o,
                                                                   int ldo, float* __restrict__ lse, int L, int d, int H,
-                                                                  int halo, int hs, int W) {
+                                                                  int halo, int hs, int W, int hp) {
     extern __shared__ float sm[];
     const int hd = d / H, b = blockIdx.x / H, h = blockIdx.x % H, Lp = L + 2 * halo;
     float* Ks = sm;
@@ -47,15 +47,15 @@ __global__ void __launch_bounds__(ATT_WARPS * 32) attn_fwd_kernel(const T* __res
     float* Qs = Ps + ATT_WARPS * L;          // [ATT_WARPS][hs]
     const size_t row0 = (size_t)b * Lp + halo;
     const T* base = qkv + row0 * ld3;
-    load_head<T>(base, ld3, d + h * hd, L, hd, hs, Ks);
-    load_head<T>(base, ld3, 2 * d + h * hd, L, hd, hs, Vs);
+    load_head<T>(base, ld3, H * hp + h * hp, L, hd, hs, Ks);
+    load_head<T>(base, ld3, 2 * H * hp + h * hp, L, hd, hs, Vs);
     __syncthreads();
     const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
     const float sc = rsqrtf((float)hd);
     float* pw = Ps + wid * L;
     float* qw = Qs + wid * hs;
     for (int i = wid; i < L; i += ATT_WARPS) {
-        for (int e = lane; e < hd; e += 32) qw[e] = ldv<T>(base + (size_t)i * ld3 + h * hd + e) * sc;
+        for (int e = lane; e < hd; e += 32) qw[e] = ldv<T>(base + (size_t)i * ld3 + h * hp + e) * sc;
         __syncwarp();
         float s[ATT_JMAX];
         float mx = -INFINITY;
@@ -84,7 +84,7 @@ __global__ void __launch_bounds__(ATT_WARPS * 32) attn_fwd_kernel(const T* __res
         const float inv = 1.f / sum;
         const int e0 = lane % W;
         if (lane < W) {
-            T* orow = o + (row0 + i) * ldo + h * hd;
+            T* orow = o + (row0 + i) * ldo + h * hp;
             if (e0 < hd) stf<T>(orow + e0, o0 * inv);
             if (e0 + 32 < hd) stf<T>(orow + e0 + 32, o1 * inv);
         }
@@ -99,7 +99,7 @@ __global__ void __launch_bounds__(ATT_WARPS * 32) attn_bwd_kernel(const T* __res
                                                                   const T* __restrict__ dout, int lddo,
                                                                   T* __restrict__ dqkv, int lddqkv,
                                                                   const float* __restrict__ lse, int L, int d, int H,
-                                                                  int halo, int hs, int W) {
+                                                                  int halo, int hs, int W, int hp) {
     extern __shared__ float sm[];
     const int hd = d / H, b = blockIdx.x / H, h = blockIdx.x % H, Lp = L + 2 * halo;
     float* Qs = sm;
@@ -112,15 +112,15 @@ __global__ void __launch_bounds__(ATT_WARPS * 32) attn_bwd_kernel(const T* __res
     float* Ss = Ps + ATT_WARPS * L;          // [ATT_WARPS][L]
     const size_t row0 = (size_t)b * Lp + halo;
     const T* base = qkv + row0 * ld3;
-    load_head<T>(base, ld3, h * hd, L, hd, hs, Qs);
-    load_head<T>(base, ld3, d + h * hd, L, hd, hs, Ks);
-    load_head<T>(base, ld3, 2 * d + h * hd, L, hd, hs, Vs);
-    load_head<T>(dout + row0 * lddo, lddo, h * hd, L, hd, hs, Gs);
+    load_head<T>(base, ld3, h * hp, L, hd, hs, Qs);
+    load_head<T>(base, ld3, H * hp + h * hp, L, hd, hs, Ks);
+    load_head<T>(base, ld3, 2 * H * hp + h * hp, L, hd, hs, Vs);
+    load_head<T>(dout + row0 * lddo, lddo, h * hp, L, hd, hs, Gs);
     for (int i = threadIdx.x; i < L; i += blockDim.x) Ls[i] = lse[((size_t)b * H + h) * L + i];
     __syncthreads();
     for (int i = threadIdx.x; i < L; i += blockDim.x) {
         float a = 0.f;
-        for (int e = 0; e < hd; ++e) a = fmaf(Gs[i * hs + e], ldv<T>(o + (row0 + i) * ldo + h * hd + e), a);
+        for (int e = 0; e < hd; ++e) a = fmaf(Gs[i * hs + e], ldv<T>(o + (row0 + i) * ldo + h * hp + e), a);
         Ds[i] = a;
     }
     __syncthreads();
@@ -145,7 +145,7 @@ __global__ void __launch_bounds__(ATT_WARPS * 32) attn_bwd_kernel(const T* __res
         float o0, o1;
         row_times_matrix(sw, Ks, L, hd, hs, W, lane, o0, o1);
         if (lane < W) {
-            T* dq = dqkv + (row0 + i) * lddqkv + h * hd;
+            T* dq = dqkv + (row0 + i) * lddqkv + h * hp;
             if (e0 < hd) stf<T>(dq + e0, o0);
             if (e0 + 32 < hd) stf<T>(dq + e0 + 32, o1);
         }
@@ -168,8 +168,8 @@ __global__ void __launch_bounds__(ATT_WARPS * 32) attn_bwd_kernel(const T* __res
         row_times_matrix(sw, Qs, L, hd, hs, W, lane, k0, k1);
         row_times_matrix(pw, Gs, L, hd, hs, W, lane, v0, v1);
         if (lane < W) {
-            T* dk = dqkv + (row0 + j) * lddqkv + d + h * hd;
-            T* dv = dqkv + (row0 + j) * lddqkv + 2 * d + h * hd;
+            T* dk = dqkv + (row0 + j) * lddqkv + H * hp + h * hp;
+            T* dv = dqkv + (row0 + j) * lddqkv + 2 * H * hp + h * hp;
             if (e0 < hd) { stf<T>(dk + e0, k0); stf<T>(dv + e0, v0); }
             if (e0 + 32 < hd) { stf<T>(dk + e0 + 32, k1); stf<T>(dv + e0 + 32, v1); }
         }
@@ -181,7 +181,7 @@ static int head_stride(int hd) { return hd | 1; }                  // odd stride
 static int lane_width(int hd) { int w = 1; while (w < hd && w < 32) w <<= 1; return w; }
 
 extern "C" int csi_attn_fwd_simt(const void* qkv, int ld3, void* o, int ldo, int dtype, float* lse, int B, int L, int d,
-                                 int H, int halo, void* stream) {
+                                 int H, int hp, int halo, void* stream) {
     CSI_CHECK_ARG(qkv && o && lse, "null pointer");
     CSI_CHECK_ARG(H > 0 && d % H == 0 && d / H <= 64 && L <= 32 * ATT_JMAX, "head_dim <= 64 and L <= 640");
     if (B == 0) return CSI_OK;
@@ -190,10 +190,10 @@ extern "C" int csi_attn_fwd_simt(const void* qkv, int ld3, void* o, int ldo, int
     CSI_CHECK_ARG(smem <= 227 * 1024, "head does not fit in shared memory");
     if (dtype == CSI_BF16) {
         CSI_CUDA(cudaFuncSetAttribute(attn_fwd_kernel<bf16>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-        attn_fwd_kernel<bf16><<<B * H, ATT_WARPS * 32, smem, ST(stream)>>>((const bf16*)qkv, ld3, (bf16*)o, ldo, lse, L, d, H, halo, hs, W);
+        attn_fwd_kernel<bf16><<<B * H, ATT_WARPS * 32, smem, ST(stream)>>>((const bf16*)qkv, ld3, (bf16*)o, ldo, lse, L, d, H, halo, hs, W, hp);
     } else {
         CSI_CUDA(cudaFuncSetAttribute(attn_fwd_kernel<float>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-        attn_fwd_kernel<float><<<B * H, ATT_WARPS * 32, smem, ST(stream)>>>((const float*)qkv, ld3, (float*)o, ldo, lse, L, d, H, halo, hs, W);
+        attn_fwd_kernel<float><<<B * H, ATT_WARPS * 32, smem, ST(stream)>>>((const float*)qkv, ld3, (float*)o, ldo, lse, L, d, H, halo, hs, W, hp);
     }
     CSI_LAUNCH_CHECK();
     return CSI_OK;
@@ -201,7 +201,7 @@ extern "C" int csi_attn_fwd_simt(const void* qkv, int ld3, void* o, int ldo, int
 
 extern "C" int csi_attn_bwd_simt(const void* qkv, int ld3, const void* o, int ldo, const void* dout, int lddo,
                                  void* dqkv, int lddqkv, int dtype, const float* lse, int B, int L, int d, int H,
-                                 int halo, void* stream) {
+                                 int hp, int halo, void* stream) {
     CSI_CHECK_ARG(qkv && o && dout && dqkv && lse, "null pointer");
     CSI_CHECK_ARG(H > 0 && d % H == 0 && d / H <= 64, "head_dim <= 64");
     if (B == 0) return CSI_OK;
@@ -211,12 +211,12 @@ extern "C" int csi_attn_bwd_simt(const void* qkv, int ld3, const void* o, int ld
     if (dtype == CSI_BF16) {
         CSI_CUDA(cudaFuncSetAttribute(attn_bwd_kernel<bf16>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
         attn_bwd_kernel<bf16><<<B * H, ATT_WARPS * 32, smem, ST(stream)>>>((const bf16*)qkv, ld3, (const bf16*)o, ldo, (const bf16*)dout,
-                                                                         lddo, (bf16*)dqkv, lddqkv, lse, L, d, H, halo, hs, W);
+                                                                         lddo, (bf16*)dqkv, lddqkv, lse, L, d, H, halo, hs, W, hp);
     } else {
         CSI_CUDA(cudaFuncSetAttribute(attn_bwd_kernel<float>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
         attn_bwd_kernel<float><<<B * H, ATT_WARPS * 32, smem, ST(stream)>>>((const float*)qkv, ld3, (const float*)o, ldo,
                                                                           (const float*)dout, lddo, (float*)dqkv, lddqkv, lse, L, d, H,
-                                                                          halo, hs, W);
+                                                                          halo, hs, W, hp);
     }
     CSI_LAUNCH_CHECK();
     return CSI_OK;

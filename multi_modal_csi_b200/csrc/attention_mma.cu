@@ -1,7 +1,8 @@
 // Tensor-core attention core for bf16 activations (that.py:149, nn.MultiheadAttention with need_weights discarded):
-// one CTA per (sample, head); the head's Q, K, V (and dO in backward) live in shared memory as zero-padded
-// [tokens][head_dim] tiles, scores/probabilities only ever exist in registers.  Matrix products use
-// mma.sync.m16n8k16 (bf16 in, fp32 accumulate) fed by ldmatrix; head dims 27/15/54 are zero-padded to 32/16/64.
+// one CTA per (sample, head); the head's Q, K, V (and dO in backward) live in shared memory, scores/probabilities
+// only ever exist in registers.  Matrix products use mma.sync.m16n8k16 (bf16 in, fp32 accumulate) fed by ldmatrix.
+// Heads are stored with a pitch of HDP = 16/32/64 elements (head dims 15/27/54 zero-padded by the in-projection's
+// weight layout), so every head row is a whole number of aligned 16-byte chunks: tiles move with 128-bit accesses.
 //   forward : flash-style online softmax over 64-key blocks, one 16-query tile per warp iteration
 //   backward: pass A (per 16-query tile)  S, dP -> dS -> dQ = dS K
 //             pass B (per 16-key tile)    S^T, dP^T -> dV = P^T dO, dK = dS^T Q     (no atomics, no cross-warp sums)
@@ -28,6 +29,11 @@ __device__ __forceinline__ uint32_t pack_bf16(float lo, float hi) {
     __nv_bfloat162 v = __floats2bfloat162_rn(lo, hi);
     return *reinterpret_cast<uint32_t*>(&v);
 }
+__device__ __forceinline__ float fast_exp2(float x) {
+    float y;
+    asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
+    return y;
+}
 
 // per-lane smem addresses of the three fragment kinds (LDS = row stride in elements)
 template <int LDS> __device__ __forceinline__ const bf16* a_frag_ptr(const bf16* s, int row0, int col0, int lane) {
@@ -42,39 +48,36 @@ template <int LDS> __device__ __forceinline__ const bf16* bt_frag_ptr(const bf16
     return s + (k0 + (lane & 7) + ((lane >> 3) & 1) * 8) * LDS + n0 + (lane >> 4) * 8;
 }
 
-// global [L rows of one head, hd valid columns at arbitrary 2-byte alignment] -> smem [LP][LDS].  The tile must have been
-// zeroed (zero_tiles) before; 8 independent loads are issued per thread before any of them is consumed, so the copy is
-// bandwidth- rather than latency-bound.
-template <int LDS>
-__device__ __forceinline__ void load_head_tile(const bf16* __restrict__ src, int ld, int L, int hd, bf16* __restrict__ dst) {
-    // EPR = lanes per row (power of two >= hd, <= HDP): no integer division, 8 rows in flight per thread
-    constexpr int EPR = LDS - 8;
-    const int e = threadIdx.x & (EPR - 1), r0 = threadIdx.x / EPR, rstep = blockDim.x / EPR;
-    if (e >= hd) return;
-    for (int base = r0; base < L; base += 8 * rstep) {
-        bf16 v[8];
+// global head tile [L rows x HDP cols, 16-byte aligned rows of pitch ld] -> smem [LP][LDS]; rows >= L are zeroed.
+// One 128-bit load + one 128-bit store per 8 elements, 4 loads in flight per thread.
+template <int HDP, int LDS>
+__device__ __forceinline__ void load_head_tile(const bf16* __restrict__ src, int ld, int L, int LP, bf16* __restrict__ dst) {
+    constexpr int CPR = HDP / 8;                                   // 16-byte chunks per row
+    const int total = LP * CPR, stride = blockDim.x;
+    for (int base = threadIdx.x; base < total; base += 4 * stride) {
+        uint4 v[4];
 #pragma unroll
-        for (int u = 0; u < 8; ++u) {
-            const int l = base + u * rstep;
-            if (l < L) v[u] = src[(size_t)l * ld + e];
+        for (int u = 0; u < 4; ++u) {
+            const int i = base + u * stride, l = i / CPR, c = i % CPR;
+            v[u] = make_uint4(0u, 0u, 0u, 0u);
+            if (i < total && l < L) v[u] = *reinterpret_cast<const uint4*>(src + (size_t)l * ld + c * 8);
         }
 #pragma unroll
-        for (int u = 0; u < 8; ++u) {
-            const int l = base + u * rstep;
-            if (l < L) dst[l * LDS + e] = v[u];
+        for (int u = 0; u < 4; ++u) {
+            const int i = base + u * stride, l = i / CPR, c = i % CPR;
+            if (i < total) *reinterpret_cast<uint4*>(dst + l * LDS + c * 8) = v[u];
         }
     }
 }
-__device__ __forceinline__ float fast_exp2(float x) {
-    float y;
-    asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
-    return y;
+// smem [L][LDS] -> global head tile (128-bit stores, padding columns included: they hold zeros)
+template <int HDP, int LDS>
+__device__ __forceinline__ void store_head_tile(const bf16* __restrict__ src, bf16* __restrict__ dst, int ld, int L) {
+    constexpr int CPR = HDP / 8;
+    for (int i = threadIdx.x; i < L * CPR; i += blockDim.x) {
+        const int l = i / CPR, c = i % CPR;
+        *reinterpret_cast<uint4*>(dst + (size_t)l * ld + c * 8) = *reinterpret_cast<const uint4*>(src + l * LDS + c * 8);
+    }
 }
-__device__ __forceinline__ void zero_tiles(void* p, int bytes) {
-    uint4* q = reinterpret_cast<uint4*>(p);
-    for (int i = threadIdx.x; i < bytes / 16; i += blockDim.x) q[i] = make_uint4(0u, 0u, 0u, 0u);
-}
-
 // accumulator tile (16 rows x NTO*8 cols, mma C layout) -> bf16 smem rows [row0, row0+16)
 template <int LDS, int NTO>
 __device__ __forceinline__ void stage_tile(bf16* __restrict__ dst, int row0, const float (&acc)[NTO][4], float s0, float s1, int g, int t) {
@@ -83,15 +86,6 @@ __device__ __forceinline__ void stage_tile(bf16* __restrict__ dst, int row0, con
         const int col = no * 8 + 2 * t;
         *reinterpret_cast<__nv_bfloat162*>(dst + (row0 + g) * LDS + col) = __floats2bfloat162_rn(acc[no][0] * s0, acc[no][1] * s0);
         *reinterpret_cast<__nv_bfloat162*>(dst + (row0 + g + 8) * LDS + col) = __floats2bfloat162_rn(acc[no][2] * s1, acc[no][3] * s1);
-    }
-}
-// smem [L][LDS] -> global rows of one head (hd valid columns): consecutive threads write consecutive elements, so a warp
-// store fills whole 32-byte sectors instead of one sector per 2-byte element
-template <int LDS>
-__device__ __forceinline__ void flush_head_tile(const bf16* __restrict__ src, bf16* __restrict__ dst, int ld, int L, int hd) {
-    for (int i = threadIdx.x; i < L * hd; i += blockDim.x) {
-        const int l = i / hd, e = i - l * hd;
-        dst[(size_t)l * ld + e] = src[l * LDS + e];
     }
 }
 
@@ -106,17 +100,15 @@ __global__ void __launch_bounds__(AM_WARPS * 32) attn_fwd_mma_kernel(const bf16*
     bf16* Ks = Qs + LP * LDS;
     bf16* Vs = Ks + LP * LDS;
     const size_t row0 = (size_t)b * Lp + halo;
-    const bf16* base = qkv + row0 * ld3 + h * hd;
-    zero_tiles(Qs, 3 * LP * LDS * 2);
-    __syncthreads();
-    load_head_tile<LDS>(base, ld3, L, hd, Qs);
-    load_head_tile<LDS>(base + d, ld3, L, hd, Ks);
-    load_head_tile<LDS>(base + 2 * d, ld3, L, hd, Vs);
+    const bf16* base = qkv + row0 * ld3 + h * HDP;
+    load_head_tile<HDP, LDS>(base, ld3, L, LP, Qs);
+    load_head_tile<HDP, LDS>(base + H * HDP, ld3, L, LP, Ks);
+    load_head_tile<HDP, LDS>(base + 2 * H * HDP, ld3, L, LP, Vs);
     __syncthreads();
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, g = lane >> 2, t = lane & 3;
-    const float c = rsqrtf((float)hd) * LOG2E;
+    const float sc = rsqrtf((float)hd), c = sc * LOG2E;
     const int npair = LP / 16;
-    for (int qt = warp; qt < LP / 16; qt += AM_WARPS) {
+    for (int qt = warp; qt < npair; qt += AM_WARPS) {
         uint32_t qa[KS][4];
 #pragma unroll
         for (int ks = 0; ks < KS; ++ks) ldsm_x4(qa[ks], a_frag_ptr<LDS>(Qs, qt * 16, ks * 16, lane));
@@ -141,8 +133,6 @@ __global__ void __launch_bounds__(AM_WARPS * 32) attn_fwd_mma_kernel(const bf16*
                     }
                 }
             }
-            float mx0 = -INFINITY, mx1 = -INFINITY;
-#pragma unroll
             if (pb * 16 + 64 > L) {                             // only the last key block has columns >= L (warp-uniform)
 #pragma unroll
                 for (int nt = 0; nt < 8; ++nt) {
@@ -151,6 +141,7 @@ __global__ void __launch_bounds__(AM_WARPS * 32) attn_fwd_mma_kernel(const bf16*
                     if (col + 1 >= L) s[nt][1] = s[nt][3] = -INFINITY;
                 }
             }
+            float mx0 = -INFINITY, mx1 = -INFINITY;
 #pragma unroll
             for (int nt = 0; nt < 8; ++nt) {
                 mx0 = fmaxf(mx0, fmaxf(s[nt][0], s[nt][1]));
@@ -194,7 +185,6 @@ __global__ void __launch_bounds__(AM_WARPS * 32) attn_fwd_mma_kernel(const bf16*
         l1 += __shfl_xor_sync(0xffffffffu, l1, 1); l1 += __shfl_xor_sync(0xffffffffu, l1, 2);
         const float i0 = 1.f / l0, i1 = 1.f / l1;
         const int r0 = qt * 16 + g, r1 = r0 + 8;
-        const float sc = rsqrtf((float)hd);
         __syncwarp();                                              // all lanes hold their Q fragments of this tile
         stage_tile<LDS, NTO>(Qs, qt * 16, oacc, i0, i1, g, t);    // O overwrites the (now dead) Q rows of this tile
         if (t == 0) {
@@ -203,7 +193,7 @@ __global__ void __launch_bounds__(AM_WARPS * 32) attn_fwd_mma_kernel(const bf16*
         }
     }
     __syncthreads();
-    flush_head_tile<LDS>(Qs, o + row0 * ldo + h * hd, ldo, L, hd);
+    store_head_tile<HDP, LDS>(Qs, o + row0 * ldo + h * HDP, ldo, L);
 }
 
 template <int HDP>
@@ -211,7 +201,7 @@ __global__ void __launch_bounds__(AM_WARPS * 32) attn_bwd_mma_kernel(const bf16*
                                                                      int ldo, const bf16* __restrict__ dout, int lddo,
                                                                      bf16* __restrict__ dqkv, int lddqkv, const float* __restrict__ lse,
                                                                      int L, int d, int H, int halo) {
-    constexpr int LDS = HDP + 8, KS = HDP / 16, NTO = HDP / 8;
+    constexpr int LDS = HDP + 8, KS = HDP / 16, NTO = HDP / 8, CPR = HDP / 8;
     extern __shared__ __align__(16) uint8_t sm_raw[];
     const int hd = d / H, b = blockIdx.x / H, h = blockIdx.x % H, Lp = L + 2 * halo;
     const int LP = (L + 15) & ~15;
@@ -222,29 +212,31 @@ __global__ void __launch_bounds__(AM_WARPS * 32) attn_bwd_mma_kernel(const bf16*
     float* Ls = reinterpret_cast<float*>(Gs + LP * LDS);      // lse * log2(e)
     float* Ds = Ls + LP;                                      // rowsum(dO * O)
     const size_t row0 = (size_t)b * Lp + halo;
-    const bf16* base = qkv + row0 * ld3 + h * hd;
-    zero_tiles(Qs, 4 * LP * LDS * 2);
-    __syncthreads();
-    load_head_tile<LDS>(base, ld3, L, hd, Qs);
-    load_head_tile<LDS>(base + d, ld3, L, hd, Ks);
-    load_head_tile<LDS>(base + 2 * d, ld3, L, hd, Vs);
-    load_head_tile<LDS>(dout + row0 * lddo + h * hd, lddo, L, hd, Gs);
+    const bf16* base = qkv + row0 * ld3 + h * HDP;
+    load_head_tile<HDP, LDS>(base, ld3, L, LP, Qs);
+    load_head_tile<HDP, LDS>(base + H * HDP, ld3, L, LP, Ks);
+    load_head_tile<HDP, LDS>(base + 2 * H * HDP, ld3, L, LP, Vs);
+    load_head_tile<HDP, LDS>(dout + row0 * lddo + h * HDP, lddo, L, LP, Gs);
     for (int i = threadIdx.x; i < LP; i += blockDim.x) Ls[i] = i < L ? lse[((size_t)b * H + h) * L + i] * LOG2E : 0.f;
     __syncthreads();
-    // D_i = rowsum(dO_i * O_i): 8 lanes per row, each with its O loads issued together
-    for (int i = threadIdx.x >> 3; i < LP; i += blockDim.x >> 3) {
-        const int sub = threadIdx.x & 7;
+    // D_i = rowsum(dO_i * O_i): CPR lanes per row, one 128-bit O load each
+    for (int i = threadIdx.x; i < LP * CPR; i += blockDim.x) {
+        const int l = i / CPR, cch = i % CPR;
         float a = 0.f;
-        if (i < L) {
-            const bf16* orow = o + (row0 + i) * ldo + h * hd;
-            bf16 ov[8];
+        if (l < L) {
+            const uint4 ov = *reinterpret_cast<const uint4*>(o + (row0 + l) * ldo + h * HDP + cch * 8);
+            const uint4 gv = *reinterpret_cast<const uint4*>(Gs + l * LDS + cch * 8);
+            const __nv_bfloat162* oh = reinterpret_cast<const __nv_bfloat162*>(&ov);
+            const __nv_bfloat162* gh = reinterpret_cast<const __nv_bfloat162*>(&gv);
 #pragma unroll
-            for (int u = 0; u < 8; ++u) { const int e = sub + 8 * u; if (e < hd) ov[u] = orow[e]; }
-#pragma unroll
-            for (int u = 0; u < 8; ++u) { const int e = sub + 8 * u; if (e < hd) a = fmaf(__bfloat162float(Gs[i * LDS + e]), __bfloat162float(ov[u]), a); }
+            for (int u = 0; u < 4; ++u) {
+                const float2 x = __bfloat1622float2(oh[u]), y = __bfloat1622float2(gh[u]);
+                a = fmaf(x.x, y.x, a); a = fmaf(x.y, y.y, a);
+            }
         }
-        a += __shfl_xor_sync(0xffffffffu, a, 1); a += __shfl_xor_sync(0xffffffffu, a, 2); a += __shfl_xor_sync(0xffffffffu, a, 4);
-        if (sub == 0) Ds[i] = a;
+#pragma unroll
+        for (int off = 1; off < CPR; off <<= 1) a += __shfl_xor_sync(0xffffffffu, a, off);
+        if (cch == 0) Ds[l] = a;
     }
     __syncthreads();
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, g = lane >> 2, t = lane & 3;
@@ -295,19 +287,12 @@ __global__ void __launch_bounds__(AM_WARPS * 32) attn_bwd_mma_kernel(const bf16*
                 mma16816(dq[no + 1], da, kb[2], kb[3]);
             }
         }
+        // dQ: bf16x2 stores straight from the accumulator layout (Q and dO tiles are still needed by pass B)
 #pragma unroll
         for (int no = 0; no < NTO; ++no) {
             const int col = no * 8 + 2 * t;
-            if (r0 < L) {
-                bf16* dst = dqkv + (row0 + r0) * lddqkv + h * hd + col;
-                if (col < hd) dst[0] = __float2bfloat16_rn(dq[no][0]);
-                if (col + 1 < hd) dst[1] = __float2bfloat16_rn(dq[no][1]);
-            }
-            if (r1 < L) {
-                bf16* dst = dqkv + (row0 + r1) * lddqkv + h * hd + col;
-                if (col < hd) dst[0] = __float2bfloat16_rn(dq[no][2]);
-                if (col + 1 < hd) dst[1] = __float2bfloat16_rn(dq[no][3]);
-            }
+            if (r0 < L) *reinterpret_cast<__nv_bfloat162*>(dqkv + (row0 + r0) * lddqkv + h * HDP + col) = __floats2bfloat162_rn(dq[no][0], dq[no][1]);
+            if (r1 < L) *reinterpret_cast<__nv_bfloat162*>(dqkv + (row0 + r1) * lddqkv + h * HDP + col) = __floats2bfloat162_rn(dq[no][2], dq[no][3]);
         }
     }
     // ---------------- pass B: dK, dV (rows of the accumulators are keys, columns of S^T are queries)
@@ -338,11 +323,11 @@ __global__ void __launch_bounds__(AM_WARPS * 32) attn_bwd_mma_kernel(const bf16*
             for (int nt = 0; nt < 2; ++nt) {
                 const int q0 = qp * 16 + nt * 8 + 2 * t, q1 = q0 + 1;
                 const bool v0 = q0 < L, v1 = q1 < L;
-                const float lq0 = Ls[q0], lq1 = Ls[q1], dd0 = Ds[q0], dd1 = Ds[q1];
-                pt[nt][0] = v0 ? fast_exp2(st[nt][0] * c - lq0) : 0.f; pt[nt][1] = v1 ? fast_exp2(st[nt][1] * c - lq1) : 0.f;
-                pt[nt][2] = v0 ? fast_exp2(st[nt][2] * c - lq0) : 0.f; pt[nt][3] = v1 ? fast_exp2(st[nt][3] * c - lq1) : 0.f;
-                dst_[nt][0] = pt[nt][0] * (dpt[nt][0] - dd0) * sc; dst_[nt][1] = pt[nt][1] * (dpt[nt][1] - dd1) * sc;
-                dst_[nt][2] = pt[nt][2] * (dpt[nt][2] - dd0) * sc; dst_[nt][3] = pt[nt][3] * (dpt[nt][3] - dd1) * sc;
+                const float2 lq = *reinterpret_cast<const float2*>(Ls + q0), dd = *reinterpret_cast<const float2*>(Ds + q0);
+                pt[nt][0] = v0 ? fast_exp2(st[nt][0] * c - lq.x) : 0.f; pt[nt][1] = v1 ? fast_exp2(st[nt][1] * c - lq.y) : 0.f;
+                pt[nt][2] = v0 ? fast_exp2(st[nt][2] * c - lq.x) : 0.f; pt[nt][3] = v1 ? fast_exp2(st[nt][3] * c - lq.y) : 0.f;
+                dst_[nt][0] = pt[nt][0] * (dpt[nt][0] - dd.x) * sc; dst_[nt][1] = pt[nt][1] * (dpt[nt][1] - dd.y) * sc;
+                dst_[nt][2] = pt[nt][2] * (dpt[nt][2] - dd.x) * sc; dst_[nt][3] = pt[nt][3] * (dpt[nt][3] - dd.y) * sc;
             }
             uint32_t pa[4] = {pack_bf16(pt[0][0], pt[0][1]), pack_bf16(pt[0][2], pt[0][3]), pack_bf16(pt[1][0], pt[1][1]),
                               pack_bf16(pt[1][2], pt[1][3])};
@@ -364,52 +349,55 @@ __global__ void __launch_bounds__(AM_WARPS * 32) attn_bwd_mma_kernel(const bf16*
         stage_tile<LDS, NTO>(Vs, kt * 16, dv, 1.f, 1.f, g, t);
     }
     __syncthreads();
-    flush_head_tile<LDS>(Ks, dqkv + row0 * lddqkv + d + h * hd, lddqkv, L, hd);
-    flush_head_tile<LDS>(Vs, dqkv + row0 * lddqkv + 2 * d + h * hd, lddqkv, L, hd);
+    store_head_tile<HDP, LDS>(Ks, dqkv + row0 * lddqkv + H * HDP + h * HDP, lddqkv, L);
+    store_head_tile<HDP, LDS>(Vs, dqkv + row0 * lddqkv + 2 * H * HDP + h * HDP, lddqkv, L);
 }
 
 static int pad_hd(int hd) { return hd <= 16 ? 16 : (hd <= 32 ? 32 : 64); }
 
-extern "C" int csi_attn_mma_ok(int L, int d, int H) {
+// eligible: head pitch is exactly the padded MMA width and everything fits in shared memory
+extern "C" int csi_attn_mma_ok(int L, int d, int H, int hp) {
     if (H <= 0 || d % H) return 0;
     const int hd = d / H;
-    if (hd > 64) return 0;
-    const int LP = (L + 15) & ~15, LDS = pad_hd(hd) + 8;
+    if (hd > 64 || hp != pad_hd(hd)) return 0;
+    const int LP = (L + 15) & ~15, LDS = hp + 8;
     return ((size_t)4 * LP * LDS * 2 + 2 * (size_t)LP * 4) <= 200 * 1024;
 }
 
-extern "C" int csi_attn_fwd_mma(const void* qkv, int ld3, void* o, int ldo, float* lse, int B, int L, int d, int H, int halo,
-                                void* stream) {
+extern "C" int csi_attn_fwd_mma(const void* qkv, int ld3, void* o, int ldo, float* lse, int B, int L, int d, int H, int hp,
+                                int halo, void* stream) {
     CSI_CHECK_ARG(qkv && o && lse, "null pointer");
-    CSI_CHECK_ARG(csi_attn_mma_ok(L, d, H), "shape not eligible");
+    CSI_CHECK_ARG(csi_attn_mma_ok(L, d, H, hp), "shape not eligible");
+    CSI_CHECK_ARG(ld3 % 8 == 0 && ldo % 8 == 0 && ld3 >= 3 * H * hp && ldo >= H * hp, "head-padded leading dimensions expected");
     if (B == 0) return CSI_OK;
-    const int hdp = pad_hd(d / H), LP = (L + 15) & ~15;
-    const size_t smem = (size_t)3 * LP * (hdp + 8) * 2;
+    const int LP = (L + 15) & ~15;
+    const size_t smem = (size_t)3 * LP * (hp + 8) * 2;
 #define GO(HDP)                                                                                                        \
     do {                                                                                                               \
         CSI_CUDA(cudaFuncSetAttribute(attn_fwd_mma_kernel<HDP>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem)); \
         attn_fwd_mma_kernel<HDP><<<B * H, AM_WARPS * 32, smem, ST(stream)>>>((const bf16*)qkv, ld3, (bf16*)o, ldo, lse, L, d, H, halo); \
     } while (0)
-    if (hdp == 16) GO(16); else if (hdp == 32) GO(32); else GO(64);
+    if (hp == 16) GO(16); else if (hp == 32) GO(32); else GO(64);
 #undef GO
     CSI_LAUNCH_CHECK();
     return CSI_OK;
 }
 
 extern "C" int csi_attn_bwd_mma(const void* qkv, int ld3, const void* o, int ldo, const void* dout, int lddo, void* dqkv,
-                                int lddqkv, const float* lse, int B, int L, int d, int H, int halo, void* stream) {
+                                int lddqkv, const float* lse, int B, int L, int d, int H, int hp, int halo, void* stream) {
     CSI_CHECK_ARG(qkv && o && dout && dqkv && lse, "null pointer");
-    CSI_CHECK_ARG(csi_attn_mma_ok(L, d, H), "shape not eligible");
+    CSI_CHECK_ARG(csi_attn_mma_ok(L, d, H, hp), "shape not eligible");
+    CSI_CHECK_ARG(ld3 % 8 == 0 && ldo % 8 == 0 && lddo % 8 == 0 && lddqkv % 8 == 0, "head-padded leading dimensions expected");
     if (B == 0) return CSI_OK;
-    const int hdp = pad_hd(d / H), LP = (L + 15) & ~15;
-    const size_t smem = (size_t)4 * LP * (hdp + 8) * 2 + 2 * (size_t)LP * 4;
+    const int LP = (L + 15) & ~15;
+    const size_t smem = (size_t)4 * LP * (hp + 8) * 2 + 2 * (size_t)LP * 4;
 #define GO(HDP)                                                                                                        \
     do {                                                                                                               \
         CSI_CUDA(cudaFuncSetAttribute(attn_bwd_mma_kernel<HDP>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem)); \
         attn_bwd_mma_kernel<HDP><<<B * H, AM_WARPS * 32, smem, ST(stream)>>>((const bf16*)qkv, ld3, (const bf16*)o, ldo,   \
                                                                             (const bf16*)dout, lddo, (bf16*)dqkv, lddqkv, lse, L, d, H, halo); \
     } while (0)
-    if (hdp == 16) GO(16); else if (hdp == 32) GO(32); else GO(64);
+    if (hp == 16) GO(16); else if (hp == 32) GO(32); else GO(64);
 #undef GO
     CSI_LAUNCH_CHECK();
     return CSI_OK;

@@ -115,4 +115,12 @@ __device__ __forceinline__ float drop_scale1(const DropCtx& d, uint32_t site, un
 __device__ __forceinline__ float leaky(float v) { return v > 0.f ? v : LEAKY_SLOPE * v; }
 __device__ __forceinline__ float leaky_grad(float v) { return v > 0.f ? 1.f : LEAKY_SLOPE; }
 
+// head-padding index maps (csi_grp in csi_that.h)
+__host__ __device__ __forceinline__ int grp_to_padded(int i, csi_grp g) { return g.pad ? (i / g.valid) * g.pad + i % g.valid : i; }
+__host__ __device__ __forceinline__ int grp_to_compact(int ip, csi_grp g) {
+    if (!g.pad) return ip;
+    const int r = ip % g.pad;
+    return r < g.valid ? (ip / g.pad) * g.valid + r : -1;
+}
+
 static inline int cdiv(long long a, long long b) { return (int)((a + b - 1) / b); }

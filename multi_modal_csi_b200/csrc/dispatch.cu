@@ -7,10 +7,10 @@
 extern "C" int csi_gemm_nt_simt(const void*, int, const void*, int, int, void*, int, int, int, int, const csi_seg*, int,
                                 const float*, const float*, int, float, unsigned, const unsigned long long*, void*);
 extern "C" int csi_gemm_tn_simt(const void*, int, const void*, int, int, float*, int, int, int, int, const csi_seg_tn*,
-                                int, void*);
-extern "C" int csi_attn_fwd_simt(const void*, int, void*, int, int, float*, int, int, int, int, int, void*);
+                                int, csi_grp, csi_grp, void*);
+extern "C" int csi_attn_fwd_simt(const void*, int, void*, int, int, float*, int, int, int, int, int, int, void*);
 extern "C" int csi_attn_bwd_simt(const void*, int, const void*, int, const void*, int, void*, int, int, const float*, int,
-                                 int, int, int, int, void*);
+                                 int, int, int, int, int, void*);
 extern "C" int csi_gemm_nt_tc(const void*, int, const void*, int, void*, int, int, int, int, const csi_seg*, int,
                               const float*, const float*, int, float, unsigned, const unsigned long long*, void*);
 extern "C" int csi_gemm_nt_tc_ok(int lda, int ldb, int ldc, int M, int N, const csi_seg* segs, int nseg);
@@ -21,13 +21,14 @@ static bool gemm_v1() {
     if (g_gemm_v1 < 0) { const char* e = getenv("CSI_GEMM_V1"); g_gemm_v1 = (e && e[0] == '1') ? 1 : 0; }
     return g_gemm_v1 == 1;
 }
-extern "C" int csi_gemm_tn_tc(const void*, int, const void*, int, float*, int, int, int, int, const csi_seg_tn*, int, void*);
+extern "C" int csi_gemm_tn_tc(const void*, int, const void*, int, float*, int, int, int, int, const csi_seg_tn*, int, csi_grp,
+                              csi_grp, void*);
 extern "C" int csi_gemm_tn_tc_ok(int lda, int ldb, int M, int Na, const csi_seg_tn* segs, int nseg);
 
-extern "C" int csi_attn_mma_ok(int L, int d, int H);
-extern "C" int csi_attn_fwd_mma(const void*, int, void*, int, float*, int, int, int, int, int, void*);
+extern "C" int csi_attn_mma_ok(int L, int d, int H, int hp);
+extern "C" int csi_attn_fwd_mma(const void*, int, void*, int, float*, int, int, int, int, int, int, void*);
 extern "C" int csi_attn_bwd_mma(const void*, int, const void*, int, const void*, int, void*, int, const float*, int, int, int,
-                                int, int, void*);
+                                int, int, int, void*);
 
 static int g_force_simt = -1;
 static bool force_simt() {
@@ -54,22 +55,23 @@ extern "C" int csi_gemm_nt(const void* A, int lda, const void* Bw, int ldb, int 
 }
 
 extern "C" int csi_gemm_tn(const void* A, int lda, const void* Bv, int ldb, int ab_dtype, float* C, int ldc,
-                           int c_col_stride, int M, int Na, const csi_seg_tn* segs, int nseg, void* stream) {
+                           int c_col_stride, int M, int Na, const csi_seg_tn* segs, int nseg, csi_grp i_grp, csi_grp q_grp,
+                           void* stream) {
     if (ab_dtype == CSI_BF16 && !force_simt() && csi_gemm_tn_tc_ok(lda, ldb, M, Na, segs, nseg))
-        return csi_gemm_tn_tc(A, lda, Bv, ldb, C, ldc, c_col_stride, M, Na, segs, nseg, stream);
-    return csi_gemm_tn_simt(A, lda, Bv, ldb, ab_dtype, C, ldc, c_col_stride, M, Na, segs, nseg, stream);
+        return csi_gemm_tn_tc(A, lda, Bv, ldb, C, ldc, c_col_stride, M, Na, segs, nseg, i_grp, q_grp, stream);
+    return csi_gemm_tn_simt(A, lda, Bv, ldb, ab_dtype, C, ldc, c_col_stride, M, Na, segs, nseg, i_grp, q_grp, stream);
 }
 
 extern "C" int csi_attn_fwd(const void* qkv, int ld3, void* o, int ldo, int dtype, float* lse, int B, int L, int d,
-                            int H, int halo, void* stream) {
-    if (dtype == CSI_BF16 && !force_simt() && csi_attn_mma_ok(L, d, H))
-        return csi_attn_fwd_mma(qkv, ld3, o, ldo, lse, B, L, d, H, halo, stream);
-    return csi_attn_fwd_simt(qkv, ld3, o, ldo, dtype, lse, B, L, d, H, halo, stream);
+                            int H, int hp, int halo, void* stream) {
+    if (dtype == CSI_BF16 && !force_simt() && csi_attn_mma_ok(L, d, H, hp))
+        return csi_attn_fwd_mma(qkv, ld3, o, ldo, lse, B, L, d, H, hp, halo, stream);
+    return csi_attn_fwd_simt(qkv, ld3, o, ldo, dtype, lse, B, L, d, H, hp, halo, stream);
 }
 
 extern "C" int csi_attn_bwd(const void* qkv, int ld3, const void* o, int ldo, const void* dout, int lddo, void* dqkv,
-                            int lddqkv, int dtype, const float* lse, int B, int L, int d, int H, int halo, void* stream) {
-    if (dtype == CSI_BF16 && !force_simt() && csi_attn_mma_ok(L, d, H))
-        return csi_attn_bwd_mma(qkv, ld3, o, ldo, dout, lddo, dqkv, lddqkv, lse, B, L, d, H, halo, stream);
-    return csi_attn_bwd_simt(qkv, ld3, o, ldo, dout, lddo, dqkv, lddqkv, dtype, lse, B, L, d, H, halo, stream);
+                            int lddqkv, int dtype, const float* lse, int B, int L, int d, int H, int hp, int halo, void* stream) {
+    if (dtype == CSI_BF16 && !force_simt() && csi_attn_mma_ok(L, d, H, hp))
+        return csi_attn_bwd_mma(qkv, ld3, o, ldo, dout, lddo, dqkv, lddqkv, lse, B, L, d, H, hp, halo, stream);
+    return csi_attn_bwd_simt(qkv, ld3, o, ldo, dout, lddo, dqkv, lddqkv, dtype, lse, B, L, d, H, hp, halo, stream);
 }

@@ -12,7 +12,7 @@ void csi_set_error(const char* fmt, ...) {
     va_list ap; va_start(ap, fmt); vsnprintf(g_err, sizeof(g_err), fmt, ap); va_end(ap);
 }
 extern "C" const char* csi_last_error(void) { return g_err; }
-extern "C" int csi_abi_version(void) { return 1; }
+extern "C" int csi_abi_version(void) { return 2; }
 extern "C" int csi_device_arch(int device) {
     cudaDeviceProp p;
     CSI_CUDA(cudaGetDeviceProperties(&p, device));
@@ -488,7 +488,7 @@ extern "C" int csi_layernorm_bwd(const void* dy, int lddy, int dy_dtype, const f
 template <typename T, bool SQ>
 __global__ void __launch_bounds__(CR_THREADS) colreduce_kernel(const T* __restrict__ A, int lda, int B, int L, int halo,
                                                                int ncols, int CH, int RL, float* __restrict__ out_f,
-                                                               double* __restrict__ out_d) {
+                                                               double* __restrict__ out_d, csi_grp grp) {
     extern __shared__ float red[];                      // [RL][CH*8] (x2 when SQ)
     const int ch = threadIdx.x % CH, rl = threadIdx.x / CH;
     const int Lp = L + 2 * halo, total = B * L;
@@ -516,29 +516,29 @@ __global__ void __launch_bounds__(CR_THREADS) colreduce_kernel(const T* __restri
         float s = 0.f, s2 = 0.f;
         for (int i = 0; i < RL; ++i) { s += red[i * CH * 8 + c]; if (SQ) s2 += red[(RL + i) * CH * 8 + c]; }
         if (SQ) { atomicAdd(out_d + c, (double)s); atomicAdd(out_d + ncols + c, (double)s2); }
-        else atomicAdd(out_f + c, s);
+        else { const int cc = grp_to_compact(c, grp); if (cc >= 0) atomicAdd(out_f + cc, s); }
     }
 }
 
 template <bool SQ>
 static int colreduce_launch(const void* A, int lda, int dtype, int B, int L, int halo, int ncols, float* out_f, double* out_d,
-                            cudaStream_t s) {
+                            csi_grp grp, cudaStream_t s) {
     const int CH = (ncols + 7) / 8;
     if (CH > CR_THREADS) { csi_set_error("colreduce: more than 2048 columns"); return CSI_ERR_ARG; }
     const int RL = CR_THREADS / CH;
     const size_t smem = (size_t)RL * CH * 8 * sizeof(float) * (SQ ? 2 : 1);
     const int grid = cdiv(B * L, CR_ROWS);
-    if (dtype == CSI_BF16) colreduce_kernel<bf16, SQ><<<grid, CR_THREADS, smem, s>>>((const bf16*)A, lda, B, L, halo, ncols, CH, RL, out_f, out_d);
-    else colreduce_kernel<float, SQ><<<grid, CR_THREADS, smem, s>>>((const float*)A, lda, B, L, halo, ncols, CH, RL, out_f, out_d);
+    if (dtype == CSI_BF16) colreduce_kernel<bf16, SQ><<<grid, CR_THREADS, smem, s>>>((const bf16*)A, lda, B, L, halo, ncols, CH, RL, out_f, out_d, grp);
+    else colreduce_kernel<float, SQ><<<grid, CR_THREADS, smem, s>>>((const float*)A, lda, B, L, halo, ncols, CH, RL, out_f, out_d, grp);
     return CSI_OK;
 }
 
-extern "C" int csi_colsum_tokens(const void* A, int lda, int dtype, int B, int L, int halo, int ncols, float* out,
+extern "C" int csi_colsum_tokens(const void* A, int lda, int dtype, int B, int L, int halo, int ncols, csi_grp grp, float* out,
                                  void* stream) {
     CSI_CHECK_ARG(A && out, "null pointer");
     CSI_CHECK_ARG(lda % 8 == 0 && ((ncols + 7) & ~7) <= lda, "lda must be a multiple of 8 covering ncols rounded up to 8");
     if (B * L == 0 || ncols == 0) return CSI_OK;
-    int rc = colreduce_launch<false>(A, lda, dtype, B, L, halo, ncols, out, nullptr, ST(stream));
+    int rc = colreduce_launch<false>(A, lda, dtype, B, L, halo, ncols, out, nullptr, grp, ST(stream));
     if (rc) return rc;
     CSI_LAUNCH_CHECK();
     return CSI_OK;
@@ -549,7 +549,7 @@ extern "C" int csi_bn_stats(const void* z, int ldz, int dtype, int B, int L, int
     CSI_CHECK_ARG(z && sums, "null pointer");
     CSI_CHECK_ARG(ldz % 8 == 0 && ((ncols + 7) & ~7) <= ldz, "ldz must be a multiple of 8 covering ncols");
     if (B * L == 0) return CSI_OK;
-    int rc = colreduce_launch<true>(z, ldz, dtype, B, L, halo, ncols, nullptr, sums, ST(stream));
+    int rc = colreduce_launch<true>(z, ldz, dtype, B, L, halo, ncols, nullptr, sums, csi_grp{0, 0}, ST(stream));
     if (rc) return rc;
     CSI_LAUNCH_CHECK();
     return CSI_OK;
@@ -1054,8 +1054,9 @@ __global__ void pack_kernel(const float* __restrict__ params, T* __restrict__ pa
     for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < total; i += gridDim.x * blockDim.x) {
         const int j = i % e.k, c = (i / e.k) % e.C, n = i / (e.k * e.C);
         const float v = params[e.src_off + i];
-        const long long dst = e.mode == 0 ? (long long)n * e.ld + (long long)j * e.P + c
-                                          : (long long)c * e.ld + (long long)(e.seg_base + j) * e.P + n;
+        const int np = grp_to_padded(n, e.gn), cp = grp_to_padded(c, e.gc);
+        const long long dst = e.mode == 0 ? (long long)np * e.ld + (long long)j * e.P + cp
+                                          : (long long)cp * e.ld + (long long)(e.seg_base + j) * e.P + np;
         stf<T>(packed + e.dst_off + dst, v);
     }
 }

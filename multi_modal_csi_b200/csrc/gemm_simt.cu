@@ -129,7 +129,7 @@ extern "C" int csi_gemm_nt_simt(const void* A, int lda, const void* Bw, int ldb,
 template <typename TA>
 __global__ void __launch_bounds__(256) gemm_tn_kernel(const TA* __restrict__ A, int lda, const TA* __restrict__ Bv,
                                                       int ldb, float* __restrict__ C, int ldc, int cs, int M, int Na,
-                                                      SegListTN segs, int qtiles_per_seg) {
+                                                      SegListTN segs, int qtiles_per_seg, csi_grp ig, csi_grp qg) {
     __shared__ float As[TN_BK][TN_BI + 4];
     __shared__ float Bs[TN_BK][TN_BQ + 4];
     const int tid = threadIdx.x, tx = tid & 15, ty = tid >> 4;
@@ -172,17 +172,22 @@ __global__ void __launch_bounds__(256) gemm_tn_kernel(const TA* __restrict__ A, 
     for (int i = 0; i < 4; ++i) {
         const int ii = i0 + ty * 4 + i;
         if (ii >= Na) continue;
+        const int ic = grp_to_compact(ii, ig);
+        if (ic < 0) continue;
 #pragma unroll
         for (int j = 0; j < 4; ++j) {
             const int q = q0 + tx * 4 + j;
             if (q >= sg.nlen) continue;
-            atomicAdd(C + (long long)ii * ldc + sg.c_off + (long long)q * cs, acc[i][j]);
+            const int qc = grp_to_compact(q, qg);
+            if (qc < 0) continue;
+            atomicAdd(C + (long long)ic * ldc + sg.c_off + (long long)qc * cs, acc[i][j]);
         }
     }
 }
 
 extern "C" int csi_gemm_tn_simt(const void* A, int lda, const void* Bv, int ldb, int ab_dtype, float* C, int ldc,
-                                int c_col_stride, int M, int Na, const csi_seg_tn* segs, int nseg, void* stream) {
+                                int c_col_stride, int M, int Na, const csi_seg_tn* segs, int nseg, csi_grp ig, csi_grp qg,
+                                void* stream) {
     CSI_CHECK_ARG(A && Bv && C && segs, "null pointer");
     CSI_CHECK_ARG(nseg >= 1 && nseg <= CSI_MAX_SEGS, "1..32 segments");
     if (M == 0 || Na == 0) return CSI_OK;
@@ -193,9 +198,9 @@ extern "C" int csi_gemm_tn_simt(const void* A, int lda, const void* Bv, int ldb,
     const int qt = cdiv(maxn, TN_BQ);
     dim3 grid(cdiv(Na, TN_BI), qt * nseg, cdiv(M, TN_CHUNK));
     if (ab_dtype == CSI_BF16)
-        gemm_tn_kernel<bf16><<<grid, 256, 0, ST(stream)>>>((const bf16*)A, lda, (const bf16*)Bv, ldb, C, ldc, c_col_stride, M, Na, sl, qt);
+        gemm_tn_kernel<bf16><<<grid, 256, 0, ST(stream)>>>((const bf16*)A, lda, (const bf16*)Bv, ldb, C, ldc, c_col_stride, M, Na, sl, qt, ig, qg);
     else
-        gemm_tn_kernel<float><<<grid, 256, 0, ST(stream)>>>((const float*)A, lda, (const float*)Bv, ldb, C, ldc, c_col_stride, M, Na, sl, qt);
+        gemm_tn_kernel<float><<<grid, 256, 0, ST(stream)>>>((const float*)A, lda, (const float*)Bv, ldb, C, ldc, c_col_stride, M, Na, sl, qt, ig, qg);
     CSI_LAUNCH_CHECK();
     return CSI_OK;
 }

@@ -235,6 +235,7 @@ struct TnParams {
     float* C; int ldc; int cs; int M, Na, BN, chunk, qtiles;
     int row_base;
     uint32_t tmem_cols;
+    csi_grp ig, qg;
 };
 
 __global__ void __launch_bounds__(TC_THREADS) gemm_tn_tc_kernel(const __grid_constant__ CUtensorMap tmA,
@@ -311,16 +312,20 @@ __global__ void __launch_bounds__(TC_THREADS) gemm_tn_tc_kernel(const __grid_con
         const int i = i0 + q * 32 + lane;
         mbar_wait(&tmem_full_bar, 0);
         tc_fence_after();
-        float* crow = p.C + (size_t)i * p.ldc + sg.c_off;
+        const int ic = i < p.Na ? grp_to_compact(i, p.ig) : -1;
+        float* crow = p.C + (size_t)(ic < 0 ? 0 : ic) * p.ldc + sg.c_off;
         for (int c0 = 0; c0 < p.BN; c0 += 16) {
             uint32_t r[16];
             tmem_ld16(tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)c0, r);
             tmem_ld_wait();
-            if (i < p.Na) {
+            if (ic >= 0) {
 #pragma unroll
                 for (int j = 0; j < 16; ++j) {
                     const int qq = q0 + c0 + j;
-                    if (qq < sg.nlen) atomicAdd(crow + (size_t)qq * p.cs, __uint_as_float(r[j]));
+                    if (qq < sg.nlen) {
+                        const int qc = grp_to_compact(qq, p.qg);
+                        if (qc >= 0) atomicAdd(crow + (size_t)qc * p.cs, __uint_as_float(r[j]));
+                    }
                 }
             }
         }
@@ -342,7 +347,7 @@ extern "C" int csi_gemm_tn_tc_ok(int lda, int ldb, int M, int Na, const csi_seg_
 }
 
 extern "C" int csi_gemm_tn_tc(const void* A, int lda, const void* Bv, int ldb, float* C, int ldc, int c_col_stride, int M,
-                              int Na, const csi_seg_tn* segs, int nseg, void* stream) {
+                              int Na, const csi_seg_tn* segs, int nseg, csi_grp ig, csi_grp qg, void* stream) {
     CSI_CHECK_ARG(A && Bv && C && segs, "null pointer");
     CSI_CHECK_ARG(csi_gemm_tn_tc_ok(lda, ldb, M, Na, segs, nseg), "shape not eligible for the tcgen05 kernel");
     SegListTN sl;
@@ -379,6 +384,7 @@ extern "C" int csi_gemm_tn_tc(const void* A, int lda, const void* Bv, int ldb, f
     TnParams p;
     p.C = C; p.ldc = ldc; p.cs = c_col_stride; p.M = M; p.Na = Na; p.BN = BN; p.chunk = chunk; p.qtiles = qtiles;
     p.row_base = -min_shift;
+    p.ig = ig; p.qg = qg;
     uint32_t cols = 32;
     while ((int)cols < BN) cols <<= 1;
     p.tmem_cols = cols;

@@ -55,6 +55,8 @@ class THATEngine:
         self.pack = LY.build_pack_plan(geom, arena)
         self.packed = torch.zeros(self.pack.size, dtype=act_dtype, device=self.dev)
         self.pack_table = ops.make_pack_table(self.pack.entries, self.dev)
+        self.packed_bias = torch.zeros(max(self.pack.bias_size, 1), dtype=torch.float32, device=self.dev)
+        self.bias_table = ops.make_pack_table(self.pack.bias_entries, self.dev)
         self.rng = torch.tensor([seed, 0], dtype=torch.int64, device=self.dev)      # {seed, step}
         self.opt_step = torch.ones(1, dtype=torch.int64, device=self.dev)           # 1-based Adam step
         self._alloc()
@@ -77,6 +79,11 @@ class THATEngine:
         m = self.pack.mats[key]
         return self.packed[m.off:m.off + m.rows * m.ld].view(m.rows, m.ld)
 
+    def PB(self, name):
+        """Head-padded fp32 copy of a bias vector."""
+        m = self.pack.bias_mats[name]
+        return self.packed_bias[m.off:m.off + m.rows]
+
     # ------------------------------------------------------------------ buffers
     def _alloc(self):
         dev, B, adt, f32 = self.dev, self.B, self.adt, torch.float32
@@ -88,7 +95,7 @@ class THATEngine:
                 st["enc"].append({
                     "t0": _TokBuf(rows, Dp, adt, dev), "mean0": torch.zeros(rows, device=dev),
                     "rstd0": torch.zeros(rows, device=dev),
-                    "qkv": _TokBuf(rows, sg.ld3, adt, dev), "o": _TokBuf(rows, Dp, adt, dev),
+                    "qkv": _TokBuf(rows, sg.ld3, adt, dev), "o": _TokBuf(rows, sg.dh, adt, dev),
                     "lse": torch.zeros(B * sg.H * sg.L, device=dev),
                     "t": _TokBuf(rows, Dp, f32, dev),
                     "s": _TokBuf(rows, Dp, adt, dev), "mean1": torch.zeros(rows, device=dev),
@@ -108,7 +115,7 @@ class THATEngine:
             st["ds"] = _TokBuf(rows, Dp, adt, dev)
             st["dt"] = _TokBuf(rows, Dp, f32, dev)
             st["dtm"] = _TokBuf(rows, Dp, adt, dev)
-            st["do"] = _TokBuf(rows, Dp, adt, dev)
+            st["do"] = _TokBuf(rows, sg.dh, adt, dev)
             st["dqkv"] = _TokBuf(rows, sg.ld3, adt, dev)
             st["dt0"] = _TokBuf(rows, Dp, adt, dev)
             st["dp"] = _TokBuf(rows, 2 * sg.head_np, adt, dev)
@@ -152,6 +159,8 @@ class THATEngine:
         """fp32 master weights -> GEMM operand copies (forward + data-gradient layouts) in the act dtype."""
         self.ops.pack_weights(self.params, self.packed, self.pack_table, len(self.pack.entries),
                               self.pack.max_elems)
+        self.ops.pack_weights(self.params, self.packed_bias, self.bias_table, len(self.pack.bias_entries),
+                              max(3 * sg.d for sg in self.g.streams))
         self.weights_dirty = False
 
     def _bn3(self, sg: StreamGeom, e: int, leaf: str, grad=False, buf=False):
@@ -198,10 +207,10 @@ class THATEngine:
                 ops.layernorm_fwd(x_in.t, self.P(p + "layer_norm_0.weight"), self.P(p + "layer_norm_0.bias"),
                                   a["t0"].t, a["mean0"], a["rstd0"], B, L, d, HALO, LN_EPS)
                 ops.gemm_nt(a["t0"].t, self.W("f:" + p + "layer_attention.in_proj_weight"), a["qkv"].t, rows,
-                            3 * d, one, self.P(p + "layer_attention.in_proj_bias"), None, 0.0, 0, self.rng)
-                ops.attn_fwd(a["qkv"].t, a["o"].t, a["lse"], B, L, d, sg.H, HALO)
+                            sg.ld3, one, self.PB(p + "layer_attention.in_proj_bias"), None, 0.0, 0, self.rng)
+                ops.attn_fwd(a["qkv"].t, a["o"].t, a["lse"], B, L, d, sg.H, sg.hp, HALO)
                 ops.gemm_nt(a["o"].t, self.W("f:" + p + "layer_attention.out_proj.weight"), a["t"].t, rows, d,
-                            one, self.P(p + "layer_attention.out_proj.bias"), x_in.t, pd,
+                            [(0, 0, 0, sg.dh)], self.P(p + "layer_attention.out_proj.bias"), x_in.t, pd,
                             site(si, e, LY.SITE_ATTN), self.rng)
                 ops.layernorm_fwd(a["t"].t, self.P(p + "layer_norm_1.weight"), self.P(p + "layer_norm_1.bias"),
                                   a["s"].t, a["mean1"], a["rstd1"], B, L, d, HALO, LN_EPS)
@@ -327,14 +336,15 @@ class THATEngine:
                                   self.G(p + "layer_norm_1.weight"), self.G(p + "layer_norm_1.bias"), B, L, d, HALO)
                 one = [(0, 0, 0, d)]
                 w = p + "layer_attention.out_proj."
-                ops.gemm_tn(st["dtm"].t, a["o"].t, self.G(w + "weight"), d, 1, rows, d, one)
+                ops.gemm_tn(st["dtm"].t, a["o"].t, self.G(w + "weight"), d, 1, rows, d, [(0, 0, 0, sg.dh)],
+                            (0, 0), sg.grp)
                 ops.colsum_tokens(st["dtm"].t, B, L, HALO, d, self.G(w + "bias"))
-                ops.gemm_nt(st["dtm"].t, self.W("b:" + w + "weight"), st["do"].t, rows, d, [(0, 0, 0, Dp)], None,
+                ops.gemm_nt(st["dtm"].t, self.W("b:" + w + "weight"), st["do"].t, rows, sg.dh, [(0, 0, 0, Dp)], None,
                             None, 0.0, 0, self.rng)
-                ops.attn_bwd(a["qkv"].t, a["o"].t, st["do"].t, st["dqkv"].t, a["lse"], B, L, d, sg.H, HALO)
+                ops.attn_bwd(a["qkv"].t, a["o"].t, st["do"].t, st["dqkv"].t, a["lse"], B, L, d, sg.H, sg.hp, HALO)
                 w = p + "layer_attention.in_proj_"
-                ops.gemm_tn(st["dqkv"].t, a["t0"].t, self.G(w + "weight"), d, 1, rows, 3 * d, one)
-                ops.colsum_tokens(st["dqkv"].t, B, L, HALO, 3 * d, self.G(w + "bias"))
+                ops.gemm_tn(st["dqkv"].t, a["t0"].t, self.G(w + "weight"), d, 1, rows, sg.ld3, one, sg.grp, (0, 0))
+                ops.colsum_tokens(st["dqkv"].t, B, L, HALO, sg.ld3, self.G(w + "bias"), sg.grp)
                 ops.gemm_nt(st["dqkv"].t, self.W("b:" + w + "weight"), st["dt0"].t, rows, d, [(0, 0, 0, sg.ld3)],
                             None, None, 0.0, 0, self.rng)
                 ops.layernorm_bwd(st["dt0"].t, x_in.t, self.P(p + "layer_norm_0.weight"), a["mean0"], a["rstd0"],

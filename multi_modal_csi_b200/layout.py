@@ -49,12 +49,29 @@ class StreamGeom:
         return self.L + 2 * HALO
 
     @property
-    def ld3(self) -> int:
-        return ru(3 * self.d, 16)
-
-    @property
     def hd(self) -> int:
         return self.d // self.H
+
+    @property
+    def hp(self) -> int:
+        """Head pitch: heads are stored zero-padded to 16/32/64 channels so every head row is 16-byte aligned."""
+        hd = self.hd
+        return 16 if hd <= 16 else 32 if hd <= 32 else 64 if hd <= 64 else ru(hd, 16)
+
+    @property
+    def dh(self) -> int:
+        """Width of a head-padded [*, d] activation (attention output and its gradient)."""
+        return self.H * self.hp
+
+    @property
+    def ld3(self) -> int:
+        """Width of the head-padded q | k | v buffer."""
+        return 3 * self.H * self.hp
+
+    @property
+    def grp(self):
+        """(valid, pad) of the head padding, the csi_grp of include/csi_that.h."""
+        return (self.hd, self.hp)
 
     @property
     def head_np(self) -> int:
@@ -189,7 +206,10 @@ class PackedMat:
 @dataclass
 class PackPlan:
     mats: Dict[str, PackedMat]
-    entries: List[Tuple[int, int, int, int, int, int, int, int, int]]   # csi_pack_entry fields
+    entries: List[tuple]           # csi_pack_entry fields (src, dst, N, C, k, ld, mode, P, seg_base, gn, gc)
+    bias_entries: List[tuple]      # same, destination = the fp32 packed-bias arena
+    bias_mats: Dict[str, PackedMat]
+    bias_size: int
     size: int
     max_elems: int
 
@@ -211,21 +231,30 @@ def build_pack_plan(g: ModelGeom, arena: Arena) -> PackPlan:
         off += ru(rows * ld, 64)
         return mats[name]
 
-    def add(name, N, C, k, dst: PackedMat, mode, P, seg_base):
+    NOG = (0, 0)
+
+    def add(name, N, C, k, dst: PackedMat, mode, P, seg_base, gn=NOG, gc=NOG):
         nonlocal max_elems
-        entries.append((arena.offsets[name], dst.off, N, C, k, dst.ld, mode, P, seg_base))
+        entries.append((arena.offsets[name], dst.off, N, C, k, dst.ld, mode, P, seg_base, gn, gc))
         max_elems = max(max_elems, N * C * k)
+
+    bias_entries, bias_mats, boff = [], {}, 0
 
     for s in g.streams:
         d, Dp = s.d, s.Dp
         for e in range(s.n_enc):
             p = s.prefix(e)
+            # attention projections use the head-padded feature order (q|k|v and the attention output)
             w = p + "layer_attention.in_proj_weight"
-            add(w, 3 * d, d, 1, alloc("f:" + w, 3 * d, Dp), 0, Dp, 0)
-            add(w, 3 * d, d, 1, alloc("b:" + w, d, s.ld3), 1, s.ld3, 0)
+            add(w, 3 * d, d, 1, alloc("f:" + w, s.ld3, Dp), 0, Dp, 0, gn=s.grp)
+            add(w, 3 * d, d, 1, alloc("b:" + w, d, s.ld3), 1, s.ld3, 0, gn=s.grp)
+            bname = p + "layer_attention.in_proj_bias"
+            bias_mats[bname] = PackedMat(boff, s.ld3, 1)
+            bias_entries.append((arena.offsets[bname], boff, 3 * d, 1, 1, 1, 0, 1, 0, s.grp, NOG))
+            boff += ru(s.ld3, 64)
             w = p + "layer_attention.out_proj.weight"
-            add(w, d, d, 1, alloc("f:" + w, d, Dp), 0, Dp, 0)
-            add(w, d, d, 1, alloc("b:" + w, d, Dp), 1, Dp, 0)
+            add(w, d, d, 1, alloc("f:" + w, d, s.dh), 0, s.dh, 0, gc=s.grp)
+            add(w, d, d, 1, alloc("b:" + w, s.dh, Dp), 1, Dp, 0, gc=s.grp)
             bmat = alloc("b:" + p + "layer_cnn", d, s.nseg_conv * Dp)
             seg = 0
             for j, k in enumerate(s.kernels):
@@ -244,7 +273,8 @@ def build_pack_plan(g: ModelGeom, arena: Arena) -> PackPlan:
     w = "layer_output.weight"
     add(w, g.out, FEAT, 1, alloc("f:" + w, g.out, FEAT), 0, FEAT, 0)
     add(w, g.out, FEAT, 1, alloc("b:" + w, FEAT, g.ld_out), 1, g.ld_out, 0)
-    return PackPlan(mats, entries, off, max_elems)
+    return PackPlan(mats=mats, entries=entries, size=off, max_elems=max_elems, bias_entries=bias_entries,
+                    bias_mats=bias_mats, bias_size=boff)
 
 
 # dropout site ids (unique per mask): stream*1000 + encoder*16 + kind

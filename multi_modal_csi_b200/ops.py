@@ -13,7 +13,7 @@ import torch
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.path.join(_HERE, "libcsi_that.so")
-ABI_VERSION = 1
+ABI_VERSION = 2
 
 
 class Seg(C.Structure):
@@ -28,10 +28,18 @@ class Ptr3(C.Structure):
     _fields_ = [("p", C.c_void_p * 3)]
 
 
+class Grp(C.Structure):
+    """csi_grp: head padding (valid, pad); (0, 0) = none."""
+    _fields_ = [("valid", C.c_int), ("pad", C.c_int)]
+
+
+NO_GRP = (0, 0)
+
+
 class PackEntry(C.Structure):
     _fields_ = [("src_off", C.c_longlong), ("dst_off", C.c_longlong), ("N", C.c_int), ("C", C.c_int),
                 ("k", C.c_int), ("ld", C.c_int), ("mode", C.c_int), ("P", C.c_int), ("seg_base", C.c_int),
-                ("reserved", C.c_int)]
+                ("gn", Grp), ("gc", Grp), ("reserved", C.c_int)]
 
 
 _lib = None
@@ -150,7 +158,7 @@ class NativeOps:
     def make_pack_table(self, entries, device):
         arr = (PackEntry * len(entries))()
         for i, e in enumerate(entries):
-            arr[i] = PackEntry(*e, 0)
+            arr[i] = PackEntry(*e[:9], Grp(*e[9]), Grp(*e[10]), 0)
         raw = bytes(arr)
         t = torch.frombuffer(bytearray(raw), dtype=torch.uint8).clone().to(device)
         return t
@@ -237,24 +245,24 @@ class NativeOps:
                                       len(segs), _p(bias), _p(residual), _ld(residual), C.c_float(drop_p),
                                       C.c_uint(drop_site), _p(rng), **wk)
 
-    def gemm_tn(self, A, Bv, Cm, ldc, c_col_stride, M, Na, segs):
+    def gemm_tn(self, A, Bv, Cm, ldc, c_col_stride, M, Na, segs, i_grp=NO_GRP, q_grp=NO_GRP):
         wk = self._work("gemm_tn", locals())
         arr = (SegTN * len(segs))(*[SegTN(*s) for s in segs])
         self._call("csi_gemm_tn", _p(A), _ld(A), _p(Bv), _ld(Bv), _dt(A), _p(Cm), ldc, c_col_stride, M, Na, arr,
-                                      len(segs), **wk)
+                   len(segs), Grp(*i_grp), Grp(*q_grp), **wk)
 
-    def colsum_tokens(self, A, B, L, halo, ncols, out):
+    def colsum_tokens(self, A, B, L, halo, ncols, out, grp=NO_GRP):
         wk = self._work("colsum_tokens", locals())
-        self._call("csi_colsum_tokens", _p(A), _ld(A), _dt(A), B, L, halo, ncols, _p(out), **wk)
+        self._call("csi_colsum_tokens", _p(A), _ld(A), _dt(A), B, L, halo, ncols, Grp(*grp), _p(out), **wk)
 
-    def attn_fwd(self, qkv, o, lse, B, L, d, H, halo):
+    def attn_fwd(self, qkv, o, lse, B, L, d, H, hp, halo):
         wk = self._work("attn_fwd", locals())
-        self._call("csi_attn_fwd", _p(qkv), _ld(qkv), _p(o), _ld(o), _dt(qkv), _p(lse), B, L, d, H, halo, **wk)
+        self._call("csi_attn_fwd", _p(qkv), _ld(qkv), _p(o), _ld(o), _dt(qkv), _p(lse), B, L, d, H, hp, halo, **wk)
 
-    def attn_bwd(self, qkv, o, dout, dqkv, lse, B, L, d, H, halo):
+    def attn_bwd(self, qkv, o, dout, dqkv, lse, B, L, d, H, hp, halo):
         wk = self._work("attn_bwd", locals())
         self._call("csi_attn_bwd", _p(qkv), _ld(qkv), _p(o), _ld(o), _p(dout), _ld(dout), _p(dqkv), _ld(dqkv),
-                                       _dt(qkv), _p(lse), B, L, d, H, halo, **wk)
+                                       _dt(qkv), _p(lse), B, L, d, H, hp, halo, **wk)
 
     def bn_stats(self, z, B, L, halo, ncols, sums):
         wk = self._work("bn_stats", locals())

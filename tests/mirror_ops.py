@@ -34,17 +34,24 @@ class MirrorOps:
         return list(entries)
 
     # ------------------------------------------------------------------ pack
+    @staticmethod
+    def _padded_index(n, grp, device):
+        """compact index -> head-padded index (csi_grp)."""
+        idx = torch.arange(n, device=device)
+        valid, pad = grp
+        return idx if not pad else (idx // valid) * pad + idx % valid
+
     def pack_weights(self, params, packed, table, n_entries, max_elems):
-        for (src, dst, N, C, k, ld, mode, P, seg_base) in table:
+        for (src, dst, N, C, k, ld, mode, P, seg_base, gn, gc) in table:
             w = params[src:src + N * C * k].view(N, C, k)
-            if mode == 0:
-                m = packed[dst:dst + N * ld].view(N, ld)
-                for j in range(k):
-                    m[:, j * P:j * P + C] = w[:, :, j].to(packed.dtype)
-            else:
-                m = packed[dst:dst + C * ld].view(C, ld)
-                for j in range(k):
-                    m[:, (seg_base + j) * P:(seg_base + j) * P + N] = w[:, :, j].t().to(packed.dtype)
+            ni, ci = self._padded_index(N, gn, params.device), self._padded_index(C, gc, params.device)
+            rows = (int(ni.max()) if mode == 0 else int(ci.max())) + 1
+            m = packed[dst:dst + rows * ld].view(rows, ld)
+            for j in range(k):
+                if mode == 0:
+                    m[ni[:, None], (j * P + ci)[None, :]] = w[:, :, j].to(packed.dtype)
+                else:
+                    m[ci[:, None], ((seg_base + j) * P + ni)[None, :]] = w[:, :, j].t().to(packed.dtype)
 
     # ------------------------------------------------------------------ input stage
     def pool_dual(self, x, offs, lens, B, T, F, pe, left, right, halo, augment, rng):
@@ -132,45 +139,64 @@ class MirrorOps:
             acc += residual[:M, :N]
         C[:M, :N] = acc.to(C.dtype)
 
-    def gemm_tn(self, A, Bv, C, ldc, c_col_stride, M, Na, segs):
-        a = A[:M, :Na].float()
+    @staticmethod
+    def _compact_cols(n, grp, device):
+        """indices of the non-padding entries among n head-padded entries."""
+        idx = torch.arange(n, device=device)
+        valid, pad = grp
+        return idx if not pad else idx[idx % pad < valid]
+
+    def gemm_tn(self, A, Bv, C, ldc, c_col_stride, M, Na, segs, i_grp=(0, 0), q_grp=(0, 0)):
+        isel = self._compact_cols(Na, i_grp, A.device)
+        a = A[:M, :Na].float()[:, isel]
         for (shift, boff, coff, nlen) in segs:
-            b = _rows_view(Bv, shift, M)[:, boff:boff + nlen].float()
-            r = a.t() @ b                                               # [Na, nlen]
-            cv = C.as_strided((Na, nlen), (ldc, c_col_stride), C.storage_offset() + coff)
+            qsel = self._compact_cols(nlen, q_grp, A.device)
+            b = _rows_view(Bv, shift, M)[:, boff:boff + nlen].float()[:, qsel]
+            r = a.t() @ b                                               # [Na_compact, nlen_compact]
+            cv = C.as_strided((len(isel), len(qsel)), (ldc, c_col_stride), C.storage_offset() + coff)
             cv.add_(r)
 
-    def colsum_tokens(self, A, B, L, halo, ncols, out):
+    def colsum_tokens(self, A, B, L, halo, ncols, out, grp=(0, 0)):
         rows = B * (L + 2 * halo)
         v = _valid_rows(B, L, halo, A.device)[:, None]
         a = A[:rows, :ncols].float()
-        out[:ncols].add_(torch.where(v, a, torch.zeros_like(a)).sum(0))
+        sel = self._compact_cols(ncols, grp, A.device)
+        out[:len(sel)].add_(torch.where(v, a, torch.zeros_like(a)).sum(0)[sel])
 
     # ------------------------------------------------------------------ attention
-    def _split(self, qkv, B, L, d, H, halo):
+    @staticmethod
+    def _heads(buf, B, L, H, hd, hp, halo, which=0):
+        """[B,H,L,hd] view (copy) of head-padded columns [which*H*hp + h*hp, +hd) of a token buffer."""
         Lp = L + 2 * halo
-        hd = d // H
-        t = qkv[:B * Lp].view(B, Lp, -1)[:, halo:halo + L].float()
-        q, k, v = t[..., :d], t[..., d:2 * d], t[..., 2 * d:3 * d]
-        f = lambda u: u.reshape(B, L, H, hd).permute(0, 2, 1, 3)
-        return f(q), f(k), f(v)
+        t = buf[:B * Lp].view(B, Lp, -1)[:, halo:halo + L, which * H * hp:(which + 1) * H * hp].float()
+        return t.reshape(B, L, H, hp)[..., :hd].permute(0, 2, 1, 3)
 
-    def attn_fwd(self, qkv, o, lse, B, L, d, H, halo):
-        Lp, hd = L + 2 * halo, d // H
-        q, k, v = self._split(qkv, B, L, d, H, halo)
+    @staticmethod
+    def _put_heads(buf, val, B, L, H, hd, hp, halo, which=0):
+        Lp = L + 2 * halo
+        dst = buf[:B * Lp].view(B, Lp, -1)[:, halo:halo + L, which * H * hp:(which + 1) * H * hp]
+        full = torch.zeros(B, L, H, hp, dtype=torch.float32, device=buf.device)
+        full[..., :hd] = val.permute(0, 2, 1, 3)
+        dst.copy_(full.reshape(B, L, H * hp).to(buf.dtype))
+
+    def _split(self, qkv, B, L, d, H, hp, halo):
+        hd = d // H
+        return tuple(self._heads(qkv, B, L, H, hd, hp, halo, w) for w in range(3))
+
+    def attn_fwd(self, qkv, o, lse, B, L, d, H, hp, halo):
+        hd = d // H
+        q, k, v = self._split(qkv, B, L, d, H, hp, halo)
         s = (q @ k.transpose(-1, -2)) * (1.0 / math.sqrt(hd))
         l = torch.logsumexp(s, dim=-1)
         p = torch.exp(s - l[..., None])
-        oo = (p @ v).permute(0, 2, 1, 3).reshape(B, L, d)
-        o[:B * Lp].view(B, Lp, -1)[:, halo:halo + L, :d] = oo.to(o.dtype)
+        self._put_heads(o, p @ v, B, L, H, hd, hp, halo)
         lse[:B * H * L] = l.reshape(-1)
 
-    def attn_bwd(self, qkv, o, dout, dqkv, lse, B, L, d, H, halo):
-        Lp, hd = L + 2 * halo, d // H
+    def attn_bwd(self, qkv, o, dout, dqkv, lse, B, L, d, H, hp, halo):
+        hd = d // H
         sc = 1.0 / math.sqrt(hd)
-        q, k, v = self._split(qkv, B, L, d, H, halo)
-        f = lambda u: u[:B * Lp].view(B, Lp, -1)[:, halo:halo + L, :d].float().reshape(B, L, H, hd).permute(0, 2, 1, 3)
-        oo, do = f(o), f(dout)
+        q, k, v = self._split(qkv, B, L, d, H, hp, halo)
+        oo, do = self._heads(o, B, L, H, hd, hp, halo), self._heads(dout, B, L, H, hd, hp, halo)
         l = lse[:B * H * L].view(B, H, L)
         p = torch.exp((q @ k.transpose(-1, -2)) * sc - l[..., None])
         dv = p.transpose(-1, -2) @ do
@@ -179,11 +205,8 @@ class MirrorOps:
         ds = p * (dp - D) * sc
         dq = ds @ k
         dk = ds.transpose(-1, -2) @ q
-        g = lambda u: u.permute(0, 2, 1, 3).reshape(B, L, d)
-        dst = dqkv[:B * Lp].view(B, Lp, -1)
-        dst[:, halo:halo + L, :d] = g(dq).to(dqkv.dtype)
-        dst[:, halo:halo + L, d:2 * d] = g(dk).to(dqkv.dtype)
-        dst[:, halo:halo + L, 2 * d:3 * d] = g(dv).to(dqkv.dtype)
+        for w, val in enumerate((dq, dk, dv)):
+            self._put_heads(dqkv, val, B, L, H, hd, hp, halo, w)
 
     # ------------------------------------------------------------------ batchnorm + activation
     def bn_stats(self, z, B, L, halo, ncols, sums):

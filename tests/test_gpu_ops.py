@@ -263,6 +263,19 @@ def test_gemm_tn_weight_gradients(ops, mir, dt):
     gw2 = torch.zeros(N * d * k, device="cuda")
     ops.gemm_tn(dY2, X, gw2, d * k, k, rows, N, [(t, 0, t, d) for t in range(k)])
     assert relerr(gw2.view(N, d, k), w.grad) < (1e-5 if dt == torch.float32 else 1e-5)
+    # head-padded operands: rows / columns of padding are skipped and the result lands in the compact layout
+    H, hd, hp = 10, 27, 32
+    A2 = padded_heads(B, L, H, hd, hp, 1, dt, g)                     # [rows, 320]: 10 heads x (27 valid + 5 pad)
+    outs = []
+    for o in (ops, mir):
+        c1 = torch.zeros(H * hd * d, device="cuda")
+        o.gemm_tn(A2, X, c1, d, 1, rows, H * hp, [(0, 0, 0, d)], (hd, hp), (0, 0))          # rows compacted
+        c2 = torch.zeros(d * H * hd, device="cuda")
+        o.gemm_tn(X, A2, c2, H * hd, 1, rows, d, [(0, 0, 0, H * hp)], (0, 0), (hd, hp))     # columns compacted
+        outs.append((c1, c2))
+    assert relerr(outs[0][0], outs[1][0]) < 2e-5 and relerr(outs[0][1], outs[1][1]) < 2e-5
+    dense = valid(A2, B, L, H * hp).reshape(-1, H, hp)[..., :hd].reshape(-1, H * hd)
+    assert relerr(outs[0][0].view(H * hd, d), dense.t() @ valid(X, B, L, d).reshape(-1, d)) < 2e-5
 
 
 @pytest.mark.parametrize("dt", DT)
@@ -281,34 +294,55 @@ def test_colsum(ops, mir, dt):
     out = torch.zeros(13, device="cuda")
     ops.colsum_tokens(x, 37, 1, 0, 13, out)
     assert relerr(out, x[:, :13].sum(0)) < 1e-5
+    # head-padded columns are compacted: 4 heads of 3 valid + 1 padding column
+    out = torch.zeros(12, device="cuda")
+    ops.colsum_tokens(x, 37, 1, 0, 16, out, (3, 4))
+    assert relerr(out, x.view(37, 4, 4)[:, :, :3].reshape(37, 12).sum(0)) < 1e-5
 
 
 # ------------------------------------------------------------------------------------------------ attention
+def head_pitch(hd):
+    return 16 if hd <= 16 else 32 if hd <= 32 else 64
+
+
+def padded_heads(B, L, H, hd, hp, nw, dt, g):
+    """Token buffer [rows, nw*H*hp] with N(0,1) in the hd valid columns of every head and zeros in the padding."""
+    _, buf = tokbuf(B, L, nw * H * hp, dt)
+    v = torch.randn(B, L, nw * H, hp, device="cuda", generator=g)
+    v[..., hd:] = 0
+    buf.view(B, L + 2 * HALO, -1)[:, HALO:HALO + L] = v.reshape(B, L, nw * H * hp).to(dt)
+    return buf
+
+
 @pytest.mark.parametrize("dt", DT)
 @pytest.mark.parametrize("B,L,d", [(2, 20, 30), (2, 30, 20), (2, 150, 270), (2, 270, 150), (1, 150, 540), (1, 540, 150)])
 def test_attention(ops, mir, dt, B, L, d):
     H = 10
+    hd = d // H
+    hp = head_pitch(hd)
     g = gen(10)
-    ld3 = ru(3 * d, 16)
-    _, qkv = tokbuf(B, L, ld3, dt, fill=1.0, gen=g, ncols=3 * d)
-    _, do = tokbuf(B, L, ru(d, 16), dt, fill=1.0, gen=g, ncols=d)
+    qkv = padded_heads(B, L, H, hd, hp, 3, dt, g)
+    do = padded_heads(B, L, H, hd, hp, 1, dt, g)
     res = []
     for o in (ops, mir):
-        _, out = tokbuf(B, L, ru(d, 16), dt)
+        _, out = tokbuf(B, L, H * hp, dt)
         lse = torch.zeros(B * H * L, device="cuda")
-        o.attn_fwd(qkv, out, lse, B, L, d, H, HALO)
-        _, dqkv = tokbuf(B, L, ld3, dt)
-        o.attn_bwd(qkv, out, do, dqkv, lse, B, L, d, H, HALO)
+        o.attn_fwd(qkv, out, lse, B, L, d, H, hp, HALO)
+        _, dqkv = tokbuf(B, L, 3 * H * hp, dt)
+        o.attn_bwd(qkv, out, do, dqkv, lse, B, L, d, H, hp, HALO)
         res.append((out.float(), lse, dqkv.float()))
     tol = 2e-5 if dt == torch.float32 else 1.5e-2
     for i, (a, b) in enumerate(zip(*res)):
         assert relerr(a, b) < tol, i
+    # padding columns of the outputs are zero
+    assert float(valid(res[0][0], B, L, H * hp).reshape(B, L, H, hp)[..., hd:].abs().max()) == 0.0
+    assert float(valid(res[0][2], B, L, 3 * H * hp).reshape(B, L, 3 * H, hp)[..., hd:].abs().max()) == 0.0
     # against torch's scaled_dot_product_attention
-    t = valid(qkv, B, L, 3 * d)
-    hd = d // H
-    q, k, v = [u.reshape(B, L, H, hd).transpose(1, 2) for u in (t[..., :d], t[..., d:2 * d], t[..., 2 * d:])]
-    ref = torch.nn.functional.scaled_dot_product_attention(q, k, v).transpose(1, 2).reshape(B, L, d)
-    assert relerr(valid(res[0][0], B, L, d), ref) < (1e-5 if dt == torch.float32 else 1e-2)
+    t = valid(qkv, B, L, 3 * H * hp).reshape(B, L, 3, H, hp)[..., :hd]
+    q, k, v = [t[:, :, w].transpose(1, 2) for w in range(3)]
+    ref = torch.nn.functional.scaled_dot_product_attention(q, k, v).transpose(1, 2)          # [B,L,H,hd]
+    got = valid(res[0][0], B, L, H * hp).reshape(B, L, H, hp)[..., :hd]
+    assert relerr(got, ref) < (1e-5 if dt == torch.float32 else 1e-2)
 
 
 # ------------------------------------------------------------------------------------------------ batchnorm block

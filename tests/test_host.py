@@ -273,7 +273,8 @@ def test_library_exports_every_declared_symbol():
     assert not missing, missing
     assert set(ops.EXPORTS) <= declared
     assert lib.csi_abi_version() == ops.ABI_VERSION
-    assert ctypes.sizeof(ops.PackEntry) == 48 and ctypes.sizeof(ops.Seg) == 16 and ctypes.sizeof(ops.Ptr3) == 24
+    assert ctypes.sizeof(ops.PackEntry) == 64 and ctypes.sizeof(ops.Seg) == 16 and ctypes.sizeof(ops.Ptr3) == 24
+    assert ctypes.sizeof(ops.Grp) == 8
 
 
 # ------------------------------------------------------------------------------------------------ train loop
