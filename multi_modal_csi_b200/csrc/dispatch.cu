@@ -16,6 +16,14 @@ extern "C" int csi_gemm_nt_tc(const void*, int, const void*, int, void*, int, in
 extern "C" int csi_gemm_nt_tc_ok(int lda, int ldb, int ldc, int M, int N, const csi_seg* segs, int nseg);
 extern "C" int csi_gemm_nt_tc2(const void*, int, const void*, int, void*, int, int, int, int, const csi_seg*, int,
                                const float*, const float*, int, float, unsigned, const unsigned long long*, void*);
+extern "C" int csi_gemm_nt_tc3(const void*, int, const void*, int, void*, int, int, int, int, const csi_seg*, int,
+                               const float*, const float*, int, float, unsigned, const unsigned long long*, void*);
+static int g_gemm_v2 = -1;
+static bool gemm_v2() {
+    if (g_gemm_v2 < 0) { const char* e = getenv("CSI_GEMM_V2"); g_gemm_v2 = (e && e[0] == '1') ? 1 : 0; }
+    return g_gemm_v2 == 1;
+}
+extern "C" int csi_set_gemm_v2(int on) { g_gemm_v2 = on ? 1 : 0; return CSI_OK; }
 static int g_gemm_v1 = -1;
 static bool gemm_v1() {
     if (g_gemm_v1 < 0) { const char* e = getenv("CSI_GEMM_V1"); g_gemm_v1 = (e && e[0] == '1') ? 1 : 0; }
@@ -44,6 +52,9 @@ extern "C" int csi_gemm_nt(const void* A, int lda, const void* Bw, int ldb, int 
     const int es = c_dtype == CSI_BF16 ? 2 : 4;
     const bool v2_ok = ((long long)ldc * es) % 16 == 0 && (reinterpret_cast<uintptr_t>(C) & 15) == 0 &&
                        (!residual || (c_dtype != CSI_BF16 && ldr % 4 == 0 && (reinterpret_cast<uintptr_t>(residual) & 15) == 0));
+    if (ab_dtype == CSI_BF16 && !force_simt() && !gemm_v1() && !gemm_v2() && v2_ok && csi_gemm_nt_tc_ok(lda, ldb, ldc, M, N, segs, nseg))
+        return csi_gemm_nt_tc3(A, lda, Bw, ldb, C, ldc, c_dtype, M, N, segs, nseg, bias, residual, ldr, drop_p, drop_site,
+                               rng, stream);
     if (ab_dtype == CSI_BF16 && !force_simt() && !gemm_v1() && v2_ok && csi_gemm_nt_tc_ok(lda, ldb, ldc, M, N, segs, nseg))
         return csi_gemm_nt_tc2(A, lda, Bw, ldb, C, ldc, c_dtype, M, N, segs, nseg, bias, residual, ldr, drop_p, drop_site,
                                rng, stream);

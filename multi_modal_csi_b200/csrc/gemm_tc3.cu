@@ -1,0 +1,447 @@
+// Persistent tcgen05 NT GEMM with TAP SHARING (production path of csi_gemm_nt for bf16 operands).
+//
+//   C[m,n] = sum_seg A[(m+shift_seg)*lda + aoff_seg + q] * B[n*ldb + boff_seg + q]   (+bias) -> dropout -> (+residual)
+//
+// The GEMMs of this model are bound by L2 -> SM operand traffic, not by the tensor pipe (N is only 128..270, so a
+// 128 x BN tile re-reads its A tile for every tap of a Conv1d).  Segments that read the SAME columns of A at different
+// row shifts (the taps of one Conv1d / of one branch in the data-gradient) are therefore grouped: per 64-channel block
+// the A tile is fetched ONCE as a (128 + span) x 64 box and every tap's UMMA reads it through a shared-memory descriptor
+// whose start address is advanced by (shift - min_shift) rows of 128 B.  The 128B swizzle is a function of the absolute
+// shared-memory address (TMA writes and UMMA reads agree), so a row-shifted view of the same stage is a valid K-major
+// operand.  B (weights) tiles stream through their own ring, one per (tap, channel block).
+//
+//   warp 0      TMA producer: A ring (box rows = 128 + span) and B ring (BN x 64), mbarrier tx-count
+//   warp 1      tcgen05.mma issuer (UMMA 128 x BN x 16, bf16 -> fp32), two TMEM accumulators
+//   warps 2-5   epilogue: tcgen05.ld -> bias / Philox dropout / fp32 residual -> swizzled smem panel -> TMA store
+#include "tc_common.cuh"
+
+#define ST(s) ((cudaStream_t)(s))
+#define T3_THREADS 192
+#define T3_MAX_STAGES 8
+
+__device__ __forceinline__ uint32_t pack2_bf16(float lo, float hi) {
+    __nv_bfloat162 v = __floats2bfloat162_rn(lo, hi);
+    return *reinterpret_cast<uint32_t*>(&v);
+}
+
+__device__ __forceinline__ bool elect_one() {
+    uint32_t pred;
+    asm volatile("{\n.reg .pred p;\nelect.sync _|p, 0xffffffff;\nselp.b32 %0, 1, 0, p;\n}" : "=r"(pred));
+    return pred != 0;
+}
+__device__ __forceinline__ void mbar_wait_u(uint32_t bar, uint32_t parity) {
+    asm volatile(
+        "{\n"
+        ".reg .pred P1;\n"
+        "LAB_WAIT:\n"
+        "mbarrier.try_wait.parity.shared::cta.b64 P1, [%0], %1;\n"
+        "@P1 bra DONE;\n"
+        "bra LAB_WAIT;\n"
+        "DONE:\n"
+        "}\n" ::"r"(bar), "r"(parity) : "memory");
+}
+__device__ __forceinline__ void mbar_expect_tx_u(uint32_t bar, uint32_t bytes) {
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void tma_load_2d_u(const CUtensorMap* tm, uint32_t bar, uint32_t dst, int c0, int c1) {
+    asm volatile(
+        "cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4}], [%2];"
+        ::"r"(dst), "l"(reinterpret_cast<uint64_t>(tm)), "r"(bar), "r"(c0), "r"(c1) : "memory");
+}
+__device__ __forceinline__ void umma_commit_u(uint32_t bar) {
+    asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(bar) : "memory");
+}
+
+struct T3Tap { short a_row_off; short pad; int b_col_off; };
+struct T3Group { int a_col_off, klen, min_shift, tap0, ntaps; };
+struct T3Plan {
+    T3Group g[CSI_MAX_SEGS];
+    T3Tap t[CSI_MAX_SEGS];
+    int ng;
+};
+
+struct Nt3Params {
+    int M, N, BN, ntn, ntiles, nsa, nsb, a_rows;
+    void* C; int ldc;
+    const float* bias; const float* residual; int ldr;
+    float drop_p; unsigned drop_site; const unsigned long long* rng;
+    int row_base, desc_mode;
+};
+
+// K-major SW128 descriptor with an explicit matrix-base-offset field (bits [49,52))
+__device__ __forceinline__ uint64_t make_kmajor_desc_bo(uint32_t saddr, uint32_t base_off) {
+    return make_kmajor_desc(saddr) | ((uint64_t)(base_off & 7u) << 49);
+}
+
+template <typename TC, bool RES>
+__global__ void __launch_bounds__(T3_THREADS, 1) gemm_nt_tc3_kernel(const __grid_constant__ CUtensorMap tmA,
+                                                                    const __grid_constant__ CUtensorMap tmB,
+                                                                    const __grid_constant__ CUtensorMap tmC, Nt3Params p,
+                                                                    const __grid_constant__ T3Plan plan) {
+    constexpr int PW = 128 / (int)sizeof(TC);
+    extern __shared__ __align__(1024) uint8_t smem_raw[];
+    __shared__ __align__(8) uint64_t full_a[T3_MAX_STAGES];
+    __shared__ __align__(8) uint64_t empty_a[T3_MAX_STAGES];
+    __shared__ __align__(8) uint64_t full_b[T3_MAX_STAGES];
+    __shared__ __align__(8) uint64_t empty_b[T3_MAX_STAGES];
+    __shared__ __align__(8) uint64_t tmem_full_bar[2];
+    __shared__ __align__(8) uint64_t tmem_empty_bar[2];
+    __shared__ uint32_t tmem_base_smem;
+    __shared__ float sbias[2][256];
+
+    uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const uint32_t a_bytes = (uint32_t)p.a_rows * 128u, b_bytes = (uint32_t)p.BN * 128u;
+    const int NSA = p.nsa, NSB = p.nsb;
+    uint8_t* a_ring = smem;
+    uint8_t* b_ring = smem + (size_t)NSA * a_bytes;
+    uint8_t* cstage = b_ring + (size_t)NSB * b_bytes;             // 4 warps x 2 buffers x (32 rows x 128 B)
+
+    if (threadIdx.x == 0) {
+        tma_prefetch_desc(&tmA);
+        tma_prefetch_desc(&tmB);
+        tma_prefetch_desc(&tmC);
+        for (int s = 0; s < NSA; ++s) { mbar_init(&full_a[s], 1); mbar_init(&empty_a[s], 1); }
+        for (int s = 0; s < NSB; ++s) { mbar_init(&full_b[s], 1); mbar_init(&empty_b[s], 1); }
+        for (int a = 0; a < 2; ++a) { mbar_init(&tmem_full_bar[a], 1); mbar_init(&tmem_empty_bar[a], 4); }
+        fence_barrier_init();
+    }
+    if (warp == 1) tmem_alloc(&tmem_base_smem, 512);
+    tc_fence_before();
+    __syncthreads();
+    tc_fence_after();
+    const uint32_t tmem_base = tmem_base_smem;
+
+    // Producer and MMA warps run their loops warp-uniformly (all 32 lanes wait on the barriers) and issue the
+    // asynchronous instructions from one elected lane: the issue path is a single instruction stream whose latency
+    // per stage must stay below the stage's tensor time (4 x 72 clk for a 128x144 tile), so it carries no integer
+    // division (stage/phase are running counters) and no per-lane divergence.
+    if (warp == 0) {
+        int sa = 0, sb = 0;
+        uint32_t pa = 1, pb = 1;                                 // parity to wait for on the empty barriers
+        const uint32_t a_ring_u = smem_u32(a_ring), b_ring_u = smem_u32(b_ring);
+        const uint32_t full_a_u = smem_u32(&full_a[0]), empty_a_u = smem_u32(&empty_a[0]);
+        const uint32_t full_b_u = smem_u32(&full_b[0]), empty_b_u = smem_u32(&empty_b[0]);
+        const bool leader = elect_one();
+        for (int tile = blockIdx.x; tile < p.ntiles; tile += gridDim.x) {
+            const int mt = tile / p.ntn;
+            const int m0 = mt * TC_BM + p.row_base, n0 = (tile - mt * p.ntn) * p.BN;
+            for (int gi = 0; gi < plan.ng; ++gi) {
+                const int g_col = plan.g[gi].a_col_off, g_klen = plan.g[gi].klen, g_row = m0 + plan.g[gi].min_shift;
+                const int tap0 = plan.g[gi].tap0, ntaps = plan.g[gi].ntaps;
+                for (int k0 = 0; k0 < g_klen; k0 += TC_BK) {
+                    mbar_wait_u(empty_a_u + 8u * sa, pa);
+                    if (leader) {
+                        mbar_expect_tx_u(full_a_u + 8u * sa, a_bytes);
+                        tma_load_2d_u(&tmA, full_a_u + 8u * sa, a_ring_u + (uint32_t)sa * a_bytes, g_col + k0, g_row);
+                    }
+                    if (++sa == NSA) { sa = 0; pa ^= 1u; }
+                    for (int t = 0; t < ntaps; ++t) {
+                        mbar_wait_u(empty_b_u + 8u * sb, pb);
+                        if (leader) {
+                            mbar_expect_tx_u(full_b_u + 8u * sb, b_bytes);
+                            tma_load_2d_u(&tmB, full_b_u + 8u * sb, b_ring_u + (uint32_t)sb * b_bytes,
+                                          plan.t[tap0 + t].b_col_off + k0, n0);
+                        }
+                        if (++sb == NSB) { sb = 0; pb ^= 1u; }
+                    }
+                }
+            }
+        }
+    } else if (warp == 1) {
+        const uint32_t idesc = make_idesc(TC_BM, p.BN);
+        int sa = 0, sb = 0;
+        uint32_t pa = 0, pb = 0;                                 // parity to wait for on the full barriers
+        uint32_t acc = 0, pacc = 1;                              // accumulator buffer and parity of its empty barrier
+        const uint32_t a_ring_u = smem_u32(a_ring), b_ring_u = smem_u32(b_ring);
+        const uint32_t full_a_u = smem_u32(&full_a[0]), empty_a_u = smem_u32(&empty_a[0]);
+        const uint32_t full_b_u = smem_u32(&full_b[0]), empty_b_u = smem_u32(&empty_b[0]);
+        const uint32_t tfull_u = smem_u32(&tmem_full_bar[0]), tempty_u = smem_u32(&tmem_empty_bar[0]);
+        const bool leader = elect_one();
+        const uint32_t dmode = (uint32_t)p.desc_mode;
+        for (int tile = blockIdx.x; tile < p.ntiles; tile += gridDim.x) {
+            mbar_wait_u(tempty_u + 8u * acc, pacc);              // epilogue has drained this accumulator
+            tc_fence_after();
+            const uint32_t tacc = tmem_base + acc * 256u;
+            uint32_t accum = 0;
+            for (int gi = 0; gi < plan.ng; ++gi) {
+                const int g_klen = plan.g[gi].klen, tap0 = plan.g[gi].tap0, ntaps = plan.g[gi].ntaps;
+                for (int k0 = 0; k0 < g_klen; k0 += TC_BK) {
+                    mbar_wait_u(full_a_u + 8u * sa, pa);
+                    const uint32_t a_addr = a_ring_u + (uint32_t)sa * a_bytes;
+                    const bool full_k = (g_klen - k0) >= TC_BK;
+                    const int ksteps = full_k ? 4 : ((g_klen - k0) >> 4);
+                    for (int t = 0; t < ntaps; ++t) {
+                        mbar_wait_u(full_b_u + 8u * sb, pb);
+                        tc_fence_after();
+                        if (leader) {
+                            const uint32_t roff = (uint32_t)plan.t[tap0 + t].a_row_off;
+                            const uint64_t adesc = make_kmajor_desc_bo(a_addr + roff * 128u, dmode ? roff : 0u);
+                            const uint64_t bdesc = make_kmajor_desc(b_ring_u + (uint32_t)sb * b_bytes);
+                            if (full_k) {
+                                umma_bf16(tacc, adesc, bdesc, idesc, accum);
+                                umma_bf16(tacc, adesc + 2, bdesc + 2, idesc, 1u);
+                                umma_bf16(tacc, adesc + 4, bdesc + 4, idesc, 1u);
+                                umma_bf16(tacc, adesc + 6, bdesc + 6, idesc, 1u);
+                            } else {
+                                for (int k = 0; k < ksteps; ++k)
+                                    umma_bf16(tacc, adesc + (uint64_t)(2 * k), bdesc + (uint64_t)(2 * k), idesc, (accum | (uint32_t)k) ? 1u : 0u);
+                            }
+                            umma_commit_u(empty_b_u + 8u * sb);
+                        }
+                        accum = 1;
+                        if (++sb == NSB) { sb = 0; pb ^= 1u; }
+                    }
+                    if (leader) umma_commit_u(empty_a_u + 8u * sa);
+                    if (++sa == NSA) { sa = 0; pa ^= 1u; }
+                }
+            }
+            if (leader) umma_commit_u(tfull_u + 8u * acc);
+            acc ^= 1u;
+            if (acc == 0) pacc ^= 1u;
+        }
+    } else {
+        const int q = warp & 3, ew = warp - 2;
+        const int et = threadIdx.x - 64;                            // 0..127 among the epilogue threads
+        const bool drop = p.drop_p > 0.f;
+        DropCtx dc;
+        if (drop) dc = drop_ctx(p.rng, p.drop_p);
+        const int ld8 = ((p.N + 15) & ~15) >> 3;
+        uint8_t* mybuf = cstage + (size_t)ew * 2 * 4096;
+        int ti = 0, sbuf = 0;
+        for (int tile = blockIdx.x; tile < p.ntiles; tile += gridDim.x, ++ti) {
+            const int acc = ti & 1;
+            const uint32_t aph = (uint32_t)(ti >> 1) & 1u;
+            const int m0 = (tile / p.ntn) * TC_BM, n0 = (tile % p.ntn) * p.BN;
+            const int m = m0 + q * 32 + lane;
+            if (p.bias) {
+                for (int i = et; i < p.BN; i += 128) sbias[acc][i] = (n0 + i) < p.N ? p.bias[n0 + i] : 0.f;
+                named_bar_sync(1, 128);
+            }
+            const float* rrow = (RES && m < p.M) ? p.residual + (size_t)m * p.ldr : nullptr;
+            float rnext[RES ? PW : 1];
+            auto fetch_res = [&](int pc0) {
+                if constexpr (!RES) return;
+#pragma unroll
+                for (int j = 0; j < (RES ? PW : 0); j += 4) {
+                    const int n = n0 + pc0 + j;
+                    if (rrow && n + 3 < p.N) {
+                        const float4 v = *reinterpret_cast<const float4*>(rrow + n);
+                        rnext[j] = v.x; rnext[j + 1] = v.y; rnext[j + 2] = v.z; rnext[j + 3] = v.w;
+                    } else {
+#pragma unroll
+                        for (int u = 0; u < 4; ++u) rnext[j + u] = (rrow && n + u < p.N) ? rrow[n + u] : 0.f;
+                    }
+                }
+            };
+            if constexpr (RES) fetch_res(0);
+            mbar_wait(&tmem_full_bar[acc], aph);
+            tc_fence_after();
+            const uint32_t tacc = tmem_base + (uint32_t)(acc * 256) + ((uint32_t)(q * 32) << 16);
+            for (int pc0 = 0; pc0 < p.BN; pc0 += PW) {
+                float v[PW];
+                uint32_t r[PW];
+                // all TMEM loads of the panel are issued before the single wait
+#pragma unroll
+                for (int c = 0; c < PW; c += 16) {
+                    if (pc0 + c < p.BN) tmem_ld16(tacc + (uint32_t)(pc0 + c), r + c);
+                    else {
+#pragma unroll
+                        for (int j = 0; j < 16; ++j) r[c + j] = 0u;
+                    }
+                }
+                tmem_ld_wait();
+#pragma unroll
+                for (int j = 0; j < PW; ++j) v[j] = __uint_as_float(r[j]);
+                float res[RES ? PW : 1];
+                if constexpr (RES) {
+#pragma unroll
+                    for (int j = 0; j < PW; ++j) res[j] = rnext[j];
+                    if (pc0 + PW < p.BN) fetch_res(pc0 + PW);
+                }
+#pragma unroll
+                for (int g8 = 0; g8 < PW / 8; ++g8) {
+                    float ks[8];
+                    if (drop) drop_scales8(dc, p.drop_site, (unsigned long long)m * ld8 + ((n0 + pc0) >> 3) + g8, ks);
+#pragma unroll
+                    for (int j = 0; j < 8; ++j) {
+                        float x = v[g8 * 8 + j];
+                        if (p.bias) x += sbias[acc][min(pc0 + g8 * 8 + j, 255)];
+                        if (drop) x *= ks[j];
+                        if constexpr (RES) x += res[g8 * 8 + j];
+                        v[g8 * 8 + j] = x;
+                    }
+                }
+                if (pc0 + PW <= p.BN) {
+                    // full panel: stage the 32 x 128 B slice of this warp (row = lane) with the TMA 128B swizzle and
+                    // bulk-store it (the tensor map clips rows >= M and columns >= N)
+                    if (lane == 0) tma_store_wait_read<1>();        // the buffer used two panels ago has been read
+                    __syncwarp();
+                    uint8_t* buf = mybuf + (size_t)sbuf * 4096;
+                    uint8_t* rowp = buf + lane * 128;
+#pragma unroll
+                    for (int c16 = 0; c16 < 8; ++c16) {
+                        uint4 u;
+                        if constexpr (sizeof(TC) == 2) {
+                            u.x = pack2_bf16(v[c16 * 8 + 0], v[c16 * 8 + 1]); u.y = pack2_bf16(v[c16 * 8 + 2], v[c16 * 8 + 3]);
+                            u.z = pack2_bf16(v[c16 * 8 + 4], v[c16 * 8 + 5]); u.w = pack2_bf16(v[c16 * 8 + 6], v[c16 * 8 + 7]);
+                        } else {
+                            u.x = __float_as_uint(v[c16 * 4 + 0]); u.y = __float_as_uint(v[c16 * 4 + 1]);
+                            u.z = __float_as_uint(v[c16 * 4 + 2]); u.w = __float_as_uint(v[c16 * 4 + 3]);
+                        }
+                        *reinterpret_cast<uint4*>(rowp + ((c16 ^ (lane & 7)) << 4)) = u;
+                    }
+                    fence_proxy_async();
+                    __syncwarp();
+                    if (lane == 0) {
+                        tma_store_2d(&tmC, buf, n0 + pc0, m0 + q * 32);
+                        tma_store_commit();
+                    }
+                    sbuf ^= 1;
+                } else if (m < p.M) {
+                    // ragged last panel of the tile (BN is a multiple of 16, not of the panel width): direct stores
+                    TC* crow = reinterpret_cast<TC*>(p.C) + (size_t)m * p.ldc;
+#pragma unroll
+                    for (int j = 0; j < PW; j += 2) {
+                        const int n = n0 + pc0 + j;
+                        if (pc0 + j < p.BN && n < p.N) {
+                            if (n + 1 < p.N) st2<TC>(crow + n, make_float2(v[j], v[j + 1]));
+                            else stf<TC>(crow + n, v[j]);
+                        }
+                    }
+                }
+            }
+            tc_fence_before();
+            __syncwarp();
+            if (lane == 0) mbar_arrive(&tmem_empty_bar[acc]);
+        }
+        if (lane == 0) tma_store_wait_all();
+    }
+    tc_fence_before();
+    __syncthreads();
+    if (warp == 1) {
+        tc_fence_after();
+        tmem_dealloc(tmem_base, 512);
+    }
+}
+
+static int pick_bn3(int N) {
+    const int tiles = (N + 255) / 256;
+    int bn = ((N + tiles - 1) / tiles + 15) & ~15;
+    if (bn < 16) bn = 16;
+    return bn;
+}
+
+static int g_num_sms3 = 0;
+static int g_desc_mode = 0;       // 0: base-offset field left 0 (swizzle follows the absolute address); 1: base offset = row % 8
+static int g_tap_share = 1;
+extern "C" int csi_set_gemm_desc_mode(int mode) { g_desc_mode = mode ? 1 : 0; return CSI_OK; }
+extern "C" int csi_set_gemm_tap_share(int on) { g_tap_share = on ? 1 : 0; return CSI_OK; }
+
+// row-box map for A: box = box_rows x 64 columns (box_rows <= 256)
+extern "C" int csi_gemm_nt_tc3(const void* A, int lda, const void* Bw, int ldb, void* C, int ldc, int c_dtype, int M, int N,
+                               const csi_seg* segs, int nseg, const float* bias, const float* residual, int ldr,
+                               float drop_p, unsigned drop_site, const unsigned long long* rng, void* stream) {
+    CSI_CHECK_ARG(A && Bw && C && segs, "null pointer");
+    CSI_CHECK_ARG(!(drop_p > 0.f) || rng, "dropout needs rng");
+    CSI_CHECK_ARG(nseg >= 1 && nseg <= CSI_MAX_SEGS, "1..32 segments");
+    const int es = c_dtype == CSI_BF16 ? 2 : 4;
+    CSI_CHECK_ARG((ldc * es) % 16 == 0 && (reinterpret_cast<uintptr_t>(C) & 15) == 0, "C must be 16-byte aligned with a 16-byte row pitch");
+    CSI_CHECK_ARG(!residual || (ldr % 4 == 0 && (reinterpret_cast<uintptr_t>(residual) & 15) == 0), "residual must be 16-byte aligned");
+    CSI_CHECK_ARG(!(residual && c_dtype == CSI_BF16), "residual is only fused for fp32 output");
+    // ---- group consecutive segments that read the same A columns at row shifts within a 16-row window
+    T3Plan plan;
+    plan.ng = 0;
+    int min_shift = 0, max_shift = 0, a_cols = 0, b_cols = 0, span = 0;
+    for (int i = 0; i < nseg; ++i) {
+        const csi_seg s = segs[i];
+        if (s.a_row_shift < min_shift) min_shift = s.a_row_shift;
+        if (s.a_row_shift > max_shift) max_shift = s.a_row_shift;
+        if (s.a_col_off + s.klen > a_cols) a_cols = s.a_col_off + s.klen;
+        if (s.b_col_off + s.klen > b_cols) b_cols = s.b_col_off + s.klen;
+        bool joined = false;
+        if (g_tap_share && plan.ng > 0) {
+            T3Group& g = plan.g[plan.ng - 1];
+            if (g.a_col_off == s.a_col_off && g.klen == s.klen) {
+                int lo = g.min_shift, hi = g.min_shift;
+                for (int t = 0; t < g.ntaps; ++t) {
+                    const int sh = g.min_shift + plan.t[g.tap0 + t].a_row_off;
+                    if (sh > hi) hi = sh;
+                }
+                const int nlo = s.a_row_shift < lo ? s.a_row_shift : lo, nhi = s.a_row_shift > hi ? s.a_row_shift : hi;
+                if (nhi - nlo <= 16) {
+                    if (nlo != lo)
+                        for (int t = 0; t < g.ntaps; ++t) plan.t[g.tap0 + t].a_row_off = (short)(plan.t[g.tap0 + t].a_row_off + (lo - nlo));
+                    g.min_shift = nlo;
+                    plan.t[g.tap0 + g.ntaps].a_row_off = (short)(s.a_row_shift - nlo);
+                    plan.t[g.tap0 + g.ntaps].pad = 0;
+                    plan.t[g.tap0 + g.ntaps].b_col_off = s.b_col_off;
+                    ++g.ntaps;
+                    if (nhi - nlo > span) span = nhi - nlo;
+                    joined = true;
+                }
+            }
+        }
+        if (!joined) {
+            T3Group& g = plan.g[plan.ng];
+            g.a_col_off = s.a_col_off; g.klen = s.klen; g.min_shift = s.a_row_shift; g.tap0 = i; g.ntaps = 1;
+            plan.t[i].a_row_off = 0; plan.t[i].pad = 0; plan.t[i].b_col_off = s.b_col_off;
+            ++plan.ng;
+        }
+    }
+    CSI_CHECK_ARG(a_cols <= lda && b_cols <= ldb, "segment exceeds the row pitch");
+    if (g_num_sms3 == 0) {
+        int dev = 0;
+        CSI_CUDA(cudaGetDevice(&dev));
+        CSI_CUDA(cudaDeviceGetAttribute(&g_num_sms3, cudaDevAttrMultiProcessorCount, dev));
+    }
+    const int BN = pick_bn3(N);
+    const int a_rows = TC_BM + ((span + 7) & ~7);
+    CUtensorMap tmA, tmB, tmC;
+    const bf16* a_base = reinterpret_cast<const bf16*>(A) + (long long)min_shift * lda;
+    int rc = make_map(&tmA, a_base, (long long)M + (max_shift - min_shift), a_cols, lda, a_rows);
+    if (rc) return rc;
+    rc = make_map(&tmB, Bw, N, b_cols, ldb, BN);
+    if (rc) return rc;
+    rc = make_map_ex(&tmC, C, M, N, ldc, 32, 128 / es, es);
+    if (rc) return rc;
+    Nt3Params p;
+    p.M = M; p.N = N; p.BN = BN; p.C = C; p.ldc = ldc; p.a_rows = a_rows;
+    p.ntn = (N + BN - 1) / BN;
+    const int mtiles = (M + TC_BM - 1) / TC_BM;
+    p.ntiles = p.ntn * mtiles;
+    p.bias = bias; p.residual = residual; p.ldr = ldr;
+    p.drop_p = drop_p; p.drop_site = drop_site; p.rng = rng;
+    p.row_base = -min_shift;
+    p.desc_mode = g_desc_mode;
+    const size_t a_bytes = (size_t)a_rows * 128, b_bytes = (size_t)BN * 128;
+    const size_t fixed = 1024 + 4 * 2 * 4096;
+    const size_t budget = 220 * 1024 - fixed;
+    int nsa, nsb;
+    if (span == 0) {                                   // every group is a single tap: A and B stages pair up
+        nsa = (int)(budget / (a_bytes + b_bytes));
+        if (nsa > T3_MAX_STAGES) nsa = T3_MAX_STAGES;
+        if (nsa < 2) nsa = 2;
+        nsb = nsa;
+    } else {
+        nsa = 3;
+        nsb = (int)((budget - nsa * a_bytes) / b_bytes);
+        if (nsb > T3_MAX_STAGES) nsb = T3_MAX_STAGES;
+        if (nsb < 2) nsb = 2;
+    }
+    p.nsa = nsa; p.nsb = nsb;
+    const size_t smem = fixed + nsa * a_bytes + nsb * b_bytes;
+    int grid = g_num_sms3;
+    if (p.ntiles < grid) grid = p.ntiles;
+#define LAUNCH3(TC, RES)                                                                                                \
+    do {                                                                                                                \
+        CSI_CUDA(cudaFuncSetAttribute(gemm_nt_tc3_kernel<TC, RES>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem)); \
+        gemm_nt_tc3_kernel<TC, RES><<<grid, T3_THREADS, smem, ST(stream)>>>(tmA, tmB, tmC, p, plan);                    \
+    } while (0)
+    if (c_dtype == CSI_BF16) LAUNCH3(bf16, false);
+    else if (residual) LAUNCH3(float, true);
+    else LAUNCH3(float, false);
+#undef LAUNCH3
+    CSI_LAUNCH_CHECK();
+    return CSI_OK;
+}

@@ -102,6 +102,8 @@ class NativeOps:
         self.launches = 0
         self._prof = None
         self._only = None
+        self._tag = ""
+        self.last_calls = []
 
     # -------------------------------------------------------------- helpers
     def _st(self):
@@ -134,7 +136,8 @@ class NativeOps:
         if prof:
             e1 = torch.cuda.Event(enable_timing=True)
             e1.record(torch.cuda.current_stream(self.device))
-            self._prof.append((short, e0, e1, flops, nbytes))
+            self._prof.append((short, e0, e1, flops, nbytes, self._tag))
+        self._tag = ""
 
     def start_profile(self, only=None):
         """Record a CUDA-event pair around every launch of the named ops (all ops when only is None)."""
@@ -144,7 +147,8 @@ class NativeOps:
         """-> {op: (total_ms, launches, {"flops": f, "bytes": b})}; synchronises."""
         torch.cuda.synchronize(self.device)
         out = {}
-        for name, e0, e1, fl, nb in (self._prof or []):
+        self.last_calls = [(name, e0.elapsed_time(e1), fl, nb, tag) for name, e0, e1, fl, nb, tag in (self._prof or [])]
+        for name, e0, e1, fl, nb, _tag in (self._prof or []):
             ms, n, w = out.get(name, (0.0, 0, {"flops": 0, "bytes": 0}))
             w["flops"] += fl
             w["bytes"] += nb
@@ -240,6 +244,8 @@ class NativeOps:
 
     def gemm_nt(self, A, Bw, Cm, M, N, segs, bias, residual, drop_p, drop_site, rng):
         wk = self._work("gemm_nt", locals())
+        if self._prof is not None:
+            self._tag = f"M={M} N={N} K={sum(s[3] for s in segs)} nseg={len(segs)} out={Cm.dtype} res={residual is not None} drop={drop_p}"
         arr = (Seg * len(segs))(*[Seg(*s) for s in segs])
         self._call("csi_gemm_nt", _p(A), _ld(A), _p(Bw), _ld(Bw), _dt(A), _p(Cm), _ld(Cm), _dt(Cm), M, N, arr,
                                       len(segs), _p(bias), _p(residual), _ld(residual), C.c_float(drop_p),
@@ -247,6 +253,8 @@ class NativeOps:
 
     def gemm_tn(self, A, Bv, Cm, ldc, c_col_stride, M, Na, segs, i_grp=NO_GRP, q_grp=NO_GRP):
         wk = self._work("gemm_tn", locals())
+        if self._prof is not None:
+            self._tag = f"M={M} Na={Na} nlen={sum(s[3] for s in segs)} nseg={len(segs)} cs={c_col_stride}"
         arr = (SegTN * len(segs))(*[SegTN(*s) for s in segs])
         self._call("csi_gemm_tn", _p(A), _ld(A), _p(Bv), _ld(Bv), _dt(A), _p(Cm), ldc, c_col_stride, M, Na, arr,
                    len(segs), Grp(*i_grp), Grp(*q_grp), **wk)

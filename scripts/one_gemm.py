@@ -1,0 +1,19 @@
+"""A few launches of one NT GEMM shape (for ncu): argv = M N Dp k v2 reps."""
+import sys, os, math
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+import torch
+from multi_modal_csi_b200.ops import NativeOps
+M, N, Dp, k, v2, reps = [int(a) for a in sys.argv[1:7]]
+ops = NativeOps(torch.device("cuda", 0))
+ops.lib.csi_set_gemm_v2(v2)
+GUARD = 16
+full = torch.randn(M + 2 * GUARD, Dp, device="cuda").to(torch.bfloat16)
+A = full[GUARD:GUARD + M]
+W = (torch.randn(N, k * Dp, device="cuda") / math.sqrt(k * Dp)).to(torch.bfloat16)
+Cm = torch.zeros(M, (N + 15) // 16 * 16, dtype=torch.bfloat16, device="cuda")
+pl = (k - 1) // 2
+segs = [(j - pl, 0, j * Dp, Dp) for j in range(k)]
+for _ in range(reps):
+    ops.gemm_nt(A, W, Cm, M, N, segs, None, None, 0.0, 0, None)
+torch.cuda.synchronize()
+print("ok")
