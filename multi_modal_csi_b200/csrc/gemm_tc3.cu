@@ -16,7 +16,8 @@
 #include "tc_common.cuh"
 
 #define ST(s) ((cudaStream_t)(s))
-#define T3_THREADS 192
+#define T3_THREADS 320
+#define T3_EPI_THREADS 256
 #define T3_MAX_STAGES 8
 
 __device__ __forceinline__ uint32_t pack2_bf16(float lo, float hi) {
@@ -76,7 +77,8 @@ __device__ __forceinline__ uint64_t make_kmajor_desc_bo(uint32_t saddr, uint32_t
 template <typename TC, bool RES>
 __global__ void __launch_bounds__(T3_THREADS, 1) gemm_nt_tc3_kernel(const __grid_constant__ CUtensorMap tmA,
                                                                     const __grid_constant__ CUtensorMap tmB,
-                                                                    const __grid_constant__ CUtensorMap tmC, Nt3Params p,
+                                                                    const __grid_constant__ CUtensorMap tmC,
+                                                                    const __grid_constant__ CUtensorMap tmCt, Nt3Params p,
                                                                     const __grid_constant__ T3Plan plan) {
     constexpr int PW = 128 / (int)sizeof(TC);
     extern __shared__ __align__(1024) uint8_t smem_raw[];
@@ -87,7 +89,7 @@ __global__ void __launch_bounds__(T3_THREADS, 1) gemm_nt_tc3_kernel(const __grid
     __shared__ __align__(8) uint64_t tmem_full_bar[2];
     __shared__ __align__(8) uint64_t tmem_empty_bar[2];
     __shared__ uint32_t tmem_base_smem;
-    __shared__ float sbias[2][256];
+    __shared__ __align__(16) float sbias[2][256];
 
     uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
@@ -95,15 +97,16 @@ __global__ void __launch_bounds__(T3_THREADS, 1) gemm_nt_tc3_kernel(const __grid
     const int NSA = p.nsa, NSB = p.nsb;
     uint8_t* a_ring = smem;
     uint8_t* b_ring = smem + (size_t)NSA * a_bytes;
-    uint8_t* cstage = b_ring + (size_t)NSB * b_bytes;             // 4 warps x 2 buffers x (32 rows x 128 B)
+    uint8_t* cstage = b_ring + (size_t)NSB * b_bytes;             // 8 warps x 2 buffers x (32 rows x 128 B)
 
     if (threadIdx.x == 0) {
         tma_prefetch_desc(&tmA);
         tma_prefetch_desc(&tmB);
         tma_prefetch_desc(&tmC);
+        tma_prefetch_desc(&tmCt);
         for (int s = 0; s < NSA; ++s) { mbar_init(&full_a[s], 1); mbar_init(&empty_a[s], 1); }
         for (int s = 0; s < NSB; ++s) { mbar_init(&full_b[s], 1); mbar_init(&empty_b[s], 1); }
-        for (int a = 0; a < 2; ++a) { mbar_init(&tmem_full_bar[a], 1); mbar_init(&tmem_empty_bar[a], 4); }
+        for (int a = 0; a < 2; ++a) { mbar_init(&tmem_full_bar[a], 1); mbar_init(&tmem_empty_bar[a], T3_EPI_THREADS / 32); }
         fence_barrier_init();
     }
     if (warp == 1) tmem_alloc(&tmem_base_smem, 512);
@@ -201,22 +204,25 @@ __global__ void __launch_bounds__(T3_THREADS, 1) gemm_nt_tc3_kernel(const __grid
             if (acc == 0) pacc ^= 1u;
         }
     } else {
-        const int q = warp & 3, ew = warp - 2;
-        const int et = threadIdx.x - 64;                            // 0..127 among the epilogue threads
+        // 8 epilogue warps: warp w drains TMEM lane quarter w % 4; the two warps of a quarter take alternate panels
+        const int q = warp & 3, ew = warp - 2, half = ew >> 2;
+        const int et = threadIdx.x - 64;                            // 0..255 among the epilogue threads
         const bool drop = p.drop_p > 0.f;
         DropCtx dc;
         if (drop) dc = drop_ctx(p.rng, p.drop_p);
         const int ld8 = ((p.N + 15) & ~15) >> 3;
         uint8_t* mybuf = cstage + (size_t)ew * 2 * 4096;
+        const int npan = (p.BN + PW - 1) / PW;
         int ti = 0, sbuf = 0;
         for (int tile = blockIdx.x; tile < p.ntiles; tile += gridDim.x, ++ti) {
             const int acc = ti & 1;
             const uint32_t aph = (uint32_t)(ti >> 1) & 1u;
-            const int m0 = (tile / p.ntn) * TC_BM, n0 = (tile % p.ntn) * p.BN;
+            const int mt = tile / p.ntn;
+            const int m0 = mt * TC_BM, n0 = (tile - mt * p.ntn) * p.BN;
             const int m = m0 + q * 32 + lane;
             if (p.bias) {
-                for (int i = et; i < p.BN; i += 128) sbias[acc][i] = (n0 + i) < p.N ? p.bias[n0 + i] : 0.f;
-                named_bar_sync(1, 128);
+                sbias[acc][et] = (et < p.BN && (n0 + et) < p.N) ? p.bias[n0 + et] : 0.f;
+                named_bar_sync(1, T3_EPI_THREADS);
             }
             const float* rrow = (RES && m < p.M) ? p.residual + (size_t)m * p.ldr : nullptr;
             float rnext[RES ? PW : 1];
@@ -234,17 +240,19 @@ __global__ void __launch_bounds__(T3_THREADS, 1) gemm_nt_tc3_kernel(const __grid
                     }
                 }
             };
-            if constexpr (RES) fetch_res(0);
+            if constexpr (RES) { if (half < npan) fetch_res(half * PW); }
             mbar_wait(&tmem_full_bar[acc], aph);
             tc_fence_after();
             const uint32_t tacc = tmem_base + (uint32_t)(acc * 256) + ((uint32_t)(q * 32) << 16);
-            for (int pc0 = 0; pc0 < p.BN; pc0 += PW) {
+            for (int pi = half; pi < npan; pi += 2) {
+                const int pc0 = pi * PW;
+                const int width = min(PW, p.BN - pc0);              // multiple of 16
                 float v[PW];
                 uint32_t r[PW];
                 // all TMEM loads of the panel are issued before the single wait
 #pragma unroll
                 for (int c = 0; c < PW; c += 16) {
-                    if (pc0 + c < p.BN) tmem_ld16(tacc + (uint32_t)(pc0 + c), r + c);
+                    if (c < width) tmem_ld16(tacc + (uint32_t)(pc0 + c), r + c);
                     else {
 #pragma unroll
                         for (int j = 0; j < 16; ++j) r[c + j] = 0u;
@@ -253,31 +261,34 @@ __global__ void __launch_bounds__(T3_THREADS, 1) gemm_nt_tc3_kernel(const __grid
                 tmem_ld_wait();
 #pragma unroll
                 for (int j = 0; j < PW; ++j) v[j] = __uint_as_float(r[j]);
-                float res[RES ? PW : 1];
-                if constexpr (RES) {
+                if (p.bias) {
 #pragma unroll
-                    for (int j = 0; j < PW; ++j) res[j] = rnext[j];
-                    if (pc0 + PW < p.BN) fetch_res(pc0 + PW);
-                }
-#pragma unroll
-                for (int g8 = 0; g8 < PW / 8; ++g8) {
-                    float ks[8];
-                    if (drop) drop_scales8(dc, p.drop_site, (unsigned long long)m * ld8 + ((n0 + pc0) >> 3) + g8, ks);
-#pragma unroll
-                    for (int j = 0; j < 8; ++j) {
-                        float x = v[g8 * 8 + j];
-                        if (p.bias) x += sbias[acc][min(pc0 + g8 * 8 + j, 255)];
-                        if (drop) x *= ks[j];
-                        if constexpr (RES) x += res[g8 * 8 + j];
-                        v[g8 * 8 + j] = x;
+                    for (int j = 0; j < PW; j += 4) {
+                        const float4 b4 = *reinterpret_cast<const float4*>(&sbias[acc][pc0 + j]);
+                        v[j] += b4.x; v[j + 1] += b4.y; v[j + 2] += b4.z; v[j + 3] += b4.w;
                     }
                 }
-                if (pc0 + PW <= p.BN) {
-                    // full panel: stage the 32 x 128 B slice of this warp (row = lane) with the TMA 128B swizzle and
-                    // bulk-store it (the tensor map clips rows >= M and columns >= N)
-                    if (lane == 0) tma_store_wait_read<1>();        // the buffer used two panels ago has been read
-                    __syncwarp();
-                    uint8_t* buf = mybuf + (size_t)sbuf * 4096;
+                if (drop) {
+#pragma unroll
+                    for (int g8 = 0; g8 < PW / 8; ++g8) {
+                        float ks[8];
+                        drop_scales8(dc, p.drop_site, (unsigned long long)m * ld8 + ((n0 + pc0) >> 3) + g8, ks);
+#pragma unroll
+                        for (int j = 0; j < 8; ++j) v[g8 * 8 + j] *= ks[j];
+                    }
+                }
+                if constexpr (RES) {
+#pragma unroll
+                    for (int j = 0; j < PW; ++j) v[j] += rnext[j];
+                    if (pi + 2 < npan) fetch_res(pc0 + 2 * PW);
+                }
+                // stage the 32-row slice of this warp (row = lane) and bulk-store it; the tensor maps clip rows >= M and
+                // columns >= N.  Full panels are 128-byte rows in the TMA 128B swizzle; the narrower last panel of a tile
+                // uses linear rows of width*es bytes and its own (unswizzled) tensor map.
+                if (lane == 0) tma_store_wait_read<1>();            // the buffer used two panels ago has been read
+                __syncwarp();
+                uint8_t* buf = mybuf + (size_t)sbuf * 4096;
+                if (width == PW) {
                     uint8_t* rowp = buf + lane * 128;
 #pragma unroll
                     for (int c16 = 0; c16 < 8; ++c16) {
@@ -291,25 +302,32 @@ __global__ void __launch_bounds__(T3_THREADS, 1) gemm_nt_tc3_kernel(const __grid
                         }
                         *reinterpret_cast<uint4*>(rowp + ((c16 ^ (lane & 7)) << 4)) = u;
                     }
-                    fence_proxy_async();
-                    __syncwarp();
-                    if (lane == 0) {
-                        tma_store_2d(&tmC, buf, n0 + pc0, m0 + q * 32);
-                        tma_store_commit();
-                    }
-                    sbuf ^= 1;
-                } else if (m < p.M) {
-                    // ragged last panel of the tile (BN is a multiple of 16, not of the panel width): direct stores
-                    TC* crow = reinterpret_cast<TC*>(p.C) + (size_t)m * p.ldc;
+                } else {
+                    const int pitch = width * (int)sizeof(TC);
+                    uint8_t* rowp = buf + lane * pitch;
 #pragma unroll
-                    for (int j = 0; j < PW; j += 2) {
-                        const int n = n0 + pc0 + j;
-                        if (pc0 + j < p.BN && n < p.N) {
-                            if (n + 1 < p.N) st2<TC>(crow + n, make_float2(v[j], v[j + 1]));
-                            else stf<TC>(crow + n, v[j]);
+                    for (int c16 = 0; c16 < 8; ++c16) {
+                        if (c16 * 16 < pitch) {
+                            uint4 u;
+                            if constexpr (sizeof(TC) == 2) {
+                                u.x = pack2_bf16(v[c16 * 8 + 0], v[c16 * 8 + 1]); u.y = pack2_bf16(v[c16 * 8 + 2], v[c16 * 8 + 3]);
+                                u.z = pack2_bf16(v[c16 * 8 + 4], v[c16 * 8 + 5]); u.w = pack2_bf16(v[c16 * 8 + 6], v[c16 * 8 + 7]);
+                            } else {
+                                u.x = __float_as_uint(v[c16 * 4 + 0]); u.y = __float_as_uint(v[c16 * 4 + 1]);
+                                u.z = __float_as_uint(v[c16 * 4 + 2]); u.w = __float_as_uint(v[c16 * 4 + 3]);
+                            }
+                            *reinterpret_cast<uint4*>(rowp + (c16 << 4)) = u;
                         }
                     }
                 }
+                fence_proxy_async();
+                __syncwarp();
+                if (lane == 0) {
+                    if (width == PW) tma_store_2d(&tmC, buf, n0 + pc0, m0 + q * 32);
+                    else tma_store_2d(&tmCt, buf, n0 + pc0, m0 + q * 32);
+                    tma_store_commit();
+                }
+                sbuf ^= 1;
             }
             tc_fence_before();
             __syncwarp();
@@ -405,6 +423,12 @@ extern "C" int csi_gemm_nt_tc3(const void* A, int lda, const void* Bw, int ldb, 
     if (rc) return rc;
     rc = make_map_ex(&tmC, C, M, N, ldc, 32, 128 / es, es);
     if (rc) return rc;
+    const int tail = BN % (128 / es);                  // last panel of a tile when BN is not a whole number of panels
+    CUtensorMap tmCt = tmC;
+    if (tail) {
+        rc = make_map_ex(&tmCt, C, M, N, ldc, 32, tail, es, false);
+        if (rc) return rc;
+    }
     Nt3Params p;
     p.M = M; p.N = N; p.BN = BN; p.C = C; p.ldc = ldc; p.a_rows = a_rows;
     p.ntn = (N + BN - 1) / BN;
@@ -415,7 +439,7 @@ extern "C" int csi_gemm_nt_tc3(const void* A, int lda, const void* Bw, int ldb, 
     p.row_base = -min_shift;
     p.desc_mode = g_desc_mode;
     const size_t a_bytes = (size_t)a_rows * 128, b_bytes = (size_t)BN * 128;
-    const size_t fixed = 1024 + 4 * 2 * 4096;
+    const size_t fixed = 1024 + 8 * 2 * 4096;
     const size_t budget = 220 * 1024 - fixed;
     int nsa, nsb;
     if (span == 0) {                                   // every group is a single tap: A and B stages pair up
@@ -436,7 +460,7 @@ extern "C" int csi_gemm_nt_tc3(const void* A, int lda, const void* Bw, int ldb, 
 #define LAUNCH3(TC, RES)                                                                                                \
     do {                                                                                                                \
         CSI_CUDA(cudaFuncSetAttribute(gemm_nt_tc3_kernel<TC, RES>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem)); \
-        gemm_nt_tc3_kernel<TC, RES><<<grid, T3_THREADS, smem, ST(stream)>>>(tmA, tmB, tmC, p, plan);                    \
+        gemm_nt_tc3_kernel<TC, RES><<<grid, T3_THREADS, smem, ST(stream)>>>(tmA, tmB, tmC, tmCt, p, plan);                    \
     } while (0)
     if (c_dtype == CSI_BF16) LAUNCH3(bf16, false);
     else if (residual) LAUNCH3(float, true);

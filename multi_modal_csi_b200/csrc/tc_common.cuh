@@ -119,7 +119,7 @@ static inline EncodeTiledFn get_encode() {
 
 // generic 2D row-major map: element size es bytes, box = box_rows x box_cols (box_cols*es <= 128), 128B swizzle
 static inline int make_map_ex(CUtensorMap* tm, const void* base, long long rows, long long cols, long long ld, int box_rows,
-                              int box_cols, int es) {
+                              int box_cols, int es, bool swizzle128 = true) {
     EncodeTiledFn enc = get_encode();
     if (!enc) { csi_set_error("cuTensorMapEncodeTiled not available"); return CSI_ERR_CUDA; }
     cuuint64_t dims[2] = {(cuuint64_t)cols, (cuuint64_t)rows};
@@ -127,7 +127,8 @@ static inline int make_map_ex(CUtensorMap* tm, const void* base, long long rows,
     cuuint32_t box[2] = {(cuuint32_t)box_cols, (cuuint32_t)box_rows};
     cuuint32_t estr[2] = {1, 1};
     CUresult r = enc(tm, es == 2 ? CU_TENSOR_MAP_DATA_TYPE_BFLOAT16 : CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 2, const_cast<void*>(base),
-                     dims, strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B,
+                     dims, strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
+                     swizzle128 ? CU_TENSOR_MAP_SWIZZLE_128B : CU_TENSOR_MAP_SWIZZLE_NONE,
                      CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
     if (r != CUDA_SUCCESS) { csi_set_error("cuTensorMapEncodeTiled failed (%d)", (int)r); return CSI_ERR_CUDA; }
     return CSI_OK;
