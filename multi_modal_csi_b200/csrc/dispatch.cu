@@ -32,6 +32,14 @@ static bool gemm_v1() {
 extern "C" int csi_gemm_tn_tc(const void*, int, const void*, int, float*, int, int, int, int, const csi_seg_tn*, int, csi_grp,
                               csi_grp, void*);
 extern "C" int csi_gemm_tn_tc_ok(int lda, int ldb, int M, int Na, const csi_seg_tn* segs, int nseg);
+extern "C" int csi_gemm_tn_tc3(const void*, int, const void*, int, float*, int, int, int, int, const csi_seg_tn*, int, csi_grp,
+                               csi_grp, void*);
+static int g_tn_v1 = -1;
+static bool tn_v1() {
+    if (g_tn_v1 < 0) { const char* e = getenv("CSI_GEMM_TN_V1"); g_tn_v1 = (e && e[0] == '1') ? 1 : 0; }
+    return g_tn_v1 == 1;
+}
+extern "C" int csi_set_gemm_tn_v1(int on) { g_tn_v1 = on ? 1 : 0; return CSI_OK; }
 
 extern "C" int csi_attn_mma_ok(int L, int d, int H, int hp);
 extern "C" int csi_attn_fwd_mma(const void*, int, void*, int, float*, int, int, int, int, int, int, void*);
@@ -68,6 +76,8 @@ extern "C" int csi_gemm_nt(const void* A, int lda, const void* Bw, int ldb, int 
 extern "C" int csi_gemm_tn(const void* A, int lda, const void* Bv, int ldb, int ab_dtype, float* C, int ldc,
                            int c_col_stride, int M, int Na, const csi_seg_tn* segs, int nseg, csi_grp i_grp, csi_grp q_grp,
                            void* stream) {
+    if (ab_dtype == CSI_BF16 && !force_simt() && !tn_v1() && csi_gemm_tn_tc_ok(lda, ldb, M, Na, segs, nseg))
+        return csi_gemm_tn_tc3(A, lda, Bv, ldb, C, ldc, c_col_stride, M, Na, segs, nseg, i_grp, q_grp, stream);
     if (ab_dtype == CSI_BF16 && !force_simt() && csi_gemm_tn_tc_ok(lda, ldb, M, Na, segs, nseg))
         return csi_gemm_tn_tc(A, lda, Bv, ldb, C, ldc, c_col_stride, M, Na, segs, nseg, i_grp, q_grp, stream);
     return csi_gemm_tn_simt(A, lda, Bv, ldb, ab_dtype, C, ldc, c_col_stride, M, Na, segs, nseg, i_grp, q_grp, stream);
