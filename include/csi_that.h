@@ -155,17 +155,20 @@ int csi_bn_eval_prepare(int Dp, int d, int nbr, csi_ptr3 conv_bias, csi_ptr3 run
 int csi_bn_act_fwd(const void* z, int ldz, int dtype, const float* mean, const float* invstd, csi_ptr3 gamma,
                    csi_ptr3 beta, const float* t_res, int ldt, float* out, int ldo, int B, int L, int d,
                    int halo, int nbr, float p_branch, unsigned site_branch, float p_out, unsigned site_out,
-                   const unsigned long long* rng, void* stream);
-/* red: [2, nbr*Dp] doubles (sum dy, sum dy*zhat), accumulated */
+                   const unsigned long long* rng, unsigned int* masks, void* stream);
+/* masks (optional, may be NULL): one 32-bit word per (token row, 8-channel group), index row*(Dp/8) + group, holding
+ * the dropout KEEP bits of that group: byte br = branch br, byte 3 = the output dropout.  bn_act_fwd writes it, the two
+ * backward kernels read it instead of regenerating the Philox decisions (identical bits either way).
+ * red: [2, nbr*Dp] doubles (sum dy, sum dy*zhat), accumulated */
 int csi_bn_act_bwd_reduce(const float* dout, int lddo, const void* z, int ldz, int dtype, const float* mean,
                           const float* invstd, csi_ptr3 gamma, csi_ptr3 beta, int B, int L, int d, int halo,
                           int nbr, float p_branch, unsigned site_branch, float p_out, unsigned site_out,
-                          const unsigned long long* rng, double* red, void* stream);
+                          const unsigned long long* rng, const unsigned int* masks, double* red, void* stream);
 int csi_bn_act_bwd_dz(const float* dout, int lddo, const void* z, int ldz, int dtype, const float* mean,
                       const float* invstd, csi_ptr3 gamma, csi_ptr3 beta, const double* red, int B, int L,
                       int d, int halo, int nbr, float p_branch, unsigned site_branch, float p_out,
-                      unsigned site_out, const unsigned long long* rng, void* dz, int lddz, csi_ptr3 dgamma,
-                      csi_ptr3 dbeta, void* stream);
+                      unsigned site_out, const unsigned long long* rng, const unsigned int* masks, void* dz, int lddz,
+                      csi_ptr3 dgamma, csi_ptr3 dbeta, void* stream);
 
 /* ---- a11: head Conv1d (valid) + LeakyReLU + sum over time (that.py:268-272,287-291).
  * p: token buffer [rows, ldp] of conv pre-activations; columns [0,n0) come from a kernel of size k0 and

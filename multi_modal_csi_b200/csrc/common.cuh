@@ -106,6 +106,14 @@ __device__ __forceinline__ void drop_scales8(const DropCtx& d, uint32_t site, un
 #pragma unroll
     for (int j = 0; j < 8; ++j) ks[j] = field16(g, j) >= d.thr ? d.inv_keep : 0.f;
 }
+// keep bits (bit j = channel j of the group is kept) -- the same decisions as drop_scales8
+__device__ __forceinline__ uint32_t drop_bits8(const DropCtx& d, uint32_t site, unsigned long long idx8) {
+    const uint4 g = rng_group(d.k, site, idx8);
+    uint32_t m = 0;
+#pragma unroll
+    for (int j = 0; j < 8; ++j) m |= (field16(g, j) >= d.thr ? 1u : 0u) << j;
+    return m;
+}
 // keep-scale of one element
 __device__ __forceinline__ float drop_scale1(const DropCtx& d, uint32_t site, unsigned long long row, int ld8, int col) {
     const uint4 g = rng_group(d.k, site, row * (unsigned long long)ld8 + (col >> 3));

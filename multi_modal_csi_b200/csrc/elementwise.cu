@@ -12,7 +12,7 @@ void csi_set_error(const char* fmt, ...) {
     va_list ap; va_start(ap, fmt); vsnprintf(g_err, sizeof(g_err), fmt, ap); va_end(ap);
 }
 extern "C" const char* csi_last_error(void) { return g_err; }
-extern "C" int csi_abi_version(void) { return 2; }
+extern "C" int csi_abi_version(void) { return 3; }
 extern "C" int csi_device_arch(int device) {
     cudaDeviceProp p;
     CSI_CUDA(cudaGetDeviceProperties(&p, device));
@@ -20,6 +20,16 @@ extern "C" int csi_device_arch(int device) {
 }
 
 #define ST(s) ((cudaStream_t)(s))
+static int g_num_sms_ew = 0;
+static inline int num_sms() {
+    if (g_num_sms_ew == 0) {
+        int dev = 0;
+        if (cudaGetDevice(&dev) != cudaSuccess || cudaDeviceGetAttribute(&g_num_sms_ew, cudaDevAttrMultiProcessorCount, dev) != cudaSuccess ||
+            g_num_sms_ew <= 0)
+            g_num_sms_ew = 148;
+    }
+    return g_num_sms_ew;
+}
 #define SITE_AUG 9001u
 #define SITE_AUG_SCALE 9002u
 
@@ -632,7 +642,8 @@ template <typename T>
 __global__ void __launch_bounds__(BNA_THREADS, 2) bn_act_fwd_kernel(
     const T* __restrict__ z, int ldz, const float* __restrict__ mean, const float* __restrict__ invstd, csi_ptr3 gamma,
     csi_ptr3 beta, const float* __restrict__ t_res, int ldt, float* __restrict__ out, int ldo, int B, int L, int d, int Dp,
-    int halo, int nbr, DropCfg dcfg, const unsigned long long* __restrict__ rng, int CH, int RL) {
+    int halo, int nbr, DropCfg dcfg, const unsigned long long* __restrict__ rng, int CH, int RL,
+    unsigned int* __restrict__ masks) {
     const int ch = threadIdx.x % CH, rl = threadIdx.x / CH;
     if (rl >= RL) return;
     const int Lp = L + 2 * halo, total = B * L, ld8 = Dp >> 3;
@@ -666,37 +677,43 @@ __global__ void __launch_bounds__(BNA_THREADS, 2) bn_act_fwd_kernel(
         for (int br = 0; br < 3; ++br) zc[br] = zn[br];
         if (r + RL < r1) fetch(r + RL);
         float acc[8] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
+        unsigned int word = 0xffffffffu;                          // keep bits: byte br = branch br, byte 3 = output dropout
 #pragma unroll
         for (int br = 0; br < 3; ++br) {
             if (br < nbr) {
-                float zv[8], ks[8];
+                float zv[8];
                 zc[br].get(zv);
-                if (db) drop_scales8(cb, dcfg.site_branch + br, idx8, ks);
+                unsigned int kb = 0xffu;
+                if (db) kb = drop_bits8(cb, dcfg.site_branch + br, idx8);
+                word = (word & ~(0xffu << (8 * br))) | (kb << (8 * br));
 #pragma unroll
                 for (int j = 0; j < 8; ++j) {
                     float y = zv[j] * a[br][j] + b[br][j];
-                    if (db) y *= ks[j];
+                    if (db) y = ((kb >> j) & 1u) ? y * cb.inv_keep : 0.f;
                     acc[j] += leaky(y);
                 }
             }
         }
-        float tv[8], ks[8];
+        float tv[8];
         tc.get(tv);
-        if (dro) drop_scales8(co, dcfg.site_out, idx8, ks);
+        unsigned int ko = 0xffu;
+        if (dro) ko = drop_bits8(co, dcfg.site_out, idx8);
+        word = (word & 0x00ffffffu) | (ko << 24);
 #pragma unroll
         for (int j = 0; j < 8; ++j) {
             float v = acc[j] * inv;
-            if (dro) v *= ks[j];
+            if (dro) v = ((ko >> j) & 1u) ? v * co.inv_keep : 0.f;
             tv[j] += v;
         }
         store8f<float>(out + row * ldo + ch * 8, tv);
+        if (masks) masks[idx8] = word;
     }
 }
 
 extern "C" int csi_bn_act_fwd(const void* z, int ldz, int dtype, const float* mean, const float* invstd,
                               csi_ptr3 gamma, csi_ptr3 beta, const float* t_res, int ldt, float* out, int ldo, int B,
                               int L, int d, int halo, int nbr, float p_branch, unsigned site_branch, float p_out,
-                              unsigned site_out, const unsigned long long* rng, void* stream) {
+                              unsigned site_out, const unsigned long long* rng, unsigned int* masks, void* stream) {
     CSI_CHECK_ARG(z && mean && invstd && t_res && out, "null pointer");
     CSI_CHECK_ARG(nbr >= 1 && nbr <= 3, "bad shape");
     CSI_CHECK_ARG(!(p_branch > 0.f || p_out > 0.f) || rng, "dropout needs rng");
@@ -708,100 +725,115 @@ extern "C" int csi_bn_act_fwd(const void* z, int ldz, int dtype, const float* me
     const int grid = cdiv(B * L, RL * BNA_ITERS);
     if (dtype == CSI_BF16)
         bn_act_fwd_kernel<bf16><<<grid, BNA_THREADS, 0, ST(stream)>>>((const bf16*)z, ldz, mean, invstd, gamma, beta, t_res, ldt,
-                                                                       out, ldo, B, L, d, Dp, halo, nbr, dc, rng, CH, RL);
+                                                                       out, ldo, B, L, d, Dp, halo, nbr, dc, rng, CH, RL, masks);
     else
         bn_act_fwd_kernel<float><<<grid, BNA_THREADS, 0, ST(stream)>>>((const float*)z, ldz, mean, invstd, gamma, beta, t_res, ldt,
-                                                                        out, ldo, B, L, d, Dp, halo, nbr, dc, rng, CH, RL);
+                                                                        out, ldo, B, L, d, Dp, halo, nbr, dc, rng, CH, RL, masks);
     CSI_LAUNCH_CHECK();
     return CSI_OK;
 }
 
-// Backward: thread = (8-channel chunk, branch) x row lane.
+// Backward: thread = (8-channel chunk, branch) x row lane.  The grid is two CTAs per SM, each walking one contiguous
+// slab of token rows (no wave tail); every thread keeps two rows of loads in flight.
 //   MODE 0: per-channel sums of dy and dy*zhat -> red (doubles, atomics)
 //   MODE 1: dz = gamma*invstd*(dy - s1/n - zhat*s2/n), plus dgamma/dbeta written once by CTA 0
-#define BNB_ROWS 64
+#define BNB_MAXT 224
+struct RowWalk {
+    int b, l, L, Lp, halo;
+    __device__ __forceinline__ void init(int r, int L_, int halo_) { L = L_; halo = halo_; Lp = L_ + 2 * halo_; b = r / L_; l = r - b * L_; }
+    __device__ __forceinline__ size_t row() const { return (size_t)b * Lp + halo + l; }
+    __device__ __forceinline__ void advance(int step) { l += step; while (l >= L) { l -= L; ++b; } }
+};
+
 template <typename T, int MODE>
-__global__ void __launch_bounds__(BNA_THREADS, 2) bn_act_bwd_kernel(
+__global__ void __launch_bounds__(BNB_MAXT, 2) bn_act_bwd_kernel(
     const float* __restrict__ dout, int lddo, const T* __restrict__ z, int ldz, const float* __restrict__ mean,
     const float* __restrict__ invstd, csi_ptr3 gamma, csi_ptr3 beta, double* __restrict__ red, int B, int L, int d, int Dp,
     int halo, int nbr, DropCfg dcfg, const unsigned long long* __restrict__ rng, T* __restrict__ dz, int lddz,
-    csi_ptr3 dgamma, csi_ptr3 dbeta, int CH, int RL) {
+    csi_ptr3 dgamma, csi_ptr3 dbeta, int CH, int RL, int rows_per_cta, const unsigned int* __restrict__ masks) {
     extern __shared__ float sred[];                               // MODE 0: [RL][CH*nbr][16]
-    const int combo = threadIdx.x % (CH * nbr), rl = threadIdx.x / (CH * nbr);
+    const int ncombo = CH * nbr;
+    const int combo = threadIdx.x % ncombo, rl = threadIdx.x / ncombo;       // blockDim.x == RL * ncombo
     const int ch = combo % CH, br = combo / CH;
-    const int Lp = L + 2 * halo, total = B * L, ld8 = Dp >> 3, nc = nbr * Dp;
-    const int r0 = blockIdx.x * BNB_ROWS, r1 = min(total, r0 + BNB_ROWS);
+    const int total = B * L, ld8 = Dp >> 3, nc = nbr * Dp;
+    const int r0 = blockIdx.x * rows_per_cta, r1 = min(total, r0 + rows_per_cta);
     const int q0 = br * Dp + ch * 8, c0 = ch * 8;
-    float a[8], b[8], gi[8], mu[8], is[8], k1[8], k2[8];
-    float s1[8], s2[8];
-    if (rl < RL) {
-        const float* ga = (const float*)gamma.p[br];
-        bn_affine8(mean, invstd, ga, (const float*)beta.p[br], q0, c0, d, a, b);
+    // y = zh*ga + be ; zh = (z - mu)*is ; MODE 1: dz = gi*dy - gk1 - zh*gk2
+    float mu[8], is[8], ga[8], be[8], gi[8], gk1[8], gk2[8], s1[8], s2[8];
+    {
+        const float* gp = (const float*)gamma.p[br];
+        const float* bp = (const float*)beta.p[br];
         const float invn = 1.0f / ((float)B * (float)L);
 #pragma unroll
         for (int j = 0; j < 8; ++j) {
             const bool ok = (c0 + j) < d;
             mu[j] = ok ? mean[q0 + j] : 0.f;
             is[j] = ok ? invstd[q0 + j] : 0.f;
-            gi[j] = a[j];                                         // gamma * invstd
+            ga[j] = ok ? gp[c0 + j] : 0.f;
+            be[j] = ok ? bp[c0 + j] : 0.f;
             s1[j] = s2[j] = 0.f;
-            if (MODE == 1) { k1[j] = ok ? (float)red[q0 + j] * invn : 0.f; k2[j] = ok ? (float)red[nc + q0 + j] * invn : 0.f; }
-        }
-        const bool db = dcfg.p_branch > 0.f, dro = dcfg.p_out > 0.f;
-        DropCtx cb, co;
-        if (db) cb = drop_ctx(rng, dcfg.p_branch);
-        if (dro) co = drop_ctx(rng, dcfg.p_out);
-        const float inv = 1.0f / nbr;
-        Raw8<float> gn;
-        Raw8<T> zn;
-        auto fetch = [&](int r) {
-            const size_t row = (size_t)(r / L) * Lp + halo + (r % L);
-            gn.load(dout + row * lddo + c0);
-            zn.load(z + row * ldz + q0);
-        };
-        if (r0 + rl < r1) fetch(r0 + rl);
-        for (int r = r0 + rl; r < r1; r += RL) {
-            const size_t row = (size_t)(r / L) * Lp + halo + (r % L);
-            const unsigned long long idx8 = (unsigned long long)row * ld8 + ch;
-            float g[8], zv[8], kb[8], ko[8];
-            gn.get(g);
-            zn.get(zv);
-            if (r + RL < r1) fetch(r + RL);
-            if (db) drop_scales8(cb, dcfg.site_branch + br, idx8, kb);
-            if (dro) drop_scales8(co, dcfg.site_out, idx8, ko);
-            float o[8];
-#pragma unroll
-            for (int j = 0; j < 8; ++j) {
-                float gg = g[j] * inv;
-                if (dro) gg *= ko[j];
-                float y = zv[j] * a[j] + b[j];
-                float ksj = 1.f;
-                if (db) { ksj = kb[j]; y *= ksj; }
-                const float dy = gg * leaky_grad(y) * ksj;
-                const float zh = (zv[j] - mu[j]) * is[j];
-                if (MODE == 0) { s1[j] += dy; s2[j] += dy * zh; }
-                else o[j] = gi[j] * (dy - k1[j] - zh * k2[j]);
+            if (MODE == 1) {
+                gi[j] = ga[j] * is[j];
+                gk1[j] = ok ? gi[j] * (float)red[q0 + j] * invn : 0.f;
+                gk2[j] = ok ? gi[j] * (float)red[nc + q0 + j] * invn : 0.f;
             }
-            if (MODE == 1) store8f<T>(dz + row * lddz + q0, o);
-        }
-        if (MODE == 0) {
-#pragma unroll
-            for (int j = 0; j < 8; ++j) {
-                sred[((rl * CH * nbr + combo) * 2 + 0) * 8 + j] = s1[j];
-                sred[((rl * CH * nbr + combo) * 2 + 1) * 8 + j] = s2[j];
-            }
-        }
-        if (MODE == 1 && blockIdx.x == 0 && rl == 0) {
-            float* dg = (float*)dgamma.p[br];
-            float* dbp = (float*)dbeta.p[br];
-#pragma unroll
-            for (int j = 0; j < 8; ++j)
-                if (c0 + j < d) { dg[c0 + j] += (float)red[nc + q0 + j]; dbp[c0 + j] += (float)red[q0 + j]; }
         }
     }
+    const bool db = dcfg.p_branch > 0.f, dro = dcfg.p_out > 0.f;
+    DropCtx cb, co;
+    if (db) cb = drop_ctx(rng, dcfg.p_branch);
+    if (dro) co = drop_ctx(rng, dcfg.p_out);
+    const float inv = 1.0f / nbr;
+    const float sc_o = inv * (dro ? co.inv_keep : 1.f), sc_b = db ? cb.inv_keep : 1.f;
+    auto process = [&](size_t row, const Raw8<float>& gn, const Raw8<T>& zn, unsigned int word) {
+        const unsigned long long idx8 = (unsigned long long)row * ld8 + ch;
+        float g[8], zv[8], o[8];
+        gn.get(g);
+        zn.get(zv);
+        unsigned int kb = 0xffu, ko = 0xffu;                      // keep bits of the branch / output dropout
+        if (masks) { kb = (word >> (8 * br)) & 0xffu; ko = word >> 24; }
+        else {
+            if (db) kb = drop_bits8(cb, dcfg.site_branch + br, idx8);
+            if (dro) ko = drop_bits8(co, dcfg.site_out, idx8);
+        }
+#pragma unroll
+        for (int j = 0; j < 8; ++j) {
+            const float zh = (zv[j] - mu[j]) * is[j];
+            const float y = zh * ga[j] + be[j];                    // sign(y) is not changed by the (non-negative) keep scale
+            const bool keep = ((kb >> j) & (ko >> j) & 1u) != 0u;
+            const float dy = keep ? g[j] * sc_o * sc_b * leaky_grad(y) : 0.f;
+            if (MODE == 0) { s1[j] += dy; s2[j] += dy * zh; }
+            else o[j] = gi[j] * dy - gk1[j] - zh * gk2[j];
+        }
+        if (MODE == 1) store8f<T>(dz + row * lddz + q0, o);
+    };
+    RowWalk w;
+    w.init(min(r0 + rl, total - 1), L, halo);
+    for (int r = r0 + rl; r < r1; r += 2 * RL) {
+        const size_t rowA = w.row();
+        w.advance(RL);
+        const bool hasB = r + RL < r1;
+        const size_t rowB = hasB ? w.row() : rowA;
+        w.advance(RL);
+        Raw8<float> gA, gB;
+        Raw8<T> zA, zB;
+        unsigned int wA = 0, wB = 0;
+        gA.load(dout + rowA * lddo + c0);
+        zA.load(z + rowA * ldz + q0);
+        if (masks) wA = masks[rowA * ld8 + ch];
+        gB.load(dout + rowB * lddo + c0);
+        zB.load(z + rowB * ldz + q0);
+        if (masks) wB = masks[rowB * ld8 + ch];
+        process(rowA, gA, zA, wA);
+        if (hasB) process(rowB, gB, zB, wB);
+    }
     if (MODE == 0) {
+#pragma unroll
+        for (int j = 0; j < 8; ++j) {
+            sred[((rl * ncombo + combo) * 2 + 0) * 8 + j] = s1[j];
+            sred[((rl * ncombo + combo) * 2 + 1) * 8 + j] = s2[j];
+        }
         __syncthreads();
-        const int ncombo = CH * nbr;
         for (int e = threadIdx.x; e < ncombo * 16; e += blockDim.x) {
             const int cmb = e / 16, which = (e / 8) & 1, j = e & 7;
             const int cc = (cmb % CH) * 8 + j, bb = cmb / CH;
@@ -811,25 +843,37 @@ __global__ void __launch_bounds__(BNA_THREADS, 2) bn_act_bwd_kernel(
             atomicAdd(red + which * nc + bb * Dp + cc, (double)s);
         }
     }
+    if (MODE == 1 && blockIdx.x == 0 && rl == 0) {
+        float* dg = (float*)dgamma.p[br];
+        float* dbp = (float*)dbeta.p[br];
+#pragma unroll
+        for (int j = 0; j < 8; ++j)
+            if (c0 + j < d) { dg[c0 + j] += (float)red[nc + q0 + j]; dbp[c0 + j] += (float)red[q0 + j]; }
+    }
 }
 
 template <int MODE>
 static int bn_bwd_launch(const float* dout, int lddo, const void* z, int ldz, int dtype, const float* mean, const float* invstd,
                          csi_ptr3 gamma, csi_ptr3 beta, double* red, int B, int L, int d, int halo, int nbr, DropCfg dc,
-                         const unsigned long long* rng, void* dz, int lddz, csi_ptr3 dgamma, csi_ptr3 dbeta, cudaStream_t s) {
+                         const unsigned long long* rng, void* dz, int lddz, csi_ptr3 dgamma, csi_ptr3 dbeta, const unsigned int* masks,
+                         cudaStream_t s) {
     const int Dp = (d + 15) & ~15, CH = Dp / 8;
-    if (CH * nbr > BNA_THREADS) { csi_set_error("bn_act_bwd: more than %d channels", BNA_THREADS * 8 / nbr); return CSI_ERR_ARG; }
-    const int RL = BNA_THREADS / (CH * nbr);
+    if (CH * nbr > BNB_MAXT) { csi_set_error("bn_act_bwd: more than %d channels", BNB_MAXT * 8 / nbr); return CSI_ERR_ARG; }
+    const int RL = BNB_MAXT / (CH * nbr), threads = RL * CH * nbr;
     const size_t smem = MODE == 0 ? (size_t)RL * CH * nbr * 16 * sizeof(float) : 0;
-    const int grid = cdiv(B * L, BNB_ROWS);
+    int grid = 2 * num_sms();
+    const int total = B * L;
+    if (grid > cdiv(total, 2 * RL)) grid = cdiv(total, 2 * RL);
+    const int rows_per_cta = cdiv(total, grid);
+    grid = cdiv(total, rows_per_cta);
     if (dtype == CSI_BF16) {
-        if (smem > 48 * 1024) cudaFuncSetAttribute(bn_act_bwd_kernel<bf16, MODE>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-        bn_act_bwd_kernel<bf16, MODE><<<grid, BNA_THREADS, smem, s>>>(dout, lddo, (const bf16*)z, ldz, mean, invstd, gamma, beta, red, B, L,
-                                                                      d, Dp, halo, nbr, dc, rng, (bf16*)dz, lddz, dgamma, dbeta, CH, RL);
+        bn_act_bwd_kernel<bf16, MODE><<<grid, threads, smem, s>>>(dout, lddo, (const bf16*)z, ldz, mean, invstd, gamma, beta, red, B, L,
+                                                                  d, Dp, halo, nbr, dc, rng, (bf16*)dz, lddz, dgamma, dbeta, CH, RL,
+                                                                  rows_per_cta, masks);
     } else {
-        if (smem > 48 * 1024) cudaFuncSetAttribute(bn_act_bwd_kernel<float, MODE>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-        bn_act_bwd_kernel<float, MODE><<<grid, BNA_THREADS, smem, s>>>(dout, lddo, (const float*)z, ldz, mean, invstd, gamma, beta, red, B,
-                                                                       L, d, Dp, halo, nbr, dc, rng, (float*)dz, lddz, dgamma, dbeta, CH, RL);
+        bn_act_bwd_kernel<float, MODE><<<grid, threads, smem, s>>>(dout, lddo, (const float*)z, ldz, mean, invstd, gamma, beta, red, B,
+                                                                   L, d, Dp, halo, nbr, dc, rng, (float*)dz, lddz, dgamma, dbeta, CH,
+                                                                   RL, rows_per_cta, masks);
     }
     return CSI_OK;
 }
@@ -837,14 +881,14 @@ static int bn_bwd_launch(const float* dout, int lddo, const void* z, int ldz, in
 extern "C" int csi_bn_act_bwd_reduce(const float* dout, int lddo, const void* z, int ldz, int dtype, const float* mean,
                                      const float* invstd, csi_ptr3 gamma, csi_ptr3 beta, int B, int L, int d, int halo,
                                      int nbr, float p_branch, unsigned site_branch, float p_out, unsigned site_out,
-                                     const unsigned long long* rng, double* red, void* stream) {
+                                     const unsigned long long* rng, const unsigned int* masks, double* red, void* stream) {
     CSI_CHECK_ARG(dout && z && mean && invstd && red, "null pointer");
     CSI_CHECK_ARG(nbr >= 1 && nbr <= 3, "bad shape");
     if (B * L == 0) return CSI_OK;
     DropCfg dc{p_branch, p_out, site_branch, site_out};
     csi_ptr3 none{{nullptr, nullptr, nullptr}};
     int rc = bn_bwd_launch<0>(dout, lddo, z, ldz, dtype, mean, invstd, gamma, beta, red, B, L, d, halo, nbr, dc, rng, nullptr, 0,
-                              none, none, ST(stream));
+                              none, none, masks, ST(stream));
     if (rc) return rc;
     CSI_LAUNCH_CHECK();
     return CSI_OK;
@@ -853,14 +897,14 @@ extern "C" int csi_bn_act_bwd_reduce(const float* dout, int lddo, const void* z,
 extern "C" int csi_bn_act_bwd_dz(const float* dout, int lddo, const void* z, int ldz, int dtype, const float* mean,
                                  const float* invstd, csi_ptr3 gamma, csi_ptr3 beta, const double* red, int B, int L, int d,
                                  int halo, int nbr, float p_branch, unsigned site_branch, float p_out, unsigned site_out,
-                                 const unsigned long long* rng, void* dz, int lddz, csi_ptr3 dgamma, csi_ptr3 dbeta,
-                                 void* stream) {
+                                 const unsigned long long* rng, const unsigned int* masks, void* dz, int lddz, csi_ptr3 dgamma,
+                                 csi_ptr3 dbeta, void* stream) {
     CSI_CHECK_ARG(dout && z && mean && invstd && red && dz, "null pointer");
     CSI_CHECK_ARG(nbr >= 1 && nbr <= 3, "bad shape");
     if (B * L == 0) return CSI_OK;
     DropCfg dc{p_branch, p_out, site_branch, site_out};
     int rc = bn_bwd_launch<1>(dout, lddo, z, ldz, dtype, mean, invstd, gamma, beta, const_cast<double*>(red), B, L, d, halo, nbr,
-                              dc, rng, dz, lddz, dgamma, dbeta, ST(stream));
+                              dc, rng, dz, lddz, dgamma, dbeta, masks, ST(stream));
     if (rc) return rc;
     CSI_LAUNCH_CHECK();
     return CSI_OK;

@@ -104,6 +104,8 @@ class THATEngine:
                     "bn_mean": torch.zeros(3 * Dp, device=dev), "bn_invstd": torch.zeros(3 * Dp, device=dev),
                     "bn_sums": torch.zeros(2 * 3 * Dp, dtype=torch.float64, device=dev),
                     "out": _TokBuf(rows, Dp, f32, dev),
+                    # dropout keep bits of the BN block (3 branches + output), written by bn_act_fwd for its backward
+                    "dmask": torch.zeros(rows * (Dp // 8), dtype=torch.int32, device=dev),
                 })
             st["hn"] = _TokBuf(rows, Dp, adt, dev)
             st["meanf"] = torch.zeros(rows, device=dev)
@@ -232,7 +234,8 @@ class THATEngine:
                     ops.bn_eval_prepare(Dp, d, 3, cb, rm, rv, BN_EPS, a["bn_mean"], a["bn_invstd"])
                 ops.bn_act_fwd(a["z"].t, a["bn_mean"], a["bn_invstd"], self._bn3(sg, e, "1.weight"),
                                self._bn3(sg, e, "1.bias"), a["t"].t, a["out"].t, B, L, d, HALO, 3,
-                               pd, site(si, e, LY.SITE_BRANCH), pd, site(si, e, LY.SITE_SUM), self.rng)
+                               pd, site(si, e, LY.SITE_BRANCH), pd, site(si, e, LY.SITE_SUM), self.rng,
+                               a["dmask"] if pd > 0.0 else None)
                 x_in = a["out"]
             st["x_last"] = x_in
             nm = f"layer_{sg.name}_norm."
@@ -317,10 +320,11 @@ class THATEngine:
                 sb, so = site(si, e, LY.SITE_BRANCH), site(si, e, LY.SITE_SUM)
                 st["red"].zero_()
                 ops.bn_act_bwd_reduce(dout.t, a["z"].t, a["bn_mean"], a["bn_invstd"], gam, bet, B, L, d, HALO, 3,
-                                      pd, sb, pd, so, self.rng, st["red"])
+                                      pd, sb, pd, so, self.rng, st["red"], a["dmask"] if pd > 0.0 else None)
                 ops.bn_act_bwd_dz(dout.t, a["z"].t, a["bn_mean"], a["bn_invstd"], gam, bet, st["red"], B, L, d,
                                   HALO, 3, pd, sb, pd, so, self.rng, st["dz"].t,
-                                  self._bn3(sg, e, "1.weight", grad=True), self._bn3(sg, e, "1.bias", grad=True))
+                                  self._bn3(sg, e, "1.weight", grad=True), self._bn3(sg, e, "1.bias", grad=True),
+                                  a["dmask"] if pd > 0.0 else None)
                 dsegs, seg = [], 0
                 for j, k in enumerate(sg.kernels):
                     pl = (k - 1) // 2

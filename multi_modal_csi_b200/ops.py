@@ -13,7 +13,7 @@ import torch
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.path.join(_HERE, "libcsi_that.so")
-ABI_VERSION = 2
+ABI_VERSION = 3
 
 
 class Seg(C.Structure):
@@ -288,28 +288,28 @@ class NativeOps:
                                               self._ptr3(run_var), C.c_float(eps), _p(mean), _p(invstd), **wk)
 
     def bn_act_fwd(self, z, mean, invstd, gamma, beta, t_res, out, B, L, d, halo, nbr, p_branch, site_branch, p_out,
-                   site_out, rng):
+                   site_out, rng, masks=None):
         wk = self._work("bn_act_fwd", locals())
         self._call("csi_bn_act_fwd", _p(z), _ld(z), _dt(z), _p(mean), _p(invstd), self._ptr3(gamma),
                                          self._ptr3(beta), _p(t_res), _ld(t_res), _p(out), _ld(out), B, L, d, halo,
                                          nbr, C.c_float(p_branch), C.c_uint(site_branch), C.c_float(p_out),
-                                         C.c_uint(site_out), _p(rng), **wk)
+                                         C.c_uint(site_out), _p(rng), _p(masks), **wk)
 
     def bn_act_bwd_reduce(self, dout, z, mean, invstd, gamma, beta, B, L, d, halo, nbr, p_branch, site_branch, p_out,
-                          site_out, rng, red):
+                          site_out, rng, red, masks=None):
         wk = self._work("bn_act_bwd_reduce", locals())
         self._call("csi_bn_act_bwd_reduce", _p(dout), _ld(dout), _p(z), _ld(z), _dt(z), _p(mean), _p(invstd),
                                                 self._ptr3(gamma), self._ptr3(beta), B, L, d, halo, nbr,
                                                 C.c_float(p_branch), C.c_uint(site_branch), C.c_float(p_out),
-                                                C.c_uint(site_out), _p(rng), _p(red), **wk)
+                                                C.c_uint(site_out), _p(rng), _p(masks), _p(red), **wk)
 
     def bn_act_bwd_dz(self, dout, z, mean, invstd, gamma, beta, red, B, L, d, halo, nbr, p_branch, site_branch, p_out,
-                      site_out, rng, dz, dgamma, dbeta):
+                      site_out, rng, dz, dgamma, dbeta, masks=None):
         wk = self._work("bn_act_bwd_dz", locals())
         self._call("csi_bn_act_bwd_dz", _p(dout), _ld(dout), _p(z), _ld(z), _dt(z), _p(mean), _p(invstd),
                                             self._ptr3(gamma), self._ptr3(beta), _p(red), B, L, d, halo, nbr,
                                             C.c_float(p_branch), C.c_uint(site_branch), C.c_float(p_out),
-                                            C.c_uint(site_out), _p(rng), _p(dz), _ld(dz), self._ptr3(dgamma),
+                                            C.c_uint(site_out), _p(rng), _p(masks), _p(dz), _ld(dz), self._ptr3(dgamma),
                                             self._ptr3(dbeta), **wk)
 
     def head_reduce_fwd(self, p, B, L, halo, N, n0, k0, k1, feat):

@@ -247,7 +247,7 @@ class MirrorOps:
         return rows, Dp, zh, y
 
     def bn_act_fwd(self, z, mean, invstd, gamma, beta, t_res, out, B, L, d, halo, nbr, p_branch, site_branch,
-                   p_out, site_out, rng):
+                   p_out, site_out, rng, masks=None):
         assert p_branch == 0.0 and p_out == 0.0
         rows, Dp, zh, y = self._bn_common(z, mean, invstd, gamma, beta, B, L, d, halo, nbr)
         acc = sum(torch.nn.functional.leaky_relu(u, LEAKY) for u in y) / nbr
@@ -261,7 +261,7 @@ class MirrorOps:
                 for u in y]
 
     def bn_act_bwd_reduce(self, dout, z, mean, invstd, gamma, beta, B, L, d, halo, nbr, p_branch, site_branch,
-                          p_out, site_out, rng, red):
+                          p_out, site_out, rng, red, masks=None):
         assert p_branch == 0.0 and p_out == 0.0
         rows, Dp, zh, y = self._bn_common(z, mean, invstd, gamma, beta, B, L, d, halo, nbr)
         dy = self._bn_dy(dout, y, rows, d, nbr)
@@ -273,7 +273,7 @@ class MirrorOps:
             red[nc + br * Dp:nc + br * Dp + d].add_((dd * zh[br].double()).sum(0))
 
     def bn_act_bwd_dz(self, dout, z, mean, invstd, gamma, beta, red, B, L, d, halo, nbr, p_branch, site_branch,
-                      p_out, site_out, rng, dz, dgamma, dbeta):
+                      p_out, site_out, rng, dz, dgamma, dbeta, masks=None):
         assert p_branch == 0.0 and p_out == 0.0
         rows, Dp, zh, y = self._bn_common(z, mean, invstd, gamma, beta, B, L, d, halo, nbr)
         dy = self._bn_dy(dout, y, rows, d, nbr)

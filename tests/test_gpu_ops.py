@@ -347,6 +347,40 @@ def test_attention(ops, mir, dt, B, L, d):
 
 # ------------------------------------------------------------------------------------------------ batchnorm block
 @pytest.mark.parametrize("dt", DT)
+def test_bn_block_stored_dropout_masks(ops, dt):
+    """The keep bits bn_act_fwd stores are exactly the Philox decisions: the backward kernels give bit-identical results
+    whether they read the stored words or regenerate them, and the drop rate / keep pattern is the one of the forward."""
+    B, L, d = 3, 150, 270
+    Dp = ru(d, 16)
+    g = gen(12)
+    _, z = tokbuf(B, L, 3 * Dp, dt, fill=1.0, gen=g, ncols=3 * Dp)
+    _, t = tokbuf(B, L, Dp, torch.float32, fill=1.0, gen=g, ncols=d)
+    _, dout = tokbuf(B, L, Dp, torch.float32, fill=1.0, gen=g, ncols=d)
+    gam = [1 + 0.1 * torch.randn(d, device="cuda", generator=g) for _ in range(3)]
+    bet = [0.1 * torch.randn(d, device="cuda", generator=g) for _ in range(3)]
+    mean, inv = 0.1 * torch.randn(3 * Dp, device="cuda", generator=g), 1 + 0.1 * torch.rand(3 * Dp, device="cuda", generator=g)
+    rng = torch.tensor([77, 5], dtype=torch.int64, device="cuda")
+    rows = z.shape[0]
+    outs = []
+    for use_masks in (False, True):
+        masks = torch.zeros(rows * (Dp // 8), dtype=torch.int32, device="cuda") if use_masks else None
+        _, out = tokbuf(B, L, Dp, torch.float32)
+        ops.bn_act_fwd(z, mean, inv, gam, bet, t, out, B, L, d, HALO, 3, 0.1, 40, 0.1, 50, rng, masks)
+        red = torch.zeros(2 * 3 * Dp, dtype=torch.float64, device="cuda")
+        ops.bn_act_bwd_reduce(dout, z, mean, inv, gam, bet, B, L, d, HALO, 3, 0.1, 40, 0.1, 50, rng, red, masks)
+        _, dz = tokbuf(B, L, 3 * Dp, dt)
+        dg = [torch.zeros(d, device="cuda") for _ in range(3)]
+        db = [torch.zeros(d, device="cuda") for _ in range(3)]
+        ops.bn_act_bwd_dz(dout, z, mean, inv, gam, bet, red, B, L, d, HALO, 3, 0.1, 40, 0.1, 50, rng, dz, dg, db, masks)
+        outs.append((out.clone(), red.clone(), dz.float().clone(), torch.cat(dg), torch.cat(db), masks))
+    for a, b in zip(outs[0][:5], outs[1][:5]):
+        assert torch.equal(a, b)
+    m = outs[1][5].view(B, L + 2 * HALO, Dp // 8)[:, HALO:HALO + L, :d // 8]
+    bits = torch.stack([(m >> s) & 1 for s in range(32)], -1).float()
+    assert abs(bits.mean().item() - 0.9) < 0.01
+
+
+@pytest.mark.parametrize("dt", DT)
 @pytest.mark.parametrize("B,L,d", SHAPES)
 def test_bn_block(ops, mir, dt, B, L, d):
     Dp = ru(d, 16)
