@@ -9,7 +9,7 @@
 #include "common.cuh"
 
 #define ST(s) ((cudaStream_t)(s))
-#define AM_WARPS 4
+#define AM_MAX_WARPS 8
 #define LOG2E 1.4426950408889634f
 
 __device__ __forceinline__ void ldsm_x4(uint32_t (&r)[4], const bf16* p) {
@@ -90,7 +90,7 @@ __device__ __forceinline__ void stage_tile(bf16* __restrict__ dst, int row0, con
 }
 
 template <int HDP>
-__global__ void __launch_bounds__(AM_WARPS * 32) attn_fwd_mma_kernel(const bf16* __restrict__ qkv, int ld3, bf16* __restrict__ o,
+__global__ void __launch_bounds__(AM_MAX_WARPS * 32) attn_fwd_mma_kernel(const bf16* __restrict__ qkv, int ld3, bf16* __restrict__ o,
                                                                      int ldo, float* __restrict__ lse, int L, int d, int H, int halo) {
     constexpr int LDS = HDP + 8, KS = HDP / 16, NTO = HDP / 8;
     extern __shared__ __align__(16) uint8_t sm_raw[];
@@ -108,7 +108,7 @@ __global__ void __launch_bounds__(AM_WARPS * 32) attn_fwd_mma_kernel(const bf16*
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, g = lane >> 2, t = lane & 3;
     const float sc = rsqrtf((float)hd), c = sc * LOG2E;
     const int npair = LP / 16;
-    for (int qt = warp; qt < npair; qt += AM_WARPS) {
+    for (int qt = warp; qt < npair; qt += (int)(blockDim.x >> 5)) {
         uint32_t qa[KS][4];
 #pragma unroll
         for (int ks = 0; ks < KS; ++ks) ldsm_x4(qa[ks], a_frag_ptr<LDS>(Qs, qt * 16, ks * 16, lane));
@@ -197,7 +197,7 @@ __global__ void __launch_bounds__(AM_WARPS * 32) attn_fwd_mma_kernel(const bf16*
 }
 
 template <int HDP>
-__global__ void __launch_bounds__(AM_WARPS * 32) attn_bwd_mma_kernel(const bf16* __restrict__ qkv, int ld3, const bf16* __restrict__ o,
+__global__ void __launch_bounds__(AM_MAX_WARPS * 32) attn_bwd_mma_kernel(const bf16* __restrict__ qkv, int ld3, const bf16* __restrict__ o,
                                                                      int ldo, const bf16* __restrict__ dout, int lddo,
                                                                      bf16* __restrict__ dqkv, int lddqkv, const float* __restrict__ lse,
                                                                      int L, int d, int H, int halo) {
@@ -243,7 +243,7 @@ __global__ void __launch_bounds__(AM_WARPS * 32) attn_bwd_mma_kernel(const bf16*
     const float sc = rsqrtf((float)hd), c = sc * LOG2E;
     const int ntile = LP / 16;
     // ---------------- pass A: dQ
-    for (int qt = warp; qt < ntile; qt += AM_WARPS) {
+    for (int qt = warp; qt < ntile; qt += (int)(blockDim.x >> 5)) {
         uint32_t qa[KS][4], ga[KS][4];
 #pragma unroll
         for (int ks = 0; ks < KS; ++ks) {
@@ -296,7 +296,7 @@ __global__ void __launch_bounds__(AM_WARPS * 32) attn_bwd_mma_kernel(const bf16*
         }
     }
     // ---------------- pass B: dK, dV (rows of the accumulators are keys, columns of S^T are queries)
-    for (int kt = warp; kt < ntile; kt += AM_WARPS) {
+    for (int kt = warp; kt < ntile; kt += (int)(blockDim.x >> 5)) {
         uint32_t ka[KS][4], va[KS][4];
 #pragma unroll
         for (int ks = 0; ks < KS; ++ks) {
@@ -353,6 +353,13 @@ __global__ void __launch_bounds__(AM_WARPS * 32) attn_bwd_mma_kernel(const bf16*
     store_head_tile<HDP, LDS>(Vs, dqkv + row0 * lddqkv + 2 * H * HDP + h * HDP, lddqkv, L);
 }
 
+// warps per CTA: the 16-row tiles of a head are dealt round-robin, so pick the count that leaves no idle round
+static int am_warps(int LP) {
+    const int ntile = LP / 16, rounds = (ntile + 5) / 6;
+    int w = (ntile + rounds - 1) / rounds;
+    if (w > AM_MAX_WARPS) w = AM_MAX_WARPS;
+    return w < 1 ? 1 : w;
+}
 static int pad_hd(int hd) { return hd <= 16 ? 16 : (hd <= 32 ? 32 : 64); }
 
 // eligible: head pitch is exactly the padded MMA width and everything fits in shared memory
@@ -375,7 +382,7 @@ extern "C" int csi_attn_fwd_mma(const void* qkv, int ld3, void* o, int ldo, floa
 #define GO(HDP)                                                                                                        \
     do {                                                                                                               \
         CSI_CUDA(cudaFuncSetAttribute(attn_fwd_mma_kernel<HDP>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem)); \
-        attn_fwd_mma_kernel<HDP><<<B * H, AM_WARPS * 32, smem, ST(stream)>>>((const bf16*)qkv, ld3, (bf16*)o, ldo, lse, L, d, H, halo); \
+        attn_fwd_mma_kernel<HDP><<<B * H, am_warps(LP) * 32, smem, ST(stream)>>>((const bf16*)qkv, ld3, (bf16*)o, ldo, lse, L, d, H, halo); \
     } while (0)
     if (hp == 16) GO(16); else if (hp == 32) GO(32); else GO(64);
 #undef GO
@@ -394,7 +401,7 @@ extern "C" int csi_attn_bwd_mma(const void* qkv, int ld3, const void* o, int ldo
 #define GO(HDP)                                                                                                        \
     do {                                                                                                               \
         CSI_CUDA(cudaFuncSetAttribute(attn_bwd_mma_kernel<HDP>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem)); \
-        attn_bwd_mma_kernel<HDP><<<B * H, AM_WARPS * 32, smem, ST(stream)>>>((const bf16*)qkv, ld3, (const bf16*)o, ldo,   \
+        attn_bwd_mma_kernel<HDP><<<B * H, am_warps(LP) * 32, smem, ST(stream)>>>((const bf16*)qkv, ld3, (const bf16*)o, ldo,   \
                                                                             (const bf16*)dout, lddo, (bf16*)dqkv, lddqkv, lse, L, d, H, halo); \
     } while (0)
     if (hp == 16) GO(16); else if (hp == 32) GO(32); else GO(64);

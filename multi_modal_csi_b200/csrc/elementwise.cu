@@ -79,6 +79,14 @@ template <> struct Raw8<float> {
     }
 };
 
+// valid token r = (sample b, position l) -> physical row b*Lp + halo + l, advanced without divisions
+struct RowWalk {
+    int b, l, L, Lp, halo;
+    __device__ __forceinline__ void init(int r, int L_, int halo_) { L = L_; halo = halo_; Lp = L_ + 2 * halo_; b = r / L_; l = r - b * L_; }
+    __device__ __forceinline__ size_t row() const { return (size_t)b * Lp + halo + l; }
+    __device__ __forceinline__ void advance(int step) { l += step; while (l >= L) { l -= L; ++b; } }
+};
+
 // ------------------------------------------------------------------------------------------------ pool_dual
 // One CTA = (sample, 16 pooled tokens).  A work item is (token, 4 consecutive features): 20 x 2 float2 loads, one
 // Philox call per (time step, 4 features) when augmenting (2 Box-Muller pairs from 16-bit uniforms + 4 keep bits).
@@ -642,12 +650,11 @@ template <typename T>
 __global__ void __launch_bounds__(BNA_THREADS, 2) bn_act_fwd_kernel(
     const T* __restrict__ z, int ldz, const float* __restrict__ mean, const float* __restrict__ invstd, csi_ptr3 gamma,
     csi_ptr3 beta, const float* __restrict__ t_res, int ldt, float* __restrict__ out, int ldo, int B, int L, int d, int Dp,
-    int halo, int nbr, DropCfg dcfg, const unsigned long long* __restrict__ rng, int CH, int RL,
+    int halo, int nbr, DropCfg dcfg, const unsigned long long* __restrict__ rng, int CH, int RL, int rows_per_cta,
     unsigned int* __restrict__ masks) {
-    const int ch = threadIdx.x % CH, rl = threadIdx.x / CH;
-    if (rl >= RL) return;
-    const int Lp = L + 2 * halo, total = B * L, ld8 = Dp >> 3;
-    const int r0 = blockIdx.x * (RL * BNA_ITERS), r1 = min(total, r0 + RL * BNA_ITERS);
+    const int ch = threadIdx.x % CH, rl = threadIdx.x / CH;       // blockDim.x == RL * CH
+    const int total = B * L, ld8 = Dp >> 3;
+    const int r0 = blockIdx.x * rows_per_cta, r1 = min(total, r0 + rows_per_cta);
     float a[3][8], b[3][8];
 #pragma unroll
     for (int br = 0; br < 3; ++br) {
@@ -658,24 +665,8 @@ __global__ void __launch_bounds__(BNA_THREADS, 2) bn_act_fwd_kernel(
     if (db) cb = drop_ctx(rng, dcfg.p_branch);
     if (dro) co = drop_ctx(rng, dcfg.p_out);
     const float inv = 1.0f / nbr;
-    Raw8<T> zn[3];
-    Raw8<float> tn;
-    auto fetch = [&](int r) {
-        const size_t row = (size_t)(r / L) * Lp + halo + (r % L);
-#pragma unroll
-        for (int br = 0; br < 3; ++br)
-            if (br < nbr) zn[br].load(z + row * ldz + br * Dp + ch * 8);
-        tn.load(t_res + row * ldt + ch * 8);
-    };
-    if (r0 + rl < r1) fetch(r0 + rl);
-    for (int r = r0 + rl; r < r1; r += RL) {
-        const size_t row = (size_t)(r / L) * Lp + halo + (r % L);
+    auto process = [&](size_t row, const Raw8<T> (&zc)[3], const Raw8<float>& tc) {
         const unsigned long long idx8 = (unsigned long long)row * ld8 + ch;
-        Raw8<T> zc[3];
-        Raw8<float> tc = tn;
-#pragma unroll
-        for (int br = 0; br < 3; ++br) zc[br] = zn[br];
-        if (r + RL < r1) fetch(r + RL);
         float acc[8] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
         unsigned int word = 0xffffffffu;                          // keep bits: byte br = branch br, byte 3 = output dropout
 #pragma unroll
@@ -707,6 +698,27 @@ __global__ void __launch_bounds__(BNA_THREADS, 2) bn_act_fwd_kernel(
         }
         store8f<float>(out + row * ldo + ch * 8, tv);
         if (masks) masks[idx8] = word;
+    };
+    RowWalk w;
+    w.init(min(r0 + rl, total - 1), L, halo);
+    for (int r = r0 + rl; r < r1; r += 2 * RL) {
+        const size_t rowA = w.row();
+        w.advance(RL);
+        const bool hasB = r + RL < r1;
+        const size_t rowB = hasB ? w.row() : rowA;
+        w.advance(RL);
+        Raw8<T> zA[3], zB[3];
+        Raw8<float> tA, tB;
+#pragma unroll
+        for (int br = 0; br < 3; ++br)
+            if (br < nbr) zA[br].load(z + rowA * ldz + br * Dp + ch * 8);
+        tA.load(t_res + rowA * ldt + ch * 8);
+#pragma unroll
+        for (int br = 0; br < 3; ++br)
+            if (br < nbr) zB[br].load(z + rowB * ldz + br * Dp + ch * 8);
+        tB.load(t_res + rowB * ldt + ch * 8);
+        process(rowA, zA, tA);
+        if (hasB) process(rowB, zB, tB);
     }
 }
 
@@ -720,15 +732,20 @@ extern "C" int csi_bn_act_fwd(const void* z, int ldz, int dtype, const float* me
     if (B * L == 0) return CSI_OK;
     const int Dp = (d + 15) & ~15, CH = Dp / 8;
     CSI_CHECK_ARG(CH <= BNA_THREADS && ldz % 8 == 0 && ldt % 4 == 0 && ldo % 4 == 0 && ldt >= Dp && ldo >= Dp, "bad leading dimension");
-    const int RL = BNA_THREADS / CH;
+    const int RL = BNA_THREADS / CH, threads = RL * CH, total = B * L;
     DropCfg dc{p_branch, p_out, site_branch, site_out};
-    const int grid = cdiv(B * L, RL * BNA_ITERS);
+    int grid = 2 * num_sms();                                      // two CTAs per SM, one contiguous slab of rows each
+    if (grid > cdiv(total, 2 * RL)) grid = cdiv(total, 2 * RL);
+    const int rows_per_cta = cdiv(total, grid);
+    grid = cdiv(total, rows_per_cta);
     if (dtype == CSI_BF16)
-        bn_act_fwd_kernel<bf16><<<grid, BNA_THREADS, 0, ST(stream)>>>((const bf16*)z, ldz, mean, invstd, gamma, beta, t_res, ldt,
-                                                                       out, ldo, B, L, d, Dp, halo, nbr, dc, rng, CH, RL, masks);
+        bn_act_fwd_kernel<bf16><<<grid, threads, 0, ST(stream)>>>((const bf16*)z, ldz, mean, invstd, gamma, beta, t_res, ldt,
+                                                                   out, ldo, B, L, d, Dp, halo, nbr, dc, rng, CH, RL, rows_per_cta,
+                                                                   masks);
     else
-        bn_act_fwd_kernel<float><<<grid, BNA_THREADS, 0, ST(stream)>>>((const float*)z, ldz, mean, invstd, gamma, beta, t_res, ldt,
-                                                                        out, ldo, B, L, d, Dp, halo, nbr, dc, rng, CH, RL, masks);
+        bn_act_fwd_kernel<float><<<grid, threads, 0, ST(stream)>>>((const float*)z, ldz, mean, invstd, gamma, beta, t_res, ldt,
+                                                                    out, ldo, B, L, d, Dp, halo, nbr, dc, rng, CH, RL, rows_per_cta,
+                                                                    masks);
     CSI_LAUNCH_CHECK();
     return CSI_OK;
 }
@@ -738,12 +755,6 @@ extern "C" int csi_bn_act_fwd(const void* z, int ldz, int dtype, const float* me
 //   MODE 0: per-channel sums of dy and dy*zhat -> red (doubles, atomics)
 //   MODE 1: dz = gamma*invstd*(dy - s1/n - zhat*s2/n), plus dgamma/dbeta written once by CTA 0
 #define BNB_MAXT 224
-struct RowWalk {
-    int b, l, L, Lp, halo;
-    __device__ __forceinline__ void init(int r, int L_, int halo_) { L = L_; halo = halo_; Lp = L_ + 2 * halo_; b = r / L_; l = r - b * L_; }
-    __device__ __forceinline__ size_t row() const { return (size_t)b * Lp + halo + l; }
-    __device__ __forceinline__ void advance(int step) { l += step; while (l >= L) { l -= L; ++b; } }
-};
 
 template <typename T, int MODE>
 __global__ void __launch_bounds__(BNB_MAXT, 2) bn_act_bwd_kernel(
