@@ -3,6 +3,7 @@
 // All of them are coalesced along the channel axis, vectorised by 2 (channel counts are even: multiples of 10)
 // and reduce with warp shuffles; none synchronises with the host.
 #include "common.cuh"
+#include <stdlib.h>
 #include <stdarg.h>
 #include <string.h>
 
@@ -302,6 +303,46 @@ extern "C" int csi_gauss_pe_bwd(const float* dleft, int ld_dleft, int B, int hal
 }
 
 // ------------------------------------------------------------------------------------------------ layernorm
+#define LNB2_WARPS 8
+__device__ __forceinline__ uint32_t ew_smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+__device__ __forceinline__ void ew_bulk_g2s(uint32_t dst, const void* src, uint32_t bytes, uint32_t bar) {
+    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
+                 ::"r"(dst), "l"(src), "r"(bytes), "r"(bar) : "memory");
+}
+__device__ __forceinline__ void ew_mbar_init(uint32_t bar, uint32_t count) {
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(bar), "r"(count));
+}
+__device__ __forceinline__ void ew_mbar_expect_tx(uint32_t bar, uint32_t bytes) {
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void ew_mbar_wait(uint32_t bar, uint32_t parity) {
+    asm volatile(
+        "{\n"
+        ".reg .pred P1;\n"
+        "LAB_WAIT:\n"
+        "mbarrier.try_wait.parity.shared::cta.b64 P1, [%0], %1;\n"
+        "@P1 bra DONE;\n"
+        "bra LAB_WAIT;\n"
+        "DONE:\n"
+        "}\n" ::"r"(bar), "r"(parity) : "memory");
+}
+template <typename T> __device__ __forceinline__ float4 lds4f(const uint8_t* p);
+template <> __device__ __forceinline__ float4 lds4f<float>(const uint8_t* p) { return *reinterpret_cast<const float4*>(p); }
+template <> __device__ __forceinline__ float4 lds4f<bf16>(const uint8_t* p) {
+    const uint2 u = *reinterpret_cast<const uint2*>(p);
+    const float2 a = __bfloat1622float2(*reinterpret_cast<const __nv_bfloat162*>(&u.x));
+    const float2 b = __bfloat1622float2(*reinterpret_cast<const __nv_bfloat162*>(&u.y));
+    return make_float4(a.x, a.y, b.x, b.y);
+}
+template <typename T> __device__ __forceinline__ void stg4f(T* p, float4 v);
+template <> __device__ __forceinline__ void stg4f<float>(float* p, float4 v) { *reinterpret_cast<float4*>(p) = v; }
+template <> __device__ __forceinline__ void stg4f<bf16>(bf16* p, float4 v) {
+    uint2 u;
+    *reinterpret_cast<__nv_bfloat162*>(&u.x) = __floats2bfloat162_rn(v.x, v.y);
+    *reinterpret_cast<__nv_bfloat162*>(&u.y) = __floats2bfloat162_rn(v.z, v.w);
+    *reinterpret_cast<uint2*>(p) = u;
+}
+
 // one warp per token row; NP = float2 pairs per lane (d <= 64*NP)
 template <typename TY, int NP>
 __global__ void __launch_bounds__(256) ln_fwd_kernel(const float* __restrict__ x, int ldx,
@@ -469,61 +510,25 @@ __global__ void __launch_bounds__(256) ln_bwd_kernel(
 // (cp.async.bulk + mbarrier, `stages` rows in flight per warp), so the memory-level parallelism does not cost registers
 // and wide rows (d = 540) prefetch as deeply as narrow ones.  A lane owns the float4 column groups lane, lane+32, ...
 // Grid = 2 CTAs per SM, each warp walks one contiguous slab of rows; dgamma/dbeta are reduced once per CTA.
-#define LNB2_WARPS 8
-__device__ __forceinline__ uint32_t ew_smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
-__device__ __forceinline__ void ew_bulk_g2s(uint32_t dst, const void* src, uint32_t bytes, uint32_t bar) {
-    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
-                 ::"r"(dst), "l"(src), "r"(bytes), "r"(bar) : "memory");
-}
-__device__ __forceinline__ void ew_mbar_init(uint32_t bar, uint32_t count) {
-    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(bar), "r"(count));
-}
-__device__ __forceinline__ void ew_mbar_expect_tx(uint32_t bar, uint32_t bytes) {
-    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(bytes) : "memory");
-}
-__device__ __forceinline__ void ew_mbar_wait(uint32_t bar, uint32_t parity) {
-    asm volatile(
-        "{\n"
-        ".reg .pred P1;\n"
-        "LAB_WAIT:\n"
-        "mbarrier.try_wait.parity.shared::cta.b64 P1, [%0], %1;\n"
-        "@P1 bra DONE;\n"
-        "bra LAB_WAIT;\n"
-        "DONE:\n"
-        "}\n" ::"r"(bar), "r"(parity) : "memory");
-}
-template <typename T> __device__ __forceinline__ float4 lds4f(const uint8_t* p);
-template <> __device__ __forceinline__ float4 lds4f<float>(const uint8_t* p) { return *reinterpret_cast<const float4*>(p); }
-template <> __device__ __forceinline__ float4 lds4f<bf16>(const uint8_t* p) {
-    const uint2 u = *reinterpret_cast<const uint2*>(p);
-    const float2 a = __bfloat1622float2(*reinterpret_cast<const __nv_bfloat162*>(&u.x));
-    const float2 b = __bfloat1622float2(*reinterpret_cast<const __nv_bfloat162*>(&u.y));
-    return make_float4(a.x, a.y, b.x, b.y);
-}
-template <typename T> __device__ __forceinline__ void stg4f(T* p, float4 v);
-template <> __device__ __forceinline__ void stg4f<float>(float* p, float4 v) { *reinterpret_cast<float4*>(p) = v; }
-template <> __device__ __forceinline__ void stg4f<bf16>(bf16* p, float4 v) {
-    uint2 u;
-    *reinterpret_cast<__nv_bfloat162*>(&u.x) = __floats2bfloat162_rn(v.x, v.y);
-    *reinterpret_cast<__nv_bfloat162*>(&u.y) = __floats2bfloat162_rn(v.z, v.w);
-    *reinterpret_cast<uint2*>(p) = u;
-}
-
 template <typename TDY, typename TM, int NQ>
 __global__ void __launch_bounds__(LNB2_WARPS * 32, 2) ln_bwd2_kernel(
-    const TDY* __restrict__ dy, int lddy, const float* __restrict__ x, int ldx, const float* __restrict__ gamma,
-    const float* __restrict__ mean, const float* __restrict__ rstd, const float* __restrict__ dres, int lddres,
-    float* __restrict__ dx, int lddx, TM* __restrict__ dxm, int lddxm, float drop_p, unsigned drop_site,
+    const TDY* __restrict__ dy, const float* __restrict__ x, const float* __restrict__ gamma,
+    const float* __restrict__ mean, const float* __restrict__ rstd, const float* __restrict__ dres,
+    float* __restrict__ dx, TM* __restrict__ dxm, float drop_p, unsigned drop_site,
     const unsigned long long* __restrict__ rng, float* __restrict__ dgamma, float* __restrict__ dbeta, int B, int L,
-    int d, int halo, int rows_per_warp, int stages, int cols) {
+    int d, int halo, int ld, int rows_per_warp, int stages, int R) {
+    // every buffer has the same row pitch ld (= cols): R consecutive PHYSICAL rows (halo rows included, they are
+    // skipped when computing) are one contiguous block, fetched with one bulk copy per operand
     extern __shared__ __align__(16) uint8_t lsm[];
     __shared__ __align__(8) uint64_t bars[LNB2_WARPS * 4];
     const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
-    const int total = B * L, nq = cols >> 2, ld8 = ((d + 15) & ~15) >> 3;
+    const int cols = ld, nq = cols >> 2, ld8 = ((d + 15) & ~15) >> 3, Lp = L + 2 * halo;
+    const int prows = B * Lp;                                     // physical rows
     const int gw = blockIdx.x * LNB2_WARPS + wid;
-    const int r0 = min(total, gw * rows_per_warp), r1 = min(total, r0 + rows_per_warp), n = r1 - r0;
-    const uint32_t x_bytes = (uint32_t)cols * 4u, dy_bytes = (uint32_t)cols * (uint32_t)sizeof(TDY);
-    const uint32_t slot_bytes = 2u * x_bytes + dy_bytes;          // [x][dres][dy]
+    const int p0 = min(prows, gw * rows_per_warp), p1 = min(prows, p0 + rows_per_warp);
+    const int n = (p1 - p0 + R - 1) / R;                          // chunks of this warp
+    const uint32_t x_bytes = (uint32_t)cols * 4u * R, dy_bytes = (uint32_t)cols * (uint32_t)sizeof(TDY) * R;
+    const uint32_t slot_bytes = 2u * x_bytes + dy_bytes;          // [x][dres][dy], R rows each
     const uint32_t tx_bytes = x_bytes + dy_bytes + (dres ? x_bytes : 0u);
     uint8_t* wbase = lsm + (size_t)wid * stages * slot_bytes;
     const uint32_t wbase_u = ew_smem_u32(wbase), bar_u = ew_smem_u32(&bars[wid * 4]);
@@ -541,77 +546,83 @@ __global__ void __launch_bounds__(LNB2_WARPS * 32, 2) ln_bwd2_kernel(
     for (int j = 0; j < NQ; ++j) ag[j] = ab[j] = make_float4(0.f, 0.f, 0.f, 0.f);
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     __syncthreads();
-    RowWalk wi, wc;                                               // issue / consume cursors
-    wi.init(min(r0, total - 1), L, halo);
-    wc = wi;
-    int si = 0, sc = 0;
+    int si = 0, sc = 0, ki = 0;
     uint32_t pc = 0;
-    auto issue = [&]() {
+    auto issue = [&]() {                                          // chunk ki -> slot si (rows past the buffer end are guard rows)
         if (lane == 0) {
-            const size_t row = wi.row();
+            const size_t row = (size_t)p0 + (size_t)ki * R;
             const uint32_t dst = wbase_u + (uint32_t)si * slot_bytes, bar = bar_u + 8u * si;
             ew_mbar_expect_tx(bar, tx_bytes);
-            ew_bulk_g2s(dst, x + row * ldx, x_bytes, bar);
-            if (dres) ew_bulk_g2s(dst + x_bytes, dres + row * lddres, x_bytes, bar);
-            ew_bulk_g2s(dst + 2u * x_bytes, dy + row * lddy, dy_bytes, bar);
+            ew_bulk_g2s(dst, x + row * ld, x_bytes, bar);
+            if (dres) ew_bulk_g2s(dst + x_bytes, dres + row * ld, x_bytes, bar);
+            ew_bulk_g2s(dst + 2u * x_bytes, dy + row * ld, dy_bytes, bar);
         }
-        wi.advance(1);
+        ++ki;
         if (++si == stages) si = 0;
     };
     const int npro = min(stages, n);
     for (int k = 0; k < npro; ++k) issue();
+    int lpos = p0 % Lp;                                           // position of the current physical row inside its sample
     for (int k = 0; k < n; ++k) {
-        const size_t row = wc.row();
-        wc.advance(1);
-        const float mu = mean[row], rs = rstd[row];
         ew_mbar_wait(bar_u + 8u * sc, pc);
         const uint8_t* slot = wbase + (size_t)sc * slot_bytes;
-        float4 xh[NQ], dv[NQ];
-        float s1 = 0.f, s2 = 0.f;
+        for (int rr = 0; rr < R; ++rr) {
+            const int prow = p0 + k * R + rr;
+            const bool valid = prow < p1 && lpos >= halo && lpos < halo + L;
+            if (++lpos == Lp) lpos = 0;
+            if (!valid) continue;                                 // warp-uniform
+            const size_t row = (size_t)prow;
+            const float mu = mean[row], rs = rstd[row];
+            const uint8_t* xs = slot + (size_t)rr * cols * 4;
+            const uint8_t* rsd = slot + x_bytes + (size_t)rr * cols * 4;
+            const uint8_t* ds = slot + 2u * x_bytes + (size_t)rr * cols * sizeof(TDY);
+            float4 xh[NQ], dv[NQ];
+            float s1 = 0.f, s2 = 0.f;
 #pragma unroll
-        for (int j = 0; j < NQ; ++j) {
-            const int qd = lane + 32 * j;
-            if (qd < nq) {
-                const float4 xv = *reinterpret_cast<const float4*>(slot + (size_t)qd * 16);
-                const float4 gm = *reinterpret_cast<const float4*>(sgam + 4 * qd);
-                dv[j] = lds4f<TDY>(slot + 2u * x_bytes + (size_t)qd * 4 * sizeof(TDY));
-                xh[j] = make_float4((xv.x - mu) * rs, (xv.y - mu) * rs, (xv.z - mu) * rs, (xv.w - mu) * rs);
-                const float4 g = make_float4(dv[j].x * gm.x, dv[j].y * gm.y, dv[j].z * gm.z, dv[j].w * gm.w);
-                s1 += (g.x + g.y) + (g.z + g.w);
-                s2 += (g.x * xh[j].x + g.y * xh[j].y) + (g.z * xh[j].z + g.w * xh[j].w);
-            } else {
-                xh[j] = dv[j] = make_float4(0.f, 0.f, 0.f, 0.f);
+            for (int j = 0; j < NQ; ++j) {
+                const int qd = lane + 32 * j;
+                if (qd < nq) {
+                    const float4 xv = *reinterpret_cast<const float4*>(xs + (size_t)qd * 16);
+                    const float4 gm = *reinterpret_cast<const float4*>(sgam + 4 * qd);
+                    dv[j] = lds4f<TDY>(ds + (size_t)qd * 4 * sizeof(TDY));
+                    xh[j] = make_float4((xv.x - mu) * rs, (xv.y - mu) * rs, (xv.z - mu) * rs, (xv.w - mu) * rs);
+                    const float4 g = make_float4(dv[j].x * gm.x, dv[j].y * gm.y, dv[j].z * gm.z, dv[j].w * gm.w);
+                    s1 += (g.x + g.y) + (g.z + g.w);
+                    s2 += (g.x * xh[j].x + g.y * xh[j].y) + (g.z * xh[j].z + g.w * xh[j].w);
+                } else {
+                    xh[j] = dv[j] = make_float4(0.f, 0.f, 0.f, 0.f);
+                }
             }
-        }
-        s1 = warp_sum(s1) * inv_d; s2 = warp_sum(s2) * inv_d;
+            s1 = warp_sum(s1) * inv_d; s2 = warp_sum(s2) * inv_d;
 #pragma unroll
-        for (int j = 0; j < NQ; ++j) {
-            const int qd = lane + 32 * j, c = 4 * qd;
-            if (qd < nq) {
-                const float4 gm = *reinterpret_cast<const float4*>(sgam + c);
-                const float4 rv = dres ? *reinterpret_cast<const float4*>(slot + x_bytes + (size_t)qd * 16) : make_float4(0.f, 0.f, 0.f, 0.f);
-                // gamma is zero beyond d, so g is; masking dv keeps stray pad values out of dgamma / dbeta
-                const bool k0 = c < d, k1 = c + 1 < d, k2 = c + 2 < d, k3 = c + 3 < d;
-                ag[j].x += k0 ? dv[j].x * xh[j].x : 0.f; ag[j].y += k1 ? dv[j].y * xh[j].y : 0.f;
-                ag[j].z += k2 ? dv[j].z * xh[j].z : 0.f; ag[j].w += k3 ? dv[j].w * xh[j].w : 0.f;
-                ab[j].x += k0 ? dv[j].x : 0.f; ab[j].y += k1 ? dv[j].y : 0.f;
-                ab[j].z += k2 ? dv[j].z : 0.f; ab[j].w += k3 ? dv[j].w : 0.f;
-                float4 o;
-                o.x = k0 ? rs * (dv[j].x * gm.x - s1 - xh[j].x * s2) + rv.x : 0.f;
-                o.y = k1 ? rs * (dv[j].y * gm.y - s1 - xh[j].y * s2) + rv.y : 0.f;
-                o.z = k2 ? rs * (dv[j].z * gm.z - s1 - xh[j].z * s2) + rv.z : 0.f;
-                o.w = k3 ? rs * (dv[j].w * gm.w - s1 - xh[j].w * s2) + rv.w : 0.f;
-                stg4f<float>(dx + row * lddx + c, o);
-                if (dxm) {
-                    if (drop) {
-                        const uint4 gq = rng_group(dc.k, drop_site, (unsigned long long)row * ld8 + (qd >> 1));
-                        const int j0 = c & 7;
-                        o.x *= field16(gq, j0) >= dc.thr ? dc.inv_keep : 0.f;
-                        o.y *= field16(gq, j0 + 1) >= dc.thr ? dc.inv_keep : 0.f;
-                        o.z *= field16(gq, j0 + 2) >= dc.thr ? dc.inv_keep : 0.f;
-                        o.w *= field16(gq, j0 + 3) >= dc.thr ? dc.inv_keep : 0.f;
+            for (int j = 0; j < NQ; ++j) {
+                const int qd = lane + 32 * j, c = 4 * qd;
+                if (qd < nq) {
+                    const float4 gm = *reinterpret_cast<const float4*>(sgam + c);
+                    const float4 rv = dres ? *reinterpret_cast<const float4*>(rsd + (size_t)qd * 16) : make_float4(0.f, 0.f, 0.f, 0.f);
+                    // gamma is zero beyond d, so g is; masking dv keeps stray pad values out of dgamma / dbeta
+                    const bool k0 = c < d, k1 = c + 1 < d, k2 = c + 2 < d, k3 = c + 3 < d;
+                    ag[j].x += k0 ? dv[j].x * xh[j].x : 0.f; ag[j].y += k1 ? dv[j].y * xh[j].y : 0.f;
+                    ag[j].z += k2 ? dv[j].z * xh[j].z : 0.f; ag[j].w += k3 ? dv[j].w * xh[j].w : 0.f;
+                    ab[j].x += k0 ? dv[j].x : 0.f; ab[j].y += k1 ? dv[j].y : 0.f;
+                    ab[j].z += k2 ? dv[j].z : 0.f; ab[j].w += k3 ? dv[j].w : 0.f;
+                    float4 o;
+                    o.x = k0 ? rs * (dv[j].x * gm.x - s1 - xh[j].x * s2) + rv.x : 0.f;
+                    o.y = k1 ? rs * (dv[j].y * gm.y - s1 - xh[j].y * s2) + rv.y : 0.f;
+                    o.z = k2 ? rs * (dv[j].z * gm.z - s1 - xh[j].z * s2) + rv.z : 0.f;
+                    o.w = k3 ? rs * (dv[j].w * gm.w - s1 - xh[j].w * s2) + rv.w : 0.f;
+                    stg4f<float>(dx + row * ld + c, o);
+                    if (dxm) {
+                        if (drop) {
+                            const uint4 gq = rng_group(dc.k, drop_site, (unsigned long long)row * ld8 + (qd >> 1));
+                            const int j0 = c & 7;
+                            o.x *= field16(gq, j0) >= dc.thr ? dc.inv_keep : 0.f;
+                            o.y *= field16(gq, j0 + 1) >= dc.thr ? dc.inv_keep : 0.f;
+                            o.z *= field16(gq, j0 + 2) >= dc.thr ? dc.inv_keep : 0.f;
+                            o.w *= field16(gq, j0 + 3) >= dc.thr ? dc.inv_keep : 0.f;
+                        }
+                        stg4f<TM>(dxm + row * ld + c, o);
                     }
-                    stg4f<TM>(dxm + row * lddxm + c, o);
                 }
             }
         }
@@ -646,29 +657,34 @@ static void ln_bwd_launch(const void* dy, int lddy, const float* x, int ldx, con
                           const float* rstd, const float* dres, int lddres, float* dx, int lddx, void* dxm, int lddxm,
                           float drop_p, unsigned site, const unsigned long long* rng, float* dgamma, float* dbeta,
                           int B, int L, int d, int halo, cudaStream_t s) {
-    const int cols = (d + 7) & ~7;
-    const bool aligned = (ldx % 4 == 0) && (lddx % 4 == 0) && (!dres || lddres % 4 == 0) && (lddy * (int)sizeof(TDY)) % 16 == 0 &&
-                         (!dxm || (lddxm * (int)sizeof(TM)) % 8 == 0) && ldx >= cols && lddy >= cols && lddx >= cols &&
-                         (!dres || lddres >= cols) && (!dxm || lddxm >= cols) &&
-                         ((uintptr_t)x % 16 == 0) && ((uintptr_t)dy % 16 == 0) && ((uintptr_t)dx % 16 == 0) &&
-                         (!dres || (uintptr_t)dres % 16 == 0) && (!dxm || (uintptr_t)dxm % 8 == 0);
-    if (aligned && cols <= 640 && B * L >= 64) {
-        const int total = B * L;
-        const size_t slot = (size_t)2 * cols * 4 + (size_t)cols * sizeof(TDY);
-        int stages = 3;
-        while (stages > 1 && (size_t)LNB2_WARPS * stages * slot > 100 * 1024) --stages;
-        const size_t smem = (size_t)LNB2_WARPS * stages * slot + (size_t)cols * 4;
+    // staged kernel: every operand shares one 16-byte aligned row pitch (true for the engine's token buffers)
+    const int ld = ldx;
+    const bool same = lddy == ld && lddx == ld && (!dres || lddres == ld) && (!dxm || lddxm == ld) && ld % 8 == 0 && ld >= d &&
+                      ((uintptr_t)x % 16 == 0) && ((uintptr_t)dy % 16 == 0) && ((uintptr_t)dx % 16 == 0) &&
+                      (!dres || (uintptr_t)dres % 16 == 0) && (!dxm || (uintptr_t)dxm % 8 == 0);
+    if (same && ld <= 640 && B * L >= 64 && halo <= 16) {
+        const int prows = B * (L + 2 * halo);
+        const size_t rowb = (size_t)2 * ld * 4 + (size_t)ld * sizeof(TDY);
+        // R rows per bulk copy, `stages` copies in flight per warp, <= ~100 KB per CTA (two CTAs per SM)
+        int R = 2, stages = 2;                         // measured: 2 x 2 ~ 1 x 3 > 4 x 1 (d = 270); what matters is ~90 KB in flight
+        if (const char* e = getenv("CSI_LN_R")) R = atoi(e);
+        if (const char* e = getenv("CSI_LN_STAGES")) stages = atoi(e);
+        if (R < 1 || R > 4 || stages < 1 || stages > 4) { R = 2; stages = 2; }
+        while (R > 1 && (size_t)LNB2_WARPS * stages * R * rowb > 100 * 1024) R >>= 1;
+        while (stages > 1 && (size_t)LNB2_WARPS * stages * R * rowb > 100 * 1024) --stages;
+        const size_t smem = (size_t)LNB2_WARPS * stages * R * rowb + (size_t)ld * 4;
         int grid = 2 * num_sms();
-        if (grid * LNB2_WARPS * 4 > total) grid = cdiv(total, LNB2_WARPS * 4);
-        const int rows_per_warp = cdiv(total, grid * LNB2_WARPS);
-        grid = cdiv(total, rows_per_warp * LNB2_WARPS);
+        if (grid * LNB2_WARPS * 4 * R > prows) grid = cdiv(prows, LNB2_WARPS * 4 * R);
+        int rows_per_warp = cdiv(prows, grid * LNB2_WARPS);
+        rows_per_warp = (rows_per_warp + R - 1) / R * R;
+        grid = cdiv(prows, rows_per_warp * LNB2_WARPS);
 #define LNB2_CASE(NQ)                                                                                                   \
         do {                                                                                                            \
             cudaFuncSetAttribute(ln_bwd2_kernel<TDY, TM, NQ>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);  \
-            ln_bwd2_kernel<TDY, TM, NQ><<<grid, LNB2_WARPS * 32, smem, s>>>((const TDY*)dy, lddy, x, ldx, gamma, mean, rstd, dres, \
-                lddres, dx, lddx, (TM*)dxm, lddxm, drop_p, site, rng, dgamma, dbeta, B, L, d, halo, rows_per_warp, stages, cols); \
+            ln_bwd2_kernel<TDY, TM, NQ><<<grid, LNB2_WARPS * 32, smem, s>>>((const TDY*)dy, x, gamma, mean, rstd, dres, dx,   \
+                (TM*)dxm, drop_p, site, rng, dgamma, dbeta, B, L, d, halo, ld, rows_per_warp, stages, R);                 \
         } while (0)
-        if (cols <= 128) LNB2_CASE(1); else if (cols <= 256) LNB2_CASE(2); else if (cols <= 384) LNB2_CASE(3);
+        if (ld <= 128) LNB2_CASE(1); else if (ld <= 256) LNB2_CASE(2); else if (ld <= 384) LNB2_CASE(3);
         else LNB2_CASE(5);
 #undef LNB2_CASE
         return;
@@ -1310,8 +1326,11 @@ __global__ void pack_kernel(const float* __restrict__ params, T* __restrict__ pa
     const csi_pack_entry e = table[blockIdx.y];
     const int total = e.N * e.C * e.k;
     for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < total; i += gridDim.x * blockDim.x) {
-        const int j = i % e.k, c = (i / e.k) % e.C, n = i / (e.k * e.C);
-        const float v = params[e.src_off + i];
+        // walk the DESTINATION in memory order (coalesced 2-byte stores); the strided fp32 reads hit L2
+        int n, c, j;
+        if (e.mode == 0) { c = i % e.C; j = (i / e.C) % e.k; n = i / (e.C * e.k); }
+        else { n = i % e.N; j = (i / e.N) % e.k; c = i / (e.N * e.k); }
+        const float v = params[e.src_off + ((long long)n * e.C + c) * e.k + j];
         const int np = grp_to_padded(n, e.gn), cp = grp_to_padded(c, e.gc);
         const long long dst = e.mode == 0 ? (long long)np * e.ld + (long long)j * e.P + cp
                                           : (long long)cp * e.ld + (long long)(e.seg_base + j) * e.P + np;
