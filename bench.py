@@ -323,8 +323,8 @@ def run_b200(args):
         dist.destroy_process_group()
 
 
-KERNEL_OF_OP = {"gemm_nt": "gemm_nt_tc2_kernel", "gemm_tn": "gemm_tn_tc_kernel", "attn_fwd": "attn_fwd_mma_kernel",
-                "attn_bwd": "attn_bwd_mma_kernel", "pool_dual": "pool_dual_kernel", "layernorm_bwd": "ln_bwd_kernel"}
+KERNEL_OF_OP = {"gemm_nt": "gemm_nt_tc3_kernel", "gemm_tn": "gemm_tn_tc3_kernel", "attn_fwd": "attn_fwd_mma_kernel",
+                "attn_bwd": "attn_bwd_mma_kernel", "pool_dual": "pool_dual_kernel", "layernorm_bwd": "ln_bwd2_kernel"}
 
 
 def dram_traffic(name):

@@ -12,6 +12,7 @@ PyTorch-operator or CPU fallback: on a non-CUDA device, or without the library, 
 from __future__ import annotations
 
 import math
+import os
 import weakref
 from collections import OrderedDict
 from typing import Optional
@@ -126,7 +127,8 @@ class THAT(torch.nn.Module):
         self.rng_seed = int(torch.initial_seed() & 0x7FFFFFFF)
         self._engine: Optional[THATEngine] = None
         self._ops_override = None            # tests only: inject the torch mirror of the kernels
-        self.use_cuda_graph = True           # fused_train_step replays forward+loss+backward as one CUDA graph
+        # fused_train_step replays forward+loss+backward as one CUDA graph (CSI_NO_GRAPH=1: eager launches, for profilers)
+        self.use_cuda_graph = os.environ.get("CSI_NO_GRAPH", "0") != "1"
         self._eager_steps = 0
         vals, bufs = _initial_values(self.geom)
         flat = torch.zeros(self.arena.size)
