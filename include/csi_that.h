@@ -186,6 +186,11 @@ int csi_dropout_rows(const float* in, int ldi, void* out, int ldo, int out_dtype
 int csi_bce_logits(const float* z, int ldz, const float* y, int ldy, int rows, int cols, float pos_weight,
                    float grad_scale, float* loss, float* dz, int lddz, void* stream);
 
+/* ---- sibling head: torch.nn.SmoothL1Loss(beta) mean of THAT_COUNT_PRED (that_count_pred.py:399) and its
+ * gradient * grad_scale; same calling convention as csi_bce_logits. */
+int csi_smooth_l1(const float* z, int ldz, const float* y, int ldy, int rows, int cols, float beta,
+                  float grad_scale, float* loss, float* dz, int lddz, void* stream);
+
 /* ---- a15: torch.optim.Adam with coupled L2 (that.py:395-397) over the flat arenas.
  * step: device int64 holding the 1-based step of THIS update.  g is multiplied by grad_scale first. */
 int csi_adam_flat(float* p, const float* g, float* m, float* v, long long n, float lr, float beta1, float beta2,

@@ -1266,6 +1266,41 @@ extern "C" int csi_bce_logits(const float* z, int ldz, const float* y, int ldy, 
     return CSI_OK;
 }
 
+// ------------------------------------------------------------------------------------------------ SmoothL1
+// torch.nn.SmoothL1Loss(reduction="mean", beta): the loss of the count-prediction sibling head
+// (model/that_count_pred.py:399, train.py:91-97):  l = 0.5 d^2 / beta if |d| < beta else |d| - 0.5 beta,  d = z - y
+__global__ void __launch_bounds__(1024) smooth_l1_kernel(const float* __restrict__ z, int ldz, const float* __restrict__ y,
+                                                         int ldy, int rows, int cols, float beta, float gscale,
+                                                         float* __restrict__ loss, float* __restrict__ dz, int lddz) {
+    __shared__ float red[32];
+    const int n = rows * cols;
+    const float invn = 1.0f / (float)n;
+    float acc = 0.f;
+    for (int i = threadIdx.x; i < n; i += blockDim.x) {
+        const int r = i / cols, c = i % cols;
+        const float dv = z[(size_t)r * ldz + c] - y[(size_t)r * ldy + c], ad = fabsf(dv);
+        const bool quad = ad < beta;
+        acc += quad ? 0.5f * dv * dv / beta : ad - 0.5f * beta;
+        if (dz) dz[(size_t)r * lddz + c] = (quad ? dv / beta : (dv > 0.f ? 1.f : -1.f)) * invn * gscale;
+    }
+    acc = warp_sum(acc);
+    if ((threadIdx.x & 31) == 0) red[threadIdx.x >> 5] = acc;
+    __syncthreads();
+    if (threadIdx.x < 32) {
+        float v = threadIdx.x < (blockDim.x >> 5) ? red[threadIdx.x] : 0.f;
+        v = warp_sum(v);
+        if (threadIdx.x == 0) loss[0] = v * invn;
+    }
+}
+
+extern "C" int csi_smooth_l1(const float* z, int ldz, const float* y, int ldy, int rows, int cols, float beta,
+                             float grad_scale, float* loss, float* dz, int lddz, void* stream) {
+    CSI_CHECK_ARG(z && y && loss && rows > 0 && cols > 0 && beta > 0.f, "bad argument");
+    smooth_l1_kernel<<<1, 1024, 0, ST(stream)>>>(z, ldz, y, ldy, rows, cols, beta, grad_scale, loss, dz, lddz);
+    CSI_LAUNCH_CHECK();
+    return CSI_OK;
+}
+
 // ------------------------------------------------------------------------------------------------ Adam
 __global__ void __launch_bounds__(256) adam_kernel(float* __restrict__ p, const float* __restrict__ g,
                                                    float* __restrict__ m, float* __restrict__ v, long long n4, float lr,

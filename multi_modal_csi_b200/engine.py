@@ -57,6 +57,7 @@ class THATEngine:
         self.pack_table = ops.make_pack_table(self.pack.entries, self.dev)
         self.packed_bias = torch.zeros(max(self.pack.bias_size, 1), dtype=torch.float32, device=self.dev)
         self.bias_table = ops.make_pack_table(self.pack.bias_entries, self.dev)
+        self.loss_kind = "bce"                     # "bce" (THAT, that.py:401) | "smooth_l1" (THAT_COUNT_PRED)
         self.rng = torch.tensor([seed, 0], dtype=torch.int64, device=self.dev)      # {seed, step}
         self.opt_step = torch.ones(1, dtype=torch.int64, device=self.dev)           # 1-based Adam step
         self._alloc()
@@ -374,7 +375,7 @@ class THATEngine:
 
     def train_body_graph(self, B: int, pos_weight: float, dropout: bool, part: int = 0):
         """Replays train_body as one CUDA graph (captured on first use for this (B, pos_weight, dropout, part))."""
-        key = (B, float(pos_weight), bool(dropout), part)
+        key = (B, float(pos_weight), bool(dropout), part, self.loss_kind)
         g = self._graphs.get(key)
         if g is None:
             torch.cuda.synchronize(self.dev)
@@ -393,8 +394,12 @@ class THATEngine:
                      want_grad: bool = True) -> torch.Tensor:
         """BCEWithLogitsLoss(pos_weight).mean() of the engine's logits against y [B,out] fp32; writes
         dL/dlogits * grad_scale into the engine's dlogits buffer.  Returns the 1-element loss tensor."""
-        self.ops.bce_logits(self.logits, y, B, self.g.out, pos_weight, grad_scale, self.loss,
-                            self.dlogits if want_grad else None)
+        if self.loss_kind == "smooth_l1":          # sibling head THAT_COUNT_PRED: SmoothL1Loss(beta=1).mean()
+            self.ops.smooth_l1(self.logits, y, B, self.g.out, 1.0, grad_scale, self.loss,
+                               self.dlogits if want_grad else None)
+        else:
+            self.ops.bce_logits(self.logits, y, B, self.g.out, pos_weight, grad_scale, self.loss,
+                                self.dlogits if want_grad else None)
         return self.loss
 
     def adam(self, m: torch.Tensor, v: torch.Tensor, lr: float, betas=(0.9, 0.999), eps: float = 1e-8,

@@ -14,7 +14,7 @@ from torch.utils.data import TensorDataset
 from .load_data import encode_data_y, load_data_x, load_data_y
 from .optim import FusedAdam
 from .preset import preset
-from .that import THAT
+from .that import THAT, THAT_COUNT_PRED
 from .train import _log, _wandb, train
 from .utils import NumpyEncoder, load_model_components, performance_metrics, save_model_components
 
@@ -110,15 +110,68 @@ def parse_args():
     return a.parse_args()
 
 
+def run_that_count_pred(data_train_x, data_train_y, data_test_x, data_test_y, var_repeat=10):
+    """model/that_count_pred.py:334-509: THAT_COUNT_PRED trained with SmoothL1 on per-activity counts (Adam without
+    weight decay, ``var_mode="count_classification"``); returns the metrics dict of the last repeat."""
+    device = torch.device("cuda" if torch.cuda.is_available() else "cpu")
+    data_valid_x, data_test_x, data_valid_y, data_test_y = train_test_split(
+        data_test_x, data_test_y, test_size=0.5, shuffle=True, random_state=39)
+    data_valid_x = data_valid_x.reshape(data_valid_x.shape[0], data_valid_x.shape[1], -1)
+    data_train_x = data_train_x.reshape(data_train_x.shape[0], data_train_x.shape[1], -1)
+    data_test_x = data_test_x.reshape(data_test_x.shape[0], data_test_x.shape[1], -1)
+    var_x_shape, var_y_shape = data_train_x[0].shape, [data_train_y[0].shape[1]]                  # that_count_pred.py:366
+    data_train_set = TensorDataset(torch.from_numpy(data_train_x), torch.from_numpy(data_train_y))
+    data_valid_set = TensorDataset(torch.from_numpy(data_valid_x), torch.from_numpy(data_valid_y))
+    dict_true_acc = None
+    for var_r in range(var_repeat):
+        print("Repeat", var_r)
+        if _wandb is not None:
+            _wandb.init(project="final_results", name=f"DEM_THAT_{var_r}_" + "_".join(preset["data"]["environment"]),
+                        config=preset, reinit=True)
+        torch.random.manual_seed(var_r + 39)
+        model_that = THAT_COUNT_PRED(var_x_shape, var_y_shape, act_dtype=preset["nn"].get("dtype", "bf16"),
+                                     max_batch=preset["nn"]["batch_size"]).to(device)
+        optimizer = FusedAdam(model_that.parameters(), lr=preset["nn"]["lr"], weight_decay=0)
+        loss_mode = "count_classification"
+        loss = torch.nn.SmoothL1Loss()
+        var_time_0 = time.time()
+        var_best_weight = train(model=model_that, optimizer=optimizer, loss=loss, data_train_set=data_train_set,
+                                data_test_set=data_valid_set, var_threshold=preset["nn"]["threshold"],
+                                var_batch_size=preset["nn"]["batch_size"], var_epochs=preset["nn"]["epoch"], device=device,
+                                var_mode=loss_mode)
+        var_time_1 = time.time()
+        model_that.load_state_dict(var_best_weight)
+        with torch.no_grad():
+            predict_test_y = model_that(torch.from_numpy(data_test_x).to(device))
+        predict_test_y = predict_test_y.detach().cpu().numpy()
+        var_time_2 = time.time()
+        dict_true_acc = performance_metrics(data_test_y.sum(axis=1), predict_test_y, var_mode=loss_mode)
+        payload = {"repeat": var_r, "train_time": var_time_1 - var_time_0, "test_time": var_time_2 - var_time_1,
+                   "TOTAL_TESTSET_ERROR": dict_true_acc["total_error"],
+                   "TOTAL_TESTSET_perfect_prediction_percentage": dict_true_acc["perfect_prediction_percentage"],
+                   "TOTAL_ACCURACY": dict_true_acc["accuracy"], "mean_count_error": dict_true_acc["mean_count_error"],
+                   "precision": dict_true_acc["precision"], "recall": dict_true_acc["recall"],
+                   "f1_score": dict_true_acc["f1_score"]}
+        for i in range(5):
+            payload[f"error_per_person_{i + 1}"] = dict_true_acc["error_per_person"][i]
+        _log(payload)
+        print(" %.6fs" % (time.time() - var_time_1), "- Total Error %.6f" % dict_true_acc["total_error"],
+              "-  perfect_prediction_percentage %.6f" % dict_true_acc["perfect_prediction_percentage"])
+    if _wandb is not None and getattr(_wandb, "run", None) is not None:
+        _wandb.finish()
+    return dict_true_acc
+
+
 def run():
-    """run_main.py:88-160 restricted to --model THAT (the only model on this path)."""
+    """run_main.py:88-160 restricted to the models on this path: THAT and its sibling THAT_COUNT_PRED."""
     var_args = parse_args()
     var_users = [u.strip() for u in var_args.users.split(",")]
     preset["repeat"] = 1 if not preset["pretrained_path"] else preset["repeat"]
-    if var_args.model != "THAT":
+    if var_args.model not in ("THAT", "THAT_COUNT_PRED"):
         raise Exception("Not valid name for model")                       # run_main.py:140
     data_train_x, data_test_x, data_train_y, data_test_y = master_splitter(preset, var_args.task, var_args.model, var_users)
-    result = run_that(data_train_x, data_train_y, data_test_x, data_test_y, var_args.repeat)
+    runner = run_that if var_args.model == "THAT" else run_that_count_pred
+    result = runner(data_train_x, data_train_y, data_test_x, data_test_y, var_args.repeat)
     result["model"], result["task"], result["data"], result["nn"] = var_args.model, var_args.task, preset["data"], preset["nn"]
     print(result)
     os.makedirs(os.path.dirname(preset["path"]["save"]) or ".", exist_ok=True)

@@ -273,14 +273,17 @@ class THAT(torch.nn.Module):
 
     # ------------------------------------------------------------------ fused train step
     def fused_train_step(self, x, y, optimizer, pos_weight: float = 4.0, augment: bool = True,
-                         grad_hook=None, offs=None, lens=None, use_graph=None):
+                         grad_hook=None, offs=None, lens=None, use_graph=None, loss_kind: str = "bce"):
         """augmentation + forward + BCE + backward + Adam as one launch sequence (train.py:84-101).
 
         x: fp32 [B,T,F] on the device (or a packed ragged arena with offs/lens); y: [B, ...] labels.
         ``grad_hook(engine)`` runs between backward and the optimizer (data-parallel all-reduce).
         Returns (loss 1-element tensor, logits [B,out]); both are views of static buffers."""
+        if loss_kind not in ("bce", "smooth_l1"):
+            raise ValueError(f"unsupported fused loss {loss_kind!r}")
         B = y.shape[0]
         eng = self._engine_for(B)
+        eng.loss_kind = loss_kind
         yf = y.reshape(B, -1)
         if yf.dtype != torch.float32:
             yf = yf.float()
@@ -306,3 +309,10 @@ class THAT(torch.nn.Module):
             grad_hook(eng)
         optimizer.fused_step(eng)
         return loss, logits
+
+
+class THAT_COUNT_PRED(THAT):
+    """model/that_count_pred.py:180-302: the count-regression sibling.  Layer for layer the same network as THAT (same
+    ``state_dict`` keys and constructor RNG order); ``var_y_shape[-1]`` is the number of activities (9) and the model is
+    trained with ``SmoothL1Loss`` on per-activity head counts (``var_mode="count_classification"``), so every backbone
+    kernel is reused unchanged and only the loss kernel differs (``csi_smooth_l1``)."""

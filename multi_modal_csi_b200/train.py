@@ -1,7 +1,8 @@
 """``train(...)`` with the signature and semantics of benchmark/wifi_csi/train.py:36-176.
 
 Kept from the reference: shuffled DataLoader with pinned memory (:48), the LAST batch of every epoch is skipped
-(:81-82), augmentation only while ``model.training`` (:88-89), ``baseline`` labels flattened to [B, -1] (:93-94), the
+(:81-82), augmentation only while ``model.training`` (:88-89), ``baseline`` labels flattened to [B, -1] (:93-94),
+``count_classification`` labels summed over users to per-activity counts (:91-92, :116-117), the
 once-per-epoch metrics of the last train batch on int-truncated logits (:105-109), whole-validation-set evaluation
 in one batch (:49,111-127), the wandb keys (:130-144), the selection rule f1 AND perfect-prediction-percentage
 (:159-166) and early stopping after ``patience`` non-improving epochs (:167-174).
@@ -64,8 +65,14 @@ def train(model, optimizer, loss, data_train_set: TensorDataset, data_test_set: 
     data_train_loader = DataLoader(data_train_set, var_batch_size, shuffle=sampler is None, sampler=sampler, pin_memory=True)
     data_test_loader = DataLoader(data_test_set, len(data_test_set))
     pos_weight = _uniform_pos_weight(loss)
-    fused = (isinstance(model, THAT) and isinstance(optimizer, FusedAdam) and pos_weight is not None
-             and var_mode == "baseline" and device.type == "cuda")
+    loss_kind = None                                    # which fused loss kernel implements ``loss``
+    if pos_weight is not None and var_mode == "baseline":
+        loss_kind = "bce"
+    elif (isinstance(loss, torch.nn.SmoothL1Loss) and loss.reduction == "mean" and float(loss.beta) == 1.0
+          and var_mode == "count_classification"):
+        loss_kind, pos_weight = "smooth_l1", 1.0
+    fused = (isinstance(model, THAT) and isinstance(optimizer, FusedAdam) and loss_kind is not None
+             and device.type == "cuda")
     sync = GradSync(model, dist.get_world_size()) if distributed and isinstance(model, THAT) else None
 
     var_best_f1_score, var_best_PPP, var_best_weight, counter = 0, 0, None, 0
@@ -83,12 +90,14 @@ def train(model, optimizer, loss, data_train_set: TensorDataset, data_test_set: 
             data_batch_x, data_batch_y = data_batch
             data_batch_x = data_batch_x.to(device, non_blocking=True)
             data_batch_y = data_batch_y.to(device, non_blocking=True)
+            if var_mode == "count_classification":
+                data_batch_y = data_batch_y.sum(axis=1)                                  # train.py:91-92
             if var_mode == "baseline":
                 data_batch_y = data_batch_y.reshape(data_batch_y.shape[0], -1)
             if fused:
                 x = data_batch_x.reshape(data_batch_x.shape[0], data_batch_x.shape[1], -1).float()
                 var_loss_train, predict_train_y = model.fused_train_step(
-                    x, data_batch_y, optimizer, pos_weight=pos_weight, augment=True, grad_hook=sync)
+                    x, data_batch_y, optimizer, pos_weight=pos_weight, augment=True, grad_hook=sync, loss_kind=loss_kind)
                 var_loss_train, predict_train_y = var_loss_train.clone(), predict_train_y.clone()
             else:
                 if model.training:
@@ -110,6 +119,8 @@ def train(model, optimizer, loss, data_train_set: TensorDataset, data_test_set: 
         with torch.no_grad():
             data_test_x, data_test_y = next(iter(data_test_loader))
             data_test_x, data_test_y = data_test_x.to(device), data_test_y.to(device)
+            if var_mode == "count_classification":
+                data_test_y = data_test_y.sum(axis=1)                                    # train.py:116-117
             if var_mode == "baseline":
                 data_test_y = data_test_y.reshape(data_test_y.shape[0], -1)
             predict_test_y = model(data_test_x)

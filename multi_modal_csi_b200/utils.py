@@ -1,7 +1,8 @@
 """Metrics, result encoding and checkpoint helpers with the semantics of benchmark/wifi_csi/utils.py.
 
 These run on the CPU in numpy once per epoch, exactly where the reference runs them (train.py:105-127); they are
-not on the accelerated path.  Only ``var_mode="baseline"`` (the BCE/THAT path) is implemented.
+not on the accelerated path.  ``var_mode="baseline"`` (BCE / THAT) and ``"count_classification"`` (SmoothL1 /
+THAT_COUNT_PRED) are implemented.
 """
 from __future__ import annotations
 
@@ -73,17 +74,28 @@ def calculate_scores(y_true, y_pred):
     return precision.mean(), recall.mean(), f1.mean(), acc.mean()
 
 
+def threshold_round(x, threshold=0.3):
+    """utils.py:137-145 (vectorised): round up iff the fractional part exceeds ``threshold``."""
+    x = np.asarray(x, dtype=float)
+    fl = np.floor(x)
+    return np.where(x - fl > threshold, np.ceil(x), fl)
+
+
 def performance_metrics(y_true, y_pred, var_mode="baseline", var_threshold=0.5):
-    """utils.py:213-270 for var_mode == "baseline".  The decision threshold is the reference's hard-coded 0.5
-    (utils.py:238 ignores ``var_threshold``); classes per user are fixed at 9 (utils.py:236)."""
-    if var_mode != "baseline":
-        raise ValueError(f"Unsupported var_mode: {var_mode}")
+    """utils.py:213-270 for var_mode "baseline" and "count_classification".  In baseline mode the decision threshold
+    is the reference's hard-coded 0.5 (utils.py:238 ignores ``var_threshold``) and classes per user are fixed at 9
+    (utils.py:236); in count mode predictions are threshold-rounded at 0.5 and clipped to [0, 5] (utils.py:229-233)."""
     y_true = np.array(y_true)
     y_pred = np.array(y_pred)
-    y_pred = (1 / (1 + np.exp(-y_pred))).astype(float)
-    y_true = y_true.reshape(y_true.shape[0], -1, 9)
-    y_pred = y_pred.reshape(y_true.shape)
-    y_pred, y_true, _ = process_predictions(y_pred, y_true, var_threshold=0.5)
+    if var_mode == "count_classification":
+        y_pred = np.clip(threshold_round(y_pred, threshold=0.5), 0, 5)
+    elif var_mode == "baseline":
+        y_pred = (1 / (1 + np.exp(-y_pred))).astype(float)
+        y_true = y_true.reshape(y_true.shape[0], -1, 9)
+        y_pred = y_pred.reshape(y_true.shape)
+        y_pred, y_true, _ = process_predictions(y_pred, y_true, var_threshold=0.5)
+    else:
+        raise ValueError(f"Unsupported var_mode: {var_mode}")
     n = y_true.shape[0]
     diff = np.abs(y_true - y_pred)
     counting = count_error(y_pred, y_true)

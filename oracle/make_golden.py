@@ -14,6 +14,7 @@ restatement or by the product package.  Fixtures:
   that_anchor_*.npz   full-size anchors (F=270/out=54 and F=540/out=90, B=4): logits, loss, per-parameter
                       grad norms, eval-mode logits, per-parameter init checksums for seed 39
   metrics.npz         utils.performance_metrics(var_mode="baseline") on seeded random logits/labels
+  that_count_pred.npz model/that_count_pred.py THAT_COUNT_PRED + SmoothL1Loss: logits, grads, 2 Adam steps, count metrics
   labels.npz + annotation_excerpt.csv   load_data.encode_* on an excerpt of dataset/annotation.csv
   augment_stats.npz   moments of train.py::apply_augmentation output (statistical fixture)
 """
@@ -194,6 +195,58 @@ def augment_case(ns):
     print("augment:", {k: float(v) for k, v in rec.items()})
 
 
+def count_pred_case(ns):
+    """Sibling head: the reference's THAT_COUNT_PRED (model/that_count_pred.py) with SmoothL1Loss on
+    per-activity counts, 2 Adam steps (weight_decay 0 as in that_count_pred.py:397), plus the count-mode metrics."""
+    import importlib.util
+    from oracle.ref_import import REF_WIFI
+    spec = importlib.util.spec_from_file_location("ref_model_that_count_pred", os.path.join(REF_WIFI, "model", "that_count_pred.py"))
+    mod = importlib.util.module_from_spec(spec)
+    spec.loader.exec_module(mod)
+    T, F, out, B = 400, 30, 9, 4
+    torch.manual_seed(39)
+    m = mod.THAT_COUNT_PRED((T, F), [out])
+    for sub in m.modules():
+        if isinstance(sub, torch.nn.Dropout):
+            sub.p = 0.0
+    g = torch.Generator().manual_seed(4321)
+    x = torch.rand(B, T, F, generator=g) * 20
+    y = torch.randint(0, 3, (B, 6, out), generator=g)          # [B, users, activities] one-hot-ish -> counts by sum(axis=1)
+    rec = {"x": x.numpy(), "y": y.numpy(), "dims": np.array([T, F, out, B])}
+    for k, v in m.state_dict().items():
+        rec["w/" + k] = v.detach().clone().numpy()
+    opt = torch.optim.Adam(m.parameters(), lr=5e-4, weight_decay=0)
+    loss = torch.nn.SmoothL1Loss()
+    losses = []
+    for s in range(2):
+        m.train()
+        pred = m(x)
+        yc = y.sum(axis=1)                                     # train.py:91-92
+        lv = loss(pred, yc.float())
+        opt.zero_grad()
+        lv.backward()
+        if s == 0:
+            rec["logits_train"] = pred.detach().numpy()
+            for k, p_ in m.named_parameters():
+                if p_.grad is not None:
+                    rec["g/" + k] = p_.grad.detach().clone().numpy()
+        opt.step()
+        losses.append(lv.item())
+    rec["traj_losses"] = np.array(losses, dtype=np.float64)
+    for k, v in m.state_dict().items():
+        rec["traj_w/" + k] = v.detach().clone().numpy()
+    # count-mode metrics (utils.py:229-233) on seeded regression outputs
+    rng = np.random.default_rng(11)
+    yt = rng.integers(0, 4, size=(48, out))
+    yp = yt + rng.normal(0, 0.45, size=(48, out))
+    res = ns.utils.performance_metrics(yt, yp, var_mode="count_classification")
+    rec["m_y_true"], rec["m_y_pred"] = yt, yp
+    for k, v in res.items():
+        rec["m/" + k] = np.asarray(v, dtype=np.float64)
+    np.savez_compressed(os.path.join(GOLD, "that_count_pred.npz"), **rec)
+    print("that_count_pred: losses", losses, "total_error", float(res["total_error"]))
+
+
 def main():
     os.makedirs(GOLD, exist_ok=True)
     torch.set_num_threads(max(1, os.cpu_count() or 1))
@@ -204,6 +257,7 @@ def main():
     metrics_case(ns)
     labels_case(ns)
     augment_case(ns)
+    count_pred_case(ns)
 
 
 if __name__ == "__main__":

@@ -327,6 +327,13 @@ class MirrorOps:
             sg = torch.sigmoid(zz)
             dz[:rows, :cols] = (sg * (pos_weight * yy + 1 - yy) - pos_weight * yy) * (grad_scale / (rows * cols))
 
+    def smooth_l1(self, z, y, rows, cols, beta, grad_scale, loss, dz):
+        d = z[:rows, :cols].float() - y[:rows, :cols].float()
+        quad = d.abs() < beta
+        loss[0] = torch.where(quad, 0.5 * d * d / beta, d.abs() - 0.5 * beta).mean()
+        if dz is not None:
+            dz[:rows, :cols] = torch.where(quad, d / beta, torch.sign(d)) * (grad_scale / (rows * cols))
+
     def adam_flat(self, p, g, m, v, n, lr, b1, b2, eps, wd, step, grad_scale):
         t = int(step.item())
         gg = g[:n] * grad_scale + wd * p[:n]

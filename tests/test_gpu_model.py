@@ -356,3 +356,42 @@ def test_full_batch_properties_b256():
         l1, _ = m.fused_train_step(x, y, opt, augment=True)
     assert np.isfinite(l0) and np.isfinite(l1.item()) and l1.item() < l0     # 4 Adam steps on one batch reduce its loss
     assert int(m.state_dict()["layer_right_encoder.0.layer_cnn.2.1.num_batches_tracked"]) == 4
+
+
+def test_count_pred_sibling_head_smooth_l1(gold):
+    """THAT_COUNT_PRED + SmoothL1Loss (model/that_count_pred.py, train.py:91-97): first-step logits and gradients and a
+    2-step Adam trajectory of the fused path against the fixture generated from the unmodified reference."""
+    from multi_modal_csi_b200 import THAT_COUNT_PRED, FusedAdam
+    g = gold("that_count_pred.npz")
+    T, F, out, B = [int(v) for v in g["dims"]]
+    sd = {k[2:]: torch.from_numpy(g[k]) for k in g.files if k.startswith("w/")}
+    x = torch.from_numpy(g["x"]).cuda()
+    yc = torch.from_numpy(g["y"]).sum(axis=1).float().cuda()              # per-activity counts (train.py:91-92)
+    # autograd path, first step: logits + gradients
+    torch.manual_seed(39)
+    m = THAT_COUNT_PRED((T, F), [out], act_dtype="fp32")
+    m.load_state_dict(sd)
+    m.dropout_enabled = False
+    m = m.to("cuda").train()
+    pred = m(x)
+    assert nrel(pred, torch.from_numpy(g["logits_train"])) < 1e-4
+    torch.nn.SmoothL1Loss()(pred, yc).backward()
+    ge, worst = grad_err(m, {k[2:]: torch.from_numpy(g[k]) for k in g.files if k.startswith("g/")})
+    assert ge < 1e-4, (ge, worst)
+    # fused path, two steps
+    mf = THAT_COUNT_PRED((T, F), [out], act_dtype="fp32")
+    mf.load_state_dict(sd)
+    mf.dropout_enabled = False
+    mf = mf.to("cuda").train()
+    opt = FusedAdam(mf.parameters(), lr=5e-4, weight_decay=0)
+    for s_ in range(2):
+        loss, _ = mf.fused_train_step(x, yc, opt, augment=False, loss_kind="smooth_l1")
+        ref = float(g["traj_losses"][s_])
+        assert abs(loss.item() - ref) < 2e-4 * max(1.0, ref)
+    # weight_decay = 0 here (that_count_pred.py:397): Adam's first steps move every weight by ~lr * sign(g), so an element
+    # whose true gradient is below the fp32 noise floor can land 2 * lr away -- allow a 1e-3 fraction of such elements
+    sdm = mf.state_dict()
+    for k in g.files:
+        if k.startswith("traj_w/") and not k.endswith(".0.bias"):
+            diff = (sdm[k[7:]].float().cpu() - torch.from_numpy(g[k]).float()).abs()
+            assert diff.max().item() < 2.1e-3 and (diff > 2e-4).float().mean().item() < 1e-3, k

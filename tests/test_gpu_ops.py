@@ -510,3 +510,18 @@ def test_pack_weights(ops, mir, dt):
         o.pack_weights(params, packed, o.make_pack_table(plan.entries, "cuda"), len(plan.entries), plan.max_elems)
         outs.append(packed.float())
     assert torch.equal(outs[0], outs[1])
+
+
+def test_smooth_l1_matches_torch(ops, mir):
+    g = gen(21)
+    rows, cols = 37, 9
+    z = torch.randn(rows, 16, device="cuda", generator=g) * 2
+    y = torch.randint(0, 4, (rows, cols), device="cuda", generator=g).float()
+    for o in (ops, mir):
+        loss, dz = torch.zeros(1, device="cuda"), torch.zeros(rows, 16, device="cuda")
+        o.smooth_l1(z, y, rows, cols, 1.0, 2.0, loss, dz)
+        zz = z[:, :cols].clone().requires_grad_(True)
+        ref = torch.nn.SmoothL1Loss()(zz, y)
+        ref.backward()
+        assert abs(loss.item() - ref.item()) < 1e-6 * max(1.0, ref.item())
+        assert relerr(dz[:, :cols], 2.0 * zz.grad) < 1e-6

@@ -262,6 +262,25 @@ def test_module_contract():
         m(torch.zeros(1, 3000, 270))
 
 
+def test_count_pred_sibling_matches_reference_fixture(gold):
+    """THAT_COUNT_PRED (model/that_count_pred.py): identical initial weights under the reference seed, and the
+    count-mode metrics of utils.py:229-233, both against fixtures generated from the unmodified reference."""
+    from multi_modal_csi_b200 import THAT_COUNT_PRED
+    from multi_modal_csi_b200.utils import performance_metrics
+    g = gold("that_count_pred.npz")
+    T, F, out, B = [int(v) for v in g["dims"]]
+    torch.manual_seed(39)
+    m = THAT_COUNT_PRED((T, F), [out])
+    sd = m.state_dict()
+    keys = [k[2:] for k in g.files if k.startswith("w/")]
+    assert sorted(keys) == sorted(sd.keys())
+    for k in keys:
+        assert torch.equal(sd[k].cpu(), torch.from_numpy(g["w/" + k])), k
+    res = performance_metrics(g["m_y_true"], g["m_y_pred"], var_mode="count_classification")
+    for k, v in res.items():
+        assert np.allclose(np.asarray(v, dtype=np.float64), g["m/" + k], rtol=1e-9, atol=1e-12, equal_nan=True), k
+
+
 # ------------------------------------------------------------------------------------------------ C ABI
 def test_library_exports_every_declared_symbol():
     from multi_modal_csi_b200 import ops
