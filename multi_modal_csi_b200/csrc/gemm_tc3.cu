@@ -224,19 +224,27 @@ __global__ void __launch_bounds__(T3_THREADS, 1) gemm_nt_tc3_kernel(const __grid
                 sbias[acc][et] = (et < p.BN && (n0 + et) < p.N) ? p.bias[n0 + et] : 0.f;
                 named_bar_sync(1, T3_EPI_THREADS);
             }
+            // fp32 residual of a FULL panel (32 rows x 128 B): fetched with coalesced 16-byte loads (lane -> row 4i + lane/8,
+            // chunk lane%8: four whole 128-byte lines per instruction instead of 32 partial ones), one panel ahead, and
+            // transposed to the row-per-lane layout through the staging buffer.  Narrow tail panels load row-per-lane.
             const float* rrow = (RES && m < p.M) ? p.residual + (size_t)m * p.ldr : nullptr;
             float rnext[RES ? PW : 1];
             auto fetch_res = [&](int pc0) {
                 if constexpr (!RES) return;
+                if (p.BN - pc0 >= PW) {
+                    const int ch = lane & 7, ncol = n0 + pc0 + ch * 4;
 #pragma unroll
-                for (int j = 0; j < (RES ? PW : 0); j += 4) {
-                    const int n = n0 + pc0 + j;
-                    if (rrow && n + 3 < p.N) {
-                        const float4 v = *reinterpret_cast<const float4*>(rrow + n);
-                        rnext[j] = v.x; rnext[j + 1] = v.y; rnext[j + 2] = v.z; rnext[j + 3] = v.w;
-                    } else {
+                    for (int i = 0; i < (RES ? PW / 4 : 0); ++i) {
+                        const int mg = m0 + q * 32 + 4 * i + (lane >> 3);
+                        float4 v4 = make_float4(0.f, 0.f, 0.f, 0.f);
+                        if (mg < p.M && ncol + 3 < p.ldr) v4 = *reinterpret_cast<const float4*>(p.residual + (size_t)mg * p.ldr + ncol);
+                        rnext[4 * i] = v4.x; rnext[4 * i + 1] = v4.y; rnext[4 * i + 2] = v4.z; rnext[4 * i + 3] = v4.w;
+                    }
+                } else {
 #pragma unroll
-                        for (int u = 0; u < 4; ++u) rnext[j + u] = (rrow && n + u < p.N) ? rrow[n + u] : 0.f;
+                    for (int j = 0; j < (RES ? PW : 0); ++j) {
+                        const int n = n0 + pc0 + j;
+                        rnext[j] = (rrow && pc0 + j < p.BN && n < p.N) ? rrow[n] : 0.f;
                     }
                 }
             };
@@ -277,17 +285,33 @@ __global__ void __launch_bounds__(T3_THREADS, 1) gemm_nt_tc3_kernel(const __grid
                         for (int j = 0; j < 8; ++j) v[g8 * 8 + j] *= ks[j];
                     }
                 }
-                if constexpr (RES) {
-#pragma unroll
-                    for (int j = 0; j < PW; ++j) v[j] += rnext[j];
-                    if (pi + 2 < npan) fetch_res(pc0 + 2 * PW);
-                }
                 // stage the 32-row slice of this warp (row = lane) and bulk-store it; the tensor maps clip rows >= M and
                 // columns >= N.  Full panels are 128-byte rows in the TMA 128B swizzle; the narrower last panel of a tile
                 // uses linear rows of width*es bytes and its own (unswizzled) tensor map.
                 if (lane == 0) tma_store_wait_read<1>();            // the buffer used two panels ago has been read
                 __syncwarp();
                 uint8_t* buf = mybuf + (size_t)sbuf * 4096;
+                if constexpr (RES) {
+                    if (width == PW) {
+                        const int ch = lane & 7;
+#pragma unroll
+                        for (int i = 0; i < PW / 4; ++i) {
+                            const int rl = 4 * i + (lane >> 3);
+                            *reinterpret_cast<float4*>(buf + rl * 128 + ((ch ^ (rl & 7)) << 4)) =
+                                make_float4(rnext[4 * i], rnext[4 * i + 1], rnext[4 * i + 2], rnext[4 * i + 3]);
+                        }
+                        __syncwarp();
+#pragma unroll
+                        for (int c16 = 0; c16 < 8; ++c16) {
+                            const float4 r4 = *reinterpret_cast<const float4*>(buf + lane * 128 + ((c16 ^ (lane & 7)) << 4));
+                            v[c16 * 4] += r4.x; v[c16 * 4 + 1] += r4.y; v[c16 * 4 + 2] += r4.z; v[c16 * 4 + 3] += r4.w;
+                        }
+                    } else {
+#pragma unroll
+                        for (int j = 0; j < PW; ++j) v[j] += rnext[j];
+                    }
+                    if (pi + 2 < npan) fetch_res(pc0 + 2 * PW);
+                }
                 if (width == PW) {
                     uint8_t* rowp = buf + lane * 128;
 #pragma unroll
