@@ -49,24 +49,20 @@ template <int LDS> __device__ __forceinline__ const bf16* bt_frag_ptr(const bf16
 }
 
 // global head tile [L rows x HDP cols, 16-byte aligned rows of pitch ld] -> smem [LP][LDS]; rows >= L are zeroed.
-// One 128-bit load + one 128-bit store per 8 elements, 4 loads in flight per thread.
+// 16-byte cp.async copies: every chunk of every tile of the head is in flight at once (no register staging, no
+// per-batch stall on the load latency); the caller waits with cp_async_wait_all() + __syncthreads().
+__device__ __forceinline__ void cp_async16(void* dst, const void* src) {
+    asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"((uint32_t)__cvta_generic_to_shared(dst)), "l"(src) : "memory");
+}
+__device__ __forceinline__ void cp_async_wait_all() { asm volatile("cp.async.commit_group;\ncp.async.wait_group 0;" ::: "memory"); }
 template <int HDP, int LDS>
 __device__ __forceinline__ void load_head_tile(const bf16* __restrict__ src, int ld, int L, int LP, bf16* __restrict__ dst) {
     constexpr int CPR = HDP / 8;                                   // 16-byte chunks per row
-    const int total = LP * CPR, stride = blockDim.x;
-    for (int base = threadIdx.x; base < total; base += 4 * stride) {
-        uint4 v[4];
-#pragma unroll
-        for (int u = 0; u < 4; ++u) {
-            const int i = base + u * stride, l = i / CPR, c = i % CPR;
-            v[u] = make_uint4(0u, 0u, 0u, 0u);
-            if (i < total && l < L) v[u] = *reinterpret_cast<const uint4*>(src + (size_t)l * ld + c * 8);
-        }
-#pragma unroll
-        for (int u = 0; u < 4; ++u) {
-            const int i = base + u * stride, l = i / CPR, c = i % CPR;
-            if (i < total) *reinterpret_cast<uint4*>(dst + l * LDS + c * 8) = v[u];
-        }
+    const int total = LP * CPR;
+    for (int i = threadIdx.x; i < total; i += blockDim.x) {
+        const int l = i / CPR, c = i % CPR;
+        if (l < L) cp_async16(dst + l * LDS + c * 8, src + (size_t)l * ld + c * 8);
+        else *reinterpret_cast<uint4*>(dst + l * LDS + c * 8) = make_uint4(0u, 0u, 0u, 0u);
     }
 }
 // smem [L][LDS] -> global head tile (128-bit stores, padding columns included: they hold zeros)
@@ -104,6 +100,7 @@ __global__ void __launch_bounds__(AM_MAX_WARPS * 32) attn_fwd_mma_kernel(const b
     load_head_tile<HDP, LDS>(base, ld3, L, LP, Qs);
     load_head_tile<HDP, LDS>(base + H * HDP, ld3, L, LP, Ks);
     load_head_tile<HDP, LDS>(base + 2 * H * HDP, ld3, L, LP, Vs);
+    cp_async_wait_all();
     __syncthreads();
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, g = lane >> 2, t = lane & 3;
     const float sc = rsqrtf((float)hd), c = sc * LOG2E;
@@ -218,6 +215,7 @@ __global__ void __launch_bounds__(AM_MAX_WARPS * 32) attn_bwd_mma_kernel(const b
     load_head_tile<HDP, LDS>(base + 2 * H * HDP, ld3, L, LP, Vs);
     load_head_tile<HDP, LDS>(dout + row0 * lddo + h * HDP, lddo, L, LP, Gs);
     for (int i = threadIdx.x; i < LP; i += blockDim.x) Ls[i] = i < L ? lse[((size_t)b * H + h) * L + i] * LOG2E : 0.f;
+    cp_async_wait_all();
     __syncthreads();
     // D_i = rowsum(dO_i * O_i): CPR lanes per row, one 128-bit O load each
     for (int i = threadIdx.x; i < LP * CPR; i += blockDim.x) {
