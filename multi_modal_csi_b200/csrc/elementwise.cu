@@ -1356,20 +1356,31 @@ extern "C" int csi_advance_counters(unsigned long long* rng, long long* step, vo
 
 // ------------------------------------------------------------------------------------------------ weight re-layout
 template <typename T>
-__global__ void pack_kernel(const float* __restrict__ params, T* __restrict__ packed,
-                            const csi_pack_entry* __restrict__ table) {
+__global__ void __launch_bounds__(256) pack_kernel(const float* __restrict__ params, T* __restrict__ packed,
+                                                   const csi_pack_entry* __restrict__ table) {
+    // blockIdx.x walks the outer index of the DESTINATION (n in mode 0, c in mode 1), threads the inner one, taps in a
+    // loop: no integer division on the hot path, coalesced stores; the strided fp32 reads hit L2 (19.6 MB of weights)
     const csi_pack_entry e = table[blockIdx.y];
-    const int total = e.N * e.C * e.k;
-    for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < total; i += gridDim.x * blockDim.x) {
-        // walk the DESTINATION in memory order (coalesced 2-byte stores); the strided fp32 reads hit L2
-        int n, c, j;
-        if (e.mode == 0) { c = i % e.C; j = (i / e.C) % e.k; n = i / (e.C * e.k); }
-        else { n = i % e.N; j = (i / e.N) % e.k; c = i / (e.N * e.k); }
-        const float v = params[e.src_off + ((long long)n * e.C + c) * e.k + j];
-        const int np = grp_to_padded(n, e.gn), cp = grp_to_padded(c, e.gc);
-        const long long dst = e.mode == 0 ? (long long)np * e.ld + (long long)j * e.P + cp
-                                          : (long long)cp * e.ld + (long long)(e.seg_base + j) * e.P + np;
-        stf<T>(packed + e.dst_off + dst, v);
+    const float* src = params + e.src_off;
+    T* dst = packed + e.dst_off;
+    if (e.mode == 0) {
+        for (int n = blockIdx.x; n < e.N; n += gridDim.x) {
+            const long long drow = (long long)grp_to_padded(n, e.gn) * e.ld;
+            for (int c = threadIdx.x; c < e.C; c += blockDim.x) {
+                const int cp = grp_to_padded(c, e.gc);
+                const float* sp = src + ((long long)n * e.C + c) * e.k;
+                for (int j = 0; j < e.k; ++j) stf<T>(dst + drow + (long long)j * e.P + cp, sp[j]);
+            }
+        }
+    } else {
+        for (int c = blockIdx.x; c < e.C; c += gridDim.x) {
+            const long long drow = (long long)grp_to_padded(c, e.gc) * e.ld;
+            for (int n = threadIdx.x; n < e.N; n += blockDim.x) {
+                const int np = grp_to_padded(n, e.gn);
+                const float* sp = src + ((long long)n * e.C + c) * e.k;
+                for (int j = 0; j < e.k; ++j) stf<T>(dst + drow + (long long)(e.seg_base + j) * e.P + np, sp[j]);
+            }
+        }
     }
 }
 
@@ -1377,8 +1388,8 @@ extern "C" int csi_pack_weights(const float* params, void* packed, int dtype, co
                                 int n_entries, int max_elems, void* stream) {
     CSI_CHECK_ARG(params && packed && table, "null pointer");
     if (n_entries == 0) return CSI_OK;
-    int bx = cdiv(max_elems, 256);
-    if (bx > 64) bx = 64;
+    (void)max_elems;
+    const int bx = 96;                                 // outer-index blocks per table entry
     dim3 grid(bx, n_entries);
     if (dtype == CSI_BF16) pack_kernel<bf16><<<grid, 256, 0, ST(stream)>>>(params, (bf16*)packed, table);
     else pack_kernel<float><<<grid, 256, 0, ST(stream)>>>(params, (float*)packed, table);
