@@ -14,6 +14,7 @@
 //   warp 1      tcgen05.mma issuer (UMMA 128 x BN x 16, bf16 -> fp32), two TMEM accumulators
 //   warps 2-5   epilogue: tcgen05.ld -> bias / Philox dropout / fp32 residual -> swizzled smem panel -> TMA store
 #include "tc_common.cuh"
+#include <stdlib.h>
 
 #define ST(s) ((cudaStream_t)(s))
 #define T3_THREADS 320
@@ -66,7 +67,7 @@ struct Nt3Params {
     void* C; int ldc;
     const float* bias; const float* residual; int ldr;
     float drop_p; unsigned drop_site; const unsigned long long* rng;
-    int row_base, desc_mode;
+    int row_base, desc_mode, pdl;
 };
 
 // K-major SW128 descriptor with an explicit matrix-base-offset field (bits [49,52))
@@ -91,6 +92,7 @@ __global__ void __launch_bounds__(T3_THREADS, 1) gemm_nt_tc3_kernel(const __grid
     __shared__ uint32_t tmem_base_smem;
     __shared__ __align__(16) float sbias[2][256];
 
+    if (p.pdl) asm volatile("griddepcontrol.launch_dependents;" ::: "memory");   // the next kernel may start its prologue
     uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const uint32_t a_bytes = (uint32_t)p.a_rows * 128u, b_bytes = (uint32_t)p.BN * 128u;
@@ -114,6 +116,9 @@ __global__ void __launch_bounds__(T3_THREADS, 1) gemm_nt_tc3_kernel(const __grid
     __syncthreads();
     tc_fence_after();
     const uint32_t tmem_base = tmem_base_smem;
+    // programmatic dependent launch: everything above overlapped the tail of the previous kernel in the stream; no
+    // global memory is touched before the previous grid has completed and flushed
+    if (p.pdl) asm volatile("griddepcontrol.wait;" ::: "memory");
 
     // Producer and MMA warps run their loops warp-uniformly (all 32 lanes wait on the barriers) and issue the
     // asynchronous instructions from one elected lane: the issue path is a single instruction stream whose latency
@@ -377,6 +382,8 @@ static int pick_bn3(int N) {
 static int g_num_sms3 = 0;
 static int g_desc_mode = 0;       // 0: base-offset field left 0 (swizzle follows the absolute address); 1: base offset = row % 8
 static int g_tap_share = 1;
+static int g_pdl3 = -1;            // programmatic dependent launch (CSI_PDL=0 disables)
+extern "C" int csi_set_gemm_pdl(int on) { g_pdl3 = on ? 1 : 0; return CSI_OK; }
 extern "C" int csi_set_gemm_desc_mode(int mode) { g_desc_mode = mode ? 1 : 0; return CSI_OK; }
 extern "C" int csi_set_gemm_tap_share(int on) { g_tap_share = on ? 1 : 0; return CSI_OK; }
 
@@ -462,6 +469,8 @@ extern "C" int csi_gemm_nt_tc3(const void* A, int lda, const void* Bw, int ldb, 
     p.drop_p = drop_p; p.drop_site = drop_site; p.rng = rng;
     p.row_base = -min_shift;
     p.desc_mode = g_desc_mode;
+    if (g_pdl3 < 0) { const char* e = getenv("CSI_PDL"); g_pdl3 = (e && e[0] == '0') ? 0 : 1; }
+    p.pdl = g_pdl3;
     const size_t a_bytes = (size_t)a_rows * 128, b_bytes = (size_t)BN * 128;
     const size_t fixed = 1024 + 8 * 2 * 4096;
     const size_t budget = 220 * 1024 - fixed;
@@ -484,7 +493,13 @@ extern "C" int csi_gemm_nt_tc3(const void* A, int lda, const void* Bw, int ldb, 
 #define LAUNCH3(TC, RES)                                                                                                \
     do {                                                                                                                \
         CSI_CUDA(cudaFuncSetAttribute(gemm_nt_tc3_kernel<TC, RES>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem)); \
-        gemm_nt_tc3_kernel<TC, RES><<<grid, T3_THREADS, smem, ST(stream)>>>(tmA, tmB, tmC, tmCt, p, plan);                    \
+        cudaLaunchConfig_t cfg = {};                                                                                    \
+        cfg.gridDim = dim3(grid); cfg.blockDim = dim3(T3_THREADS); cfg.dynamicSmemBytes = smem; cfg.stream = ST(stream); \
+        cudaLaunchAttribute at[1];                                                                                      \
+        at[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;                                                  \
+        at[0].val.programmaticStreamSerializationAllowed = p.pdl;                                                       \
+        cfg.attrs = at; cfg.numAttrs = 1;                                                                               \
+        CSI_CUDA(cudaLaunchKernelEx(&cfg, gemm_nt_tc3_kernel<TC, RES>, tmA, tmB, tmC, tmCt, p, plan));                  \
     } while (0)
     if (c_dtype == CSI_BF16) LAUNCH3(bf16, false);
     else if (residual) LAUNCH3(float, true);

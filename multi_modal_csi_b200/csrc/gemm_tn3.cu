@@ -13,6 +13,7 @@
 //   warp 0      TMA producer          warp 1      tcgen05.mma issuer (one elected lane, warp-uniform loop)
 //   warps 2-9   epilogue: tcgen05.ld -> red.global.add.f32 (two warps per TMEM lane quarter, alternate 16-column groups)
 #include "tc_common.cuh"
+#include <stdlib.h>
 
 #define ST(s) ((cudaStream_t)(s))
 #define N3_THREADS 320
@@ -147,6 +148,7 @@ __global__ void __launch_bounds__(N3_THREADS, 1) gemm_tn_tc3_kernel(const __grid
     __shared__ __align__(8) uint64_t tmem_full_bar;
     __shared__ uint32_t tmem_base_smem;
 
+    if (p.dbg & 4) asm volatile("griddepcontrol.launch_dependents;" ::: "memory");
     uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const int gi = blockIdx.y / p.qtiles, qt = blockIdx.y - gi * p.qtiles;
@@ -172,6 +174,7 @@ __global__ void __launch_bounds__(N3_THREADS, 1) gemm_tn_tc3_kernel(const __grid
     __syncthreads();
     tc_fence_after();
     const uint32_t tmem_base = tmem_base_smem;
+    if (p.dbg & 4) asm volatile("griddepcontrol.wait;" ::: "memory");      // PDL: the prologue above overlapped the previous kernel
     const uint32_t smem_u = smem_u32(smem), full_u = smem_u32(&full_bar[0]), empty_u = smem_u32(&empty_bar[0]);
 
     if (warp == 0) {
@@ -244,6 +247,8 @@ __global__ void __launch_bounds__(N3_THREADS, 1) gemm_tn_tc3_kernel(const __grid
 
 static int g_num_sms_tn3 = 0;
 static int g_tn_dbg = 0;
+static int g_tn_pdl = -1;           // programmatic dependent launch (CSI_PDL=0 disables)
+extern "C" int csi_set_gemm_tn_pdl(int on) { g_tn_pdl = on ? 1 : 0; return CSI_OK; }
 extern "C" int csi_set_tn_debug(int v) { g_tn_dbg = v; return CSI_OK; }
 
 extern "C" int csi_gemm_tn_tc3(const void* A, int lda, const void* Bv, int ldb, float* C, int ldc, int c_col_stride, int M,
@@ -334,7 +339,8 @@ extern "C" int csi_gemm_tn_tc3(const void* A, int lda, const void* Bv, int ldb, 
     Tn3Params p;
     p.C = C; p.ldc = ldc; p.cs = c_col_stride; p.M = M; p.Na = Na; p.BN = BN; p.pitch = pitch; p.chunk = chunk; p.qtiles = qtiles;
     p.row_base = -min_shift; p.rows_b = rows_b; p.nbox_b = nbox_b;
-    p.ig = ig; p.qg = qg; p.dbg = g_tn_dbg;
+    if (g_tn_pdl < 0) { const char* e = getenv("CSI_PDL"); g_tn_pdl = (e && e[0] == '0') ? 0 : 1; }
+    p.ig = ig; p.qg = qg; p.dbg = g_tn_dbg | (g_tn_pdl ? 4 : 0);
     uint32_t cols = 32;
     while ((int)cols < gtaps * pitch) cols <<= 1;
     p.tmem_cols = cols;
@@ -342,7 +348,13 @@ extern "C" int csi_gemm_tn_tc3(const void* A, int lda, const void* Bv, int ldb, 
     CSI_CHECK_ARG(smem <= 227 * 1024, "stage does not fit in shared memory");
     CSI_CUDA(cudaFuncSetAttribute(gemm_tn_tc3_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     dim3 grid(itiles, qtiles * plan.ng, zs);
-    gemm_tn_tc3_kernel<<<grid, N3_THREADS, smem, ST(stream)>>>(tmA, tmB, p, plan);
+    cudaLaunchConfig_t cfg = {};
+    cfg.gridDim = grid; cfg.blockDim = dim3(N3_THREADS); cfg.dynamicSmemBytes = smem; cfg.stream = ST(stream);
+    cudaLaunchAttribute at[1];
+    at[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+    at[0].val.programmaticStreamSerializationAllowed = g_tn_pdl;
+    cfg.attrs = at; cfg.numAttrs = 1;
+    CSI_CUDA(cudaLaunchKernelEx(&cfg, gemm_tn_tc3_kernel, tmA, tmB, p, plan));
     CSI_LAUNCH_CHECK();
     return CSI_OK;
 }
