@@ -139,7 +139,10 @@ int csi_colsum_tokens(const void* A, int lda, int dtype, int B, int L, int halo,
 int csi_attn_fwd(const void* qkv, int ld3, void* o, int ldo, int dtype, float* lse, int B, int L, int d,
                  int H, int hp, int halo, void* stream);
 int csi_attn_bwd(const void* qkv, int ld3, const void* o, int ldo, const void* dout, int lddo, void* dqkv,
-                 int lddqkv, int dtype, const float* lse, int B, int L, int d, int H, int hp, int halo, void* stream);
+                 int lddqkv, int dtype, const float* lse, int B, int L, int d, int H, int hp, int halo, float* dbias,
+                 void* stream);
+/* dbias (optional, may be NULL): fp32 [3*d], accumulated with the column sums of dq | dk | dv over the valid tokens in the
+ * compact (un-padded) channel order -- the gradient of nn.MultiheadAttention.in_proj_bias, fused into the kernel. */
 
 /* ---- a10: BatchNorm1d (train: batch statistics) -> Dropout(.1) -> LeakyReLU, mean of the 3 branches,
  * Dropout(.1), residual (that.py:126-132,160-168).  z: token buffer [rows, ldz] with branch br in columns

@@ -193,12 +193,28 @@ __global__ void __launch_bounds__(AM_MAX_WARPS * 32) attn_fwd_mma_kernel(const b
     store_head_tile<HDP, LDS>(Qs, o + row0 * ldo + h * HDP, ldo, L);
 }
 
+// lane-local column partials (accumulator layout: columns no*8 + 2t, +1; rows g, g+8) -> per-CTA shared sums
+template <int NTO>
+__device__ __forceinline__ void warp_colsum_flush(float (&c)[NTO][2], float* csum, int g, int t) {
+#pragma unroll
+    for (int no = 0; no < NTO; ++no) {
+        float c0 = c[no][0], c1 = c[no][1];
+#pragma unroll
+        for (int off = 4; off < 32; off <<= 1) {
+            c0 += __shfl_xor_sync(0xffffffffu, c0, off);
+            c1 += __shfl_xor_sync(0xffffffffu, c1, off);
+        }
+        if (g == 0) { atomicAdd(&csum[no * 8 + 2 * t], c0); atomicAdd(&csum[no * 8 + 2 * t + 1], c1); }
+    }
+}
+
 template <int HDP>
 __global__ void __launch_bounds__(AM_MAX_WARPS * 32) attn_bwd_mma_kernel(const bf16* __restrict__ qkv, int ld3, const bf16* __restrict__ o,
                                                                      int ldo, const bf16* __restrict__ dout, int lddo,
                                                                      bf16* __restrict__ dqkv, int lddqkv, const float* __restrict__ lse,
-                                                                     int L, int d, int H, int halo) {
+                                                                     int L, int d, int H, int halo, float* __restrict__ dbias) {
     constexpr int LDS = HDP + 8, KS = HDP / 16, NTO = HDP / 8, CPR = HDP / 8;
+    __shared__ float csum[3 * HDP];                            // column sums of dQ | dK | dV of this head (in_proj bias gradient)
     extern __shared__ __align__(16) uint8_t sm_raw[];
     const int hd = d / H, b = blockIdx.x / H, h = blockIdx.x % H, Lp = L + 2 * halo;
     const int LP = (L + 15) & ~15;
@@ -215,6 +231,7 @@ __global__ void __launch_bounds__(AM_MAX_WARPS * 32) attn_bwd_mma_kernel(const b
     load_head_tile<HDP, LDS>(base + 2 * H * HDP, ld3, L, LP, Vs);
     load_head_tile<HDP, LDS>(dout + row0 * lddo + h * HDP, lddo, L, LP, Gs);
     for (int i = threadIdx.x; i < LP; i += blockDim.x) Ls[i] = i < L ? lse[((size_t)b * H + h) * L + i] * LOG2E : 0.f;
+    for (int i = threadIdx.x; i < 3 * HDP; i += blockDim.x) csum[i] = 0.f;
     cp_async_wait_all();
     __syncthreads();
     // D_i = rowsum(dO_i * O_i): CPR lanes per row, one 128-bit O load each
@@ -241,6 +258,9 @@ __global__ void __launch_bounds__(AM_MAX_WARPS * 32) attn_bwd_mma_kernel(const b
     const float sc = rsqrtf((float)hd), c = sc * LOG2E;
     const int ntile = LP / 16;
     // ---------------- pass A: dQ
+    float cq[NTO][2];
+#pragma unroll
+    for (int no = 0; no < NTO; ++no) cq[no][0] = cq[no][1] = 0.f;
     for (int qt = warp; qt < ntile; qt += (int)(blockDim.x >> 5)) {
         uint32_t qa[KS][4], ga[KS][4];
 #pragma unroll
@@ -292,8 +312,20 @@ __global__ void __launch_bounds__(AM_MAX_WARPS * 32) attn_bwd_mma_kernel(const b
             if (r0 < L) *reinterpret_cast<__nv_bfloat162*>(dqkv + (row0 + r0) * lddqkv + h * HDP + col) = __floats2bfloat162_rn(dq[no][0], dq[no][1]);
             if (r1 < L) *reinterpret_cast<__nv_bfloat162*>(dqkv + (row0 + r1) * lddqkv + h * HDP + col) = __floats2bfloat162_rn(dq[no][2], dq[no][3]);
         }
+        if (dbias) {                                               // lane-local column sums of the stored (bf16) dQ rows
+#pragma unroll
+            for (int no = 0; no < NTO; ++no) {
+                const __nv_bfloat162 lo = __floats2bfloat162_rn(dq[no][0], dq[no][1]), hi = __floats2bfloat162_rn(dq[no][2], dq[no][3]);
+                cq[no][0] += (r0 < L ? __low2float(lo) : 0.f) + (r1 < L ? __low2float(hi) : 0.f);
+                cq[no][1] += (r0 < L ? __high2float(lo) : 0.f) + (r1 < L ? __high2float(hi) : 0.f);
+            }
+        }
     }
+    if (dbias) warp_colsum_flush<NTO>(cq, csum, g, t);
     // ---------------- pass B: dK, dV (rows of the accumulators are keys, columns of S^T are queries)
+    float ck[NTO][2], cv[NTO][2];
+#pragma unroll
+    for (int no = 0; no < NTO; ++no) ck[no][0] = ck[no][1] = cv[no][0] = cv[no][1] = 0.f;
     for (int kt = warp; kt < ntile; kt += (int)(blockDim.x >> 5)) {
         uint32_t ka[KS][4], va[KS][4];
 #pragma unroll
@@ -345,10 +377,32 @@ __global__ void __launch_bounds__(AM_MAX_WARPS * 32) attn_bwd_mma_kernel(const b
         __syncwarp();                                              // K/V rows of this tile are only read as its own A fragments
         stage_tile<LDS, NTO>(Ks, kt * 16, dk, 1.f, 1.f, g, t);
         stage_tile<LDS, NTO>(Vs, kt * 16, dv, 1.f, 1.f, g, t);
+        if (dbias) {
+            const bool v0 = kt * 16 + g < L, v1 = kt * 16 + g + 8 < L;
+#pragma unroll
+            for (int no = 0; no < NTO; ++no) {
+                const __nv_bfloat162 klo = __floats2bfloat162_rn(dk[no][0], dk[no][1]), khi = __floats2bfloat162_rn(dk[no][2], dk[no][3]);
+                const __nv_bfloat162 vlo = __floats2bfloat162_rn(dv[no][0], dv[no][1]), vhi = __floats2bfloat162_rn(dv[no][2], dv[no][3]);
+                ck[no][0] += (v0 ? __low2float(klo) : 0.f) + (v1 ? __low2float(khi) : 0.f);
+                ck[no][1] += (v0 ? __high2float(klo) : 0.f) + (v1 ? __high2float(khi) : 0.f);
+                cv[no][0] += (v0 ? __low2float(vlo) : 0.f) + (v1 ? __low2float(vhi) : 0.f);
+                cv[no][1] += (v0 ? __high2float(vlo) : 0.f) + (v1 ? __high2float(vhi) : 0.f);
+            }
+        }
+    }
+    if (dbias) {
+        warp_colsum_flush<NTO>(ck, csum + HDP, g, t);
+        warp_colsum_flush<NTO>(cv, csum + 2 * HDP, g, t);
     }
     __syncthreads();
     store_head_tile<HDP, LDS>(Ks, dqkv + row0 * lddqkv + H * HDP + h * HDP, lddqkv, L);
     store_head_tile<HDP, LDS>(Vs, dqkv + row0 * lddqkv + 2 * H * HDP + h * HDP, lddqkv, L);
+    if (dbias) {                                                   // one atomic per (q|k|v, channel) into the compact bias gradient
+        for (int i = threadIdx.x; i < 3 * HDP; i += blockDim.x) {
+            const int w = i / HDP, e = i - w * HDP;
+            if (e < hd) atomicAdd(dbias + w * d + h * hd + e, csum[i]);
+        }
+    }
 }
 
 // warps per CTA: the 16-row tiles of a head are dealt round-robin, so pick the count that leaves no idle round
@@ -389,7 +443,8 @@ extern "C" int csi_attn_fwd_mma(const void* qkv, int ld3, void* o, int ldo, floa
 }
 
 extern "C" int csi_attn_bwd_mma(const void* qkv, int ld3, const void* o, int ldo, const void* dout, int lddo, void* dqkv,
-                                int lddqkv, const float* lse, int B, int L, int d, int H, int hp, int halo, void* stream) {
+                                int lddqkv, const float* lse, int B, int L, int d, int H, int hp, int halo, float* dbias,
+                                void* stream) {
     CSI_CHECK_ARG(qkv && o && dout && dqkv && lse, "null pointer");
     CSI_CHECK_ARG(csi_attn_mma_ok(L, d, H, hp), "shape not eligible");
     CSI_CHECK_ARG(ld3 % 8 == 0 && ldo % 8 == 0 && lddo % 8 == 0 && lddqkv % 8 == 0, "head-padded leading dimensions expected");
@@ -400,7 +455,7 @@ extern "C" int csi_attn_bwd_mma(const void* qkv, int ld3, const void* o, int ldo
     do {                                                                                                               \
         CSI_CUDA(cudaFuncSetAttribute(attn_bwd_mma_kernel<HDP>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem)); \
         attn_bwd_mma_kernel<HDP><<<B * H, am_warps(LP) * 32, smem, ST(stream)>>>((const bf16*)qkv, ld3, (const bf16*)o, ldo,   \
-                                                                            (const bf16*)dout, lddo, (bf16*)dqkv, lddqkv, lse, L, d, H, halo); \
+                                                                            (const bf16*)dout, lddo, (bf16*)dqkv, lddqkv, lse, L, d, H, halo, dbias); \
     } while (0)
     if (hp == 16) GO(16); else if (hp == 32) GO(32); else GO(64);
 #undef GO

@@ -44,7 +44,7 @@ extern "C" int csi_set_gemm_tn_v1(int on) { g_tn_v1 = on ? 1 : 0; return CSI_OK;
 extern "C" int csi_attn_mma_ok(int L, int d, int H, int hp);
 extern "C" int csi_attn_fwd_mma(const void*, int, void*, int, float*, int, int, int, int, int, int, void*);
 extern "C" int csi_attn_bwd_mma(const void*, int, const void*, int, const void*, int, void*, int, const float*, int, int, int,
-                                int, int, int, void*);
+                                int, int, int, float*, void*);
 
 static int g_force_simt = -1;
 static bool force_simt() {
@@ -91,8 +91,12 @@ extern "C" int csi_attn_fwd(const void* qkv, int ld3, void* o, int ldo, int dtyp
 }
 
 extern "C" int csi_attn_bwd(const void* qkv, int ld3, const void* o, int ldo, const void* dout, int lddo, void* dqkv,
-                            int lddqkv, int dtype, const float* lse, int B, int L, int d, int H, int hp, int halo, void* stream) {
+                            int lddqkv, int dtype, const float* lse, int B, int L, int d, int H, int hp, int halo, float* dbias,
+                            void* stream) {
     if (dtype == CSI_BF16 && !force_simt() && csi_attn_mma_ok(L, d, H, hp))
-        return csi_attn_bwd_mma(qkv, ld3, o, ldo, dout, lddo, dqkv, lddqkv, lse, B, L, d, H, hp, halo, stream);
-    return csi_attn_bwd_simt(qkv, ld3, o, ldo, dout, lddo, dqkv, lddqkv, dtype, lse, B, L, d, H, hp, halo, stream);
+        return csi_attn_bwd_mma(qkv, ld3, o, ldo, dout, lddo, dqkv, lddqkv, lse, B, L, d, H, hp, halo, dbias, stream);
+    int rc = csi_attn_bwd_simt(qkv, ld3, o, ldo, dout, lddo, dqkv, lddqkv, dtype, lse, B, L, d, H, hp, halo, stream);
+    if (rc || !dbias) return rc;
+    // the FFMA path has no fused bias gradient: column sums of dqkv over the valid tokens, compact (un-padded) index
+    return csi_colsum_tokens(dqkv, lddqkv, dtype, B, L, halo, 3 * H * hp, csi_grp{d / H, hp}, dbias, stream);
 }

@@ -346,10 +346,11 @@ class THATEngine:
                 ops.colsum_tokens(st["dtm"].t, B, L, HALO, d, self.G(w + "bias"))
                 ops.gemm_nt(st["dtm"].t, self.W("b:" + w + "weight"), st["do"].t, rows, sg.dh, [(0, 0, 0, Dp)], None,
                             None, 0.0, 0, self.rng)
-                ops.attn_bwd(a["qkv"].t, a["o"].t, st["do"].t, st["dqkv"].t, a["lse"], B, L, d, sg.H, sg.hp, HALO)
                 w = p + "layer_attention.in_proj_"
+                # the in_proj bias gradient (column sums of dqkv) is accumulated by the attention backward kernel itself
+                ops.attn_bwd(a["qkv"].t, a["o"].t, st["do"].t, st["dqkv"].t, a["lse"], B, L, d, sg.H, sg.hp, HALO,
+                             self.G(w + "bias"))
                 ops.gemm_tn(st["dqkv"].t, a["t0"].t, self.G(w + "weight"), d, 1, rows, sg.ld3, one, sg.grp, (0, 0))
-                ops.colsum_tokens(st["dqkv"].t, B, L, HALO, sg.ld3, self.G(w + "bias"), sg.grp)
                 ops.gemm_nt(st["dqkv"].t, self.W("b:" + w + "weight"), st["dt0"].t, rows, d, [(0, 0, 0, sg.ld3)],
                             None, None, 0.0, 0, self.rng)
                 ops.layernorm_bwd(st["dt0"].t, x_in.t, self.P(p + "layer_norm_0.weight"), a["mean0"], a["rstd0"],

@@ -13,7 +13,7 @@ import torch
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.path.join(_HERE, "libcsi_that.so")
-ABI_VERSION = 3
+ABI_VERSION = 4
 
 
 class Seg(C.Structure):
@@ -267,10 +267,10 @@ class NativeOps:
         wk = self._work("attn_fwd", locals())
         self._call("csi_attn_fwd", _p(qkv), _ld(qkv), _p(o), _ld(o), _dt(qkv), _p(lse), B, L, d, H, hp, halo, **wk)
 
-    def attn_bwd(self, qkv, o, dout, dqkv, lse, B, L, d, H, hp, halo):
+    def attn_bwd(self, qkv, o, dout, dqkv, lse, B, L, d, H, hp, halo, dbias=None):
         wk = self._work("attn_bwd", locals())
         self._call("csi_attn_bwd", _p(qkv), _ld(qkv), _p(o), _ld(o), _p(dout), _ld(dout), _p(dqkv), _ld(dqkv),
-                                       _dt(qkv), _p(lse), B, L, d, H, hp, halo, **wk)
+                                       _dt(qkv), _p(lse), B, L, d, H, hp, halo, _p(dbias), **wk)
 
     def bn_stats(self, z, B, L, halo, ncols, sums):
         wk = self._work("bn_stats", locals())

@@ -192,7 +192,7 @@ class MirrorOps:
         self._put_heads(o, p @ v, B, L, H, hd, hp, halo)
         lse[:B * H * L] = l.reshape(-1)
 
-    def attn_bwd(self, qkv, o, dout, dqkv, lse, B, L, d, H, hp, halo):
+    def attn_bwd(self, qkv, o, dout, dqkv, lse, B, L, d, H, hp, halo, dbias=None):
         hd = d // H
         sc = 1.0 / math.sqrt(hd)
         q, k, v = self._split(qkv, B, L, d, H, hp, halo)
@@ -207,6 +207,9 @@ class MirrorOps:
         dk = ds.transpose(-1, -2) @ q
         for w, val in enumerate((dq, dk, dv)):
             self._put_heads(dqkv, val, B, L, H, hd, hp, halo, w)
+            if dbias is not None:                                   # in_proj bias gradient: compact channel order
+                rounded = val.to(dqkv.dtype).float() if dqkv.dtype != torch.float32 else val
+                dbias[w * d:(w + 1) * d] += rounded.sum(dim=(0, 2)).reshape(-1)
 
     # ------------------------------------------------------------------ batchnorm + activation
     def bn_stats(self, z, B, L, halo, ncols, sums):

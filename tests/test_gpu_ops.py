@@ -329,11 +329,15 @@ def test_attention(ops, mir, dt, B, L, d):
         lse = torch.zeros(B * H * L, device="cuda")
         o.attn_fwd(qkv, out, lse, B, L, d, H, hp, HALO)
         _, dqkv = tokbuf(B, L, 3 * H * hp, dt)
-        o.attn_bwd(qkv, out, do, dqkv, lse, B, L, d, H, hp, HALO)
-        res.append((out.float(), lse, dqkv.float()))
+        dbias = torch.full((3 * d,), 0.5, device="cuda")            # accumulated into, not overwritten
+        o.attn_bwd(qkv, out, do, dqkv, lse, B, L, d, H, hp, HALO, dbias)
+        res.append((out.float(), lse, dqkv.float(), dbias))
     tol = 2e-5 if dt == torch.float32 else 1.5e-2
     for i, (a, b) in enumerate(zip(*res)):
         assert relerr(a, b) < tol, i
+    # the fused in_proj bias gradient is the column sum of the stored dqkv (compact channel order)
+    cs = valid(res[0][2], B, L, 3 * H * hp).reshape(B * L, 3, H, hp)[..., :hd].sum(0).reshape(-1) + 0.5
+    assert relerr(res[0][3], cs) < 1e-5
     # padding columns of the outputs are zero
     assert float(valid(res[0][0], B, L, H * hp).reshape(B, L, H, hp)[..., hd:].abs().max()) == 0.0
     assert float(valid(res[0][2], B, L, 3 * H * hp).reshape(B, L, 3 * H, hp)[..., hd:].abs().max()) == 0.0
