@@ -21,11 +21,24 @@ def short(name):
 
 
 def one_step(rows):
-    """keep the launches of ONE train step: from the first gauss_pe_fwd launch up to (not including) the next one"""
-    starts = sorted({int(r["ID"]) for r in rows if "gauss_pe_fwd" in r["Kernel Name"]})
-    if len(starts) < 2:
+    """keep the launches of ONE train step.  Steps repeat the same kernel sequence, so the window (longer than a step)
+    is periodic: find the period S from the kernel names and keep S consecutive launches (any S consecutive launches
+    are one step's worth of work)."""
+    ids = sorted({int(r["ID"]) for r in rows})
+    name_of = {}
+    for r in rows:
+        name_of.setdefault(int(r["ID"]), r["Kernel Name"])
+    names = [name_of[i] for i in ids]
+    n = len(names)
+    S = None
+    for cand in range(50, n):
+        if all(names[i] == names[i + cand] for i in range(n - cand)) and n - cand >= 8:
+            S = cand
+            break
+    if S is None:
         return rows
-    return [r for r in rows if starts[0] <= int(r["ID"]) < starts[1]]
+    keep = set(ids[:S])
+    return [r for r in rows if int(r["ID"]) in keep]
 
 
 launches = one_step(rows_of(os.path.join(ROOT, "gpurun_out", f"launches_{tag}.csv")))
