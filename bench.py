@@ -185,7 +185,7 @@ def run_b200(args):
     model.train()
     opt = FusedAdam(model.parameters(), lr=5e-4, weight_decay=2e-4)
     sync = GradSync(model, world) if world > 1 else None
-    hook = sync                                        # GradSync: bucket 1 overlaps the right stream's backward
+    hook = sync                                        # GradSync: bucket 1 is reduced while left encoder 0 runs its backward
 
     # two distinct resident batches (each 3.3 MB/sample: far larger than the 126 MB L2 at B=256)
     host = [synth_batch(B, F, out, 1234 + rank + 100 * i) for i in range(2)]

@@ -13,6 +13,7 @@ uses the native library and fails loudly without it.
 """
 from __future__ import annotations
 
+import os
 from typing import Dict, Optional
 
 import torch
@@ -63,6 +64,9 @@ class THATEngine:
         self._alloc()
         self._graphs = {}
         self._graph_launches = {}
+        # left / right streams on two CUDA streams (see _fork); CSI_NO_CONCURRENT=1 for A/B runs
+        self.concurrent = os.environ.get("CSI_NO_CONCURRENT", "0") != "1"
+        self._side = None
         self.weights_dirty = True
 
     # ------------------------------------------------------------------ views
@@ -195,65 +199,94 @@ class THATEngine:
         ops.pool_dual(x, offs, lens, B, g.T, g.F, self.pe, self.s["left"]["x0"].t, self.s["right"]["x0"].t,
                       HALO, 1 if (training and augment) else 0, self.rng)
 
+    # ------------------------------------------------------------------ two-stream concurrency
+    def _fork(self, fn):
+        """Issue ``fn()`` on the engine's second CUDA stream, ordered after everything already on the current stream;
+        returns the join (call it where the current stream needs the results).
+
+        The left (temporal) and right (channel) streams of THAT share nothing between the pooling kernel and the
+        feature concat (that.py:257-299), so their launch sequences run side by side: the tail wave of a persistent
+        GEMM and the HBM-bound LayerNorm/BatchNorm kernels of one stream fill SMs the other leaves idle.  The same
+        fork/join is recorded into the CUDA graph during capture.  Sequential (fn runs inline) when ``concurrent`` is
+        off, on a non-CUDA device (mirror ops in the CPU tests) or while per-launch timing is being recorded."""
+        if not (self.concurrent and self.dev.type == "cuda") or getattr(self.ops, "_prof", None) is not None:
+            fn()
+            return lambda: None
+        cur = torch.cuda.current_stream(self.dev)
+        if self._side is None:
+            self._side = torch.cuda.Stream(self.dev)
+        side = self._side
+        side.wait_stream(cur)
+        with torch.cuda.stream(side):
+            fn()
+        return lambda: cur.wait_stream(side)
+
     def forward_body(self, B: int, training: bool, dropout: bool = True) -> torch.Tensor:
         ops, g = self.ops, self.g
         pd = P_DROP if (training and dropout) else 0.0
         pf = P_FEAT if (training and dropout) else 0.0
-        for si, sg in enumerate(g.streams):
-            st = self.s[sg.name]
-            rows, d, Dp, L = sg.rows(B), sg.d, sg.Dp, sg.L
-            ops.alg_scale = (L / sg.Lp) * (d / Dp)      # roofline numerators count valid tokens and true channels only
-            x_in = st["x0"]
-            one = [(0, 0, 0, Dp)]
-            for e in range(sg.n_enc):
-                a, p = st["enc"][e], sg.prefix(e)
-                ops.layernorm_fwd(x_in.t, self.P(p + "layer_norm_0.weight"), self.P(p + "layer_norm_0.bias"),
-                                  a["t0"].t, a["mean0"], a["rstd0"], B, L, d, HALO, LN_EPS)
-                ops.gemm_nt(a["t0"].t, self.W("f:" + p + "layer_attention.in_proj_weight"), a["qkv"].t, rows,
-                            sg.ld3, one, self.PB(p + "layer_attention.in_proj_bias"), None, 0.0, 0, self.rng)
-                ops.attn_fwd(a["qkv"].t, a["o"].t, a["lse"], B, L, d, sg.H, sg.hp, HALO)
-                ops.gemm_nt(a["o"].t, self.W("f:" + p + "layer_attention.out_proj.weight"), a["t"].t, rows, d,
-                            [(0, 0, 0, sg.dh)], self.P(p + "layer_attention.out_proj.bias"), x_in.t, pd,
-                            site(si, e, LY.SITE_ATTN), self.rng)
-                ops.layernorm_fwd(a["t"].t, self.P(p + "layer_norm_1.weight"), self.P(p + "layer_norm_1.bias"),
-                                  a["s"].t, a["mean1"], a["rstd1"], B, L, d, HALO, LN_EPS)
-                for j, k in enumerate(sg.kernels):
-                    pl = (k - 1) // 2
-                    segs = [(t - pl, 0, t * Dp, Dp) for t in range(k)]
-                    ops.gemm_nt(a["s"].t, self.W(f"f:{p}layer_cnn.{j}.0.weight"), a["z"].t[:, j * Dp:], rows, d,
-                                segs, None, None, 0.0, 0, self.rng)
-                cb = self._bn3(sg, e, "0.bias")
-                rm = self._bn3(sg, e, "1.running_mean", buf=True)
-                rv = self._bn3(sg, e, "1.running_var", buf=True)
-                if training:
-                    a["bn_sums"].zero_()
-                    ops.bn_stats(a["z"].t, B, L, HALO, 3 * Dp, a["bn_sums"])
-                    ops.bn_finalize(a["bn_sums"], Dp, d, 3, B * L, cb, rm, rv,
-                                    self._bn3(sg, e, "1.num_batches_tracked", buf=True), BN_MOMENTUM, BN_EPS,
-                                    a["bn_mean"], a["bn_invstd"])
-                else:
-                    ops.bn_eval_prepare(Dp, d, 3, cb, rm, rv, BN_EPS, a["bn_mean"], a["bn_invstd"])
-                ops.bn_act_fwd(a["z"].t, a["bn_mean"], a["bn_invstd"], self._bn3(sg, e, "1.weight"),
-                               self._bn3(sg, e, "1.bias"), a["t"].t, a["out"].t, B, L, d, HALO, 3,
-                               pd, site(si, e, LY.SITE_BRANCH), pd, site(si, e, LY.SITE_SUM), self.rng,
-                               a["dmask"] if pd > 0.0 else None)
-                x_in = a["out"]
-            st["x_last"] = x_in
-            nm = f"layer_{sg.name}_norm."
-            ops.layernorm_fwd(x_in.t, self.P(nm + "weight"), self.P(nm + "bias"), st["hn"].t, st["meanf"],
-                              st["rstdf"], B, L, d, HALO, LN_EPS)
-            for j, k in enumerate(sg.head_k):
-                w = f"layer_{sg.name}_cnn_{j}"
-                segs = [(t, 0, t * Dp, Dp) for t in range(k)]
-                ops.gemm_nt(st["hn"].t, self.W("f:" + w + ".weight"), st["p"].t[:, j * sg.head_np:], rows,
-                            sg.head_n, segs, self.P(w + ".bias"), None, 0.0, 0, self.rng)
-            ops.head_reduce_fwd(st["p"].t, B, L, HALO, 2 * sg.head_n, sg.head_n, sg.head_k[0], sg.head_k[1],
-                                self.feat[:, sg.feat_off:])
+        join = self._fork(lambda: self._forward_stream(1, B, training, pd))
+        self._forward_stream(0, B, training, pd)
+        join()
         ops.alg_scale = 1.0
         ops.dropout_rows(self.feat, self.featd, B, LY.FEAT, pf, LY.SITE_FEAT, self.rng)
         ops.gemm_nt(self.featd, self.W("f:layer_output.weight"), self.logits, B, g.out, [(0, 0, 0, LY.FEAT)],
                     self.P("layer_output.bias"), None, 0.0, 0, self.rng)
         return self.logits[:B, :g.out]
+
+    def _forward_stream(self, si: int, B: int, training: bool, pd: float):
+        """Encoders + head convs + time-sum of one stream (0 = left, 1 = right) into its columns of ``feat``."""
+        ops, g = self.ops, self.g
+        sg = g.streams[si]
+        st = self.s[sg.name]
+        rows, d, Dp, L = sg.rows(B), sg.d, sg.Dp, sg.L
+        ops.alg_scale = (L / sg.Lp) * (d / Dp)      # roofline numerators count valid tokens and true channels only
+        x_in = st["x0"]
+        one = [(0, 0, 0, Dp)]
+        for e in range(sg.n_enc):
+            a, p = st["enc"][e], sg.prefix(e)
+            ops.layernorm_fwd(x_in.t, self.P(p + "layer_norm_0.weight"), self.P(p + "layer_norm_0.bias"),
+                              a["t0"].t, a["mean0"], a["rstd0"], B, L, d, HALO, LN_EPS)
+            ops.gemm_nt(a["t0"].t, self.W("f:" + p + "layer_attention.in_proj_weight"), a["qkv"].t, rows,
+                        sg.ld3, one, self.PB(p + "layer_attention.in_proj_bias"), None, 0.0, 0, self.rng)
+            ops.attn_fwd(a["qkv"].t, a["o"].t, a["lse"], B, L, d, sg.H, sg.hp, HALO)
+            ops.gemm_nt(a["o"].t, self.W("f:" + p + "layer_attention.out_proj.weight"), a["t"].t, rows, d,
+                        [(0, 0, 0, sg.dh)], self.P(p + "layer_attention.out_proj.bias"), x_in.t, pd,
+                        site(si, e, LY.SITE_ATTN), self.rng)
+            ops.layernorm_fwd(a["t"].t, self.P(p + "layer_norm_1.weight"), self.P(p + "layer_norm_1.bias"),
+                              a["s"].t, a["mean1"], a["rstd1"], B, L, d, HALO, LN_EPS)
+            for j, k in enumerate(sg.kernels):
+                pl = (k - 1) // 2
+                segs = [(t - pl, 0, t * Dp, Dp) for t in range(k)]
+                ops.gemm_nt(a["s"].t, self.W(f"f:{p}layer_cnn.{j}.0.weight"), a["z"].t[:, j * Dp:], rows, d,
+                            segs, None, None, 0.0, 0, self.rng)
+            cb = self._bn3(sg, e, "0.bias")
+            rm = self._bn3(sg, e, "1.running_mean", buf=True)
+            rv = self._bn3(sg, e, "1.running_var", buf=True)
+            if training:
+                a["bn_sums"].zero_()
+                ops.bn_stats(a["z"].t, B, L, HALO, 3 * Dp, a["bn_sums"])
+                ops.bn_finalize(a["bn_sums"], Dp, d, 3, B * L, cb, rm, rv,
+                                self._bn3(sg, e, "1.num_batches_tracked", buf=True), BN_MOMENTUM, BN_EPS,
+                                a["bn_mean"], a["bn_invstd"])
+            else:
+                ops.bn_eval_prepare(Dp, d, 3, cb, rm, rv, BN_EPS, a["bn_mean"], a["bn_invstd"])
+            ops.bn_act_fwd(a["z"].t, a["bn_mean"], a["bn_invstd"], self._bn3(sg, e, "1.weight"),
+                           self._bn3(sg, e, "1.bias"), a["t"].t, a["out"].t, B, L, d, HALO, 3,
+                           pd, site(si, e, LY.SITE_BRANCH), pd, site(si, e, LY.SITE_SUM), self.rng,
+                           a["dmask"] if pd > 0.0 else None)
+            x_in = a["out"]
+        st["x_last"] = x_in
+        nm = f"layer_{sg.name}_norm."
+        ops.layernorm_fwd(x_in.t, self.P(nm + "weight"), self.P(nm + "bias"), st["hn"].t, st["meanf"],
+                          st["rstdf"], B, L, d, HALO, LN_EPS)
+        for j, k in enumerate(sg.head_k):
+            w = f"layer_{sg.name}_cnn_{j}"
+            segs = [(t, 0, t * Dp, Dp) for t in range(k)]
+            ops.gemm_nt(st["hn"].t, self.W("f:" + w + ".weight"), st["p"].t[:, j * sg.head_np:], rows,
+                        sg.head_n, segs, self.P(w + ".bias"), None, 0.0, 0, self.rng)
+        ops.head_reduce_fwd(st["p"].t, B, L, HALO, 2 * sg.head_n, sg.head_n, sg.head_k[0], sg.head_k[1],
+                            self.feat[:, sg.feat_off:])
 
     # ------------------------------------------------------------------ backward
     def backward(self, dlogits: Optional[torch.Tensor], B: int, dropout: bool = True, zero_grads: bool = True,
@@ -261,14 +294,16 @@ class THATEngine:
         """Gradient of every parameter into ``self.grads`` given dL/dlogits ([B,out] fp32; None = use the
         engine's own ``dlogits`` buffer written by ``loss_fwd_bwd``).
 
-        part 0 = everything; part 1 = output layer + left stream (fills the first gradient bucket, see
-        ``bucket_split``); part 2 = right stream.  The split lets the data-parallel all-reduce of bucket 1 overlap
-        the right stream's backward."""
+        part 0 = everything.  The data-parallel step runs it in two parts so that the all-reduce of the first
+        gradient bucket overlaps compute (``buckets``): part 1 = output layer, the whole right stream (on the
+        second CUDA stream, see ``_fork``) and the left stream down to encoder 1; part 2 = left encoder 0 and the
+        Gaussian range encoding."""
         ops, g = self.ops, self.g
         pd = P_DROP if dropout else 0.0
         pf = P_FEAT if dropout else 0.0
+        nl = g.left.n_enc
         if part == 2:
-            return self._backward_streams(B, pd, ("right",))
+            return self._backward_stream(0, B, pd, range(0, 1), head=False) if nl > 1 else None
         if zero_grads:
             self.grads.zero_()
         if dlogits is not None:
@@ -281,22 +316,41 @@ class THATEngine:
         ops.gemm_nt(self.dlogits_a, self.W("b:layer_output.weight"), self.dfeatd, B, LY.FEAT,
                     [(0, 0, 0, g.ld_out)], None, None, 0.0, 0, self.rng)
         ops.dropout_rows(self.dfeatd, self.dfeat, B, LY.FEAT, pf, LY.SITE_FEAT, self.rng)
-        self._backward_streams(B, pd, ("left",) if part == 1 else ("left", "right"))
+        join = self._fork(lambda: self._backward_stream(1, B, pd, range(0, g.right.n_enc), head=True))
+        self._backward_stream(0, B, pd, range(1 if (part == 1 and nl > 1) else 0, nl), head=True)
+        join()
 
     @property
     def bucket_split(self) -> int:
-        """Arena offset where the right stream's parameters start: gradients below it are final after part 1."""
-        return self.arena.offsets[self.g.right.prefix(0) + "layer_norm_0.weight"]
+        """Arena offset of left encoder 1's first parameter: gradients at or above it (left encoders 1.., the left
+        head, the right stream, the output layer: ~3/4 of the bytes) are final after backward part 1, the ones below
+        it (Gaussian encoding + left encoder 0) after part 2."""
+        if self.g.left.n_enc < 2:
+            return 0
+        pre = self.g.left.prefix(1)
+        split = min(off for k, off in self.arena.offsets.items() if k.startswith(pre))
+        early = ("layer_left_gaussian.", self.g.left.prefix(0))
+        assert all((off < split) == k.startswith(early) for k, off in self.arena.offsets.items())
+        return split
 
-    def _backward_streams(self, B: int, pd: float, which):
+    @property
+    def buckets(self):
+        """[(lo, hi) final after part 1, (lo, hi) final after part 2] of the flat gradient arena."""
+        return [(self.bucket_split, self.grads.numel()), (0, self.bucket_split)]
+
+    def _backward_stream(self, si: int, B: int, pd: float, encs, head: bool):
+        """Backward of one stream (0 = left, 1 = right): [head convs + final norm if ``head``] + the encoders in
+        ``encs`` (walked in reverse) [+ the Gaussian encoding when the left stream reaches encoder 0]."""
         ops, g = self.ops, self.g
-        for si, sg in enumerate(g.streams):
-            if sg.name not in which:
-                continue
-            st = self.s[sg.name]
-            rows, d, Dp, L = sg.rows(B), sg.d, sg.Dp, sg.L
-            ops.alg_scale = (L / sg.Lp) * (d / Dp)
-            Np = sg.head_np
+        sg = g.streams[si]
+        st = self.s[sg.name]
+        rows, d, Dp, L = sg.rows(B), sg.d, sg.Dp, sg.L
+        ops.alg_scale = (L / sg.Lp) * (d / Dp)
+        Np = sg.head_np
+        # the residual gradient ping-pongs between the two dout buffers, one swap per encoder walked
+        flip = (sg.n_enc - 1 - max(encs)) % 2
+        dout, dnext = (st["dout"][flip], st["dout"][1 - flip])
+        if head:
             ops.head_reduce_bwd(self.dfeat[:, sg.feat_off:], st["p"].t, B, L, HALO, 2 * sg.head_n, sg.head_n,
                                 sg.head_k[0], sg.head_k[1], st["dp"].t)
             dsegs, seg = [], 0
@@ -310,64 +364,63 @@ class THATEngine:
             ops.gemm_nt(st["dp"].t, self.W(f"b:layer_{sg.name}_cnn"), st["dhn"].t, rows, d, dsegs, None, None,
                         0.0, 0, self.rng)
             nm = f"layer_{sg.name}_norm."
-            dout, dnext = st["dout"]
             ops.layernorm_bwd(st["dhn"].t, st["x_last"].t, self.P(nm + "weight"), st["meanf"], st["rstdf"], None,
                               dout.t, None, 0.0, 0, self.rng, self.G(nm + "weight"), self.G(nm + "bias"),
                               B, L, d, HALO)
-            for e in reversed(range(sg.n_enc)):
-                a, p = st["enc"][e], sg.prefix(e)
-                x_in = st["enc"][e - 1]["out"] if e > 0 else st["x0"]
-                gam, bet = self._bn3(sg, e, "1.weight"), self._bn3(sg, e, "1.bias")
-                sb, so = site(si, e, LY.SITE_BRANCH), site(si, e, LY.SITE_SUM)
-                st["red"].zero_()
-                ops.bn_act_bwd_reduce(dout.t, a["z"].t, a["bn_mean"], a["bn_invstd"], gam, bet, B, L, d, HALO, 3,
-                                      pd, sb, pd, so, self.rng, st["red"], a["dmask"] if pd > 0.0 else None)
-                ops.bn_act_bwd_dz(dout.t, a["z"].t, a["bn_mean"], a["bn_invstd"], gam, bet, st["red"], B, L, d,
-                                  HALO, 3, pd, sb, pd, so, self.rng, st["dz"].t,
-                                  self._bn3(sg, e, "1.weight", grad=True), self._bn3(sg, e, "1.bias", grad=True),
-                                  a["dmask"] if pd > 0.0 else None)
-                dsegs, seg = [], 0
-                for j, k in enumerate(sg.kernels):
-                    pl = (k - 1) // 2
-                    ops.gemm_tn(st["dz"].t[:, j * Dp:], a["s"].t, self.G(f"{p}layer_cnn.{j}.0.weight"), d * k, k,
-                                rows, d, [(t - pl, 0, t, d) for t in range(k)])
-                    dsegs += [(pl - t, j * Dp, (seg + t) * Dp, Dp) for t in range(k)]
-                    seg += k
-                # the Conv1d biases feed a train-mode BatchNorm: their gradient is identically zero
-                ops.gemm_nt(st["dz"].t, self.W("b:" + p + "layer_cnn"), st["ds"].t, rows, d, dsegs, None, None,
-                            0.0, 0, self.rng)
-                ops.layernorm_bwd(st["ds"].t, a["t"].t, self.P(p + "layer_norm_1.weight"), a["mean1"], a["rstd1"],
-                                  dout.t, st["dt"].t, st["dtm"].t, pd, site(si, e, LY.SITE_ATTN), self.rng,
-                                  self.G(p + "layer_norm_1.weight"), self.G(p + "layer_norm_1.bias"), B, L, d, HALO)
-                one = [(0, 0, 0, d)]
-                w = p + "layer_attention.out_proj."
-                ops.gemm_tn(st["dtm"].t, a["o"].t, self.G(w + "weight"), d, 1, rows, d, [(0, 0, 0, sg.dh)],
-                            (0, 0), sg.grp)
-                ops.colsum_tokens(st["dtm"].t, B, L, HALO, d, self.G(w + "bias"))
-                ops.gemm_nt(st["dtm"].t, self.W("b:" + w + "weight"), st["do"].t, rows, sg.dh, [(0, 0, 0, Dp)], None,
-                            None, 0.0, 0, self.rng)
-                w = p + "layer_attention.in_proj_"
-                # the in_proj bias gradient (column sums of dqkv) is accumulated by the attention backward kernel itself
-                ops.attn_bwd(a["qkv"].t, a["o"].t, st["do"].t, st["dqkv"].t, a["lse"], B, L, d, sg.H, sg.hp, HALO,
-                             self.G(w + "bias"))
-                ops.gemm_tn(st["dqkv"].t, a["t0"].t, self.G(w + "weight"), d, 1, rows, sg.ld3, one, sg.grp, (0, 0))
-                ops.gemm_nt(st["dqkv"].t, self.W("b:" + w + "weight"), st["dt0"].t, rows, d, [(0, 0, 0, sg.ld3)],
-                            None, None, 0.0, 0, self.rng)
-                ops.layernorm_bwd(st["dt0"].t, x_in.t, self.P(p + "layer_norm_0.weight"), a["mean0"], a["rstd0"],
-                                  st["dt"].t, dnext.t, None, 0.0, 0, self.rng,
-                                  self.G(p + "layer_norm_0.weight"), self.G(p + "layer_norm_0.bias"), B, L, d, HALO)
-                dout, dnext = dnext, dout
-            if sg.name == "left":
-                gp = "layer_left_gaussian."
-                ops.gauss_pe_bwd(dout.t, B, HALO, self.pe_w, self.P(gp + "var_position"), self.P(gp + "var_mu"),
-                                 self.P(gp + "var_sigma"), self.P(gp + "var_embedding"), L, LY.NUM_GAUSS, g.F,
-                                 self.dpe_ws, self.G(gp + "var_embedding"), self.G(gp + "var_mu"),
-                                 self.G(gp + "var_sigma"))
+        for e in reversed(encs):
+            a, p = st["enc"][e], sg.prefix(e)
+            x_in = st["enc"][e - 1]["out"] if e > 0 else st["x0"]
+            gam, bet = self._bn3(sg, e, "1.weight"), self._bn3(sg, e, "1.bias")
+            sb, so = site(si, e, LY.SITE_BRANCH), site(si, e, LY.SITE_SUM)
+            st["red"].zero_()
+            ops.bn_act_bwd_reduce(dout.t, a["z"].t, a["bn_mean"], a["bn_invstd"], gam, bet, B, L, d, HALO, 3,
+                                  pd, sb, pd, so, self.rng, st["red"], a["dmask"] if pd > 0.0 else None)
+            ops.bn_act_bwd_dz(dout.t, a["z"].t, a["bn_mean"], a["bn_invstd"], gam, bet, st["red"], B, L, d,
+                              HALO, 3, pd, sb, pd, so, self.rng, st["dz"].t,
+                              self._bn3(sg, e, "1.weight", grad=True), self._bn3(sg, e, "1.bias", grad=True),
+                              a["dmask"] if pd > 0.0 else None)
+            dsegs, seg = [], 0
+            for j, k in enumerate(sg.kernels):
+                pl = (k - 1) // 2
+                ops.gemm_tn(st["dz"].t[:, j * Dp:], a["s"].t, self.G(f"{p}layer_cnn.{j}.0.weight"), d * k, k,
+                            rows, d, [(t - pl, 0, t, d) for t in range(k)])
+                dsegs += [(pl - t, j * Dp, (seg + t) * Dp, Dp) for t in range(k)]
+                seg += k
+            # the Conv1d biases feed a train-mode BatchNorm: their gradient is identically zero
+            ops.gemm_nt(st["dz"].t, self.W("b:" + p + "layer_cnn"), st["ds"].t, rows, d, dsegs, None, None,
+                        0.0, 0, self.rng)
+            ops.layernorm_bwd(st["ds"].t, a["t"].t, self.P(p + "layer_norm_1.weight"), a["mean1"], a["rstd1"],
+                              dout.t, st["dt"].t, st["dtm"].t, pd, site(si, e, LY.SITE_ATTN), self.rng,
+                              self.G(p + "layer_norm_1.weight"), self.G(p + "layer_norm_1.bias"), B, L, d, HALO)
+            one = [(0, 0, 0, d)]
+            w = p + "layer_attention.out_proj."
+            ops.gemm_tn(st["dtm"].t, a["o"].t, self.G(w + "weight"), d, 1, rows, d, [(0, 0, 0, sg.dh)],
+                        (0, 0), sg.grp)
+            ops.colsum_tokens(st["dtm"].t, B, L, HALO, d, self.G(w + "bias"))
+            ops.gemm_nt(st["dtm"].t, self.W("b:" + w + "weight"), st["do"].t, rows, sg.dh, [(0, 0, 0, Dp)], None,
+                        None, 0.0, 0, self.rng)
+            w = p + "layer_attention.in_proj_"
+            # the in_proj bias gradient (column sums of dqkv) is accumulated by the attention backward kernel itself
+            ops.attn_bwd(a["qkv"].t, a["o"].t, st["do"].t, st["dqkv"].t, a["lse"], B, L, d, sg.H, sg.hp, HALO,
+                         self.G(w + "bias"))
+            ops.gemm_tn(st["dqkv"].t, a["t0"].t, self.G(w + "weight"), d, 1, rows, sg.ld3, one, sg.grp, (0, 0))
+            ops.gemm_nt(st["dqkv"].t, self.W("b:" + w + "weight"), st["dt0"].t, rows, d, [(0, 0, 0, sg.ld3)],
+                        None, None, 0.0, 0, self.rng)
+            ops.layernorm_bwd(st["dt0"].t, x_in.t, self.P(p + "layer_norm_0.weight"), a["mean0"], a["rstd0"],
+                              st["dt"].t, dnext.t, None, 0.0, 0, self.rng,
+                              self.G(p + "layer_norm_0.weight"), self.G(p + "layer_norm_0.bias"), B, L, d, HALO)
+            dout, dnext = dnext, dout
+        if si == 0 and 0 in encs:
+            gp = "layer_left_gaussian."
+            ops.gauss_pe_bwd(dout.t, B, HALO, self.pe_w, self.P(gp + "var_position"), self.P(gp + "var_mu"),
+                             self.P(gp + "var_sigma"), self.P(gp + "var_embedding"), L, LY.NUM_GAUSS, g.F,
+                             self.dpe_ws, self.G(gp + "var_embedding"), self.G(gp + "var_mu"),
+                             self.G(gp + "var_sigma"))
 
     # ------------------------------------------------------------------ CUDA-graph train body
     def train_body(self, B: int, pos_weight: float, dropout: bool, part: int = 0):
         """repack + forward body + BCE + backward: a fixed launch sequence over static buffers.
-        part 1 stops after the left stream's backward, part 2 is the right stream's backward (see ``backward``)."""
+        part 1 stops before the left stream's encoder 0 backward, part 2 is that remainder (see ``backward``)."""
         if part != 2:
             self.repack()
             self.forward_body(B, True, dropout)

@@ -4,9 +4,11 @@ The reference is single-process (no collective anywhere); t
 data-parallel path adds.  Gradients already live in ONE flat fp32 arena (multi_modal_csi_b200.that.THAT.flat_grads),
 so the exchange is two large contiguous ``ncclAllReduce`` calls issued through ``torch.distributed``:
 
-  bucket 1 = [0, bucket_split)   gaussian encoding + left stream (95 % of the bytes), final once the left stream's
-                                 backward is done -> reduced on a side stream WHILE the right stream's backward runs
-  bucket 2 = [bucket_split, n)   right stream + output layer, reduced after backward
+  bucket 1 = [bucket_split, n)   left encoders 1.. + left head, right stream, output layer (~3/4 of the bytes), final
+                                 once backward part 1 is done -> reduced on a side stream WHILE left encoder 0's
+                                 backward (part 2) runs
+  bucket 2 = [0, bucket_split)   Gaussian encoding + left encoder 0, reduced after backward
+(``THATEngine.buckets``; the two THAT streams themselves run side by side on two CUDA streams, ``THATEngine._fork``)
 
 BatchNorm statistics stay per rank (DistributedDataParallel semantics).
 """

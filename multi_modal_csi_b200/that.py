@@ -293,12 +293,13 @@ class THAT(torch.nn.Module):
         run = eng.train_body_graph if (graph and x.is_cuda and self._eager_steps >= 1) else eng.train_body
         overlap = grad_hook is not None and hasattr(grad_hook, "start_bucket")
         if overlap:
-            # data parallel: all-reduce the first gradient bucket (left stream, 95 % of the bytes) on a side stream
-            # while the right stream's backward runs
+            # data parallel: all-reduce the first gradient bucket (everything but the Gaussian encoding and left
+            # encoder 0: ~3/4 of the bytes) on a side stream while the rest of the left stream's backward runs
+            (lo1, hi1), (lo2, hi2) = eng.buckets
             run(B, pos_weight, self.dropout_enabled, 1)
-            grad_hook.start_bucket(eng, 0, eng.bucket_split)
+            grad_hook.start_bucket(eng, lo1, hi1)
             run(B, pos_weight, self.dropout_enabled, 2)
-            grad_hook.finish(eng, eng.bucket_split, eng.grads.numel())
+            grad_hook.finish(eng, lo2, hi2)
         else:
             run(B, pos_weight, self.dropout_enabled)
         if run == eng.train_body:

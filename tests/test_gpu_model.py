@@ -317,6 +317,55 @@ def test_cuda_graph_step_equals_eager_step():
     assert traj[0][0] != traj[0][1]
 
 
+@pytest.mark.parametrize("graph", [False, True])
+def test_two_stream_concurrency_equals_sequential(graph):
+    """Left and right THAT streams issued on two CUDA streams (THATEngine._fork) == the same launches on one stream,
+    eagerly and through the captured graph (dropout + augmentation on: the Philox draws do not depend on the stream)."""
+    from multi_modal_csi_b200 import FusedAdam
+    T, F, out, B = 3000, 270, 54, 8
+    x, y = synth(B, T, F, out)
+    res = []
+    for conc in (False, True):
+        m = build(T, F, out, "bf16")
+        m.dropout_enabled = True
+        m.use_cuda_graph = graph
+        opt = FusedAdam(m.parameters(), lr=5e-4, weight_decay=2e-4)
+        m.train()
+        eng = m._engine_for(B)
+        eng.concurrent = conc
+        ls = []
+        for s in range(4):
+            loss, _ = m.fused_train_step(x.cuda(), y.cuda(), opt, augment=True)
+            ls.append(loss.item())
+        assert (eng._side is not None) == conc
+        res.append((ls, m.flat_grads.clone(), m.flat_params.clone()))
+    (l0, g0, p0), (l1, g1, p1) = res
+    assert all(abs(a - b) < 5e-3 * max(1.0, abs(a)) for a, b in zip(l0, l1)), (l0, l1)
+    assert nrel(p1, p0) < 1e-2
+
+
+def test_backward_parts_equal_whole():
+    """Data-parallel split of the backward pass (part 1 + part 2, engine.buckets) == one whole backward; after part 1
+    the first bucket already holds its final gradients."""
+    T, F, out, B = 400, 30, 12, 6
+    x, y = synth(B, T, F, out)
+    m = build(T, F, out, "fp32")
+    m.train()
+    eng = m._engine_for(B)
+    eng.forward(x.cuda(), B, training=True, dropout=False)
+    eng.loss_fwd_bwd(y.cuda(), B, 4.0)
+    eng.backward(None, B, dropout=False, part=0)
+    whole = eng.grads.clone()
+    eng.backward(None, B, dropout=False, part=1)
+    (lo1, hi1), (lo2, hi2) = eng.buckets
+    assert 0 < lo1 < hi1 == eng.grads.numel() and (lo2, hi2) == (0, lo1)
+    torch.cuda.synchronize()
+    assert nrel(eng.grads[lo1:hi1], whole[lo1:hi1]) < 1e-5
+    assert float(eng.grads[lo2:hi2].abs().max()) == 0.0
+    eng.backward(None, B, dropout=False, part=2)
+    assert nrel(eng.grads, whole) < 1e-5
+
+
 def test_predict_counts_matches_reference_rule(gold):
     """GPU decision rule == utils.process_predictions on the committed reference fixture (and the oracle)."""
     from oracle import that_oracle as O
