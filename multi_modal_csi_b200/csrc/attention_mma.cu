@@ -6,10 +6,14 @@
 //   forward : flash-style online softmax over 64-key blocks, one 16-query tile per warp iteration
 //   backward: pass A (per 16-query tile)  S, dP -> dS -> dQ = dS K
 //             pass B (per 16-key tile)    S^T, dP^T -> dV = P^T dO, dK = dS^T Q     (no atomics, no cross-warp sums)
+//   dK/dV tiles are staged over the K/V rows they belong to once every warp has finished pass A (mbarrier split barrier).
 #include "common.cuh"
 
 #define ST(s) ((cudaStream_t)(s))
-#define AM_MAX_WARPS 8
+#define AM_MAX_WARPS 5
+// occupancy: registers are the limit (3 CTAs/SM at ~103 regs).  CTAs have at most 5 warps; the (160 threads, 4 CTAs) bound
+// = 96 registers gives 20 resident warps per SM; the 64-wide heads need more accumulators and keep the loose bound
+template <int HDP> struct am_bounds { static constexpr int min_ctas = HDP <= 32 ? 4 : 2; };
 #define LOG2E 1.4426950408889634f
 
 __device__ __forceinline__ void ldsm_x4(uint32_t (&r)[4], const bf16* p) {
@@ -85,8 +89,76 @@ __device__ __forceinline__ void stage_tile(bf16* __restrict__ dst, int row0, con
     }
 }
 
+// One key block of the forward pass for one 16-query tile: NP pairs of 8-key n-tiles (16*NP keys) starting at pair pb.
+// S = Q K^T -> online softmax update of (m, l, O) -> O += P V.  NP is a template parameter so that the ragged last block
+// of a head is a separate straight-line instantiation instead of predicated ldmatrix/mma inside the full-block code.
+template <int HDP, int NP>
+__device__ __forceinline__ void attn_fwd_block(const bf16* __restrict__ Ks, const bf16* __restrict__ Vs, const uint32_t (&qa)[HDP / 16][4],
+                                               float (&oacc)[HDP / 8][4], float& m0, float& m1, float& l0, float& l1, int pb, int L,
+                                               float c, int lane, int t) {
+    constexpr int LDS = HDP + 8, KS = HDP / 16, NTO = HDP / 8, NT = 2 * NP;
+    float s[NT][4];
+#pragma unroll
+    for (int i = 0; i < NT; ++i) s[i][0] = s[i][1] = s[i][2] = s[i][3] = 0.f;
+#pragma unroll
+    for (int pp = 0; pp < NP; ++pp) {
+#pragma unroll
+        for (int ks = 0; ks < KS; ++ks) {
+            uint32_t kb[4];
+            ldsm_x4(kb, b_frag_ptr<LDS>(Ks, (pb + pp) * 16, ks * 16, lane));
+            mma16816(s[2 * pp], qa[ks], kb[0], kb[1]);
+            mma16816(s[2 * pp + 1], qa[ks], kb[2], kb[3]);
+        }
+    }
+    if ((pb + NP) * 16 > L) {                                  // only the last key block has columns >= L (warp-uniform)
+#pragma unroll
+        for (int nt = 0; nt < NT; ++nt) {
+            const int col = pb * 16 + nt * 8 + 2 * t;
+            if (col >= L) s[nt][0] = s[nt][2] = -INFINITY;
+            if (col + 1 >= L) s[nt][1] = s[nt][3] = -INFINITY;
+        }
+    }
+    float mx0 = -INFINITY, mx1 = -INFINITY;
+#pragma unroll
+    for (int nt = 0; nt < NT; ++nt) {
+        mx0 = fmaxf(mx0, fmaxf(s[nt][0], s[nt][1]));
+        mx1 = fmaxf(mx1, fmaxf(s[nt][2], s[nt][3]));
+    }
+    mx0 = fmaxf(mx0, __shfl_xor_sync(0xffffffffu, mx0, 1)); mx0 = fmaxf(mx0, __shfl_xor_sync(0xffffffffu, mx0, 2));
+    mx1 = fmaxf(mx1, __shfl_xor_sync(0xffffffffu, mx1, 1)); mx1 = fmaxf(mx1, __shfl_xor_sync(0xffffffffu, mx1, 2));
+    const float mn0 = fmaxf(m0, mx0), mn1 = fmaxf(m1, mx1);
+    const float al0 = fast_exp2((m0 - mn0) * c), al1 = fast_exp2((m1 - mn1) * c);
+    m0 = mn0; m1 = mn1;
+    l0 *= al0; l1 *= al1;
+#pragma unroll
+    for (int i = 0; i < NTO; ++i) { oacc[i][0] *= al0; oacc[i][1] *= al0; oacc[i][2] *= al1; oacc[i][3] *= al1; }
+    const float mc0 = mn0 * c, mc1 = mn1 * c;
+#pragma unroll
+    for (int nt = 0; nt < NT; ++nt) {
+        s[nt][0] = fast_exp2(fmaf(s[nt][0], c, -mc0)); s[nt][1] = fast_exp2(fmaf(s[nt][1], c, -mc0));
+        s[nt][2] = fast_exp2(fmaf(s[nt][2], c, -mc1)); s[nt][3] = fast_exp2(fmaf(s[nt][3], c, -mc1));
+        l0 += s[nt][0] + s[nt][1];
+        l1 += s[nt][2] + s[nt][3];
+    }
+#pragma unroll
+    for (int pp = 0; pp < NP; ++pp) {
+        uint32_t pa[4];
+        pa[0] = pack_bf16(s[2 * pp][0], s[2 * pp][1]);
+        pa[1] = pack_bf16(s[2 * pp][2], s[2 * pp][3]);
+        pa[2] = pack_bf16(s[2 * pp + 1][0], s[2 * pp + 1][1]);
+        pa[3] = pack_bf16(s[2 * pp + 1][2], s[2 * pp + 1][3]);
+#pragma unroll
+        for (int no = 0; no < NTO; no += 2) {
+            uint32_t vb[4];
+            ldsm_x4_t(vb, bt_frag_ptr<LDS>(Vs, (pb + pp) * 16, no * 8, lane));
+            mma16816(oacc[no], pa, vb[0], vb[1]);
+            mma16816(oacc[no + 1], pa, vb[2], vb[3]);
+        }
+    }
+}
+
 template <int HDP>
-__global__ void __launch_bounds__(AM_MAX_WARPS * 32) attn_fwd_mma_kernel(const bf16* __restrict__ qkv, int ld3, bf16* __restrict__ o,
+__global__ void __launch_bounds__(AM_MAX_WARPS * 32, am_bounds<HDP>::min_ctas) attn_fwd_mma_kernel(const bf16* __restrict__ qkv, int ld3, bf16* __restrict__ o,
                                                                      int ldo, float* __restrict__ lse, int L, int d, int H, int halo) {
     constexpr int LDS = HDP + 8, KS = HDP / 16, NTO = HDP / 8;
     extern __shared__ __align__(16) uint8_t sm_raw[];
@@ -104,7 +176,7 @@ __global__ void __launch_bounds__(AM_MAX_WARPS * 32) attn_fwd_mma_kernel(const b
     __syncthreads();
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, g = lane >> 2, t = lane & 3;
     const float sc = rsqrtf((float)hd), c = sc * LOG2E;
-    const int npair = LP / 16;
+    const int npair = LP / 16, nfull = npair & ~3, ntail = npair & 3;
     for (int qt = warp; qt < npair; qt += (int)(blockDim.x >> 5)) {
         uint32_t qa[KS][4];
 #pragma unroll
@@ -113,71 +185,11 @@ __global__ void __launch_bounds__(AM_MAX_WARPS * 32) attn_fwd_mma_kernel(const b
         float oacc[NTO][4];
 #pragma unroll
         for (int i = 0; i < NTO; ++i) oacc[i][0] = oacc[i][1] = oacc[i][2] = oacc[i][3] = 0.f;
-        for (int pb = 0; pb < npair; pb += 4) {                  // 64-key block = up to 4 pairs of n-tiles
-            const int np = min(4, npair - pb);
-            float s[8][4];
-#pragma unroll
-            for (int i = 0; i < 8; ++i) s[i][0] = s[i][1] = s[i][2] = s[i][3] = 0.f;
-#pragma unroll
-            for (int pp = 0; pp < 4; ++pp) {
-                if (pp < np) {
-#pragma unroll
-                    for (int ks = 0; ks < KS; ++ks) {
-                        uint32_t kb[4];
-                        ldsm_x4(kb, b_frag_ptr<LDS>(Ks, (pb + pp) * 16, ks * 16, lane));
-                        mma16816(s[2 * pp], qa[ks], kb[0], kb[1]);
-                        mma16816(s[2 * pp + 1], qa[ks], kb[2], kb[3]);
-                    }
-                }
-            }
-            if (pb * 16 + 64 > L) {                             // only the last key block has columns >= L (warp-uniform)
-#pragma unroll
-                for (int nt = 0; nt < 8; ++nt) {
-                    const int col = pb * 16 + nt * 8 + 2 * t;
-                    if (col >= L) s[nt][0] = s[nt][2] = -INFINITY;
-                    if (col + 1 >= L) s[nt][1] = s[nt][3] = -INFINITY;
-                }
-            }
-            float mx0 = -INFINITY, mx1 = -INFINITY;
-#pragma unroll
-            for (int nt = 0; nt < 8; ++nt) {
-                mx0 = fmaxf(mx0, fmaxf(s[nt][0], s[nt][1]));
-                mx1 = fmaxf(mx1, fmaxf(s[nt][2], s[nt][3]));
-            }
-            mx0 = fmaxf(mx0, __shfl_xor_sync(0xffffffffu, mx0, 1)); mx0 = fmaxf(mx0, __shfl_xor_sync(0xffffffffu, mx0, 2));
-            mx1 = fmaxf(mx1, __shfl_xor_sync(0xffffffffu, mx1, 1)); mx1 = fmaxf(mx1, __shfl_xor_sync(0xffffffffu, mx1, 2));
-            const float mn0 = fmaxf(m0, mx0), mn1 = fmaxf(m1, mx1);
-            const float al0 = fast_exp2((m0 - mn0) * c), al1 = fast_exp2((m1 - mn1) * c);
-            m0 = mn0; m1 = mn1;
-            l0 *= al0; l1 *= al1;
-#pragma unroll
-            for (int i = 0; i < NTO; ++i) { oacc[i][0] *= al0; oacc[i][1] *= al0; oacc[i][2] *= al1; oacc[i][3] *= al1; }
-            const float mc0 = mn0 * c, mc1 = mn1 * c;
-#pragma unroll
-            for (int nt = 0; nt < 8; ++nt) {
-                s[nt][0] = fast_exp2(s[nt][0] * c - mc0); s[nt][1] = fast_exp2(s[nt][1] * c - mc0);
-                s[nt][2] = fast_exp2(s[nt][2] * c - mc1); s[nt][3] = fast_exp2(s[nt][3] * c - mc1);
-                l0 += s[nt][0] + s[nt][1];
-                l1 += s[nt][2] + s[nt][3];
-            }
-#pragma unroll
-            for (int pp = 0; pp < 4; ++pp) {
-                if (pp < np) {
-                    uint32_t pa[4];
-                    pa[0] = pack_bf16(s[2 * pp][0], s[2 * pp][1]);
-                    pa[1] = pack_bf16(s[2 * pp][2], s[2 * pp][3]);
-                    pa[2] = pack_bf16(s[2 * pp + 1][0], s[2 * pp + 1][1]);
-                    pa[3] = pack_bf16(s[2 * pp + 1][2], s[2 * pp + 1][3]);
-#pragma unroll
-                    for (int no = 0; no < NTO; no += 2) {
-                        uint32_t vb[4];
-                        ldsm_x4_t(vb, bt_frag_ptr<LDS>(Vs, (pb + pp) * 16, no * 8, lane));
-                        mma16816(oacc[no], pa, vb[0], vb[1]);
-                        mma16816(oacc[no + 1], pa, vb[2], vb[3]);
-                    }
-                }
-            }
-        }
+        for (int pb = 0; pb < nfull; pb += 4)                     // 64-key blocks
+            attn_fwd_block<HDP, 4>(Ks, Vs, qa, oacc, m0, m1, l0, l1, pb, L, c, lane, t);
+        if (ntail == 1) attn_fwd_block<HDP, 1>(Ks, Vs, qa, oacc, m0, m1, l0, l1, nfull, L, c, lane, t);
+        else if (ntail == 2) attn_fwd_block<HDP, 2>(Ks, Vs, qa, oacc, m0, m1, l0, l1, nfull, L, c, lane, t);
+        else if (ntail == 3) attn_fwd_block<HDP, 3>(Ks, Vs, qa, oacc, m0, m1, l0, l1, nfull, L, c, lane, t);
         l0 += __shfl_xor_sync(0xffffffffu, l0, 1); l0 += __shfl_xor_sync(0xffffffffu, l0, 2);
         l1 += __shfl_xor_sync(0xffffffffu, l1, 1); l1 += __shfl_xor_sync(0xffffffffu, l1, 2);
         const float i0 = 1.f / l0, i1 = 1.f / l1;
@@ -191,6 +203,24 @@ __global__ void __launch_bounds__(AM_MAX_WARPS * 32) attn_fwd_mma_kernel(const b
     }
     __syncthreads();
     store_head_tile<HDP, LDS>(Qs, o + row0 * ldo + h * HDP, ldo, L);
+}
+
+__device__ __forceinline__ void am_mbar_init(uint32_t bar, uint32_t count) {
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(bar), "r"(count) : "memory");
+}
+__device__ __forceinline__ void am_mbar_arrive(uint32_t bar) {
+    asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(bar) : "memory");
+}
+__device__ __forceinline__ void am_mbar_wait(uint32_t bar, uint32_t parity) {
+    asm volatile(
+        "{\n"
+        ".reg .pred P1;\n"
+        "AM_WAIT:\n"
+        "mbarrier.try_wait.parity.shared::cta.b64 P1, [%0], %1;\n"
+        "@P1 bra AM_DONE;\n"
+        "bra AM_WAIT;\n"
+        "AM_DONE:\n"
+        "}\n" ::"r"(bar), "r"(parity) : "memory");
 }
 
 // lane-local column partials (accumulator layout: columns no*8 + 2t, +1; rows g, g+8) -> per-CTA shared sums
@@ -209,12 +239,13 @@ __device__ __forceinline__ void warp_colsum_flush(float (&c)[NTO][2], float* csu
 }
 
 template <int HDP>
-__global__ void __launch_bounds__(AM_MAX_WARPS * 32) attn_bwd_mma_kernel(const bf16* __restrict__ qkv, int ld3, const bf16* __restrict__ o,
+__global__ void __launch_bounds__(AM_MAX_WARPS * 32, am_bounds<HDP>::min_ctas) attn_bwd_mma_kernel(const bf16* __restrict__ qkv, int ld3, const bf16* __restrict__ o,
                                                                      int ldo, const bf16* __restrict__ dout, int lddo,
                                                                      bf16* __restrict__ dqkv, int lddqkv, const float* __restrict__ lse,
                                                                      int L, int d, int H, int halo, float* __restrict__ dbias) {
     constexpr int LDS = HDP + 8, KS = HDP / 16, NTO = HDP / 8, CPR = HDP / 8;
     __shared__ float csum[3 * HDP];                            // column sums of dQ | dK | dV of this head (in_proj bias gradient)
+    __shared__ __align__(8) uint64_t passA_bar;
     extern __shared__ __align__(16) uint8_t sm_raw[];
     const int hd = d / H, b = blockIdx.x / H, h = blockIdx.x % H, Lp = L + 2 * halo;
     const int LP = (L + 15) & ~15;
@@ -232,6 +263,8 @@ __global__ void __launch_bounds__(AM_MAX_WARPS * 32) attn_bwd_mma_kernel(const b
     load_head_tile<HDP, LDS>(dout + row0 * lddo + h * HDP, lddo, L, LP, Gs);
     for (int i = threadIdx.x; i < LP; i += blockDim.x) Ls[i] = i < L ? lse[((size_t)b * H + h) * L + i] * LOG2E : 0.f;
     for (int i = threadIdx.x; i < 3 * HDP; i += blockDim.x) csum[i] = 0.f;
+    const uint32_t abar = (uint32_t)__cvta_generic_to_shared(&passA_bar);
+    if (threadIdx.x == 0) am_mbar_init(abar, blockDim.x >> 5);
     cp_async_wait_all();
     __syncthreads();
     // D_i = rowsum(dO_i * O_i): CPR lanes per row, one 128-bit O load each
@@ -322,11 +355,15 @@ __global__ void __launch_bounds__(AM_MAX_WARPS * 32) attn_bwd_mma_kernel(const b
         }
     }
     if (dbias) warp_colsum_flush<NTO>(cq, csum, g, t);
+    __syncwarp();
+    if (lane == 0) am_mbar_arrive(abar);                          // this warp no longer reads K / V rows of other tiles
     // ---------------- pass B: dK, dV (rows of the accumulators are keys, columns of S^T are queries)
     float ck[NTO][2], cv[NTO][2];
 #pragma unroll
     for (int no = 0; no < NTO; ++no) ck[no][0] = ck[no][1] = cv[no][0] = cv[no][1] = 0.f;
-    for (int kt = warp; kt < ntile; kt += (int)(blockDim.x >> 5)) {
+    // tiles are dealt in the opposite order to pass A, so a warp with one tile more there has one tile less here
+    bool passA_done = false;
+    for (int kt = ntile - 1 - warp; kt >= 0; kt -= (int)(blockDim.x >> 5)) {
         uint32_t ka[KS][4], va[KS][4];
 #pragma unroll
         for (int ks = 0; ks < KS; ++ks) {
@@ -374,7 +411,10 @@ __global__ void __launch_bounds__(AM_MAX_WARPS * 32) attn_bwd_mma_kernel(const b
                 mma16816(dk[no + 1], sa, qb[2], qb[3]);
             }
         }
-        __syncwarp();                                              // K/V rows of this tile are only read as its own A fragments
+        // K/V rows of this tile are otherwise only read as its own A fragments (held in registers by now) and by pass A
+        // of the other warps: wait until every warp has left pass A (split barrier: arrived long ago, rarely blocks)
+        if (!passA_done) { am_mbar_wait(abar, 0u); passA_done = true; }
+        __syncwarp();
         stage_tile<LDS, NTO>(Ks, kt * 16, dk, 1.f, 1.f, g, t);
         stage_tile<LDS, NTO>(Vs, kt * 16, dv, 1.f, 1.f, g, t);
         if (dbias) {
@@ -407,7 +447,7 @@ __global__ void __launch_bounds__(AM_MAX_WARPS * 32) attn_bwd_mma_kernel(const b
 
 // warps per CTA: the 16-row tiles of a head are dealt round-robin, so pick the count that leaves no idle round
 static int am_warps(int LP) {
-    const int ntile = LP / 16, rounds = (ntile + 5) / 6;
+    const int ntile = LP / 16, rounds = (ntile + AM_MAX_WARPS - 1) / AM_MAX_WARPS;
     int w = (ntile + rounds - 1) / rounds;
     if (w > AM_MAX_WARPS) w = AM_MAX_WARPS;
     return w < 1 ? 1 : w;
@@ -431,10 +471,12 @@ extern "C" int csi_attn_fwd_mma(const void* qkv, int ld3, void* o, int ldo, floa
     if (B == 0) return CSI_OK;
     const int LP = (L + 15) & ~15;
     const size_t smem = (size_t)3 * LP * (hp + 8) * 2;
+    const int nw = am_warps(LP);
 #define GO(HDP)                                                                                                        \
     do {                                                                                                               \
         CSI_CUDA(cudaFuncSetAttribute(attn_fwd_mma_kernel<HDP>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem)); \
-        attn_fwd_mma_kernel<HDP><<<B * H, am_warps(LP) * 32, smem, ST(stream)>>>((const bf16*)qkv, ld3, (bf16*)o, ldo, lse, L, d, H, halo); \
+        CSI_CUDA(cudaFuncSetAttribute(attn_fwd_mma_kernel<HDP>, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared)); \
+        attn_fwd_mma_kernel<HDP><<<B * H, nw * 32, smem, ST(stream)>>>((const bf16*)qkv, ld3, (bf16*)o, ldo, lse, L, d, H, halo); \
     } while (0)
     if (hp == 16) GO(16); else if (hp == 32) GO(32); else GO(64);
 #undef GO
@@ -451,11 +493,13 @@ extern "C" int csi_attn_bwd_mma(const void* qkv, int ld3, const void* o, int ldo
     if (B == 0) return CSI_OK;
     const int LP = (L + 15) & ~15;
     const size_t smem = (size_t)4 * LP * (hp + 8) * 2 + 2 * (size_t)LP * 4;
+    const int nw = am_warps(LP);
 #define GO(HDP)                                                                                                        \
     do {                                                                                                               \
         CSI_CUDA(cudaFuncSetAttribute(attn_bwd_mma_kernel<HDP>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem)); \
-        attn_bwd_mma_kernel<HDP><<<B * H, am_warps(LP) * 32, smem, ST(stream)>>>((const bf16*)qkv, ld3, (const bf16*)o, ldo,   \
-                                                                            (const bf16*)dout, lddo, (bf16*)dqkv, lddqkv, lse, L, d, H, halo, dbias); \
+        CSI_CUDA(cudaFuncSetAttribute(attn_bwd_mma_kernel<HDP>, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared)); \
+        attn_bwd_mma_kernel<HDP><<<B * H, nw * 32, smem, ST(stream)>>>((const bf16*)qkv, ld3, (const bf16*)o, ldo,       \
+                                                                        (const bf16*)dout, lddo, (bf16*)dqkv, lddqkv, lse, L, d, H, halo, dbias); \
     } while (0)
     if (hp == 16) GO(16); else if (hp == 32) GO(32); else GO(64);
 #undef GO

@@ -92,10 +92,13 @@ struct RowWalk {
 // One CTA = (sample, 16 pooled tokens).  A work item is (token, 4 consecutive features): 20 x 2 float2 loads, one
 // Philox call per (time step, 4 features) when augmenting (2 Box-Muller pairs from 16-bit uniforms + 4 keep bits).
 #define POOL_K 20
-#define POOL_TL 16
+// 8 tokens per CTA: 19 x B CTAs of 288 threads at L=150, F=270 (every thread owns 2 of the 544 work items; ~8 waves).  With 16
+// tokens the 2560 CTAs were 2.2 waves of 8 resident CTAs and each thread looped 4.25 -> 5 times: 61 % of the machine.
+// 8 tokens = 32 bytes per row of the right-stream layout, one whole sector per store.
+#define POOL_TL 8
 
 template <bool AUG>
-__global__ void __launch_bounds__(256) pool_dual_kernel(
+__global__ void __launch_bounds__(512) pool_dual_kernel(
     const float* __restrict__ x, const long long* __restrict__ offs, const int* __restrict__ lens, int T, int F,
     const float* __restrict__ pe, int ld_pe, float* __restrict__ left, int ld_left, float* __restrict__ right,
     int ld_right, int halo, const unsigned long long* __restrict__ rng) {
@@ -188,27 +191,6 @@ __global__ void __launch_bounds__(256) pool_dual_kernel(
     }
 }
 
-extern "C" int csi_pool_dual(const float* x, const long long* offs, const int* lens, int B, int T, int F,
-                             const float* pe, int ld_pe, float* left, int ld_left, float* right, int ld_right,
-                             int halo, int augment, const unsigned long long* rng, void* stream) {
-    CSI_CHECK_ARG(x && left && right, "null pointer");
-    CSI_CHECK_ARG(T % POOL_K == 0 && F % 2 == 0 && F <= 2800, "T must be a multiple of 20, F even and <= 2800");
-    CSI_CHECK_ARG((offs == nullptr) == (lens == nullptr), "offs and lens go together");
-    CSI_CHECK_ARG(!augment || rng, "augmentation needs rng");
-    if (B == 0) return CSI_OK;
-    const int L = T / POOL_K;
-    dim3 grid(cdiv(L, POOL_TL), B);
-    const size_t smem = (size_t)POOL_TL * (F + 1) * sizeof(float);
-    if (augment) {
-        if (smem > 48 * 1024) CSI_CUDA(cudaFuncSetAttribute(pool_dual_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-        pool_dual_kernel<true><<<grid, 256, smem, ST(stream)>>>(x, offs, lens, T, F, pe, ld_pe, left, ld_left, right, ld_right, halo, rng);
-    } else {
-        if (smem > 48 * 1024) CSI_CUDA(cudaFuncSetAttribute(pool_dual_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-        pool_dual_kernel<false><<<grid, 256, smem, ST(stream)>>>(x, offs, lens, T, F, pe, ld_pe, left, ld_left, right, ld_right, halo, rng);
-    }
-    CSI_LAUNCH_CHECK();
-    return CSI_OK;
-}
 // ------------------------------------------------------------------------------------------------ gaussian PE
 __global__ void gauss_pe_fwd_kernel(const float* __restrict__ pos, const float* __restrict__ mu,
                                     const float* __restrict__ sigma, const float* __restrict__ emb, int K, int F,
@@ -326,6 +308,35 @@ __device__ __forceinline__ void ew_mbar_wait(uint32_t bar, uint32_t parity) {
         "DONE:\n"
         "}\n" ::"r"(bar), "r"(parity) : "memory");
 }
+// Two variants were measured at B=256, F=270 against the 295 us of the kernel above and removed: streaming the input
+// through a cp.async.bulk shared-memory ring four tokens ahead (359 us: 10 instead of 35 resident warps per SM), and placing
+// the dropped cells with geometric gaps instead of one 16-bit Philox field per cell (316 us: a third of the instructions,
+// but a divergent loop).  Neither load latency nor instruction count was the limit; the grid shape was (see csi_pool_dual).
+extern "C" int csi_pool_dual(const float* x, const long long* offs, const int* lens, int B, int T, int F,
+                             const float* pe, int ld_pe, float* left, int ld_left, float* right, int ld_right,
+                             int halo, int augment, const unsigned long long* rng, void* stream) {
+    CSI_CHECK_ARG(x && left && right, "null pointer");
+    CSI_CHECK_ARG(T % POOL_K == 0 && F % 2 == 0 && F <= 2800, "T must be a multiple of 20, F even and <= 2800");
+    CSI_CHECK_ARG((offs == nullptr) == (lens == nullptr), "offs and lens go together");
+    CSI_CHECK_ARG(!augment || rng, "augmentation needs rng");
+    if (B == 0) return CSI_OK;
+    const int L = T / POOL_K;
+    dim3 grid(cdiv(L, POOL_TL), B);
+    const size_t smem = (size_t)POOL_TL * (F + 1) * sizeof(float);
+    const int items = POOL_TL * ((F + 3) / 4), rounds = cdiv(items, 384);       // whole rounds of work items per thread
+    int threads = ((cdiv(items, rounds) + 31) / 32) * 32;
+    if (threads > 512) threads = 512;
+    if (augment) {
+        if (smem > 48 * 1024) CSI_CUDA(cudaFuncSetAttribute(pool_dual_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        pool_dual_kernel<true><<<grid, threads, smem, ST(stream)>>>(x, offs, lens, T, F, pe, ld_pe, left, ld_left, right, ld_right, halo, rng);
+    } else {
+        if (smem > 48 * 1024) CSI_CUDA(cudaFuncSetAttribute(pool_dual_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        pool_dual_kernel<false><<<grid, threads, smem, ST(stream)>>>(x, offs, lens, T, F, pe, ld_pe, left, ld_left, right, ld_right, halo, rng);
+    }
+    CSI_LAUNCH_CHECK();
+    return CSI_OK;
+}
+
 template <typename T> __device__ __forceinline__ float4 lds4f(const uint8_t* p);
 template <> __device__ __forceinline__ float4 lds4f<float>(const uint8_t* p) { return *reinterpret_cast<const float4*>(p); }
 template <> __device__ __forceinline__ float4 lds4f<bf16>(const uint8_t* p) {
@@ -724,20 +735,39 @@ extern "C" int csi_layernorm_bwd(const void* dy, int lddy, int dy_dtype, const f
 
 template <typename T, bool SQ>
 __global__ void __launch_bounds__(CR_THREADS) colreduce_kernel(const T* __restrict__ A, int lda, int B, int L, int halo,
-                                                               int ncols, int CH, int RL, float* __restrict__ out_f,
-                                                               double* __restrict__ out_d, csi_grp grp) {
+                                                               int ncols, int CH, int RL, int rows_per_cta,
+                                                               float* __restrict__ out_f, double* __restrict__ out_d, csi_grp grp) {
     extern __shared__ float red[];                      // [RL][CH*8] (x2 when SQ)
     const int ch = threadIdx.x % CH, rl = threadIdx.x / CH;
-    const int Lp = L + 2 * halo, total = B * L;
-    const int r0 = blockIdx.x * CR_ROWS, r1 = min(total, r0 + CR_ROWS);
+    const int total = B * L;
+    const int r0 = blockIdx.x * rows_per_cta, r1 = min(total, r0 + rows_per_cta);
     float a[8], q[8];
 #pragma unroll
     for (int j = 0; j < 8; ++j) a[j] = q[j] = 0.f;
     if (rl < RL) {
-        for (int r = r0 + rl; r < r1; r += RL) {
-            const size_t row = (size_t)(r / L) * Lp + halo + (r % L);
+        // eight rows of loads in flight per thread (the loop is latency-bound with one), rows walked without divisions
+        RowWalk w;
+        w.init(min(r0 + rl, total - 1), L, halo);
+        int r = r0 + rl;
+        for (; r + 7 * RL < r1; r += 8 * RL) {
+            Raw8<T> x[8];
+#pragma unroll
+            for (int u = 0; u < 8; ++u) {
+                x[u].load(A + w.row() * lda + ch * 8);
+                w.advance(RL);
+            }
+#pragma unroll
+            for (int u = 0; u < 8; ++u) {
+                float v[8];
+                x[u].get(v);
+#pragma unroll
+                for (int j = 0; j < 8; ++j) { a[j] += v[j]; if (SQ) q[j] += v[j] * v[j]; }
+            }
+        }
+        for (; r < r1; r += RL) {
             float v[8];
-            load8f<T>(A + row * lda + ch * 8, v);
+            load8f<T>(A + w.row() * lda + ch * 8, v);
+            w.advance(RL);
 #pragma unroll
             for (int j = 0; j < 8; ++j) { a[j] += v[j]; if (SQ) q[j] += v[j] * v[j]; }
         }
@@ -764,9 +794,14 @@ static int colreduce_launch(const void* A, int lda, int dtype, int B, int L, int
     if (CH > CR_THREADS) { csi_set_error("colreduce: more than 2048 columns"); return CSI_ERR_ARG; }
     const int RL = CR_THREADS / CH;
     const size_t smem = (size_t)RL * CH * 8 * sizeof(float) * (SQ ? 2 : 1);
-    const int grid = cdiv(B * L, CR_ROWS);
-    if (dtype == CSI_BF16) colreduce_kernel<bf16, SQ><<<grid, CR_THREADS, smem, s>>>((const bf16*)A, lda, B, L, halo, ncols, CH, RL, out_f, out_d, grp);
-    else colreduce_kernel<float, SQ><<<grid, CR_THREADS, smem, s>>>((const float*)A, lda, B, L, halo, ncols, CH, RL, out_f, out_d, grp);
+    // at most two CTAs per SM, each walking one contiguous slab of rows: every CTA ends with one atomic per column on the
+    // same ncols addresses, so fewer, longer CTAs mean fewer serialised same-address atomics
+    int grid = cdiv(B * L, CR_ROWS);
+    if (grid > 2 * num_sms()) grid = 2 * num_sms();
+    const int rows_per_cta = cdiv(B * L, grid);
+    grid = cdiv(B * L, rows_per_cta);
+    if (dtype == CSI_BF16) colreduce_kernel<bf16, SQ><<<grid, CR_THREADS, smem, s>>>((const bf16*)A, lda, B, L, halo, ncols, CH, RL, rows_per_cta, out_f, out_d, grp);
+    else colreduce_kernel<float, SQ><<<grid, CR_THREADS, smem, s>>>((const float*)A, lda, B, L, halo, ncols, CH, RL, rows_per_cta, out_f, out_d, grp);
     return CSI_OK;
 }
 
@@ -852,6 +887,14 @@ struct DropCfg {
 // x one row lane; a CTA walks BNA_ROWS valid token rows.
 #define BNA_THREADS 256
 #define BNA_ITERS 8
+// resident CTAs per SM of the BatchNorm block kernels.  CSI_BN_CTAS=3 selects a build capped at 80 registers (21 instead
+// of 14 warps per SM, the per-channel affine terms spill to local memory): measured 25-45 % SLOWER at B=256, F=270
+// (fwd 299 -> 379 us, bwd 543 -> 796 us per step), so 2 stays the default; kept for A/B runs.
+static int bn_ctas() {
+    static int v = 0;
+    if (!v) { const char* e = getenv("CSI_BN_CTAS"); v = (e && e[0] == '3') ? 3 : 2; }
+    return v;
+}
 
 // y = zhat*gamma + beta = z*a + b with a = invstd*gamma, b = beta - mean*a (0 for pad channels)
 __device__ __forceinline__ void bn_affine8(const float* __restrict__ mean, const float* __restrict__ invstd, const float* ga,
@@ -865,8 +908,8 @@ __device__ __forceinline__ void bn_affine8(const float* __restrict__ mean, const
     }
 }
 
-template <typename T>
-__global__ void __launch_bounds__(BNA_THREADS, 2) bn_act_fwd_kernel(
+template <typename T, int MINB>
+__global__ void __launch_bounds__(BNA_THREADS, MINB) bn_act_fwd_kernel(
     const T* __restrict__ z, int ldz, const float* __restrict__ mean, const float* __restrict__ invstd, csi_ptr3 gamma,
     csi_ptr3 beta, const float* __restrict__ t_res, int ldt, float* __restrict__ out, int ldo, int B, int L, int d, int Dp,
     int halo, int nbr, DropCfg dcfg, const unsigned long long* __restrict__ rng, int CH, int RL, int rows_per_cta,
@@ -953,18 +996,16 @@ extern "C" int csi_bn_act_fwd(const void* z, int ldz, int dtype, const float* me
     CSI_CHECK_ARG(CH <= BNA_THREADS && ldz % 8 == 0 && ldt % 4 == 0 && ldo % 4 == 0 && ldt >= Dp && ldo >= Dp, "bad leading dimension");
     const int RL = BNA_THREADS / CH, threads = RL * CH, total = B * L;
     DropCfg dc{p_branch, p_out, site_branch, site_out};
-    int grid = 2 * num_sms();                                      // two CTAs per SM, one contiguous slab of rows each
+    const int ctas = bn_ctas();
+    int grid = ctas * num_sms();                                   // resident CTAs only, one contiguous slab of rows each
     if (grid > cdiv(total, 2 * RL)) grid = cdiv(total, 2 * RL);
     const int rows_per_cta = cdiv(total, grid);
     grid = cdiv(total, rows_per_cta);
-    if (dtype == CSI_BF16)
-        bn_act_fwd_kernel<bf16><<<grid, threads, 0, ST(stream)>>>((const bf16*)z, ldz, mean, invstd, gamma, beta, t_res, ldt,
-                                                                   out, ldo, B, L, d, Dp, halo, nbr, dc, rng, CH, RL, rows_per_cta,
-                                                                   masks);
-    else
-        bn_act_fwd_kernel<float><<<grid, threads, 0, ST(stream)>>>((const float*)z, ldz, mean, invstd, gamma, beta, t_res, ldt,
-                                                                    out, ldo, B, L, d, Dp, halo, nbr, dc, rng, CH, RL, rows_per_cta,
-                                                                    masks);
+#define BNA_GO(T, MINB) bn_act_fwd_kernel<T, MINB><<<grid, threads, 0, ST(stream)>>>((const T*)z, ldz, mean, invstd, gamma, beta, t_res, \
+        ldt, out, ldo, B, L, d, Dp, halo, nbr, dc, rng, CH, RL, rows_per_cta, masks)
+    if (dtype == CSI_BF16) { if (ctas == 3) BNA_GO(bf16, 3); else BNA_GO(bf16, 2); }
+    else { if (ctas == 3) BNA_GO(float, 3); else BNA_GO(float, 2); }
+#undef BNA_GO
     CSI_LAUNCH_CHECK();
     return CSI_OK;
 }
@@ -975,8 +1016,8 @@ extern "C" int csi_bn_act_fwd(const void* z, int ldz, int dtype, const float* me
 //   MODE 1: dz = gamma*invstd*(dy - s1/n - zhat*s2/n), plus dgamma/dbeta written once by CTA 0
 #define BNB_MAXT 224
 
-template <typename T, int MODE>
-__global__ void __launch_bounds__(BNB_MAXT, 2) bn_act_bwd_kernel(
+template <typename T, int MODE, int MINB>
+__global__ void __launch_bounds__(BNB_MAXT, MINB) bn_act_bwd_kernel(
     const float* __restrict__ dout, int lddo, const T* __restrict__ z, int ldz, const float* __restrict__ mean,
     const float* __restrict__ invstd, csi_ptr3 gamma, csi_ptr3 beta, double* __restrict__ red, int B, int L, int d, int Dp,
     int halo, int nbr, DropCfg dcfg, const unsigned long long* __restrict__ rng, T* __restrict__ dz, int lddz,
@@ -1091,20 +1132,17 @@ static int bn_bwd_launch(const float* dout, int lddo, const void* z, int ldz, in
     if (CH * nbr > BNB_MAXT) { csi_set_error("bn_act_bwd: more than %d channels", BNB_MAXT * 8 / nbr); return CSI_ERR_ARG; }
     const int RL = BNB_MAXT / (CH * nbr), threads = RL * CH * nbr;
     const size_t smem = MODE == 0 ? (size_t)RL * CH * nbr * 16 * sizeof(float) : 0;
-    int grid = 2 * num_sms();
+    const int ctas = bn_ctas();
+    int grid = ctas * num_sms();
     const int total = B * L;
     if (grid > cdiv(total, 2 * RL)) grid = cdiv(total, 2 * RL);
     const int rows_per_cta = cdiv(total, grid);
     grid = cdiv(total, rows_per_cta);
-    if (dtype == CSI_BF16) {
-        bn_act_bwd_kernel<bf16, MODE><<<grid, threads, smem, s>>>(dout, lddo, (const bf16*)z, ldz, mean, invstd, gamma, beta, red, B, L,
-                                                                  d, Dp, halo, nbr, dc, rng, (bf16*)dz, lddz, dgamma, dbeta, CH, RL,
-                                                                  rows_per_cta, masks);
-    } else {
-        bn_act_bwd_kernel<float, MODE><<<grid, threads, smem, s>>>(dout, lddo, (const float*)z, ldz, mean, invstd, gamma, beta, red, B,
-                                                                   L, d, Dp, halo, nbr, dc, rng, (float*)dz, lddz, dgamma, dbeta, CH,
-                                                                   RL, rows_per_cta, masks);
-    }
+#define BNB_GO(T, MINB) bn_act_bwd_kernel<T, MODE, MINB><<<grid, threads, smem, s>>>(dout, lddo, (const T*)z, ldz, mean, invstd, gamma, beta, \
+        red, B, L, d, Dp, halo, nbr, dc, rng, (T*)dz, lddz, dgamma, dbeta, CH, RL, rows_per_cta, masks)
+    if (dtype == CSI_BF16) { if (ctas == 3) BNB_GO(bf16, 3); else BNB_GO(bf16, 2); }
+    else { if (ctas == 3) BNB_GO(float, 3); else BNB_GO(float, 2); }
+#undef BNB_GO
     return CSI_OK;
 }
 

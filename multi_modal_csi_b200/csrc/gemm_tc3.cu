@@ -372,11 +372,18 @@ __global__ void __launch_bounds__(T3_THREADS, 1) gemm_nt_tc3_kernel(const __grid
     }
 }
 
-static int pick_bn3(int N) {
-    const int tiles = (N + 255) / 256;
-    int bn = ((N + tiles - 1) / tiles + 15) & ~15;
-    if (bn < 16) bn = 16;
-    return bn;
+static int g_force_ntn = 0;          // > 0: split N into this many column tiles (A/B runs of the tile-shape heuristic)
+extern "C" int csi_set_gemm_ntn(int ntn) { g_force_ntn = ntn > 0 ? ntn : 0; return CSI_OK; }
+
+static int bn_for(int N, int ntn) {
+    int bn = ((N + ntn - 1) / ntn + 15) & ~15;
+    return bn < 16 ? 16 : bn;
+}
+static int pick_bn3(int N, int mtiles, int sms) {
+    const int base = (N + 255) / 256;                  // fewest column tiles that fit one accumulator (<= 256 columns)
+    if (g_force_ntn > 0) return bn_for(N, g_force_ntn < base ? base : g_force_ntn);
+    (void)mtiles; (void)sms;
+    return bn_for(N, base);
 }
 
 static int g_num_sms3 = 0;
@@ -444,7 +451,7 @@ extern "C" int csi_gemm_nt_tc3(const void* A, int lda, const void* Bw, int ldb, 
         CSI_CUDA(cudaGetDevice(&dev));
         CSI_CUDA(cudaDeviceGetAttribute(&g_num_sms3, cudaDevAttrMultiProcessorCount, dev));
     }
-    const int BN = pick_bn3(N);
+    const int BN = pick_bn3(N, (M + TC_BM - 1) / TC_BM, g_num_sms3);
     const int a_rows = TC_BM + ((span + 7) & ~7);
     CUtensorMap tmA, tmB, tmC;
     const bf16* a_base = reinterpret_cast<const bf16*>(A) + (long long)min_shift * lda;
