@@ -68,7 +68,28 @@ struct Nt3Params {
     const float* bias; const float* residual; int ldr;
     float drop_p; unsigned drop_site; const unsigned long long* rng;
     int row_base, desc_mode, pdl;
+    // tail-wave split: tiles [0, nfull) are 128 x BN; the M tiles of the last, partly filled wave are cut into `npiece`
+    // column pieces of BN2 (= one or two store panels) so that every SM gets a short piece instead of a few SMs a whole tile
+    int nfull, npiece, BN2, mt_tail;
+    int epi_bufs;                     // staging buffers per epilogue warp (1 or 2): one leaves room for a deeper B ring
+    int ksub;                         // 64-channel blocks per pipeline stage (1 or 2), see the mainloop comment
 };
+
+struct T3Tile { int mt, n0, bn; };
+__device__ __forceinline__ T3Tile t3_decode(const Nt3Params& p, int tile) {
+    T3Tile t;
+    if (tile < p.nfull) {
+        t.mt = tile / p.ntn;
+        t.n0 = (tile - t.mt * p.ntn) * p.BN;
+        t.bn = p.BN;
+    } else {
+        const int q = tile - p.nfull, m = q / p.npiece;
+        t.mt = p.mt_tail + m;
+        t.n0 = (q - m * p.npiece) * p.BN2;
+        t.bn = min(p.BN2, p.BN - t.n0);                  // the split is only used with one column tile per row tile
+    }
+    return t;
+}
 
 // K-major SW128 descriptor with an explicit matrix-base-offset field (bits [49,52))
 __device__ __forceinline__ uint64_t make_kmajor_desc_bo(uint32_t saddr, uint32_t base_off) {
@@ -78,6 +99,7 @@ __device__ __forceinline__ uint64_t make_kmajor_desc_bo(uint32_t saddr, uint32_t
 template <typename TC, bool RES>
 __global__ void __launch_bounds__(T3_THREADS, 1) gemm_nt_tc3_kernel(const __grid_constant__ CUtensorMap tmA,
                                                                     const __grid_constant__ CUtensorMap tmB,
+                                                                    const __grid_constant__ CUtensorMap tmB2,
                                                                     const __grid_constant__ CUtensorMap tmC,
                                                                     const __grid_constant__ CUtensorMap tmCt, Nt3Params p,
                                                                     const __grid_constant__ T3Plan plan) {
@@ -95,15 +117,20 @@ __global__ void __launch_bounds__(T3_THREADS, 1) gemm_nt_tc3_kernel(const __grid
     if (p.pdl) asm volatile("griddepcontrol.launch_dependents;" ::: "memory");   // the next kernel may start its prologue
     uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    // A stage of the rings holds KSUB consecutive 64-channel blocks (each its own TMA box / swizzle atom column): with
+    // narrow tiles (BN <= 160) one block is only 4 UMMAs of <= 80 clk, less than the ~500 clk the single-threaded issue
+    // loop needs per barrier round trip, so two blocks share one round trip.
     const uint32_t a_bytes = (uint32_t)p.a_rows * 128u, b_bytes = (uint32_t)p.BN * 128u;
-    const int NSA = p.nsa, NSB = p.nsb;
+    const int NSA = p.nsa, NSB = p.nsb, KSUB = p.ksub;
+    const uint32_t a_sbytes = a_bytes * (uint32_t)KSUB, b_sbytes = b_bytes * (uint32_t)KSUB;
     uint8_t* a_ring = smem;
-    uint8_t* b_ring = smem + (size_t)NSA * a_bytes;
-    uint8_t* cstage = b_ring + (size_t)NSB * b_bytes;             // 8 warps x 2 buffers x (32 rows x 128 B)
+    uint8_t* b_ring = smem + (size_t)NSA * a_sbytes;
+    uint8_t* cstage = b_ring + (size_t)NSB * b_sbytes;             // 8 warps x 2 buffers x (32 rows x 128 B)
 
     if (threadIdx.x == 0) {
         tma_prefetch_desc(&tmA);
         tma_prefetch_desc(&tmB);
+        tma_prefetch_desc(&tmB2);
         tma_prefetch_desc(&tmC);
         tma_prefetch_desc(&tmCt);
         for (int s = 0; s < NSA; ++s) { mbar_init(&full_a[s], 1); mbar_init(&empty_a[s], 1); }
@@ -132,24 +159,32 @@ __global__ void __launch_bounds__(T3_THREADS, 1) gemm_nt_tc3_kernel(const __grid
         const uint32_t full_b_u = smem_u32(&full_b[0]), empty_b_u = smem_u32(&empty_b[0]);
         const bool leader = elect_one();
         for (int tile = blockIdx.x; tile < p.ntiles; tile += gridDim.x) {
-            const int mt = tile / p.ntn;
-            const int m0 = mt * TC_BM + p.row_base, n0 = (tile - mt * p.ntn) * p.BN;
+            const T3Tile tt = t3_decode(p, tile);
+            const int m0 = tt.mt * TC_BM + p.row_base, n0 = tt.n0;
+            const bool piece = tile >= p.nfull;                  // pieces fetch BN2-row weight boxes through their own map
+            const CUtensorMap* tmb = piece ? &tmB2 : &tmB;
+            const uint32_t bb = piece ? (uint32_t)p.BN2 * 128u : b_bytes;
             for (int gi = 0; gi < plan.ng; ++gi) {
                 const int g_col = plan.g[gi].a_col_off, g_klen = plan.g[gi].klen, g_row = m0 + plan.g[gi].min_shift;
                 const int tap0 = plan.g[gi].tap0, ntaps = plan.g[gi].ntaps;
-                for (int k0 = 0; k0 < g_klen; k0 += TC_BK) {
+                for (int k0 = 0; k0 < g_klen; k0 += KSUB * TC_BK) {
+                    const int nsub = (KSUB == 2 && g_klen - k0 > TC_BK) ? 2 : 1;
                     mbar_wait_u(empty_a_u + 8u * sa, pa);
                     if (leader) {
-                        mbar_expect_tx_u(full_a_u + 8u * sa, a_bytes);
-                        tma_load_2d_u(&tmA, full_a_u + 8u * sa, a_ring_u + (uint32_t)sa * a_bytes, g_col + k0, g_row);
+                        mbar_expect_tx_u(full_a_u + 8u * sa, a_bytes * (uint32_t)nsub);
+                        tma_load_2d_u(&tmA, full_a_u + 8u * sa, a_ring_u + (uint32_t)sa * a_sbytes, g_col + k0, g_row);
+                        if (nsub == 2)
+                            tma_load_2d_u(&tmA, full_a_u + 8u * sa, a_ring_u + (uint32_t)sa * a_sbytes + a_bytes, g_col + k0 + TC_BK, g_row);
                     }
                     if (++sa == NSA) { sa = 0; pa ^= 1u; }
                     for (int t = 0; t < ntaps; ++t) {
                         mbar_wait_u(empty_b_u + 8u * sb, pb);
                         if (leader) {
-                            mbar_expect_tx_u(full_b_u + 8u * sb, b_bytes);
-                            tma_load_2d_u(&tmB, full_b_u + 8u * sb, b_ring_u + (uint32_t)sb * b_bytes,
-                                          plan.t[tap0 + t].b_col_off + k0, n0);
+                            const int bcol = plan.t[tap0 + t].b_col_off + k0;
+                            mbar_expect_tx_u(full_b_u + 8u * sb, bb * (uint32_t)nsub);
+                            tma_load_2d_u(tmb, full_b_u + 8u * sb, b_ring_u + (uint32_t)sb * b_sbytes, bcol, n0);
+                            if (nsub == 2)
+                                tma_load_2d_u(tmb, full_b_u + 8u * sb, b_ring_u + (uint32_t)sb * b_sbytes + b_bytes, bcol + TC_BK, n0);
                         }
                         if (++sb == NSB) { sb = 0; pb ^= 1u; }
                     }
@@ -157,7 +192,6 @@ __global__ void __launch_bounds__(T3_THREADS, 1) gemm_nt_tc3_kernel(const __grid
             }
         }
     } else if (warp == 1) {
-        const uint32_t idesc = make_idesc(TC_BM, p.BN);
         int sa = 0, sb = 0;
         uint32_t pa = 0, pb = 0;                                 // parity to wait for on the full barriers
         uint32_t acc = 0, pacc = 1;                              // accumulator buffer and parity of its empty barrier
@@ -168,31 +202,43 @@ __global__ void __launch_bounds__(T3_THREADS, 1) gemm_nt_tc3_kernel(const __grid
         const bool leader = elect_one();
         const uint32_t dmode = (uint32_t)p.desc_mode;
         for (int tile = blockIdx.x; tile < p.ntiles; tile += gridDim.x) {
+            const uint32_t idesc = make_idesc(TC_BM, t3_decode(p, tile).bn);
             mbar_wait_u(tempty_u + 8u * acc, pacc);              // epilogue has drained this accumulator
             tc_fence_after();
             const uint32_t tacc = tmem_base + acc * 256u;
             uint32_t accum = 0;
             for (int gi = 0; gi < plan.ng; ++gi) {
                 const int g_klen = plan.g[gi].klen, tap0 = plan.g[gi].tap0, ntaps = plan.g[gi].ntaps;
-                for (int k0 = 0; k0 < g_klen; k0 += TC_BK) {
+                for (int k0 = 0; k0 < g_klen; k0 += KSUB * TC_BK) {
+                    const int nsub = (KSUB == 2 && g_klen - k0 > TC_BK) ? 2 : 1;
                     mbar_wait_u(full_a_u + 8u * sa, pa);
-                    const uint32_t a_addr = a_ring_u + (uint32_t)sa * a_bytes;
-                    const bool full_k = (g_klen - k0) >= TC_BK;
-                    const int ksteps = full_k ? 4 : ((g_klen - k0) >> 4);
+                    const uint32_t a_addr = a_ring_u + (uint32_t)sa * a_sbytes;
+                    const int rem_last = g_klen - k0 - (nsub - 1) * TC_BK;       // channels of the last block of this stage
+                    const bool last_full = rem_last >= TC_BK;
+                    const int last_steps = last_full ? 4 : (rem_last >> 4);
                     for (int t = 0; t < ntaps; ++t) {
                         mbar_wait_u(full_b_u + 8u * sb, pb);
                         tc_fence_after();
                         if (leader) {
                             const uint32_t roff = (uint32_t)plan.t[tap0 + t].a_row_off;
-                            const uint64_t adesc = make_kmajor_desc_bo(a_addr + roff * 128u, dmode ? roff : 0u);
-                            const uint64_t bdesc = make_kmajor_desc(b_ring_u + (uint32_t)sb * b_bytes);
-                            if (full_k) {
+                            uint64_t adesc = make_kmajor_desc_bo(a_addr + roff * 128u, dmode ? roff : 0u);
+                            uint64_t bdesc = make_kmajor_desc(b_ring_u + (uint32_t)sb * b_sbytes);
+                            if (nsub == 2) {                        // first block of a two-block stage is always full
+                                umma_bf16(tacc, adesc, bdesc, idesc, accum);
+                                umma_bf16(tacc, adesc + 2, bdesc + 2, idesc, 1u);
+                                umma_bf16(tacc, adesc + 4, bdesc + 4, idesc, 1u);
+                                umma_bf16(tacc, adesc + 6, bdesc + 6, idesc, 1u);
+                                adesc = make_kmajor_desc_bo(a_addr + a_bytes + roff * 128u, dmode ? roff : 0u);
+                                bdesc = make_kmajor_desc(b_ring_u + (uint32_t)sb * b_sbytes + b_bytes);
+                                accum = 1;
+                            }
+                            if (last_full) {
                                 umma_bf16(tacc, adesc, bdesc, idesc, accum);
                                 umma_bf16(tacc, adesc + 2, bdesc + 2, idesc, 1u);
                                 umma_bf16(tacc, adesc + 4, bdesc + 4, idesc, 1u);
                                 umma_bf16(tacc, adesc + 6, bdesc + 6, idesc, 1u);
                             } else {
-                                for (int k = 0; k < ksteps; ++k)
+                                for (int k = 0; k < last_steps; ++k)
                                     umma_bf16(tacc, adesc + (uint64_t)(2 * k), bdesc + (uint64_t)(2 * k), idesc, (accum | (uint32_t)k) ? 1u : 0u);
                             }
                             umma_commit_u(empty_b_u + 8u * sb);
@@ -216,17 +262,18 @@ __global__ void __launch_bounds__(T3_THREADS, 1) gemm_nt_tc3_kernel(const __grid
         DropCtx dc;
         if (drop) dc = drop_ctx(p.rng, p.drop_p);
         const int ld8 = ((p.N + 15) & ~15) >> 3;
-        uint8_t* mybuf = cstage + (size_t)ew * 2 * 4096;
-        const int npan = (p.BN + PW - 1) / PW;
+        uint8_t* mybuf = cstage + (size_t)ew * p.epi_bufs * 4096;
+        const bool two_bufs = p.epi_bufs == 2;
         int ti = 0, sbuf = 0;
         for (int tile = blockIdx.x; tile < p.ntiles; tile += gridDim.x, ++ti) {
             const int acc = ti & 1;
             const uint32_t aph = (uint32_t)(ti >> 1) & 1u;
-            const int mt = tile / p.ntn;
-            const int m0 = mt * TC_BM, n0 = (tile - mt * p.ntn) * p.BN;
+            const T3Tile tt = t3_decode(p, tile);
+            const int m0 = tt.mt * TC_BM, n0 = tt.n0, bn = tt.bn;
+            const int npan = (bn + PW - 1) / PW;
             const int m = m0 + q * 32 + lane;
             if (p.bias) {
-                sbias[acc][et] = (et < p.BN && (n0 + et) < p.N) ? p.bias[n0 + et] : 0.f;
+                sbias[acc][et] = (et < bn && (n0 + et) < p.N) ? p.bias[n0 + et] : 0.f;
                 named_bar_sync(1, T3_EPI_THREADS);
             }
             // fp32 residual of a FULL panel (32 rows x 128 B): fetched with coalesced 16-byte loads (lane -> row 4i + lane/8,
@@ -236,7 +283,7 @@ __global__ void __launch_bounds__(T3_THREADS, 1) gemm_nt_tc3_kernel(const __grid
             float rnext[RES ? PW : 1];
             auto fetch_res = [&](int pc0) {
                 if constexpr (!RES) return;
-                if (p.BN - pc0 >= PW) {
+                if (bn - pc0 >= PW) {
                     const int ch = lane & 7, ncol = n0 + pc0 + ch * 4;
 #pragma unroll
                     for (int i = 0; i < (RES ? PW / 4 : 0); ++i) {
@@ -249,7 +296,7 @@ __global__ void __launch_bounds__(T3_THREADS, 1) gemm_nt_tc3_kernel(const __grid
 #pragma unroll
                     for (int j = 0; j < (RES ? PW : 0); ++j) {
                         const int n = n0 + pc0 + j;
-                        rnext[j] = (rrow && pc0 + j < p.BN && n < p.N) ? rrow[n] : 0.f;
+                        rnext[j] = (rrow && pc0 + j < bn && n < p.N) ? rrow[n] : 0.f;
                     }
                 }
             };
@@ -259,7 +306,7 @@ __global__ void __launch_bounds__(T3_THREADS, 1) gemm_nt_tc3_kernel(const __grid
             const uint32_t tacc = tmem_base + (uint32_t)(acc * 256) + ((uint32_t)(q * 32) << 16);
             for (int pi = half; pi < npan; pi += 2) {
                 const int pc0 = pi * PW;
-                const int width = min(PW, p.BN - pc0);              // multiple of 16
+                const int width = min(PW, bn - pc0);                // multiple of 16
                 float v[PW];
                 uint32_t r[PW];
                 // all TMEM loads of the panel are issued before the single wait
@@ -293,7 +340,7 @@ __global__ void __launch_bounds__(T3_THREADS, 1) gemm_nt_tc3_kernel(const __grid
                 // stage the 32-row slice of this warp (row = lane) and bulk-store it; the tensor maps clip rows >= M and
                 // columns >= N.  Full panels are 128-byte rows in the TMA 128B swizzle; the narrower last panel of a tile
                 // uses linear rows of width*es bytes and its own (unswizzled) tensor map.
-                if (lane == 0) tma_store_wait_read<1>();            // the buffer used two panels ago has been read
+                if (lane == 0) { if (two_bufs) tma_store_wait_read<1>(); else tma_store_wait_read<0>(); }   // the buffer about to be written has been read
                 __syncwarp();
                 uint8_t* buf = mybuf + (size_t)sbuf * 4096;
                 if constexpr (RES) {
@@ -356,7 +403,7 @@ __global__ void __launch_bounds__(T3_THREADS, 1) gemm_nt_tc3_kernel(const __grid
                     else tma_store_2d(&tmCt, buf, n0 + pc0, m0 + q * 32);
                     tma_store_commit();
                 }
-                sbuf ^= 1;
+                if (two_bufs) sbuf ^= 1;
             }
             tc_fence_before();
             __syncwarp();
@@ -472,27 +519,54 @@ extern "C" int csi_gemm_nt_tc3(const void* A, int lda, const void* Bw, int ldb, 
     p.ntn = (N + BN - 1) / BN;
     const int mtiles = (M + TC_BM - 1) / TC_BM;
     p.ntiles = p.ntn * mtiles;
+    // tail-wave split (see Nt3Params): 308 row tiles on 148 SMs are 2 full waves + 12 tiles; as 12 x 5 pieces of 64 columns
+    // the third wave costs a fraction of a tile instead of a whole one
+    static int tail_split = -1;                          // CSI_GEMM_TAILSPLIT=0 disables (A/B runs)
+    if (tail_split < 0) { const char* e = getenv("CSI_GEMM_TAILSPLIT"); tail_split = (e && e[0] == '0') ? 0 : 1; }
+    p.nfull = p.ntiles; p.npiece = 1; p.BN2 = BN; p.mt_tail = mtiles;
+    CUtensorMap tmB2 = tmB;
+    if (tail_split && p.ntn == 1 && mtiles > g_num_sms3 && BN > 64) {
+        const int leftover = mtiles % g_num_sms3, npiece = (BN + 63) / 64;
+        if (leftover > 0 && leftover * npiece <= g_num_sms3) {
+            rc = make_map(&tmB2, Bw, N, b_cols, ldb, 64);
+            if (rc) return rc;
+            p.nfull = mtiles - leftover; p.mt_tail = p.nfull; p.npiece = npiece; p.BN2 = 64;
+            p.ntiles = p.nfull + leftover * npiece;
+        }
+    }
     p.bias = bias; p.residual = residual; p.ldr = ldr;
     p.drop_p = drop_p; p.drop_site = drop_site; p.rng = rng;
     p.row_base = -min_shift;
     p.desc_mode = g_desc_mode;
     if (g_pdl3 < 0) { const char* e = getenv("CSI_PDL"); g_pdl3 = (e && e[0] == '0') ? 0 : 1; }
     p.pdl = g_pdl3;
-    const size_t a_bytes = (size_t)a_rows * 128, b_bytes = (size_t)BN * 128;
-    const size_t fixed = 1024 + 8 * 2 * 4096;
-    const size_t budget = 220 * 1024 - fixed;
-    int nsa, nsb;
-    if (span == 0) {                                   // every group is a single tap: A and B stages pair up
-        nsa = (int)(budget / (a_bytes + b_bytes));
-        if (nsa > T3_MAX_STAGES) nsa = T3_MAX_STAGES;
-        if (nsa < 2) nsa = 2;
-        nsb = nsa;
-    } else {
-        nsa = 3;
-        nsb = (int)((budget - nsa * a_bytes) / b_bytes);
-        if (nsb > T3_MAX_STAGES) nsb = T3_MAX_STAGES;
-        if (nsb < 2) nsb = 2;
+    static int ksub_env = -1;                            // CSI_GEMM_KSUB=1 forces one 64-channel block per stage (A/B runs)
+    if (ksub_env < 0) { const char* e = getenv("CSI_GEMM_KSUB"); ksub_env = (e && e[0] == '1') ? 1 : 2; }
+    // One staging buffer per epilogue warp (two were measured: no difference) leaves 32 KB more for the operand rings.
+    static int epi_bufs = 0;                             // CSI_GEMM_EPIBUF=2 restores double-buffered staging (A/B runs)
+    if (!epi_bufs) { const char* e = getenv("CSI_GEMM_EPIBUF"); epi_bufs = (e && e[0] == '2') ? 2 : 1; }
+    p.epi_bufs = epi_bufs;
+    const size_t fixed = 1024 + 8 * (size_t)epi_bufs * 4096;
+    const size_t budget = 224 * 1024 - fixed;            // + 3 KB of static shared memory = the 227 KB an SM offers
+    int ksub = (ksub_env == 2 && BN <= 160) ? 2 : 1, nsa = 0, nsb = 0;
+    size_t a_bytes = 0, b_bytes = 0;                     // per ring stage
+    for (;; ksub = 1) {
+        a_bytes = (size_t)a_rows * 128 * ksub;
+        b_bytes = (size_t)BN * 128 * ksub;
+        if (span == 0) {                               // every group is a single tap: A and B stages pair up
+            nsa = (int)(budget / (a_bytes + b_bytes));
+            if (nsa > T3_MAX_STAGES) nsa = T3_MAX_STAGES;
+            nsb = nsa;
+        } else {
+            nsa = ksub == 2 ? 2 : 3;
+            nsb = (int)((budget - nsa * a_bytes) / b_bytes);
+            if (nsb > T3_MAX_STAGES) nsb = T3_MAX_STAGES;
+        }
+        if (ksub == 1 || nsb >= 3) break;                // two-block stages need a ring of at least three
     }
+    if (nsa < 2) nsa = 2;
+    if (nsb < 2) nsb = 2;
+    p.ksub = ksub;
     p.nsa = nsa; p.nsb = nsb;
     const size_t smem = fixed + nsa * a_bytes + nsb * b_bytes;
     int grid = g_num_sms3;
@@ -506,7 +580,7 @@ extern "C" int csi_gemm_nt_tc3(const void* A, int lda, const void* Bw, int ldb, 
         at[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;                                                  \
         at[0].val.programmaticStreamSerializationAllowed = p.pdl;                                                       \
         cfg.attrs = at; cfg.numAttrs = 1;                                                                               \
-        CSI_CUDA(cudaLaunchKernelEx(&cfg, gemm_nt_tc3_kernel<TC, RES>, tmA, tmB, tmC, tmCt, p, plan));                  \
+        CSI_CUDA(cudaLaunchKernelEx(&cfg, gemm_nt_tc3_kernel<TC, RES>, tmA, tmB, tmB2, tmC, tmCt, p, plan));                  \
     } while (0)
     if (c_dtype == CSI_BF16) LAUNCH3(bf16, false);
     else if (residual) LAUNCH3(float, true);

@@ -222,6 +222,35 @@ def test_gemm_nt_linear_and_conv(ops, mir, dt, simt):
         ops.set_force_simt(False)
 
 
+@pytest.mark.parametrize("N,k,f32out", [(270, 5, False), (270, 1, True), (128, 8, False), (150, 3, False)])
+def test_gemm_nt_full_batch_tail_wave(ops, mir, N, k, f32out):
+    """B=256 token buffers: 308 row tiles on 148 SMs.  The tiles of the last, partly filled wave are cut into 64-column
+    pieces (gemm_tc3.cu, Nt3Params.nfull/npiece); rows of those tiles must come out exactly like the others."""
+    dt = torch.bfloat16
+    B, L, d = 256, 150, 270
+    Dp = ru(d, 16)
+    g = gen(16)
+    _, A = tokbuf(B, L, Dp, dt, fill=1.0, gen=g, ncols=d)
+    rows = B * (L + 2 * HALO)
+    bias = torch.randn(N, device="cuda", generator=g) if f32out else None
+    res = tokbuf(B, L, ru(N, 16), torch.float32, fill=1.0, gen=g, ncols=N)[1] if f32out else None
+    W = torch.zeros(N, k * Dp, dtype=dt, device="cuda")
+    for j in range(k):
+        W[:, j * Dp:j * Dp + d] = (torch.randn(N, d, device="cuda", generator=g) / math.sqrt(d * k)).to(dt)
+    pl = (k - 1) // 2
+    segs = [(j - pl, 0, j * Dp, Dp) for j in range(k)]
+    outs = []
+    for o in (ops, mir):
+        _, Cm = tokbuf(B, L, ru(N, 16), torch.float32 if f32out else dt)
+        o.gemm_nt(A, W, Cm, rows, N, segs, bias, res, 0.0, 0, None)
+        outs.append(Cm.float())
+    assert relerr(outs[0], outs[1]) < 6e-3
+    tail = outs[0][296 * 128:], outs[1][296 * 128:]                    # rows of the split tiles
+    assert relerr(*tail) < 6e-3
+    if outs[0].shape[1] > N:
+        assert float(outs[0][:, N:].abs().max()) == 0.0
+
+
 @pytest.mark.parametrize("dt", DT)
 @pytest.mark.parametrize("M,N,K", [(256, 54, 288), (37, 12, 288), (1000, 810, 272), (300, 16, 160)])
 def test_gemm_nt_plain(ops, mir, dt, M, N, K):
