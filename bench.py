@@ -314,7 +314,8 @@ def run_b200(args):
                                    f"[B={B}/GPU,3000,{F}], out={out}, {args.dtype} contractions / fp32 master weights",
                        "batch_per_gpu": B, "global_batch": B * world, "features": F, "parallelism": f"dp{world}",
                        "l2": "inputs (829 MB/batch at F=270) larger than the 126 MB L2; two batches alternate"},
-            "roofline": roof, "cpu_baseline": cpu, "e2e": e2e, "gpu_launches": gpu_launches,
+            "roofline": roof, "families": family_table(table, peaks), "cpu_baseline": cpu, "e2e": e2e,
+            "gpu_launches": gpu_launches,
             "clocks": clk.summary(),
             "tensor_frac_step": (TRAIN_FLOP.get(F, 0) * value / world) / (peaks.get("bf16_tflops_sustained", 1340.8) * 1e12),
         }
@@ -342,6 +343,24 @@ def dram_traffic(name):
             tot += k * (float(row["dram__bytes_read.sum"]) + float(row["dram__bytes_write.sum"]))
             n += k
     return tot / n if n else None
+
+
+def family_table(table, peaks):
+    """Every kernel family of one eagerly launched, sequential step (CUDA events around each launch, untimed pass):
+    device time, launches and the achieved algorithmic rate against the measured peak that bounds the family."""
+    hbm = peaks.get("hbm_gbs", 6650.0)
+    tf = peaks.get("bf16_tflops_sustained", 1400.0)
+    out = {}
+    for name, (ms, calls, work) in sorted(table.items(), key=lambda kv: -kv[1][0]):
+        row = {"ms": round(ms, 4), "launches": calls}
+        if ms > 0 and work.get("flops", 0) > 0 and name in ("gemm_nt", "gemm_tn", "attn_fwd", "attn_bwd"):
+            ach = work["flops"] / (ms * 1e-3) / 1e12
+            row.update({"bound": "tensor", "achieved": round(ach, 1), "unit": "TFLOP/s", "frac": round(ach / tf, 3)})
+        elif ms > 0 and work.get("bytes", 0) > 0:
+            ach = work["bytes"] / (ms * 1e-3) / 1e9
+            row.update({"bound": "hbm", "achieved": round(ach, 1), "unit": "GB/s", "frac": round(ach / hbm, 3)})
+        out[name] = row
+    return out
 
 
 def roofline(name, dom, eng, B, peaks):

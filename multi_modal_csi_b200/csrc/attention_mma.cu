@@ -24,6 +24,13 @@ __device__ __forceinline__ void ldsm_x4_t(uint32_t (&r)[4], const bf16* p) {
     const uint32_t a = (uint32_t)__cvta_generic_to_shared(p);
     asm volatile("ldmatrix.sync.aligned.m8n8.x4.trans.shared.b16 {%0,%1,%2,%3}, [%4];" : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]) : "r"(a));
 }
+// shared-window address forms: the per-lane fragment offset is computed once per kernel, tile/step offsets are immediates
+__device__ __forceinline__ void ldsm_x4_u(uint32_t (&r)[4], uint32_t a) {
+    asm volatile("ldmatrix.sync.aligned.m8n8.x4.shared.b16 {%0,%1,%2,%3}, [%4];" : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]) : "r"(a));
+}
+__device__ __forceinline__ void ldsm_x4_t_u(uint32_t (&r)[4], uint32_t a) {
+    asm volatile("ldmatrix.sync.aligned.m8n8.x4.trans.shared.b16 {%0,%1,%2,%3}, [%4];" : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]) : "r"(a));
+}
 __device__ __forceinline__ void mma16816(float (&c)[4], const uint32_t (&a)[4], uint32_t b0, uint32_t b1) {
     asm volatile("mma.sync.aligned.m16n8k16.row.col.f32.bf16.bf16.f32 {%0,%1,%2,%3}, {%4,%5,%6,%7}, {%8,%9}, {%0,%1,%2,%3};"
                  : "+f"(c[0]), "+f"(c[1]), "+f"(c[2]), "+f"(c[3])
@@ -265,32 +272,56 @@ __global__ void __launch_bounds__(AM_MAX_WARPS * 32, am_bounds<HDP>::min_ctas) a
     for (int i = threadIdx.x; i < 3 * HDP; i += blockDim.x) csum[i] = 0.f;
     const uint32_t abar = (uint32_t)__cvta_generic_to_shared(&passA_bar);
     if (threadIdx.x == 0) am_mbar_init(abar, blockDim.x >> 5);
+    // D_i = rowsum(dO_i * O_i): CPR lanes per row, one 128-bit O load each.  The O chunks of the first NOI rounds are
+    // requested BEFORE the wait on the tile copies, so the two global-memory latencies overlap instead of adding up.
+    constexpr int NOI = 4;
+    const int nchunk = LP * CPR;
+    uint4 ov[NOI];
+#pragma unroll
+    for (int it = 0; it < NOI; ++it) {
+        const int i = threadIdx.x + it * blockDim.x, l = i / CPR, cch = i % CPR;
+        ov[it] = (i < nchunk && l < L) ? *reinterpret_cast<const uint4*>(o + (row0 + l) * ldo + h * HDP + cch * 8) : make_uint4(0u, 0u, 0u, 0u);
+    }
     cp_async_wait_all();
     __syncthreads();
-    // D_i = rowsum(dO_i * O_i): CPR lanes per row, one 128-bit O load each
-    for (int i = threadIdx.x; i < LP * CPR; i += blockDim.x) {
+    auto d_row = [&](int i, const uint4& ovv) {                   // nchunk and blockDim are multiples of 32: warp-uniform
         const int l = i / CPR, cch = i % CPR;
+        const uint4 gv = *reinterpret_cast<const uint4*>(Gs + l * LDS + cch * 8);
+        const __nv_bfloat162* oh = reinterpret_cast<const __nv_bfloat162*>(&ovv);
+        const __nv_bfloat162* gh = reinterpret_cast<const __nv_bfloat162*>(&gv);
         float a = 0.f;
-        if (l < L) {
-            const uint4 ov = *reinterpret_cast<const uint4*>(o + (row0 + l) * ldo + h * HDP + cch * 8);
-            const uint4 gv = *reinterpret_cast<const uint4*>(Gs + l * LDS + cch * 8);
-            const __nv_bfloat162* oh = reinterpret_cast<const __nv_bfloat162*>(&ov);
-            const __nv_bfloat162* gh = reinterpret_cast<const __nv_bfloat162*>(&gv);
 #pragma unroll
-            for (int u = 0; u < 4; ++u) {
-                const float2 x = __bfloat1622float2(oh[u]), y = __bfloat1622float2(gh[u]);
-                a = fmaf(x.x, y.x, a); a = fmaf(x.y, y.y, a);
-            }
+        for (int u = 0; u < 4; ++u) {
+            const float2 x = __bfloat1622float2(oh[u]), y = __bfloat1622float2(gh[u]);
+            a = fmaf(x.x, y.x, a); a = fmaf(x.y, y.y, a);
         }
 #pragma unroll
         for (int off = 1; off < CPR; off <<= 1) a += __shfl_xor_sync(0xffffffffu, a, off);
-        if (cch == 0) Ds[l] = a;
+        if (cch == 0) Ds[l] = a;                                   // rows >= L: O was read as zero
+    };
+#pragma unroll
+    for (int it = 0; it < NOI; ++it) {
+        const int i = threadIdx.x + it * blockDim.x;
+        if (i < nchunk) d_row(i, ov[it]);
+    }
+    for (int i = threadIdx.x + NOI * blockDim.x; i < nchunk; i += blockDim.x) {
+        const int l = i / CPR, cch = i % CPR;
+        const uint4 o4 = l < L ? *reinterpret_cast<const uint4*>(o + (row0 + l) * ldo + h * HDP + cch * 8) : make_uint4(0u, 0u, 0u, 0u);
+        d_row(i, o4);
     }
     __syncthreads();
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, g = lane >> 2, t = lane & 3;
     const float sc = rsqrtf((float)hd), c = sc * LOG2E;
     const int ntile = LP / 16;
-    // ---------------- pass A: dQ
+    // shared-window byte addresses of the fragments of this lane; a tile of 16 rows is TILE_B bytes further on
+    constexpr uint32_t TILE_B = 32u * LDS;
+    const uint32_t a_off = 2u * (uint32_t)(((lane & 7) + ((lane >> 3) & 1) * 8) * LDS + (lane >> 4) * 8);     // A and transposed-B form
+    const uint32_t b_off = 2u * (uint32_t)(((lane & 7) + ((lane >> 4) & 1) * 8) * LDS + ((lane >> 3) & 1) * 8); // B form, [n][k] storage
+    const uint32_t Qa = (uint32_t)__cvta_generic_to_shared(Qs) + a_off, Qb = (uint32_t)__cvta_generic_to_shared(Qs) + b_off;
+    const uint32_t Ka = (uint32_t)__cvta_generic_to_shared(Ks) + a_off, Kb = (uint32_t)__cvta_generic_to_shared(Ks) + b_off;
+    const uint32_t Va = (uint32_t)__cvta_generic_to_shared(Vs) + a_off, Vb = (uint32_t)__cvta_generic_to_shared(Vs) + b_off;
+    const uint32_t Ga = (uint32_t)__cvta_generic_to_shared(Gs) + a_off, Gb = (uint32_t)__cvta_generic_to_shared(Gs) + b_off;
+    // ---------------- pass A: dQ  (the 1/sqrt(hd) factor of dS is applied once to the finished dQ / dK tiles)
     float cq[NTO][2];
 #pragma unroll
     for (int no = 0; no < NTO; ++no) cq[no][0] = cq[no][1] = 0.f;
@@ -298,21 +329,22 @@ __global__ void __launch_bounds__(AM_MAX_WARPS * 32, am_bounds<HDP>::min_ctas) a
         uint32_t qa[KS][4], ga[KS][4];
 #pragma unroll
         for (int ks = 0; ks < KS; ++ks) {
-            ldsm_x4(qa[ks], a_frag_ptr<LDS>(Qs, qt * 16, ks * 16, lane));
-            ldsm_x4(ga[ks], a_frag_ptr<LDS>(Gs, qt * 16, ks * 16, lane));
+            ldsm_x4_u(qa[ks], Qa + qt * TILE_B + ks * 32);
+            ldsm_x4_u(ga[ks], Ga + qt * TILE_B + ks * 32);
         }
         const int r0 = qt * 16 + g, r1 = r0 + 8;
         const float ls0 = Ls[r0], ls1 = Ls[r1], d0 = Ds[r0], d1 = Ds[r1];
         float dq[NTO][4];
 #pragma unroll
         for (int i = 0; i < NTO; ++i) dq[i][0] = dq[i][1] = dq[i][2] = dq[i][3] = 0.f;
-        for (int kp = 0; kp < ntile; ++kp) {                    // 16 keys per iteration
+        uint32_t tb = 0;
+        for (int kp = 0; kp < ntile; ++kp, tb += TILE_B) {      // 16 keys per iteration
             float s[2][4] = {{0.f, 0.f, 0.f, 0.f}, {0.f, 0.f, 0.f, 0.f}}, dp[2][4] = {{0.f, 0.f, 0.f, 0.f}, {0.f, 0.f, 0.f, 0.f}};
 #pragma unroll
             for (int ks = 0; ks < KS; ++ks) {
                 uint32_t kb[4], vb[4];
-                ldsm_x4(kb, b_frag_ptr<LDS>(Ks, kp * 16, ks * 16, lane));
-                ldsm_x4(vb, b_frag_ptr<LDS>(Vs, kp * 16, ks * 16, lane));
+                ldsm_x4_u(kb, Kb + tb + ks * 32);
+                ldsm_x4_u(vb, Vb + tb + ks * 32);
                 mma16816(s[0], qa[ks], kb[0], kb[1]);
                 mma16816(s[1], qa[ks], kb[2], kb[3]);
                 mma16816(dp[0], ga[ks], vb[0], vb[1]);
@@ -325,19 +357,21 @@ __global__ void __launch_bounds__(AM_MAX_WARPS * 32, am_bounds<HDP>::min_ctas) a
                 const bool v0 = col < L, v1 = (col + 1) < L;
                 const float p0 = v0 ? fast_exp2(s[nt][0] * c - ls0) : 0.f, p1 = v1 ? fast_exp2(s[nt][1] * c - ls0) : 0.f;
                 const float p2 = v0 ? fast_exp2(s[nt][2] * c - ls1) : 0.f, p3 = v1 ? fast_exp2(s[nt][3] * c - ls1) : 0.f;
-                ds[nt][0] = p0 * (dp[nt][0] - d0) * sc; ds[nt][1] = p1 * (dp[nt][1] - d0) * sc;
-                ds[nt][2] = p2 * (dp[nt][2] - d1) * sc; ds[nt][3] = p3 * (dp[nt][3] - d1) * sc;
+                ds[nt][0] = p0 * (dp[nt][0] - d0); ds[nt][1] = p1 * (dp[nt][1] - d0);
+                ds[nt][2] = p2 * (dp[nt][2] - d1); ds[nt][3] = p3 * (dp[nt][3] - d1);
             }
             uint32_t da[4] = {pack_bf16(ds[0][0], ds[0][1]), pack_bf16(ds[0][2], ds[0][3]), pack_bf16(ds[1][0], ds[1][1]),
                               pack_bf16(ds[1][2], ds[1][3])};
 #pragma unroll
             for (int no = 0; no < NTO; no += 2) {
                 uint32_t kb[4];
-                ldsm_x4_t(kb, bt_frag_ptr<LDS>(Ks, kp * 16, no * 8, lane));
+                ldsm_x4_t_u(kb, Ka + tb + no * 16);
                 mma16816(dq[no], da, kb[0], kb[1]);
                 mma16816(dq[no + 1], da, kb[2], kb[3]);
             }
         }
+#pragma unroll
+        for (int no = 0; no < NTO; ++no) { dq[no][0] *= sc; dq[no][1] *= sc; dq[no][2] *= sc; dq[no][3] *= sc; }
         // dQ: bf16x2 stores straight from the accumulator layout (Q and dO tiles are still needed by pass B)
 #pragma unroll
         for (int no = 0; no < NTO; ++no) {
@@ -367,19 +401,20 @@ __global__ void __launch_bounds__(AM_MAX_WARPS * 32, am_bounds<HDP>::min_ctas) a
         uint32_t ka[KS][4], va[KS][4];
 #pragma unroll
         for (int ks = 0; ks < KS; ++ks) {
-            ldsm_x4(ka[ks], a_frag_ptr<LDS>(Ks, kt * 16, ks * 16, lane));
-            ldsm_x4(va[ks], a_frag_ptr<LDS>(Vs, kt * 16, ks * 16, lane));
+            ldsm_x4_u(ka[ks], Ka + kt * TILE_B + ks * 32);
+            ldsm_x4_u(va[ks], Va + kt * TILE_B + ks * 32);
         }
         float dk[NTO][4], dv[NTO][4];
 #pragma unroll
         for (int i = 0; i < NTO; ++i) { dk[i][0] = dk[i][1] = dk[i][2] = dk[i][3] = 0.f; dv[i][0] = dv[i][1] = dv[i][2] = dv[i][3] = 0.f; }
-        for (int qp = 0; qp < ntile; ++qp) {                    // 16 queries per iteration
+        uint32_t tb = 0;
+        for (int qp = 0; qp < ntile; ++qp, tb += TILE_B) {      // 16 queries per iteration
             float st[2][4] = {{0.f, 0.f, 0.f, 0.f}, {0.f, 0.f, 0.f, 0.f}}, dpt[2][4] = {{0.f, 0.f, 0.f, 0.f}, {0.f, 0.f, 0.f, 0.f}};
 #pragma unroll
             for (int ks = 0; ks < KS; ++ks) {
                 uint32_t qb[4], gb[4];
-                ldsm_x4(qb, b_frag_ptr<LDS>(Qs, qp * 16, ks * 16, lane));
-                ldsm_x4(gb, b_frag_ptr<LDS>(Gs, qp * 16, ks * 16, lane));
+                ldsm_x4_u(qb, Qb + tb + ks * 32);
+                ldsm_x4_u(gb, Gb + tb + ks * 32);
                 mma16816(st[0], ka[ks], qb[0], qb[1]);
                 mma16816(st[1], ka[ks], qb[2], qb[3]);
                 mma16816(dpt[0], va[ks], gb[0], gb[1]);
@@ -393,8 +428,8 @@ __global__ void __launch_bounds__(AM_MAX_WARPS * 32, am_bounds<HDP>::min_ctas) a
                 const float2 lq = *reinterpret_cast<const float2*>(Ls + q0), dd = *reinterpret_cast<const float2*>(Ds + q0);
                 pt[nt][0] = v0 ? fast_exp2(st[nt][0] * c - lq.x) : 0.f; pt[nt][1] = v1 ? fast_exp2(st[nt][1] * c - lq.y) : 0.f;
                 pt[nt][2] = v0 ? fast_exp2(st[nt][2] * c - lq.x) : 0.f; pt[nt][3] = v1 ? fast_exp2(st[nt][3] * c - lq.y) : 0.f;
-                dst_[nt][0] = pt[nt][0] * (dpt[nt][0] - dd.x) * sc; dst_[nt][1] = pt[nt][1] * (dpt[nt][1] - dd.y) * sc;
-                dst_[nt][2] = pt[nt][2] * (dpt[nt][2] - dd.x) * sc; dst_[nt][3] = pt[nt][3] * (dpt[nt][3] - dd.y) * sc;
+                dst_[nt][0] = pt[nt][0] * (dpt[nt][0] - dd.x); dst_[nt][1] = pt[nt][1] * (dpt[nt][1] - dd.y);
+                dst_[nt][2] = pt[nt][2] * (dpt[nt][2] - dd.x); dst_[nt][3] = pt[nt][3] * (dpt[nt][3] - dd.y);
             }
             uint32_t pa[4] = {pack_bf16(pt[0][0], pt[0][1]), pack_bf16(pt[0][2], pt[0][3]), pack_bf16(pt[1][0], pt[1][1]),
                               pack_bf16(pt[1][2], pt[1][3])};
@@ -403,14 +438,16 @@ __global__ void __launch_bounds__(AM_MAX_WARPS * 32, am_bounds<HDP>::min_ctas) a
 #pragma unroll
             for (int no = 0; no < NTO; no += 2) {
                 uint32_t gb[4], qb[4];
-                ldsm_x4_t(gb, bt_frag_ptr<LDS>(Gs, qp * 16, no * 8, lane));
-                ldsm_x4_t(qb, bt_frag_ptr<LDS>(Qs, qp * 16, no * 8, lane));
+                ldsm_x4_t_u(gb, Ga + tb + no * 16);
+                ldsm_x4_t_u(qb, Qa + tb + no * 16);
                 mma16816(dv[no], pa, gb[0], gb[1]);
                 mma16816(dv[no + 1], pa, gb[2], gb[3]);
                 mma16816(dk[no], sa, qb[0], qb[1]);
                 mma16816(dk[no + 1], sa, qb[2], qb[3]);
             }
         }
+#pragma unroll
+        for (int no = 0; no < NTO; ++no) { dk[no][0] *= sc; dk[no][1] *= sc; dk[no][2] *= sc; dk[no][3] *= sc; }
         // K/V rows of this tile are otherwise only read as its own A fragments (held in registers by now) and by pass A
         // of the other warps: wait until every warp has left pass A (split barrier: arrived long ago, rarely blocks)
         if (!passA_done) { am_mbar_wait(abar, 0u); passA_done = true; }
