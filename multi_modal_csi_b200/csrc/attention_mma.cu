@@ -14,6 +14,8 @@
 // occupancy: registers are the limit (3 CTAs/SM at ~103 regs).  CTAs have at most 5 warps; the (160 threads, 4 CTAs) bound
 // = 96 registers gives 20 resident warps per SM; the 64-wide heads need more accumulators and keep the loose bound
 template <int HDP> struct am_bounds { static constexpr int min_ctas = HDP <= 32 ? 4 : 2; };
+// backward keeps twice the accumulators: 32-wide heads spill under the 96-register bound, 3 CTAs/SM (128 registers) is faster
+template <int HDP> struct am_bounds_bwd { static constexpr int min_ctas = HDP <= 16 ? 4 : (HDP <= 32 ? 3 : 2); };
 #define LOG2E 1.4426950408889634f
 
 __device__ __forceinline__ void ldsm_x4(uint32_t (&r)[4], const bf16* p) {
@@ -246,7 +248,7 @@ __device__ __forceinline__ void warp_colsum_flush(float (&c)[NTO][2], float* csu
 }
 
 template <int HDP>
-__global__ void __launch_bounds__(AM_MAX_WARPS * 32, am_bounds<HDP>::min_ctas) attn_bwd_mma_kernel(const bf16* __restrict__ qkv, int ld3, const bf16* __restrict__ o,
+__global__ void __launch_bounds__(AM_MAX_WARPS * 32, am_bounds_bwd<HDP>::min_ctas) attn_bwd_mma_kernel(const bf16* __restrict__ qkv, int ld3, const bf16* __restrict__ o,
                                                                      int ldo, const bf16* __restrict__ dout, int lddo,
                                                                      bf16* __restrict__ dqkv, int lddqkv, const float* __restrict__ lse,
                                                                      int L, int d, int H, int halo, float* __restrict__ dbias) {
