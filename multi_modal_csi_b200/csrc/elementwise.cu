@@ -1123,6 +1123,7 @@ __global__ void __launch_bounds__(BNB_MAXT, MINB) bn_act_bwd_kernel(
     }
 }
 
+
 template <int MODE>
 static int bn_bwd_launch(const float* dout, int lddo, const void* z, int ldz, int dtype, const float* mean, const float* invstd,
                          csi_ptr3 gamma, csi_ptr3 beta, double* red, int B, int L, int d, int halo, int nbr, DropCfg dc,
