@@ -778,7 +778,11 @@ __global__ void __launch_bounds__(CR_THREADS) colreduce_kernel(const T* __restri
         }
     }
     __syncthreads();
-    for (int c = threadIdx.x; c < CH * 8; c += blockDim.x) {
+    // every CTA ends with one atomic per column on the same addresses: start each CTA at a different column so that
+    // concurrent CTAs do not queue up on one address at a time
+    const int rot = (int)((blockIdx.x * 61u) % (unsigned)(CH * 8));
+    for (int c0 = threadIdx.x; c0 < CH * 8; c0 += blockDim.x) {
+        const int c = c0 + rot < CH * 8 ? c0 + rot : c0 + rot - CH * 8;
         if (c >= ncols) continue;
         float s = 0.f, s2 = 0.f;
         for (int i = 0; i < RL; ++i) { s += red[i * CH * 8 + c]; if (SQ) s2 += red[(RL + i) * CH * 8 + c]; }
@@ -1105,7 +1109,9 @@ __global__ void __launch_bounds__(BNB_MAXT, MINB) bn_act_bwd_kernel(
             sred[((rl * ncombo + combo) * 2 + 1) * 8 + j] = s2[j];
         }
         __syncthreads();
-        for (int e = threadIdx.x; e < ncombo * 16; e += blockDim.x) {
+        const int ne = ncombo * 16, rot = (int)((blockIdx.x * 61u) % (unsigned)ne);   // stagger the same-address atomics of the CTAs
+        for (int e0 = threadIdx.x; e0 < ne; e0 += blockDim.x) {
+            const int e = e0 + rot < ne ? e0 + rot : e0 + rot - ne;
             const int cmb = e / 16, which = (e / 8) & 1, j = e & 7;
             const int cc = (cmb % CH) * 8 + j, bb = cmb / CH;
             if (cc >= d) continue;
