@@ -1109,9 +1109,7 @@ __global__ void __launch_bounds__(BNB_MAXT, MINB) bn_act_bwd_kernel(
             sred[((rl * ncombo + combo) * 2 + 1) * 8 + j] = s2[j];
         }
         __syncthreads();
-        const int ne = ncombo * 16, rot = (int)((blockIdx.x * 61u) % (unsigned)ne);   // stagger the same-address atomics of the CTAs
-        for (int e0 = threadIdx.x; e0 < ne; e0 += blockDim.x) {
-            const int e = e0 + rot < ne ? e0 + rot : e0 + rot - ne;
+        for (int e = threadIdx.x; e < ncombo * 16; e += blockDim.x) {
             const int cmb = e / 16, which = (e / 8) & 1, j = e & 7;
             const int cc = (cmb % CH) * 8 + j, bb = cmb / CH;
             if (cc >= d) continue;
