@@ -336,3 +336,51 @@ def test_train_loop_semantics_on_cpu_with_mirror(monkeypatch):
     assert list(best.keys()) == list(before.keys())
     assert any(not torch.equal(best[k], before[k]) for k in best if k.endswith("weight"))
     assert int(m.state_dict()["layer_left_encoder.0.layer_cnn.0.1.num_batches_tracked"]) == 4
+
+
+def test_gradient_buckets_cover_the_arena_and_backward_parts_compose():
+    """THATEngine.buckets: [split, n) is final after backward part 1, [0, split) after part 2; split = first parameter of
+    left encoder 1; part 1 + part 2 == the whole backward (mirror kernels on CPU)."""
+    from mirror_ops import MirrorOps
+    from multi_modal_csi_b200 import THAT
+    T, F, out, B = 400, 30, 12, 3
+    torch.manual_seed(39)
+    m = THAT((T, F), (out,), act_dtype="fp32")
+    m._ops_override = MirrorOps()
+    m.dropout_enabled = False
+    m.train()
+    eng = m._engine_for(B)
+    (lo1, hi1), (lo2, hi2) = eng.buckets
+    assert (lo2, hi1) == (0, m.flat_grads.numel()) and hi2 == lo1
+    early = [k for k, off in m.arena.offsets.items() if off < lo1]
+    assert early and all(k.startswith(("layer_left_gaussian.", "layer_left_encoder.0.")) for k in early)
+    assert m.arena.offsets["layer_left_encoder.1.layer_norm_0.weight"] >= lo1
+    g = torch.Generator().manual_seed(5)
+    x = torch.rand(B, T, F, generator=g) * 20
+    y = (torch.rand(B, out, generator=g) < 0.2).float()
+    eng.forward(x, B, training=True, dropout=False)
+    eng.loss_fwd_bwd(y, B, 4.0)
+    eng.backward(None, B, dropout=False, part=0)
+    whole = eng.grads.clone()
+    eng.backward(None, B, dropout=False, part=1)
+    assert torch.allclose(eng.grads[lo1:hi1], whole[lo1:hi1], rtol=1e-5, atol=1e-8)
+    assert float(eng.grads[lo2:hi2].abs().max()) == 0.0
+    eng.backward(None, B, dropout=False, part=2)
+    assert torch.allclose(eng.grads, whole, rtol=1e-5, atol=1e-8)
+
+
+def test_bench_family_table_and_roofline_schema():
+    """bench.py's per-family table: tensor families against the bf16 peak, the others against the HBM peak."""
+    import bench
+    table = {"gemm_nt": (2.0, 48, {"flops": 2.0e12, "bytes": 1.0e9}), "layernorm_fwd": (0.25, 12, {"flops": 0, "bytes": 1.0e9}),
+             "bn_finalize": (0.04, 5, {"flops": 0, "bytes": 0})}
+    peaks = {"hbm_gbs": 6547.5, "bf16_tflops_sustained": 1340.8}
+    fam = bench.family_table(table, peaks)
+    assert list(fam) == ["gemm_nt", "layernorm_fwd", "bn_finalize"]                    # sorted by device time
+    assert fam["gemm_nt"]["bound"] == "tensor" and abs(fam["gemm_nt"]["achieved"] - 1000.0) < 1e-6
+    assert abs(fam["gemm_nt"]["frac"] - round(1000.0 / 1340.8, 3)) < 1e-9
+    assert fam["layernorm_fwd"]["bound"] == "hbm" and abs(fam["layernorm_fwd"]["achieved"] - 4000.0) < 1e-6
+    assert "bound" not in fam["bn_finalize"] and fam["bn_finalize"]["launches"] == 5
+    r = bench.roofline("gemm_nt", table, None, 256, peaks)
+    assert r["bound"] == "tensor" and r["unit"] == "TFLOP/s" and abs(r["frac"] - 1000.0 / 1340.8) < 1e-9
+    assert set(r) >= {"kernel", "bound", "achieved", "peak", "unit", "frac", "traffic", "launches", "ms_per_launch"}
