@@ -95,7 +95,7 @@ def cpu_reference_steps(B, F, out, steps, warmup, threads=None):
                 if k not in opt:
                     opt[k] = (torch.zeros_like(sd[k]), torch.zeros_like(sd[k]))
                 O.adam_update(sd[k], g, opt[k][0], opt[k][1], opt["step"], 5e-4, 2e-4)
-        float(loss)
+        float(loss.detach())
         if s >= warmup:
             times.append(time.perf_counter() - t0)
     ms = 1e3 * sum(times) / len(times)
