@@ -194,6 +194,15 @@ int csi_bce_logits(const float* z, int ldz, const float* y, int ldy, int rows, i
 int csi_smooth_l1(const float* z, int ldz, const float* y, int ldy, int rows, int cols, float beta,
                   float grad_scale, float* loss, float* dz, int lddz, void* stream);
 
+/* ---- sibling head: PermutationMatchingLoss of the five-head THAT (model/that_multi_head.py:309-342).
+ * z: fp32 [B, ldz], head h's logits at columns [h*cpitch, h*cpitch + classes); y: fp32 [B, ldy] = [B, heads, classes]
+ * targets (the class of slot t is argmax(y[b, t])).  Per sample the permutation of the heads with the smallest mean
+ * cross-entropy (first minimum in itertools.permutations order) is chosen; loss[0] = mean CE over B*heads of the matched
+ * heads; dz (optional, [B, lddz], pad columns written as 0) = its gradient * grad_scale; best_perm (optional, int32
+ * [B, heads]) = head matched to each slot. */
+int csi_perm_ce(const float* z, int ldz, const float* y, int ldy, int B, int heads, int classes, int cpitch,
+                float grad_scale, float* loss, float* dz, int lddz, int* best_perm, void* stream);
+
 /* ---- a15: torch.optim.Adam with coupled L2 (that.py:395-397) over the flat arenas.
  * step: device int64 holding the 1-based step of THIS update.  g is multiplied by grad_scale first. */
 int csi_adam_flat(float* p, const float* g, float* m, float* v, long long n, float lr, float beta1, float beta2,

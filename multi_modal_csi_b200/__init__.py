@@ -4,7 +4,7 @@ Drop-in for the ``benchmark/wifi_csi`` hot path of amirhosseinmhd/multi_modal_CS
 ``run_that``, ``preset`` and the metric/result format keep the reference's names and meaning; the arithmetic
 runs in hand-written sm_100a kernels behind the C ABI declared in ``include/csi_that.h``.
 """
-from .that import THAT, THAT_COUNT_PRED  # noqa: F401
+from .that import THAT, THAT_COUNT_PRED, THAT_MULTI_HEAD, PermutationMatchingLoss  # noqa: F401
 from .optim import FusedAdam  # noqa: F401
 
-__all__ = ["THAT", "THAT_COUNT_PRED", "FusedAdam"]
+__all__ = ["THAT", "THAT_COUNT_PRED", "THAT_MULTI_HEAD", "PermutationMatchingLoss", "FusedAdam"]

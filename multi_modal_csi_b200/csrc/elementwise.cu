@@ -1344,6 +1344,107 @@ extern "C" int csi_smooth_l1(const float* z, int ldz, const float* y, int ldy, i
     return CSI_OK;
 }
 
+// ------------------------------------------------------------------------------------------------ permutation matching
+// PermutationMatchingLoss of the five-head sibling (model/that_multi_head.py:309-342).  One thread per sample: log-sum-exp
+// of each head, the H x H cost matrix cost[h][t] = lse[h] - z[h][class of slot t], then every permutation of the heads in
+// lexicographic order (= itertools.permutations order; the FIRST minimum wins, as the reference keeps the incumbent
+// unless loss < best).  loss = mean over B*H of cost[perm[t]][t]; dz = (softmax - onehot) * grad_scale / (B*H).
+#define PCE_MAXH 6
+__global__ void __launch_bounds__(256) perm_ce_kernel(const float* __restrict__ z, int ldz, const float* __restrict__ y, int ldy,
+                                                      int B, int H, int C, int cp, float gscale, float* __restrict__ loss,
+                                                      float* __restrict__ dz, int lddz, int* __restrict__ best_out) {
+    __shared__ float red[8];
+    const float invn = 1.0f / ((float)B * (float)H);
+    float acc = 0.f;
+    for (int b = threadIdx.x; b < B; b += blockDim.x) {
+        const float* zr = z + (size_t)b * ldz;
+        const float* yr = y + (size_t)b * ldy;
+        int cls[PCE_MAXH];
+        float lse[PCE_MAXH], cost[PCE_MAXH][PCE_MAXH];
+#pragma unroll
+        for (int t = 0; t < PCE_MAXH; ++t) {
+            cls[t] = 0;
+            if (t < H) {                                          // torch.argmax: first maximum
+                float bv = yr[t * C];
+                for (int c = 1; c < C; ++c) { const float v = yr[t * C + c]; if (v > bv) { bv = v; cls[t] = c; } }
+            }
+        }
+#pragma unroll
+        for (int h = 0; h < PCE_MAXH; ++h) {
+            lse[h] = 0.f;
+            if (h < H) {
+                float m = zr[h * cp];
+                for (int c = 1; c < C; ++c) m = fmaxf(m, zr[h * cp + c]);
+                float sum = 0.f;
+                for (int c = 0; c < C; ++c) sum += __expf(zr[h * cp + c] - m);
+                lse[h] = m + __logf(sum);
+            }
+#pragma unroll
+            for (int t = 0; t < PCE_MAXH; ++t) cost[h][t] = (h < H && t < H) ? lse[h] - zr[h * cp + cls[t]] : 0.f;
+        }
+        int perm[PCE_MAXH], best[PCE_MAXH];
+#pragma unroll
+        for (int t = 0; t < PCE_MAXH; ++t) perm[t] = best[t] = t;
+        float bestv = INFINITY;
+        for (;;) {
+            float tot = 0.f;
+#pragma unroll
+            for (int t = 0; t < PCE_MAXH; ++t)
+                if (t < H) {
+                    float cv = 0.f;
+#pragma unroll
+                    for (int h = 0; h < PCE_MAXH; ++h) cv = perm[t] == h ? cost[h][t] : cv;
+                    tot += cv;
+                }
+            tot /= (float)H;
+            if (tot < bestv) {
+                bestv = tot;
+#pragma unroll
+                for (int t = 0; t < PCE_MAXH; ++t) best[t] = perm[t];
+            }
+            // next permutation in lexicographic order
+            int i = H - 2;
+            while (i >= 0 && perm[i] > perm[i + 1]) --i;
+            if (i < 0) break;
+            int j = H - 1;
+            while (perm[j] < perm[i]) --j;
+            int tmp = perm[i]; perm[i] = perm[j]; perm[j] = tmp;
+            for (int a = i + 1, e = H - 1; a < e; ++a, --e) { tmp = perm[a]; perm[a] = perm[e]; perm[e] = tmp; }
+        }
+        for (int t = 0; t < H; ++t) {
+            const int h = best[t];
+            acc += cost[h][t];
+            if (best_out) best_out[b * H + t] = h;
+            if (dz) {
+                float* dr = dz + (size_t)b * lddz + h * cp;
+                for (int c = 0; c < cp; ++c) {
+                    float g = 0.f;
+                    if (c < C) g = (__expf(zr[h * cp + c] - lse[h]) - (c == cls[t] ? 1.f : 0.f)) * invn * gscale;
+                    dr[c] = g;
+                }
+            }
+        }
+    }
+    acc = warp_sum(acc);
+    if ((threadIdx.x & 31) == 0) red[threadIdx.x >> 5] = acc;
+    __syncthreads();
+    if (threadIdx.x < 32) {
+        float v = threadIdx.x < (blockDim.x >> 5) ? red[threadIdx.x] : 0.f;
+        v = warp_sum(v);
+        if (threadIdx.x == 0) loss[0] = v * invn;
+    }
+}
+
+extern "C" int csi_perm_ce(const float* z, int ldz, const float* y, int ldy, int B, int heads, int classes, int cpitch,
+                           float grad_scale, float* loss, float* dz, int lddz, int* best_perm, void* stream) {
+    CSI_CHECK_ARG(z && y && loss && B > 0 && classes > 0, "bad argument");
+    CSI_CHECK_ARG(heads >= 1 && heads <= PCE_MAXH && cpitch >= classes && ldz >= heads * cpitch && ldy >= heads * classes &&
+                  (!dz || lddz >= heads * cpitch), "1..6 heads, head pitch >= classes");
+    perm_ce_kernel<<<1, 256, 0, ST(stream)>>>(z, ldz, y, ldy, B, heads, classes, cpitch, grad_scale, loss, dz, lddz, best_perm);
+    CSI_LAUNCH_CHECK();
+    return CSI_OK;
+}
+
 // ------------------------------------------------------------------------------------------------ Adam
 __global__ void __launch_bounds__(256) adam_kernel(float* __restrict__ p, const float* __restrict__ g,
                                                    float* __restrict__ m, float* __restrict__ v, long long n4, float lr,

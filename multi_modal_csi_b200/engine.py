@@ -141,7 +141,7 @@ class THATEngine:
         self.dlogits = torch.zeros(B, self.g.ld_out, device=dev)
         self.dlogits_a = torch.zeros(B, self.g.ld_out, dtype=adt, device=dev)
         self.loss = torch.zeros(1, device=dev)
-        self.y_static = torch.zeros(B, self.g.out, device=dev)
+        self.y_static = torch.zeros(B, self.g.n_targets, device=dev)
 
     def activation_bytes(self) -> int:
         n = 0
@@ -230,9 +230,20 @@ class THATEngine:
         join()
         ops.alg_scale = 1.0
         ops.dropout_rows(self.feat, self.featd, B, LY.FEAT, pf, LY.SITE_FEAT, self.rng)
-        ops.gemm_nt(self.featd, self.W("f:layer_output.weight"), self.logits, B, g.out, [(0, 0, 0, LY.FEAT)],
-                    self.P("layer_output.bias"), None, 0.0, 0, self.rng)
-        return self.logits[:B, :g.out]
+        if g.heads == 1:
+            ops.gemm_nt(self.featd, self.W("f:layer_output.weight"), self.logits, B, g.out, [(0, 0, 0, LY.FEAT)],
+                        self.P("layer_output.bias"), None, 0.0, 0, self.rng)
+        else:       # the `heads` output layers are one GEMM: head h owns rows h*cp.. of the packed weight (pad rows are zero)
+            ops.gemm_nt(self.featd, self.W("f:layer_output.weight"), self.logits, B, g.ld_out, [(0, 0, 0, LY.FEAT)],
+                        self.PB("layer_output.bias"), None, 0.0, 0, self.rng)
+        return self.logits_view(B)
+
+    def logits_view(self, B: int) -> torch.Tensor:
+        """[B, out] (THAT) or [B, heads, out] (multi-head sibling) view of the static logits buffer."""
+        g = self.g
+        if g.heads == 1:
+            return self.logits[:B, :g.out]
+        return self.logits[:B].view(B, g.heads, g.cp)[:, :, :g.out]
 
     def _forward_stream(self, si: int, B: int, training: bool, pd: float):
         """Encoders + head convs + time-sum of one stream (0 = left, 1 = right) into its columns of ``feat``."""
@@ -307,12 +318,16 @@ class THATEngine:
         if zero_grads:
             self.grads.zero_()
         if dlogits is not None:
-            self.dlogits[:B, :g.out].copy_(dlogits)
+            if g.heads == 1:
+                self.dlogits[:B, :g.out].copy_(dlogits)
+            else:
+                self.dlogits[:B].view(B, g.heads, g.cp)[:, :, :g.out].copy_(dlogits.reshape(B, g.heads, g.out))
         ops.alg_scale = 1.0
         ops.dropout_rows(self.dlogits, self.dlogits_a, B, g.ld_out, 0.0, 0, self.rng)      # cast to act dtype
-        ops.gemm_tn(self.dlogits_a, self.featd, self.G("layer_output.weight"), LY.FEAT, 1, B, g.out,
-                    [(0, 0, 0, LY.FEAT)])
-        ops.colsum_tokens(self.dlogits_a, B, 1, 0, g.out, self.G("layer_output.bias"))
+        for h, (wn, bn) in enumerate(g.output_names()):
+            dl = self.dlogits_a[:, h * g.cp:]
+            ops.gemm_tn(dl, self.featd, self.G(wn), LY.FEAT, 1, B, g.out, [(0, 0, 0, LY.FEAT)])
+            ops.colsum_tokens(dl, B, 1, 0, g.out, self.G(bn))
         ops.gemm_nt(self.dlogits_a, self.W("b:layer_output.weight"), self.dfeatd, B, LY.FEAT,
                     [(0, 0, 0, g.ld_out)], None, None, 0.0, 0, self.rng)
         ops.dropout_rows(self.dfeatd, self.dfeat, B, LY.FEAT, pf, LY.SITE_FEAT, self.rng)
@@ -329,7 +344,8 @@ class THATEngine:
             return 0
         pre = self.g.left.prefix(1)
         split = min(off for k, off in self.arena.offsets.items() if k.startswith(pre))
-        early = ("layer_left_gaussian.", self.g.left.prefix(0))
+        # (the heads of the multi-head sibling are registered first: they sit below the split although they are final early)
+        early = ("layer_left_gaussian.", self.g.left.prefix(0)) + (("layer_output.",) if self.g.heads > 1 else ())
         assert all((off < split) == k.startswith(early) for k, off in self.arena.offsets.items())
         return split
 
@@ -448,7 +464,11 @@ class THATEngine:
                      want_grad: bool = True) -> torch.Tensor:
         """BCEWithLogitsLoss(pos_weight).mean() of the engine's logits against y [B,out] fp32; writes
         dL/dlogits * grad_scale into the engine's dlogits buffer.  Returns the 1-element loss tensor."""
-        if self.loss_kind == "smooth_l1":          # sibling head THAT_COUNT_PRED: SmoothL1Loss(beta=1).mean()
+        if self.loss_kind == "perm_ce":            # multi-head sibling: PermutationMatchingLoss (that_multi_head.py:309-342)
+            g = self.g
+            self.ops.perm_ce(self.logits, y, B, g.heads, g.out, g.cp, grad_scale, self.loss,
+                             self.dlogits if want_grad else None)
+        elif self.loss_kind == "smooth_l1":        # sibling head THAT_COUNT_PRED: SmoothL1Loss(beta=1).mean()
             self.ops.smooth_l1(self.logits, y, B, self.g.out, 1.0, grad_scale, self.loss,
                                self.dlogits if want_grad else None)
         else:

@@ -93,6 +93,7 @@ class ModelGeom:
     T: int
     F: int
     out: int
+    heads: int = 1          # > 1: the multi-head sibling (model/that_multi_head.py): `heads` Linear(288, out) output layers
     left: StreamGeom = field(init=False)
     right: StreamGeom = field(init=False)
 
@@ -113,8 +114,25 @@ class ModelGeom:
         return (self.left, self.right)
 
     @property
-    def ld_out(self) -> int:
+    def cp(self) -> int:
+        """Column pitch of one output head in the logits buffer."""
         return ru(self.out, 16)
+
+    @property
+    def ld_out(self) -> int:
+        """Width of the logits buffer: head h occupies columns [h*cp, h*cp + out)."""
+        return self.heads * self.cp
+
+    @property
+    def n_targets(self) -> int:
+        """Label values per sample ([B, out] for THAT, [B, heads, out] for the multi-head sibling)."""
+        return self.heads * self.out
+
+    def output_names(self):
+        """(weight, bias) parameter names of the output layer(s)."""
+        if self.heads == 1:
+            return [("layer_output.weight", "layer_output.bias")]
+        return [(f"layer_output.{h}.weight", f"layer_output.{h}.bias") for h in range(self.heads)]
 
 
 def parameter_specs(g: ModelGeom) -> "OrderedDict[str, Tuple[int, ...]]":
@@ -122,6 +140,10 @@ def parameter_specs(g: ModelGeom) -> "OrderedDict[str, Tuple[int, ...]]":
     ``model.parameters()`` and the flat arena enumerate them exactly like the reference module does)."""
     sp: "OrderedDict[str, Tuple[int, ...]]" = OrderedDict()
     L, F = g.left.L, g.F
+    if g.heads > 1:                                    # that_multi_head.py:194-196: the ModuleList of heads is registered first
+        for w, b in g.output_names():
+            sp[w] = (g.out, FEAT)
+            sp[b] = (g.out,)
     sp["layer_left_gaussian.var_embedding"] = (NUM_GAUSS, F)
     sp["layer_left_gaussian.var_position"] = (L, NUM_GAUSS)
     sp["layer_left_gaussian.var_mu"] = (1, NUM_GAUSS)
@@ -159,8 +181,9 @@ def parameter_specs(g: ModelGeom) -> "OrderedDict[str, Tuple[int, ...]]":
     sp["layer_right_cnn_0.bias"] = (RIGHT_HEAD[0],)
     sp["layer_right_cnn_1.weight"] = (RIGHT_HEAD[0], L, RIGHT_HEAD[2])
     sp["layer_right_cnn_1.bias"] = (RIGHT_HEAD[0],)
-    sp["layer_output.weight"] = (g.out, FEAT)
-    sp["layer_output.bias"] = (g.out,)
+    if g.heads == 1:
+        sp["layer_output.weight"] = (g.out, FEAT)
+        sp["layer_output.bias"] = (g.out,)
     return sp
 
 
@@ -270,9 +293,19 @@ def build_pack_plan(g: ModelGeom, arena: Arena) -> PackPlan:
             add(w, s.head_n, d, k, alloc("f:" + w, s.head_n, k * Dp), 0, Dp, 0)
             add(w, s.head_n, d, k, bmat, 1, Np, seg)
             seg += k
-    w = "layer_output.weight"
-    add(w, g.out, FEAT, 1, alloc("f:" + w, g.out, FEAT), 0, FEAT, 0)
-    add(w, g.out, FEAT, 1, alloc("b:" + w, FEAT, g.ld_out), 1, g.ld_out, 0)
+    # output layer(s): one forward operand [heads*cp, 288] (head h = rows h*cp..), one data-gradient operand [288, heads*cp]
+    # (head h = segment h of width cp) and -- for several heads -- one packed bias vector with the same pitch
+    fmat = alloc("f:layer_output.weight", g.ld_out if g.heads > 1 else g.out, FEAT)
+    bmat = alloc("b:layer_output.weight", FEAT, g.ld_out)
+    for h, (w, bname) in enumerate(g.output_names()):
+        add(w, g.out, FEAT, 1, PackedMat(fmat.off + h * g.cp * FEAT, g.out, FEAT), 0, FEAT, 0)
+        add(w, g.out, FEAT, 1, bmat, 1, g.cp if g.heads > 1 else g.ld_out, h)
+        if g.heads > 1:
+            if h == 0:
+                bias_mats["layer_output.bias"] = PackedMat(boff, g.ld_out, 1)
+            bias_entries.append((arena.offsets[bname], boff + h * g.cp, g.out, 1, 1, 1, 0, 1, 0, NOG, NOG))
+    if g.heads > 1:
+        boff += ru(g.ld_out, 64)
     return PackPlan(mats=mats, entries=entries, size=off, max_elems=max_elems, bias_entries=bias_entries,
                     bias_mats=bias_mats, bias_size=boff)
 

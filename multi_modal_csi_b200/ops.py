@@ -66,7 +66,7 @@ EXPORTS = [
     "csi_layernorm_fwd", "csi_layernorm_bwd", "csi_gemm_nt", "csi_gemm_tn", "csi_colsum_tokens", "csi_attn_fwd",
     "csi_attn_bwd", "csi_bn_stats", "csi_bn_finalize", "csi_bn_eval_prepare", "csi_bn_act_fwd",
     "csi_bn_act_bwd_reduce", "csi_bn_act_bwd_dz", "csi_head_reduce_fwd", "csi_head_reduce_bwd", "csi_dropout_rows",
-    "csi_bce_logits", "csi_smooth_l1", "csi_predict_counts", "csi_adam_flat", "csi_advance_counters", "csi_pack_weights", "csi_fill_f32",
+    "csi_bce_logits", "csi_smooth_l1", "csi_perm_ce", "csi_predict_counts", "csi_adam_flat", "csi_advance_counters", "csi_pack_weights", "csi_fill_f32",
 ]
 
 
@@ -334,6 +334,10 @@ class NativeOps:
     def smooth_l1(self, z, y, rows, cols, beta, grad_scale, loss, dz):
         self._call("csi_smooth_l1", _p(z), _ld(z), _p(y), _ld(y), rows, cols, C.c_float(beta), C.c_float(grad_scale),
                    _p(loss), _p(dz), _ld(dz))
+
+    def perm_ce(self, z, y, B, heads, classes, cpitch, grad_scale, loss, dz, best_perm=None):
+        self._call("csi_perm_ce", _p(z), _ld(z), _p(y), _ld(y), B, heads, classes, cpitch, C.c_float(grad_scale),
+                   _p(loss), _p(dz), _ld(dz), _p(best_perm))
 
     def predict_counts(self, logits, rows, users, classes, threshold, counts):
         self._call("csi_predict_counts", _p(logits), _ld(logits), rows, users, classes, C.c_float(threshold), _p(counts))

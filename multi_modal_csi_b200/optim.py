@@ -36,6 +36,7 @@ class FusedAdam(torch.optim.Optimizer):
         g = self.param_groups[0]
         m, v = self._moments(engine.params)
         engine.adam(m, v, g["lr"], g["betas"], g["eps"], g["weight_decay"], self.grad_scale)
+        self._opt_called = True        # what torch's step() wrapper records; lr schedulers check it before their own step
 
     @torch.no_grad()
     def step(self, closure=None):

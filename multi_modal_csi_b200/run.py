@@ -14,9 +14,9 @@ from torch.utils.data import TensorDataset
 from .load_data import encode_data_y, load_data_x, load_data_y
 from .optim import FusedAdam
 from .preset import preset
-from .that import THAT, THAT_COUNT_PRED
+from .that import THAT, THAT_COUNT_PRED, THAT_MULTI_HEAD, PermutationMatchingLoss
 from .train import _log, _wandb, train
-from .utils import NumpyEncoder, load_model_components, performance_metrics, save_model_components
+from .utils import NumpyEncoder, load_model_components, performance_metrics, reduce_dataset, save_model_components
 
 
 def run_that(data_train_x, data_train_y, data_test_x, data_test_y, var_repeat=10):
@@ -96,6 +96,8 @@ def master_splitter(preset, var_task, var_model, var_users):
                                 var_num_users=var_users)
         X = load_data_x(preset["path"]["data_x"], data_pd_y["label"].to_list())
         y = encode_data_y(data_pd_y, var_task)
+        if var_model == "THAT_MULTI_HEAD":
+            y = reduce_dataset(y)                                          # run_main.py:39-40
         X_train, X_test, y_train, y_test = train_test_split(X, y, test_size=0.2, shuffle=True, random_state=103)
         xs_tr.append(X_train); xs_te.append(X_test); ys_tr.append(y_train); ys_te.append(y_test)
     return (np.concatenate(xs_tr, 0), np.concatenate(xs_te, 0), np.concatenate(ys_tr, 0), np.concatenate(ys_te, 0))
@@ -108,6 +110,56 @@ def parse_args():
     a.add_argument("--repeat", default=preset["repeat"], type=int)
     a.add_argument("--users", default="0, 1,2,3,4,5", type=str, help="Comma-separated list of user IDs")
     return a.parse_args()
+
+
+def run_that_multihead(data_train_x, data_train_y, data_test_x, data_test_y, var_repeat=10):
+    """model/that_multi_head.py:345-482: the five-head THAT trained with PermutationMatchingLoss (Adam without weight decay,
+    per-step cosine schedule with warm-up, ``var_mode="multi_head"``); labels are ``[N, 5, classes]`` one-hot slots
+    (``utils.reduce_dataset``).  Returns the metrics dict of the last repeat.  The reference evaluates with a helper that
+    does not exist in its utils.py (``calculate_matrix_absolute_error``, that_multi_head.py:461); the count metrics of
+    ``performance_metrics(var_mode="multi_head")`` (utils.py:220-228) are what that call is meant to produce."""
+    device = torch.device("cuda" if torch.cuda.is_available() else "cpu")
+    data_train_x = data_train_x.reshape(data_train_x.shape[0], data_train_x.shape[1], -1)
+    data_test_x = data_test_x.reshape(data_test_x.shape[0], data_test_x.shape[1], -1)
+    var_x_shape, var_y_shape = data_train_x[0].shape, [data_train_y[0].shape[1]]                  # that_multi_head.py:374
+    data_train_set = TensorDataset(torch.from_numpy(data_train_x), torch.from_numpy(data_train_y))
+    data_test_set = TensorDataset(torch.from_numpy(data_test_x), torch.from_numpy(data_test_y))
+    dict_true_acc, result_accuracy = None, []
+    for var_r in range(var_repeat):
+        print("Repeat", var_r)
+        if _wandb is not None:
+            _wandb.init(project="wifi-based-model-THAT_ENCODER", name=f"Repeat_{var_r}",
+                        config={"model": "THAT_MultiHead", "repeat": var_r}, reinit=True)
+        torch.random.manual_seed(var_r + 39)
+        model_that = THAT_MULTI_HEAD(var_x_shape, var_y_shape, act_dtype=preset["nn"].get("dtype", "bf16"),
+                                     max_batch=preset["nn"]["batch_size"]).to(device)
+        optimizer = FusedAdam(model_that.parameters(), lr=preset["nn"]["lr"], weight_decay=0)
+        loss = PermutationMatchingLoss()
+        var_mode = "multi_head"
+        var_time_0 = time.time()
+        var_best_weight = train(model=model_that, optimizer=optimizer, loss=loss, data_train_set=data_train_set,
+                                data_test_set=data_test_set, var_threshold=preset["nn"]["threshold"],
+                                var_batch_size=preset["nn"]["batch_size"], var_epochs=preset["nn"]["epoch"], device=device,
+                                var_mode=var_mode)
+        var_time_1 = time.time()
+        model_that.load_state_dict(var_best_weight)
+        with torch.no_grad():
+            predict_test_y = model_that(torch.from_numpy(data_test_x).to(device))
+        predict_test_y = predict_test_y.detach().cpu().numpy()
+        var_time_2 = time.time()
+        dict_true_acc = performance_metrics(data_test_y, predict_test_y, var_mode=var_mode)
+        _log({"repeat": var_r, "train_time": var_time_1 - var_time_0, "test_time": var_time_2 - var_time_1,
+              "TOTAL_TESTSET_ERROR": dict_true_acc["total_error"],
+              "TOTAL_TESTSET_perfect_prediction_percentage": dict_true_acc["perfect_prediction_percentage"],
+              "TOTAL_ACCURACY": dict_true_acc["accuracy"]})
+        print(" %.6fs" % (time.time() - var_time_1), "- Total Error %.6f" % dict_true_acc["total_error"],
+              "-  perfect_prediction_percentage %.6f" % dict_true_acc["perfect_prediction_percentage"])
+        result_accuracy.append(dict_true_acc["perfect_prediction_percentage"])
+    if result_accuracy:
+        _log({"avg_accuracy": sum(result_accuracy) / len(result_accuracy)})
+    if _wandb is not None and getattr(_wandb, "run", None) is not None:
+        _wandb.finish()
+    return dict_true_acc
 
 
 def run_that_count_pred(data_train_x, data_train_y, data_test_x, data_test_y, var_repeat=10):
@@ -163,14 +215,14 @@ def run_that_count_pred(data_train_x, data_train_y, data_test_x, data_test_y, va
 
 
 def run():
-    """run_main.py:88-160 restricted to the models on this path: THAT and its sibling THAT_COUNT_PRED."""
+    """run_main.py:88-160 restricted to the models on this path: THAT and its siblings THAT_COUNT_PRED / THAT_MULTI_HEAD."""
     var_args = parse_args()
     var_users = [u.strip() for u in var_args.users.split(",")]
     preset["repeat"] = 1 if not preset["pretrained_path"] else preset["repeat"]
-    if var_args.model not in ("THAT", "THAT_COUNT_PRED"):
+    if var_args.model not in ("THAT", "THAT_COUNT_PRED", "THAT_MULTI_HEAD"):
         raise Exception("Not valid name for model")                       # run_main.py:140
     data_train_x, data_test_x, data_train_y, data_test_y = master_splitter(preset, var_args.task, var_args.model, var_users)
-    runner = run_that if var_args.model == "THAT" else run_that_count_pred
+    runner = {"THAT": run_that, "THAT_COUNT_PRED": run_that_count_pred, "THAT_MULTI_HEAD": run_that_multihead}[var_args.model]
     result = runner(data_train_x, data_train_y, data_test_x, data_test_y, var_args.repeat)
     result["model"], result["task"], result["data"], result["nn"] = var_args.model, var_args.task, preset["data"], preset["nn"]
     print(result)

@@ -43,6 +43,9 @@ def _initial_values(g: LY.ModelGeom):
     bufs = OrderedDict()
     L, F = g.left.L, g.F
     K = LY.NUM_GAUSS
+    if g.heads > 1:                                    # that_multi_head.py:194-196: the heads are constructed first
+        for wn, bn in g.output_names():
+            vals[wn], vals[bn] = _kaiming_conv((g.out, LY.FEAT))
     emb = torch.zeros(K, F)
     torch.nn.init.xavier_uniform_(emb)                                               # that.py:43-45
     vals["layer_left_gaussian.var_embedding"] = emb
@@ -82,9 +85,10 @@ def _initial_values(g: LY.ModelGeom):
             w, b = _kaiming_conv((s.head_n, s.d, k))
             vals[f"layer_{s.name}_cnn_{j}.weight"] = w
             vals[f"layer_{s.name}_cnn_{j}.bias"] = b
-    w, b = _kaiming_conv((g.out, LY.FEAT))
-    vals["layer_output.weight"] = w
-    vals["layer_output.bias"] = b
+    if g.heads == 1:
+        w, b = _kaiming_conv((g.out, LY.FEAT))
+        vals["layer_output.weight"] = w
+        vals["layer_output.bias"] = b
     return vals, bufs
 
 
@@ -114,10 +118,12 @@ class _THATFunction(torch.autograd.Function):
 class THAT(torch.nn.Module):
     """``THAT(var_x_shape, var_y_shape)``: var_x_shape[-2:] = (T, F), var_y_shape[-1] = out (that.py:183-192)."""
 
+    NUM_OUTPUT_HEADS = 1
+
     def __init__(self, var_x_shape, var_y_shape, act_dtype: Optional[str] = None, max_batch: Optional[int] = None):
         super().__init__()
         F, T, out = int(var_x_shape[-1]), int(var_x_shape[-2]), int(var_y_shape[-1])
-        self.geom = LY.ModelGeom(T, F, out)
+        self.geom = LY.ModelGeom(T, F, out, self.NUM_OUTPUT_HEADS)
         self.specs = LY.parameter_specs(self.geom)
         self.arena = LY.build_arena(self.specs)
         self.act_dtype = {None: torch.bfloat16, "bf16": torch.bfloat16, "bfloat16": torch.bfloat16,
@@ -279,7 +285,7 @@ class THAT(torch.nn.Module):
         x: fp32 [B,T,F] on the device (or a packed ragged arena with offs/lens); y: [B, ...] labels.
         ``grad_hook(engine)`` runs between backward and the optimizer (data-parallel all-reduce).
         Returns (loss 1-element tensor, logits [B,out]); both are views of static buffers."""
-        if loss_kind not in ("bce", "smooth_l1"):
+        if loss_kind not in ("bce", "smooth_l1", "perm_ce"):
             raise ValueError(f"unsupported fused loss {loss_kind!r}")
         B = y.shape[0]
         eng = self._engine_for(B)
@@ -304,7 +310,7 @@ class THAT(torch.nn.Module):
             run(B, pos_weight, self.dropout_enabled)
         if run == eng.train_body:
             self._eager_steps += 1
-        loss, logits = eng.loss, eng.logits[:B, :self.geom.out]
+        loss, logits = eng.loss, eng.logits_view(B)
         self._attach_grads()
         if grad_hook is not None and not overlap:
             grad_hook(eng)
@@ -317,3 +323,48 @@ class THAT_COUNT_PRED(THAT):
     ``state_dict`` keys and constructor RNG order); ``var_y_shape[-1]`` is the number of activities (9) and the model is
     trained with ``SmoothL1Loss`` on per-activity head counts (``var_mode="count_classification"``), so every backbone
     kernel is reused unchanged and only the loss kernel differs (``csi_smooth_l1``)."""
+
+
+class THAT_MULTI_HEAD(THAT):
+    """model/that_multi_head.py:180-306: the five-head sibling.  Same backbone as THAT; ``layer_output`` is a ModuleList of
+    five ``Linear(288, out)`` heads, registered (and initialised) BEFORE the backbone, so ``state_dict`` has the reference's
+    171 keys in the reference's order.  ``forward`` returns ``[B, 5, out]`` (that_multi_head.py:304-305).  It is trained
+    with ``PermutationMatchingLoss``; the five heads run as one GEMM over a padded [5*cp, 288] operand and the loss /
+    its gradient are one kernel (``csi_perm_ce``)."""
+    NUM_OUTPUT_HEADS = 5
+
+
+class _PermCE(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, pred, target):
+        from .ops import NativeOps
+        B, H, C = pred.shape
+        cp = LY.ru(C, 16)
+        z = torch.zeros(B, H * cp, device=pred.device)
+        z.view(B, H, cp)[:, :, :C] = pred.detach().float()
+        y = target.detach().reshape(B, H * C).float().contiguous()
+        loss = torch.zeros(1, device=pred.device)
+        dz = torch.zeros(B, H * cp, device=pred.device)
+        NativeOps(pred.device).perm_ce(z, y, B, H, C, cp, 1.0, loss, dz)
+        ctx.save_for_backward(dz.view(B, H, cp)[:, :, :C])
+        return loss[0]
+
+    @staticmethod
+    def backward(ctx, g):
+        (dz,) = ctx.saved_tensors
+        return dz * g, None
+
+
+class PermutationMatchingLoss(torch.nn.Module):
+    """model/that_multi_head.py:309-342 for predictions / targets ``[B, heads, classes]`` on a CUDA device: per sample
+    the permutation of the heads with the smallest mean cross-entropy against ``argmax(targets)`` (first minimum in
+    ``itertools.permutations`` order), loss = mean cross-entropy of the matched heads.  One kernel (``csi_perm_ce``)
+    instead of the reference's B x 120 Python loop; ``train()`` / ``fused_train_step(loss_kind="perm_ce")`` fuse it."""
+
+    def forward(self, predictions, targets):
+        if predictions.dim() != 3 or predictions.shape != targets.shape:
+            raise ValueError(f"expected predictions and targets [B, heads, classes], got {tuple(predictions.shape)} "
+                             f"and {tuple(targets.shape)}")
+        if predictions.device.type != "cuda":
+            raise RuntimeError("PermutationMatchingLoss runs csi_perm_ce on a CUDA device; there is no CPU path")
+        return _PermCE.apply(predictions, targets)

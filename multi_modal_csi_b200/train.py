@@ -25,6 +25,7 @@ from torch.utils.data.distributed import DistributedSampler
 
 from .optim import FusedAdam
 from .parallel import GradSync
+from .that import PermutationMatchingLoss
 from .that import THAT
 from .utils import performance_metrics
 
@@ -57,6 +58,20 @@ def _uniform_pos_weight(loss):
     return v if bool((pw == v).all()) else None
 
 
+def cosine_schedule_with_warmup(optimizer, num_warmup_steps, num_training_steps, min_lr_ratio=0.1):
+    """train.py:26-33 (``get_cosine_schedule_with_warmup``): LambdaLR, linear warm-up then cosine decay floored at
+    ``min_lr_ratio``.  FusedAdam reads ``param_groups[0]["lr"]`` on the host at every step, so the schedule needs no kernel."""
+    import math
+
+    def lr_lambda(current_step):
+        if current_step < num_warmup_steps:
+            return float(current_step) / float(max(1, num_warmup_steps))
+        progress = float(current_step - num_warmup_steps) / float(max(1, num_training_steps - num_warmup_steps))
+        return max(min_lr_ratio, 0.5 * (1.0 + math.cos(math.pi * progress)))
+
+    return torch.optim.lr_scheduler.LambdaLR(optimizer, lr_lambda)
+
+
 def train(model, optimizer, loss, data_train_set: TensorDataset, data_test_set: TensorDataset, var_threshold: float,
           var_batch_size: int, var_epochs: int, device, var_mode: str, patience: int = 150):
     device = torch.device(device)
@@ -71,12 +86,20 @@ def train(model, optimizer, loss, data_train_set: TensorDataset, data_test_set: 
     elif (isinstance(loss, torch.nn.SmoothL1Loss) and loss.reduction == "mean" and float(loss.beta) == 1.0
           and var_mode == "count_classification"):
         loss_kind, pos_weight = "smooth_l1", 1.0
+    elif isinstance(loss, PermutationMatchingLoss) and var_mode == "multi_head":
+        loss_kind, pos_weight = "perm_ce", 1.0
     fused = (isinstance(model, THAT) and isinstance(optimizer, FusedAdam) and loss_kind is not None
              and device.type == "cuda")
     sync = GradSync(model, dist.get_world_size()) if distributed and isinstance(model, THAT) else None
 
     var_best_f1_score, var_best_PPP, var_best_weight, counter = 0, 0, None, 0
     var_epoch_saved = None
+    scheduler = None
+    if var_mode == "multi_head":                        # train.py:57-63: per-step cosine schedule with linear warm-up
+        from .preset import preset
+        sch = preset["nn"]["scheduler"]
+        scheduler = cosine_schedule_with_warmup(optimizer, sch["num_warmup_epochs"] * len(data_train_loader),
+                                                preset["nn"]["epoch"] * len(data_train_loader), sch["min_lr_ratio"])
     for var_epoch in range(var_epochs):
         var_time_e0 = time.time()
         model.train()
@@ -99,6 +122,8 @@ def train(model, optimizer, loss, data_train_set: TensorDataset, data_test_set: 
                 var_loss_train, predict_train_y = model.fused_train_step(
                     x, data_batch_y, optimizer, pos_weight=pos_weight, augment=True, grad_hook=sync, loss_kind=loss_kind)
                 var_loss_train, predict_train_y = var_loss_train.clone(), predict_train_y.clone()
+                if scheduler is not None:
+                    scheduler.step()
             else:
                 if model.training:
                     data_batch_x = apply_augmentation(data_batch_x)
@@ -109,6 +134,8 @@ def train(model, optimizer, loss, data_train_set: TensorDataset, data_test_set: 
                 if sync is not None:
                     sync.hook(model._engine)
                 optimizer.step()
+                if scheduler is not None:
+                    scheduler.step()                                                     # train.py:101-102
         if predict_train_y is None:
             raise ValueError("training set smaller than two batches: the reference loop skips the last batch (train.py:81)")
         data_batch_y = data_batch_y.detach().cpu().numpy()

@@ -82,12 +82,24 @@ def threshold_round(x, threshold=0.3):
 
 
 def performance_metrics(y_true, y_pred, var_mode="baseline", var_threshold=0.5):
-    """utils.py:213-270 for var_mode "baseline" and "count_classification".  In baseline mode the decision threshold
+    """utils.py:213-270 for var_mode "baseline", "count_classification" and "multi_head".  In baseline mode the decision threshold
     is the reference's hard-coded 0.5 (utils.py:238 ignores ``var_threshold``) and classes per user are fixed at 9
     (utils.py:236); in count mode predictions are threshold-rounded at 0.5 and clipped to [0, 5] (utils.py:229-233)."""
     y_true = np.array(y_true)
     y_pred = np.array(y_pred)
-    if var_mode == "count_classification":
+    if var_mode == "multi_head":
+        # utils.py:220-228: per head the arg-max class, one-hot, summed over the heads = per-class counts; the last class
+        # ("nobody") is dropped.  The reference first takes ``y_pred[-1]`` (it expects a stack of per-stage outputs
+        # [S, B, heads, classes]; with the [B, heads, classes] array its own model returns, that line breaks the unpacking
+        # that follows): a 4-D input is reduced the reference's way, a 3-D one is used as it is.
+        if y_pred.ndim == 4:
+            y_pred = y_pred[-1]
+        if y_pred.ndim != 3 or y_true.ndim != 3:
+            raise ValueError(f"multi_head metrics need [B, heads, classes] predictions and targets, got {y_pred.shape} / {y_true.shape}")
+        num_classes = y_pred.shape[-1]
+        y_pred = np.eye(num_classes)[np.argmax(y_pred, axis=-1)].sum(axis=1)[:, :-1]
+        y_true = y_true.sum(axis=1)[:, :-1]
+    elif var_mode == "count_classification":
         y_pred = np.clip(threshold_round(y_pred, threshold=0.5), 0, 5)
     elif var_mode == "baseline":
         y_pred = (1 / (1 + np.exp(-y_pred))).astype(float)
@@ -111,6 +123,23 @@ def performance_metrics(y_true, y_pred, var_mode="baseline", var_threshold=0.5):
         "recall": recall,
         "f1_score": f1,
     }
+
+
+def reduce_dataset(data, num_object_queries=None):
+    """utils.py:272-287: labels [N, 6 users, 9 activities] -> [N, 5 slots, 10 classes] for the multi-head sibling: the first
+    all-zero user row is dropped, a "nobody" class column is appended and set on the remaining empty rows (optionally
+    padded with "nobody" rows up to ``num_object_queries``)."""
+    nobody = np.zeros(data.shape[-1] + 1)
+    nobody[-1] = 1
+    out = []
+    for sample in data:
+        new = np.delete(sample, (sample.sum(axis=1) == 0).argmax(), axis=0)
+        new = np.hstack((new, np.zeros((new.shape[0], 1))))
+        new[new.sum(axis=1) == 0, :] = nobody
+        if num_object_queries:
+            new = np.concatenate((new, np.repeat([nobody], num_object_queries - new.shape[0], axis=0)))
+        out.append(new)
+    return np.array(out)
 
 
 def save_model_components(preset, model):

@@ -15,6 +15,7 @@ restatement or by the product package.  Fixtures:
                       grad norms, eval-mode logits, per-parameter init checksums for seed 39
   metrics.npz         utils.performance_metrics(var_mode="baseline") on seeded random logits/labels
   that_count_pred.npz model/that_count_pred.py THAT_COUNT_PRED + SmoothL1Loss: logits, grads, 2 Adam steps, count metrics
+  that_multi_head.npz model/that_multi_head.py five-head THAT + PermutationMatchingLoss: logits, grads, 2 Adam steps, loss KATs
   labels.npz + annotation_excerpt.csv   load_data.encode_* on an excerpt of dataset/annotation.csv
   augment_stats.npz   moments of train.py::apply_augmentation output (statistical fixture)
 """
@@ -247,6 +248,63 @@ def count_pred_case(ns):
     print("that_count_pred: losses", losses, "total_error", float(res["total_error"]))
 
 
+def multi_head_case(ns):
+    """Sibling head: the reference's five-head THAT (model/that_multi_head.py:180-306) with
+    PermutationMatchingLoss (:309-342), one forward + backward and 2 Adam steps (weight_decay 0, :414-416).  The
+    reference's ``multi_head`` metrics branch does not run (utils.py:221 indexes ``y_pred[-1]`` of a [B,5,C] array and then
+    unpacks three dimensions), so only model + loss are pinned."""
+    import importlib.util
+    from oracle.ref_import import REF_WIFI
+    spec = importlib.util.spec_from_file_location("ref_model_that_multi_head", os.path.join(REF_WIFI, "model", "that_multi_head.py"))
+    mod = importlib.util.module_from_spec(spec)
+    spec.loader.exec_module(mod)
+    T, F, C, B, H = 400, 30, 10, 6, 5
+    torch.manual_seed(39)
+    m = mod.THAT((T, F), [C])
+    for sub in m.modules():
+        if isinstance(sub, torch.nn.Dropout):
+            sub.p = 0.0
+    g = torch.Generator().manual_seed(8642)
+    x = torch.rand(B, T, F, generator=g) * 20
+    cls = torch.randint(0, C, (B, H), generator=g)
+    cls[:, 3:] = C - 1                                          # most slots empty: the last class is "nobody" (utils.py:227)
+    y = torch.nn.functional.one_hot(cls, C).float()             # [B, 5, C]
+    rec = {"x": x.numpy(), "y": y.numpy(), "dims": np.array([T, F, C, B, H])}
+    for k, v in m.state_dict().items():
+        rec["w/" + k] = v.detach().clone().numpy()
+    opt = torch.optim.Adam(m.parameters(), lr=5e-4, weight_decay=0)
+    loss = mod.PermutationMatchingLoss()
+    losses = []
+    for s in range(2):
+        m.train()
+        pred = m(x)                                             # [B, 5, C]
+        lv = loss(pred, y)
+        opt.zero_grad()
+        lv.backward()
+        if s == 0:
+            rec["logits_train"] = pred.detach().numpy()
+            for k, p_ in m.named_parameters():
+                if p_.grad is not None:
+                    rec["g/" + k] = p_.grad.detach().clone().numpy()
+        opt.step()
+        losses.append(lv.item())
+    rec["traj_losses"] = np.array(losses, dtype=np.float64)
+    for k, v in m.state_dict().items():
+        rec["traj_w/" + k] = v.detach().clone().numpy()
+    # known answers for the loss alone (ties included: two identical heads)
+    gl = torch.Generator().manual_seed(77)
+    lp = torch.randn(16, H, C, generator=gl)
+    lp[5, 1] = lp[5, 0]
+    lt = torch.nn.functional.one_hot(torch.randint(0, C, (16, H), generator=gl), C).float()
+    lp.requires_grad_(True)
+    lv = loss(lp, lt)
+    lv.backward()
+    rec["loss_pred"], rec["loss_target"] = lp.detach().numpy(), lt.numpy()
+    rec["loss_value"], rec["loss_grad"] = np.float64(lv.item()), lp.grad.numpy()
+    np.savez_compressed(os.path.join(GOLD, "that_multi_head.npz"), **rec)
+    print("that_multi_head: losses", losses, "loss-only", lv.item(), "keys", len(m.state_dict()))
+
+
 def main():
     os.makedirs(GOLD, exist_ok=True)
     torch.set_num_threads(max(1, os.cpu_count() or 1))
@@ -258,6 +316,7 @@ def main():
     labels_case(ns)
     augment_case(ns)
     count_pred_case(ns)
+    multi_head_case(ns)
 
 
 if __name__ == "__main__":

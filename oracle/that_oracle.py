@@ -149,7 +149,14 @@ def that_forward(sd: Dict[str, torch.Tensor], x: torch.Tensor, training: bool = 
     right = right.transpose(1, 2)
     right = drop(torch.cat([_head(sd, "layer_right_cnn_0", right), _head(sd, "layer_right_cnn_1", right)], -1), 0.5)
 
-    return Fn.linear(torch.cat([left, right], -1), sd["layer_output.weight"], sd["layer_output.bias"])
+    feat = torch.cat([left, right], -1)
+    if "layer_output.0.weight" in sd:
+        # model/that_multi_head.py:194-196,304-305: five Linear(288, out) heads stacked -> [B, 5, out]
+        n = 0
+        while f"layer_output.{n}.weight" in sd:
+            n += 1
+        return torch.stack([Fn.linear(feat, sd[f"layer_output.{h}.weight"], sd[f"layer_output.{h}.bias"]) for h in range(n)], 1)
+    return Fn.linear(feat, sd["layer_output.weight"], sd["layer_output.bias"])
 
 
 # ----------------------------------------------------------------------------------------------
@@ -158,6 +165,26 @@ def that_forward(sd: Dict[str, torch.Tensor], x: torch.Tensor, training: bool = 
 def bce_with_logits(z: torch.Tensor, y: torch.Tensor, pos_weight: float = 4.0) -> torch.Tensor:
     """mean over B*out of -(w*y*log sigmoid(z) + (1-y)*log sigmoid(-z))   (that.py:401, train.py:97)."""
     return -(pos_weight * y * Fn.logsigmoid(z) + (1 - y) * Fn.logsigmoid(-z)).mean()
+
+
+def permutation_matching_loss(pred: torch.Tensor, target: torch.Tensor):
+    """model/that_multi_head.py:309-342 (PermutationMatchingLoss).  pred, target: [B, H, C]; the target class of slot t is
+    argmax(target[b, t]).  Per sample the permutation perm (slot t is scored against head perm[t]) with the smallest mean
+    cross-entropy is chosen -- the FIRST one in itertools.permutations order on ties, because the reference keeps the
+    incumbent unless ``loss < best`` -- and the loss is the mean cross-entropy of the re-ordered heads over B*H.
+    Returns (loss, best permutation per sample [B, H])."""
+    from itertools import permutations
+    B, H, C = pred.shape
+    logp = Fn.log_softmax(pred, dim=-1)                                     # [B, H, C]
+    cls = target.argmax(dim=-1)                                             # [B, H]
+    # cost[b, h, t] = CE(head h, class of slot t)
+    cost = -logp.gather(2, cls.unsqueeze(1).expand(B, H, H))                # [B, H(head), H(slot)]
+    perms = torch.tensor(list(permutations(range(H))), dtype=torch.long)    # [P, H]
+    slot = torch.arange(H)
+    tot = cost.detach()[:, perms, slot].sum(-1) / H                         # [B, P] mean CE of each permutation
+    best = perms[tot.argmin(dim=1)]                                         # first minimum = reference tie rule
+    loss = cost[torch.arange(B).unsqueeze(1), best, slot].mean()
+    return loss, best
 
 
 def apply_augmentation(x: torch.Tensor, gen: Optional[torch.Generator] = None) -> torch.Tensor:

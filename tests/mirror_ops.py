@@ -337,6 +337,26 @@ class MirrorOps:
         if dz is not None:
             dz[:rows, :cols] = torch.where(quad, d / beta, torch.sign(d)) * (grad_scale / (rows * cols))
 
+    def perm_ce(self, z, y, B, heads, classes, cpitch, grad_scale, loss, dz, best_perm=None):
+        """PermutationMatchingLoss (model/that_multi_head.py:309-342): first minimum over itertools.permutations."""
+        from itertools import permutations
+        zz = z[:B, :heads * cpitch].float().view(B, heads, cpitch)[:, :, :classes]
+        cls = y[:B, :heads * classes].float().view(B, heads, classes).argmax(-1)
+        logp = torch.log_softmax(zz, -1)
+        cost = -logp.gather(2, cls.unsqueeze(1).expand(B, heads, heads))            # [B, head, slot]
+        perms = torch.tensor(list(permutations(range(heads))), dtype=torch.long, device=z.device)
+        slot = torch.arange(heads, device=z.device)
+        best = perms[(cost[:, perms, slot].sum(-1) / heads).argmin(1)]               # [B, slot] -> head
+        loss[0] = cost[torch.arange(B, device=z.device).unsqueeze(1), best, slot].mean()
+        if best_perm is not None:
+            best_perm[:B * heads] = best.reshape(-1).to(best_perm.dtype)
+        if dz is not None:
+            g = torch.softmax(zz, -1)
+            onehot = torch.zeros_like(g)
+            onehot[torch.arange(B, device=z.device).unsqueeze(1), best, cls] = 1.0
+            dz[:B, :heads * cpitch] = 0
+            dz[:B, :heads * cpitch].view(B, heads, cpitch)[:, :, :classes] = (g - onehot) * (grad_scale / (B * heads))
+
     def adam_flat(self, p, g, m, v, n, lr, b1, b2, eps, wd, step, grad_scale):
         t = int(step.item())
         gg = g[:n] * grad_scale + wd * p[:n]

@@ -444,3 +444,76 @@ def test_count_pred_sibling_head_smooth_l1(gold):
         if k.startswith("traj_w/") and not k.endswith(".0.bias"):
             diff = (sdm[k[7:]].float().cpu() - torch.from_numpy(g[k]).float()).abs()
             assert diff.max().item() < 2.1e-3 and (diff > 2e-4).float().mean().item() < 1e-3, k
+
+
+@pytest.mark.parametrize("mode", ["fp32", "bf16"])
+def test_multi_head_sibling_perm_ce(gold, mode):
+    """THAT_MULTI_HEAD + PermutationMatchingLoss (model/that_multi_head.py): logits [B,5,C], loss and gradients of the
+    autograd path, and a 2-step Adam trajectory of the fused path (csi_perm_ce), against the reference fixture."""
+    from multi_modal_csi_b200 import THAT_MULTI_HEAD, FusedAdam, PermutationMatchingLoss
+    g = gold("that_multi_head.npz")
+    T, F, C, B, H = [int(v) for v in g["dims"]]
+    sd = {k[2:]: torch.from_numpy(g[k]) for k in g.files if k.startswith("w/")}
+    x, y = torch.from_numpy(g["x"]).cuda(), torch.from_numpy(g["y"]).cuda()
+    tl, tg = TOL[mode]
+    m = THAT_MULTI_HEAD((T, F), [C], act_dtype=mode)
+    m.load_state_dict(sd)
+    m.dropout_enabled = False
+    m = m.to("cuda").train()
+    pred = m(x)
+    assert pred.shape == (B, H, C)
+    assert nrel(pred, torch.from_numpy(g["logits_train"])) < tl
+    loss = PermutationMatchingLoss()(pred, y)
+    assert abs(loss.item() - float(g["traj_losses"][0])) < 10 * tl * float(g["traj_losses"][0])
+    loss.backward()
+    ge, worst = grad_err(m, {k[2:]: torch.from_numpy(g[k]) for k in g.files if k.startswith("g/")})
+    assert ge < tg, (ge, worst)
+    # loss kernel alone against the reference's known answers (one sample has two identical heads: tie rule)
+    lp = torch.from_numpy(g["loss_pred"]).cuda().requires_grad_(True)
+    lv = PermutationMatchingLoss()(lp, torch.from_numpy(g["loss_target"]).cuda())
+    lv.backward()
+    assert abs(lv.item() - float(g["loss_value"])) < 1e-5
+    assert nrel(lp.grad, torch.from_numpy(g["loss_grad"])) < 1e-5
+    if mode != "fp32":
+        return
+    mf = THAT_MULTI_HEAD((T, F), [C], act_dtype="fp32")
+    mf.load_state_dict(sd)
+    mf.dropout_enabled = False
+    mf = mf.to("cuda").train()
+    opt = FusedAdam(mf.parameters(), lr=5e-4, weight_decay=0)
+    for s_ in range(2):
+        loss, logits = mf.fused_train_step(x, y, opt, augment=False, loss_kind="perm_ce")
+        ref = float(g["traj_losses"][s_])
+        assert logits.shape == (B, H, C) and abs(loss.item() - ref) < 2e-4 * max(1.0, ref)
+    sdm = mf.state_dict()
+    for k in g.files:                       # weight_decay 0: see test_count_pred_sibling_head_smooth_l1 for the tolerance
+        if k.startswith("traj_w/") and not k.endswith(".0.bias"):
+            diff = (sdm[k[7:]].float().cpu() - torch.from_numpy(g[k]).float()).abs()
+            assert diff.max().item() < 2.1e-3 and (diff > 2e-4).float().mean().item() < 1e-3, k
+
+
+def test_multi_head_train_loop_with_schedule(monkeypatch):
+    """train(..., var_mode="multi_head") (train.py:57-63,101-102): fused step with csi_perm_ce, per-step cosine schedule
+    with warm-up driving FusedAdam's learning rate, multi_head count metrics at the end of every epoch."""
+    from torch.utils.data import TensorDataset
+    from multi_modal_csi_b200 import THAT_MULTI_HEAD, FusedAdam, PermutationMatchingLoss
+    from multi_modal_csi_b200.preset import preset
+    from multi_modal_csi_b200.train import train
+    monkeypatch.setenv("WANDB_MODE", "disabled")
+    T, F, C, H, N = 400, 30, 10, 5, 16
+    g = torch.Generator().manual_seed(3)
+    x = torch.rand(N, T, F, generator=g) * 20
+    y = torch.nn.functional.one_hot(torch.randint(0, C, (N, H), generator=g), C).float()
+    monkeypatch.setitem(preset["nn"], "epoch", 3)
+    monkeypatch.setitem(preset["nn"], "scheduler", {"type": "cosine_warmup", "num_warmup_epochs": 1, "min_lr_ratio": 0.05})
+    torch.manual_seed(39)
+    m = THAT_MULTI_HEAD((T, F), [C], act_dtype="bf16", max_batch=4).to("cuda")
+    opt = FusedAdam(m.parameters(), lr=1e-3, weight_decay=0)
+    w0 = m.flat_params.clone()
+    sd = train(m, opt, PermutationMatchingLoss(), TensorDataset(x[:12], y[:12]), TensorDataset(x[12:], y[12:]), 0.5, 4, 3,
+               torch.device("cuda"), "multi_head")
+    assert set(sd.keys()) == set(m.state_dict().keys()) and len(sd) == 171
+    assert not torch.equal(w0, m.flat_params) and bool(torch.isfinite(m.flat_params).all())
+    # 3 epochs x 3 loader batches, the last batch of every epoch skipped (train.py:81): 6 scheduler steps, warm-up of 3
+    lr = opt.param_groups[0]["lr"]
+    assert 0.05e-3 <= lr < 1e-3

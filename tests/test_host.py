@@ -130,7 +130,9 @@ def test_metrics_match_reference_fixture(gold):
         assert np.allclose(np.asarray(v, dtype=np.float64), g["mq/" + k], rtol=1e-9, atol=1e-12, equal_nan=True), k
     json.dumps(res, cls=NumpyEncoder)
     with pytest.raises(ValueError):
-        performance_metrics(g["y_true"], g["logits"], var_mode="multi_head")
+        performance_metrics(g["y_true"], g["logits"], var_mode="multi_head")       # needs [B, heads, classes] arrays
+    with pytest.raises(ValueError):
+        performance_metrics(g["y_true"], g["logits"], var_mode="no_such_mode")
 
 
 def test_label_encoders_match_reference_fixture(gold):
@@ -279,6 +281,67 @@ def test_count_pred_sibling_matches_reference_fixture(gold):
     res = performance_metrics(g["m_y_true"], g["m_y_pred"], var_mode="count_classification")
     for k, v in res.items():
         assert np.allclose(np.asarray(v, dtype=np.float64), g["m/" + k], rtol=1e-9, atol=1e-12, equal_nan=True), k
+
+
+def test_multi_head_sibling_matches_reference_fixture(gold):
+    """Five-head THAT + PermutationMatchingLoss (model/that_multi_head.py:180-342) against the fixture generated from the
+    unmodified reference: initial weights under the reference seed (171 keys, heads registered first), the oracle's
+    forward and loss, the loss-only known answers (ties included), and the engine's launch sequence through the mirror
+    kernels (logits, loss, every gradient)."""
+    from mirror_ops import MirrorOps
+    from oracle import that_oracle as O
+    from multi_modal_csi_b200 import THAT_MULTI_HEAD
+    from multi_modal_csi_b200.utils import performance_metrics
+    g = gold("that_multi_head.npz")
+    T, F, C, B, H = [int(v) for v in g["dims"]]
+    torch.manual_seed(39)
+    m = THAT_MULTI_HEAD((T, F), [C], act_dtype="fp32")
+    sd = m.state_dict()
+    keys = [k[2:] for k in g.files if k.startswith("w/")]
+    assert list(sd.keys()) == keys and len(keys) == 171                  # same keys in the same (registration) order
+    for k in keys:
+        assert torch.equal(sd[k].cpu(), torch.from_numpy(g["w/" + k])), k
+    x, y = torch.from_numpy(g["x"]), torch.from_numpy(g["y"])
+    # oracle restatement
+    sd_o = {k: v.clone() for k, v in sd.items()}
+    pred = O.that_forward(sd_o, x, training=True)
+    assert pred.shape == (B, H, C) and torch.allclose(pred, torch.from_numpy(g["logits_train"]), rtol=1e-4, atol=1e-5)
+    lv, _ = O.permutation_matching_loss(pred, y)
+    assert abs(lv.item() - float(g["traj_losses"][0])) < 1e-5
+    lp = torch.from_numpy(g["loss_pred"]).requires_grad_(True)
+    lk, best = O.permutation_matching_loss(lp, torch.from_numpy(g["loss_target"]))
+    lk.backward()
+    assert abs(lk.item() - float(g["loss_value"])) < 1e-6 and torch.allclose(lp.grad, torch.from_numpy(g["loss_grad"]), atol=1e-7)
+    assert sorted(best[5].tolist()) == list(range(H))                    # the sample with two identical heads
+    # engine sequencing + the mirror of csi_perm_ce
+    m._ops_override = MirrorOps()
+    m.dropout_enabled = False
+    m.train()
+    eng = m._engine_for(B)
+    logits = eng.forward(x, B, training=True, dropout=False)
+    assert torch.allclose(logits, torch.from_numpy(g["logits_train"]), rtol=1e-4, atol=1e-5)
+    eng.loss_kind = "perm_ce"
+    loss = eng.loss_fwd_bwd(y.reshape(B, -1).float(), B)
+    assert abs(loss.item() - float(g["traj_losses"][0])) < 1e-5
+    eng.backward(None, B, dropout=False)
+    m._attach_grads()
+    for k, p in m.named_parameters():
+        if "g/" + k in g.files and not k.endswith(".0.bias"):            # conv biases feed a train-mode BatchNorm: exactly 0 here
+            r = torch.from_numpy(g["g/" + k])
+            assert ((p.grad - r).norm() / (r.norm() + 1e-12)).item() < 2e-4, k
+    # count metrics of the multi_head mode (utils.py:220-228 as intended: 3-D predictions, last class dropped)
+    res = performance_metrics(g["y"], g["logits_train"], var_mode="multi_head")
+    cnt_pred = np.eye(C)[g["logits_train"].argmax(-1)].sum(1)[:, :-1]
+    assert np.isclose(res["total_error"], np.abs(g["y"].sum(1)[:, :-1] - cnt_pred).sum() / B)
+    res4 = performance_metrics(g["y"], g["logits_train"][None], var_mode="multi_head")      # reference-style stacked input
+    assert np.isclose(res4["total_error"], res["total_error"])
+    # label transform of run_main.py:39-40 (utils.py:272-287): [6 users, 9 activities] -> [5 slots, 10 classes]
+    from multi_modal_csi_b200.utils import reduce_dataset
+    lab = np.zeros((2, 6, 9))
+    lab[0, 0, 3] = lab[0, 2, 5] = 1
+    red = reduce_dataset(lab)
+    assert red.shape == (2, 5, 10) and red[0].argmax(-1).tolist() == [3, 5, 9, 9, 9] and red[1].argmax(-1).tolist() == [9] * 5
+    assert np.all(red.sum(-1) == 1)
 
 
 # ------------------------------------------------------------------------------------------------ C ABI
