@@ -93,6 +93,12 @@ class THATEngine:
     def _alloc(self):
         dev, B, adt, f32 = self.dev, self.B, self.adt, torch.float32
         self.s: Dict[str, dict] = {}
+        # BatchNorm statistics of every encoder live in two fp64 pools (forward sums, backward sums) so that one fill
+        # per pass zeroes them all instead of one tiny fill per encoder
+        n_stat = sum(sg.n_enc * 2 * 3 * sg.Dp for sg in self.g.streams)
+        self.stat_pool = torch.zeros(n_stat, dtype=torch.float64, device=dev)
+        self.red_pool = torch.zeros(n_stat, dtype=torch.float64, device=dev)
+        stat_off = 0
         for sg in self.g.streams:
             rows, Dp = sg.rows(B), sg.Dp
             st = {"x0": _TokBuf(rows, Dp, f32, dev), "enc": []}
@@ -107,7 +113,8 @@ class THATEngine:
                     "rstd1": torch.zeros(rows, device=dev),
                     "z": _TokBuf(rows, 3 * Dp, adt, dev),
                     "bn_mean": torch.zeros(3 * Dp, device=dev), "bn_invstd": torch.zeros(3 * Dp, device=dev),
-                    "bn_sums": torch.zeros(2 * 3 * Dp, dtype=torch.float64, device=dev),
+                    "bn_sums": self.stat_pool[stat_off + len(st["enc"]) * 6 * Dp:stat_off + (len(st["enc"]) + 1) * 6 * Dp],
+                    "red": self.red_pool[stat_off + len(st["enc"]) * 6 * Dp:stat_off + (len(st["enc"]) + 1) * 6 * Dp],
                     "out": _TokBuf(rows, Dp, f32, dev),
                     # dropout keep bits of the BN block (3 branches + output), written by bn_act_fwd for its backward
                     "dmask": torch.zeros(rows * (Dp // 8), dtype=torch.int32, device=dev),
@@ -127,7 +134,7 @@ class THATEngine:
             st["dt0"] = _TokBuf(rows, Dp, adt, dev)
             st["dp"] = _TokBuf(rows, 2 * sg.head_np, adt, dev)
             st["dhn"] = _TokBuf(rows, Dp, adt, dev)
-            st["red"] = torch.zeros(2 * 3 * Dp, dtype=torch.float64, device=dev)
+            stat_off += sg.n_enc * 6 * Dp
             self.s[sg.name] = st
         L, F = self.g.left.L, self.g.F
         self.pe = torch.zeros(L, self.g.left.Dp, device=dev)
@@ -225,6 +232,8 @@ class THATEngine:
         ops, g = self.ops, self.g
         pd = P_DROP if (training and dropout) else 0.0
         pf = P_FEAT if (training and dropout) else 0.0
+        if training:
+            self.stat_pool.zero_()
         join = self._fork(lambda: self._forward_stream(1, B, training, pd))
         self._forward_stream(0, B, training, pd)
         join()
@@ -275,7 +284,6 @@ class THATEngine:
             rm = self._bn3(sg, e, "1.running_mean", buf=True)
             rv = self._bn3(sg, e, "1.running_var", buf=True)
             if training:
-                a["bn_sums"].zero_()
                 ops.bn_stats(a["z"].t, B, L, HALO, 3 * Dp, a["bn_sums"])
                 ops.bn_finalize(a["bn_sums"], Dp, d, 3, B * L, cb, rm, rv,
                                 self._bn3(sg, e, "1.num_batches_tracked", buf=True), BN_MOMENTUM, BN_EPS,
@@ -317,6 +325,7 @@ class THATEngine:
             return self._backward_stream(0, B, pd, range(0, 1), head=False) if nl > 1 else None
         if zero_grads:
             self.grads.zero_()
+        self.red_pool.zero_()                             # parts 1 and 2 use disjoint slices: zeroed once, here
         if dlogits is not None:
             if g.heads == 1:
                 self.dlogits[:B, :g.out].copy_(dlogits)
@@ -388,10 +397,9 @@ class THATEngine:
             x_in = st["enc"][e - 1]["out"] if e > 0 else st["x0"]
             gam, bet = self._bn3(sg, e, "1.weight"), self._bn3(sg, e, "1.bias")
             sb, so = site(si, e, LY.SITE_BRANCH), site(si, e, LY.SITE_SUM)
-            st["red"].zero_()
             ops.bn_act_bwd_reduce(dout.t, a["z"].t, a["bn_mean"], a["bn_invstd"], gam, bet, B, L, d, HALO, 3,
-                                  pd, sb, pd, so, self.rng, st["red"], a["dmask"] if pd > 0.0 else None)
-            ops.bn_act_bwd_dz(dout.t, a["z"].t, a["bn_mean"], a["bn_invstd"], gam, bet, st["red"], B, L, d,
+                                  pd, sb, pd, so, self.rng, a["red"], a["dmask"] if pd > 0.0 else None)
+            ops.bn_act_bwd_dz(dout.t, a["z"].t, a["bn_mean"], a["bn_invstd"], gam, bet, a["red"], B, L, d,
                               HALO, 3, pd, sb, pd, so, self.rng, st["dz"].t,
                               self._bn3(sg, e, "1.weight", grad=True), self._bn3(sg, e, "1.bias", grad=True),
                               a["dmask"] if pd > 0.0 else None)
