@@ -16,6 +16,8 @@ the algorithm of the reference files below (paths relative to /root/reference):
   * benchmark/wifi_csi/that.py:393-397        Adam(lr, weight_decay) coupled L2 -> :func:`adam_update`
   * benchmark/wifi_csi/utils.py:147-183,213-270  prediction rule + metrics -> :func:`predict_counts`
   * benchmark/wifi_csi/load_data.py:62-78     front zero-pad to T -> :func:`front_pad`
+  * benchmark/wifi_csi/model/that_multi_head.py:194-196,304-342  five output heads + PermutationMatchingLoss
+                                              -> :func:`that_forward` (stacked heads), :func:`permutation_matching_loss`
 
 Pinning: the reference ships no tests or golden vectors for this path, so the
 restatement is pinned against (1) the unmodified reference executed in the build container

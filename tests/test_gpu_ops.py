@@ -564,3 +564,61 @@ def test_smooth_l1_matches_torch(ops, mir):
         ref.backward()
         assert abs(loss.item() - ref.item()) < 1e-6 * max(1.0, ref.item())
         assert relerr(dz[:, :cols], 2.0 * zz.grad) < 1e-6
+
+
+# ------------------------------------------------------------------------------------------------ edge cases / errors
+def test_empty_batches_and_argument_errors(ops):
+    """B = 0 is a no-op for every row-walking entry point (nothing launched, buffers untouched); malformed calls return a
+    negative csi_status with a message in csi_last_error() -- surfaced as RuntimeError by the binding, never a crash."""
+    L, d = 150, 270
+    Dp = ru(d, 16)
+    _, x = tokbuf(1, L, Dp, torch.float32, fill=1.0, gen=gen(20), ncols=d)
+    _, y = tokbuf(1, L, Dp, torch.bfloat16)
+    mean, rstd = torch.full((x.shape[0],), 7.0, device="cuda"), torch.full((x.shape[0],), 7.0, device="cuda")
+    g, b = torch.ones(d, device="cuda"), torch.zeros(d, device="cuda")
+    ops.layernorm_fwd(x, g, b, y, mean, rstd, 0, L, d, HALO, 1e-6)
+    sums = torch.zeros(2 * Dp, dtype=torch.float64, device="cuda")
+    ops.bn_stats(y, 0, L, HALO, Dp, sums)
+    raw = torch.zeros(1, 3000, 270, device="cuda")
+    _, left = tokbuf(1, L, Dp, torch.float32)
+    _, right = tokbuf(1, d, ru(L, 16), torch.float32)
+    ops.pool_dual(raw, None, None, 0, 3000, 270, None, left, right, HALO, 0, None)
+    torch.cuda.synchronize()
+    assert float(y.float().abs().max()) == 0.0 and float(mean.min()) == 7.0 and float(sums.abs().max()) == 0.0
+    assert float(left.abs().max()) == 0.0
+    with pytest.raises(RuntimeError, match="multiple of 20"):
+        ops.pool_dual(raw, None, None, 1, 2999, 270, None, left, right, HALO, 0, None)
+    with pytest.raises(RuntimeError, match="rng"):
+        ops.pool_dual(raw, None, None, 1, 3000, 270, None, left, right, HALO, 1, None)      # augmentation without rng
+    with pytest.raises(RuntimeError, match="heads"):
+        z = torch.zeros(2, 7 * 16, device="cuda")
+        ops.perm_ce(z, torch.zeros(2, 70, device="cuda"), 2, 7, 10, 16, 1.0, torch.zeros(1, device="cuda"), None)
+
+
+def test_perm_ce_matches_mirror(ops, mir):
+    """csi_perm_ce against the torch mirror on random logits with duplicated target classes.  (Permutations that tie
+    exactly in real arithmetic -- two slots with the same class -- differ by summation order in fp32, so WHICH of them
+    wins is implementation noise in the reference as well; loss and gradient do not depend on it.  The reference's own
+    tie sample with two identical heads is pinned by the fixture test in test_gpu_model.py.)"""
+    B, H, C, cp = 300, 5, 10, 16
+    g = gen(21)
+    z = torch.zeros(B, H * cp, device="cuda")
+    v = torch.randn(B, H, C, device="cuda", generator=g)
+    z.view(B, H, cp)[:, :, :C] = v
+    cls = torch.randint(0, C, (B, H), device="cuda", generator=g)
+    cls[::4, 1] = cls[::4, 3]                                          # identical target classes
+    y = torch.nn.functional.one_hot(cls, C).float().reshape(B, H * C).contiguous()
+    outs = []
+    for o in (ops, mir):
+        loss, dz = torch.zeros(1, device="cuda"), torch.full((B, H * cp), 3.0, device="cuda")
+        best = torch.zeros(B * H, dtype=torch.int32, device="cuda")
+        o.perm_ce(z, y, B, H, C, cp, 2.0, loss, dz, best)
+        outs.append((loss.clone(), dz, best))
+    assert abs(outs[0][0].item() - outs[1][0].item()) < 1e-5
+    assert relerr(outs[0][1], outs[1][1]) < 1e-5
+    # the matched heads are a permutation, and they agree with the mirror wherever the slot's class is unique in the sample
+    bk, bm = outs[0][2].view(B, H).long(), outs[1][2].view(B, H).long()
+    assert bool((bk.sort(1).values == torch.arange(H, device="cuda")).all())
+    uniq = (cls.unsqueeze(2) == cls.unsqueeze(1)).sum(2) == 1
+    assert torch.equal(bk[uniq], bm[uniq])
+    assert float(outs[0][1].view(B, H, cp)[:, :, C:].abs().max()) == 0.0                  # pad columns are written as zero
