@@ -15,6 +15,7 @@ restatement or by the product package.  Fixtures:
                       grad norms, eval-mode logits, per-parameter init checksums for seed 39
   metrics.npz         utils.performance_metrics(var_mode="baseline") on seeded random logits/labels
   that_count_pred.npz model/that_count_pred.py THAT_COUNT_PRED + SmoothL1Loss: logits, grads, 2 Adam steps, count metrics
+  cnn2d_anchor.npz    model/cnn_2d.py CNN_2D (CSI-as-image): init checksums, logits, loss, gradient norms
   that_multi_head.npz model/that_multi_head.py five-head THAT + PermutationMatchingLoss: logits, grads, 2 Adam steps, loss KATs
   labels.npz + annotation_excerpt.csv   load_data.encode_* on an excerpt of dataset/annotation.csv
   augment_stats.npz   moments of train.py::apply_augmentation output (statistical fixture)
@@ -305,6 +306,48 @@ def multi_head_case(ns):
     print("that_multi_head: losses", losses, "loss-only", lv.item(), "keys", len(m.state_dict()))
 
 
+def cnn2d_case(ns):
+    """CSI-as-image path (BASELINE config 4's in-reference analogue): model/cnn_2d.py CNN_2D at the full
+    feature width (F=270; the 27/15/7 kernels with strides 7/3/1 need it) on a short window, BCE(pos_weight=6).  Only
+    checksums and outputs are stored: weights are re-created from the reference seed by oracle.cnn2d_oracle.cnn2d_init
+    and the input from its generator seed."""
+    import importlib.util
+    from oracle.ref_import import REF_WIFI
+    spec = importlib.util.spec_from_file_location("ref_model_cnn_2d", os.path.join(REF_WIFI, "model", "cnn_2d.py"))
+    mod = importlib.util.module_from_spec(spec)
+    spec.loader.exec_module(mod)
+    T, F, out, B = 300, 270, 54, 3
+    torch.manual_seed(39)
+    m = mod.CNN_2D((T, F), (out,))
+    for sub in m.modules():
+        if isinstance(sub, torch.nn.Dropout):
+            sub.p = 0.0
+    rec = {"dims": np.array([T, F, out, B]), "keys": np.array(list(m.state_dict().keys()))}
+    for k, v in m.state_dict().items():
+        rec["init_sum/" + k] = np.float64(v.double().sum().item())
+        rec["init_abs/" + k] = np.float64(v.double().abs().sum().item())
+    g = torch.Generator().manual_seed(2468)
+    x = torch.rand(B, T, F, generator=g) * 20
+    y = (torch.rand(B, out, generator=g) < 0.15).float()
+    m.train()
+    logits = m(x)
+    loss = torch.nn.BCEWithLogitsLoss(pos_weight=torch.full((out,), 6.0))(logits, y)
+    loss.backward()
+    rec["logits_train"] = logits.detach().numpy()
+    rec["loss"] = np.float64(loss.item())
+    for k, p_ in m.named_parameters():
+        rec["gnorm/" + k] = np.float64(p_.grad.double().norm().item())
+        rec["gsum/" + k] = np.float64(p_.grad.double().sum().item())
+    for k, v in m.state_dict().items():
+        if "running" in k:
+            rec["stat/" + k] = v.detach().clone().numpy()
+    m.eval()
+    with torch.no_grad():
+        rec["logits_eval"] = m(x).numpy()
+    np.savez_compressed(os.path.join(GOLD, "cnn2d_anchor.npz"), **rec)
+    print("cnn2d_anchor: loss", loss.item(), "logits[0,:3]", logits[0, :3].tolist())
+
+
 def main():
     os.makedirs(GOLD, exist_ok=True)
     torch.set_num_threads(max(1, os.cpu_count() or 1))
@@ -317,6 +360,7 @@ def main():
     augment_case(ns)
     count_pred_case(ns)
     multi_head_case(ns)
+    cnn2d_case(ns)
 
 
 if __name__ == "__main__":

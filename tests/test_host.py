@@ -344,6 +344,34 @@ def test_multi_head_sibling_matches_reference_fixture(gold):
     assert np.all(red.sum(-1) == 1)
 
 
+def test_cnn2d_oracle_matches_reference_fixture(gold):
+    """Groundwork for the CSI-as-image path: the restatement of model/cnn_2d.py (CNN_2D) reproduces the
+    reference's initial weights under its seed (same RNG draw order), logits, loss, gradient norms, running statistics
+    and eval-mode logits.  No CUDA path is built on it yet."""
+    from oracle import cnn2d_oracle as C
+    g = gold("cnn2d_anchor.npz")
+    T, F, out, B = [int(v) for v in g["dims"]]
+    torch.manual_seed(39)
+    sd = C.cnn2d_init(out)
+    assert list(sd.keys()) == [str(k) for k in g["keys"]]
+    for k, v in sd.items():
+        assert abs(v.double().sum().item() - float(g["init_sum/" + k])) <= 1e-6 * max(1.0, float(g["init_abs/" + k])), k
+    gen = torch.Generator().manual_seed(2468)
+    x = torch.rand(B, T, F, generator=gen) * 20
+    y = (torch.rand(B, out, generator=gen) < 0.15).float()
+    logits, loss, grads = C.loss_and_grads(sd, x, y)
+    assert torch.allclose(logits, torch.from_numpy(g["logits_train"]), rtol=1e-4, atol=2e-5)
+    assert abs(loss.item() - float(g["loss"])) < 1e-5
+    for k, gr in grads.items():
+        ref = float(g["gnorm/" + k])
+        assert abs(gr.double().norm().item() - ref) <= 2e-4 * ref + 1e-9, k
+    C.cnn2d_forward(sd, x, training=True, update_stats=True)
+    for k in sd:
+        if "running" in k:
+            assert np.allclose(sd[k].numpy(), g["stat/" + k], rtol=1e-4, atol=1e-6), k
+    assert torch.allclose(C.cnn2d_forward(sd, x, training=False), torch.from_numpy(g["logits_eval"]), rtol=1e-4, atol=2e-5)
+
+
 # ------------------------------------------------------------------------------------------------ C ABI
 def test_library_exports_every_declared_symbol():
     from multi_modal_csi_b200 import ops
