@@ -1,6 +1,6 @@
 """Times csi_gemm_nt (tcgen05 v3) on the THAT step shapes with the output split into 1..4 column tiles per row tile
-(csi_set_gemm_ntn): the 308 row tiles of the left stream are 2.08 waves on 148 SMs, so narrower tiles trade operand
-re-reads for a fuller last wave.  Prints microseconds per call."""
+(csi_set_gemm_ntn; values below the minimum that fits one 256-column accumulator are raised to it, so N=270 runs with 2
+column tiles for ntn=1 and ntn=2).  Result at B=256: more column tiles never helped.  Prints us per call."""
 import sys, os, math, ctypes
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 import torch
@@ -13,6 +13,7 @@ rng = torch.tensor([1, 0], dtype=torch.int64, device="cuda")
 
 def run(M, N, Dp, k, cdt, res, ntn, reps=20):
     ops.lib.csi_set_gemm_ntn(ctypes.c_int(ntn))
+    torch.manual_seed(1)                                   # same operands for every ntn: the outputs must agree
     full = torch.randn(M + 2 * GUARD, Dp, device="cuda").to(torch.bfloat16)
     A = full[GUARD:GUARD + M]
     W = (torch.randn(N, k * Dp, device="cuda") / math.sqrt(k * Dp)).to(torch.bfloat16)
