@@ -475,3 +475,35 @@ def test_bench_family_table_and_roofline_schema():
     r = bench.roofline("gemm_nt", table, None, 256, peaks)
     assert r["bound"] == "tensor" and r["unit"] == "TFLOP/s" and abs(r["frac"] - 1000.0 / 1340.8) < 1e-9
     assert set(r) >= {"kernel", "bound", "achieved", "peak", "unit", "frac", "traffic", "launches", "ms_per_launch"}
+
+
+def test_cosine_schedule_with_warmup_matches_reference_formula():
+    """train.py:26-33: linear warm-up, cosine decay, floor at min_lr_ratio -- checked against the closed form and, in the
+    build container, against the reference's own get_cosine_schedule_with_warmup."""
+    import math
+    from multi_modal_csi_b200.train import cosine_schedule_with_warmup
+    lr0, warm, total, floor = 2e-3, 5, 40, 0.05
+    p = torch.nn.Parameter(torch.zeros(1))
+    opt = torch.optim.SGD([p], lr=lr0)
+    sch = cosine_schedule_with_warmup(opt, warm, total, floor)
+    ours = []
+    for _ in range(total + 3):
+        ours.append(opt.param_groups[0]["lr"])
+        opt.step()
+        sch.step()
+
+    def closed(s):
+        if s < warm:
+            return lr0 * s / warm
+        return lr0 * max(floor, 0.5 * (1.0 + math.cos(math.pi * (s - warm) / (total - warm))))
+    assert all(abs(a - closed(s)) < 1e-12 for s, a in enumerate(ours))
+    assert ours[0] == 0.0 and abs(ours[warm] - lr0) < 1e-15 and abs(ours[-1] - lr0 * floor) < 1e-15
+    from oracle.ref_import import reference_available, load_reference
+    if reference_available():
+        ref_train = load_reference().train
+        opt2 = torch.optim.SGD([torch.nn.Parameter(torch.zeros(1))], lr=lr0)
+        sch2 = ref_train.get_cosine_schedule_with_warmup(opt2, warm, total, floor)
+        for s in range(total + 3):
+            assert abs(opt2.param_groups[0]["lr"] - ours[s]) < 1e-15, s
+            opt2.step()
+            sch2.step()
