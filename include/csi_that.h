@@ -216,6 +216,14 @@ int csi_pack_weights(const float* params, void* packed, int dtype, const csi_pac
 
 /* Test hook: 1 = route every contraction/attention call to the FFMA kernels, 0 = tensor-core kernels where eligible. */
 int csi_set_force_simt(int on);
+/* bf16 dispatch is never silent: every bf16 contraction / attention call is counted by the kernel class that served it
+ * (tcgen05 / FFMA fallback for a shape the tcgen05 kernel cannot take / mma.sync attention).  In strict mode (on = 1:
+ * bench.py, the full-size tests) a bf16 call that would fall back to FFMA returns CSI_ERR_ARG instead. */
+int csi_set_strict_tc(int on);
+int csi_dispatch_counts(long long* tcgen05_calls, long long* ffma_fallback_calls, long long* mma_sync_calls, int reset);
+/* Attention core implementation per direction: 0 = measured-best per shape (default), 1 = tcgen05/TMEM kernels wherever
+ * eligible, 2 = mma.sync kernels only (dispatch.cu holds the measurements behind mode 0). */
+int csi_set_attn_impl(int fwd_mode, int bwd_mode);
 
 /* ---- a16: the reference decision rule (utils.py:147-183,234-239): sigmoid -> per user the arg-max class counts iff
  * its probability exceeds `threshold` (the reference hard-codes 0.5) -> per-class counts.  logits: fp32 [rows, ldz]

@@ -39,7 +39,8 @@ class _TokBuf:
 class THATEngine:
     def __init__(self, geom: ModelGeom, max_batch: int, params: torch.Tensor, grads: torch.Tensor,
                  arena: LY.Arena, buffers: Dict[str, torch.Tensor], frozen: Dict[str, torch.Tensor],
-                 act_dtype: torch.dtype = torch.bfloat16, ops=None, seed: int = 0):
+                 act_dtype: torch.dtype = torch.bfloat16, ops=None, seed: int = 0, rng: Optional[torch.Tensor] = None,
+                 opt_step: Optional[torch.Tensor] = None):
         self.g = geom
         self.B = int(max_batch)
         self.params = params              # flat fp32 arena (views of it are the nn.Parameters)
@@ -59,8 +60,11 @@ class THATEngine:
         self.packed_bias = torch.zeros(max(self.pack.bias_size, 1), dtype=torch.float32, device=self.dev)
         self.bias_table = ops.make_pack_table(self.pack.bias_entries, self.dev)
         self.loss_kind = "bce"                     # "bce" (THAT, that.py:401) | "smooth_l1" (THAT_COUNT_PRED)
-        self.rng = torch.tensor([seed, 0], dtype=torch.int64, device=self.dev)      # {seed, step}
-        self.opt_step = torch.ones(1, dtype=torch.int64, device=self.dev)           # 1-based Adam step
+        # {seed, step} of the Philox streams and the 1-based Adam step: device tensors owned by the model (THAT._counters)
+        # so that a rebuilt engine continues them; a bare engine (tests) makes its own
+        self.rng = rng if rng is not None else torch.tensor([seed, 0], dtype=torch.int64, device=self.dev)
+        self.opt_step = opt_step if opt_step is not None else torch.ones(1, dtype=torch.int64, device=self.dev)
+        self.rng_used = False             # a train-mode forward has drawn masks from the current Philox step
         self._alloc()
         self._graphs = {}
         self._graph_launches = {}
@@ -168,6 +172,11 @@ class THATEngine:
             walk(st)
         return n
 
+    def _alg(self, flops):
+        """Algorithmic FLOPs (true d, L, k: no head / channel / halo padding) of the NEXT contraction call: the roofline
+        numerator ops.NativeOps._work reports for it (BASELINE.md section 3 counts the same way)."""
+        self.ops.alg_flops = int(flops)
+
     # ------------------------------------------------------------------ weights
     def repack(self):
         """fp32 master weights -> GEMM operand copies (forward + data-gradient layouts) in the act dtype."""
@@ -239,6 +248,7 @@ class THATEngine:
         join()
         ops.alg_scale = 1.0
         ops.dropout_rows(self.feat, self.featd, B, LY.FEAT, pf, LY.SITE_FEAT, self.rng)
+        self._alg(2 * B * LY.FEAT * g.out * g.heads)
         if g.heads == 1:
             ops.gemm_nt(self.featd, self.W("f:layer_output.weight"), self.logits, B, g.out, [(0, 0, 0, LY.FEAT)],
                         self.P("layer_output.bias"), None, 0.0, 0, self.rng)
@@ -267,9 +277,11 @@ class THATEngine:
             a, p = st["enc"][e], sg.prefix(e)
             ops.layernorm_fwd(x_in.t, self.P(p + "layer_norm_0.weight"), self.P(p + "layer_norm_0.bias"),
                               a["t0"].t, a["mean0"], a["rstd0"], B, L, d, HALO, LN_EPS)
+            self._alg(2 * B * L * d * 3 * d)
             ops.gemm_nt(a["t0"].t, self.W("f:" + p + "layer_attention.in_proj_weight"), a["qkv"].t, rows,
                         sg.ld3, one, self.PB(p + "layer_attention.in_proj_bias"), None, 0.0, 0, self.rng)
             ops.attn_fwd(a["qkv"].t, a["o"].t, a["lse"], B, L, d, sg.H, sg.hp, HALO)
+            self._alg(2 * B * L * d * d)
             ops.gemm_nt(a["o"].t, self.W("f:" + p + "layer_attention.out_proj.weight"), a["t"].t, rows, d,
                         [(0, 0, 0, sg.dh)], self.P(p + "layer_attention.out_proj.bias"), x_in.t, pd,
                         site(si, e, LY.SITE_ATTN), self.rng)
@@ -278,6 +290,7 @@ class THATEngine:
             for j, k in enumerate(sg.kernels):
                 pl = (k - 1) // 2
                 segs = [(t - pl, 0, t * Dp, Dp) for t in range(k)]
+                self._alg(2 * B * L * d * d * k)
                 ops.gemm_nt(a["s"].t, self.W(f"f:{p}layer_cnn.{j}.0.weight"), a["z"].t[:, j * Dp:], rows, d,
                             segs, None, None, 0.0, 0, self.rng)
             cb = self._bn3(sg, e, "0.bias")
@@ -302,6 +315,7 @@ class THATEngine:
         for j, k in enumerate(sg.head_k):
             w = f"layer_{sg.name}_cnn_{j}"
             segs = [(t, 0, t * Dp, Dp) for t in range(k)]
+            self._alg(2 * B * (L - k + 1) * d * sg.head_n * k)          # valid convolution: L - k + 1 outputs per sample
             ops.gemm_nt(st["hn"].t, self.W("f:" + w + ".weight"), st["p"].t[:, j * sg.head_np:], rows,
                         sg.head_n, segs, self.P(w + ".bias"), None, 0.0, 0, self.rng)
         ops.head_reduce_fwd(st["p"].t, B, L, HALO, 2 * sg.head_n, sg.head_n, sg.head_k[0], sg.head_k[1],
@@ -335,8 +349,10 @@ class THATEngine:
         ops.dropout_rows(self.dlogits, self.dlogits_a, B, g.ld_out, 0.0, 0, self.rng)      # cast to act dtype
         for h, (wn, bn) in enumerate(g.output_names()):
             dl = self.dlogits_a[:, h * g.cp:]
+            self._alg(2 * B * LY.FEAT * g.out)
             ops.gemm_tn(dl, self.featd, self.G(wn), LY.FEAT, 1, B, g.out, [(0, 0, 0, LY.FEAT)])
             ops.colsum_tokens(dl, B, 1, 0, g.out, self.G(bn))
+        self._alg(2 * B * LY.FEAT * g.out * g.heads)
         ops.gemm_nt(self.dlogits_a, self.W("b:layer_output.weight"), self.dfeatd, B, LY.FEAT,
                     [(0, 0, 0, g.ld_out)], None, None, 0.0, 0, self.rng)
         ops.dropout_rows(self.dfeatd, self.dfeat, B, LY.FEAT, pf, LY.SITE_FEAT, self.rng)
@@ -381,11 +397,13 @@ class THATEngine:
             dsegs, seg = [], 0
             for j, k in enumerate(sg.head_k):
                 w = f"layer_{sg.name}_cnn_{j}"
+                self._alg(2 * B * (L - k + 1) * d * sg.head_n * k)
                 ops.gemm_tn(st["dp"].t[:, j * Np:], st["hn"].t, self.G(w + ".weight"), d * k, k, rows, sg.head_n,
                             [(t, 0, t, d) for t in range(k)])
                 ops.colsum_tokens(st["dp"].t[:, j * Np:], B, L, HALO, sg.head_n, self.G(w + ".bias"))
                 dsegs += [(-t, j * Np, (seg + t) * Np, Np) for t in range(k)]
                 seg += k
+            self._alg(sum(2 * B * (L - k + 1) * d * sg.head_n * k for k in sg.head_k))
             ops.gemm_nt(st["dp"].t, self.W(f"b:layer_{sg.name}_cnn"), st["dhn"].t, rows, d, dsegs, None, None,
                         0.0, 0, self.rng)
             nm = f"layer_{sg.name}_norm."
@@ -406,11 +424,13 @@ class THATEngine:
             dsegs, seg = [], 0
             for j, k in enumerate(sg.kernels):
                 pl = (k - 1) // 2
+                self._alg(2 * B * L * d * d * k)
                 ops.gemm_tn(st["dz"].t[:, j * Dp:], a["s"].t, self.G(f"{p}layer_cnn.{j}.0.weight"), d * k, k,
                             rows, d, [(t - pl, 0, t, d) for t in range(k)])
                 dsegs += [(pl - t, j * Dp, (seg + t) * Dp, Dp) for t in range(k)]
                 seg += k
             # the Conv1d biases feed a train-mode BatchNorm: their gradient is identically zero
+            self._alg(2 * B * L * d * d * sum(sg.kernels))
             ops.gemm_nt(st["dz"].t, self.W("b:" + p + "layer_cnn"), st["ds"].t, rows, d, dsegs, None, None,
                         0.0, 0, self.rng)
             ops.layernorm_bwd(st["ds"].t, a["t"].t, self.P(p + "layer_norm_1.weight"), a["mean1"], a["rstd1"],
@@ -418,16 +438,20 @@ class THATEngine:
                               self.G(p + "layer_norm_1.weight"), self.G(p + "layer_norm_1.bias"), B, L, d, HALO)
             one = [(0, 0, 0, d)]
             w = p + "layer_attention.out_proj."
+            self._alg(2 * B * L * d * d)
             ops.gemm_tn(st["dtm"].t, a["o"].t, self.G(w + "weight"), d, 1, rows, d, [(0, 0, 0, sg.dh)],
                         (0, 0), sg.grp)
             ops.colsum_tokens(st["dtm"].t, B, L, HALO, d, self.G(w + "bias"))
+            self._alg(2 * B * L * d * d)
             ops.gemm_nt(st["dtm"].t, self.W("b:" + w + "weight"), st["do"].t, rows, sg.dh, [(0, 0, 0, Dp)], None,
                         None, 0.0, 0, self.rng)
             w = p + "layer_attention.in_proj_"
             # the in_proj bias gradient (column sums of dqkv) is accumulated by the attention backward kernel itself
             ops.attn_bwd(a["qkv"].t, a["o"].t, st["do"].t, st["dqkv"].t, a["lse"], B, L, d, sg.H, sg.hp, HALO,
                          self.G(w + "bias"))
+            self._alg(2 * B * L * d * 3 * d)
             ops.gemm_tn(st["dqkv"].t, a["t0"].t, self.G(w + "weight"), d, 1, rows, sg.ld3, one, sg.grp, (0, 0))
+            self._alg(2 * B * L * d * 3 * d)
             ops.gemm_nt(st["dqkv"].t, self.W("b:" + w + "weight"), st["dt0"].t, rows, d, [(0, 0, 0, sg.ld3)],
                         None, None, 0.0, 0, self.rng)
             ops.layernorm_bwd(st["dt0"].t, x_in.t, self.P(p + "layer_norm_0.weight"), a["mean0"], a["rstd0"],
@@ -484,9 +508,29 @@ class THATEngine:
                                 self.dlogits if want_grad else None)
         return self.loss
 
+    # The Philox step is a property of the forward/backward pair, not of the optimizer: backward regenerates the masks
+    # its forward drew, then the step moves on -- whichever optimizer (or none) follows.
+    def begin_train_forward(self):
+        """Call before a train-mode forward: if the previous train forward never reached ``end_train_step`` (no
+        backward, e.g. two forwards in a row) its masks must not be reused."""
+        if self.rng_used:
+            self.ops.advance_counters(self.rng, None)
+        self.rng_used = True
+
+    def end_train_step(self):
+        """Call after the backward that belongs to the last train forward (autograd path)."""
+        if self.rng_used:
+            self.ops.advance_counters(self.rng, None)
+        self.rng_used = False
+
     def adam(self, m: torch.Tensor, v: torch.Tensor, lr: float, betas=(0.9, 0.999), eps: float = 1e-8,
-             weight_decay: float = 0.0, grad_scale: float = 1.0):
+             weight_decay: float = 0.0, grad_scale: float = 1.0, advance_rng: bool = False):
+        """One fused Adam launch over the arena; advances the Adam step and, on the fused train step
+        (``advance_rng``), the Philox step in the same tiny launch."""
         self.ops.adam_flat(self.params, self.grads, m, v, self.params.numel(), lr, betas[0], betas[1], eps,
                            weight_decay, self.opt_step, grad_scale)
-        self.ops.advance_counters(self.rng, self.opt_step)
+        adv = advance_rng and self.rng_used
+        self.ops.advance_counters(self.rng if adv else None, self.opt_step)
+        if adv:
+            self.rng_used = False
         self.weights_dirty = True

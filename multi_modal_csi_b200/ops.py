@@ -67,6 +67,7 @@ EXPORTS = [
     "csi_attn_bwd", "csi_bn_stats", "csi_bn_finalize", "csi_bn_eval_prepare", "csi_bn_act_fwd",
     "csi_bn_act_bwd_reduce", "csi_bn_act_bwd_dz", "csi_head_reduce_fwd", "csi_head_reduce_bwd", "csi_dropout_rows",
     "csi_bce_logits", "csi_smooth_l1", "csi_perm_ce", "csi_predict_counts", "csi_adam_flat", "csi_advance_counters", "csi_pack_weights", "csi_fill_f32",
+    "csi_set_force_simt", "csi_set_strict_tc", "csi_dispatch_counts", "csi_set_attn_impl",
 ]
 
 
@@ -159,6 +160,20 @@ class NativeOps:
     def set_force_simt(self, on: bool):
         self.lib.csi_set_force_simt(C.c_int(1 if on else 0))
 
+    def set_strict_tc(self, on: bool):
+        """Strict mode: a bf16 contraction whose shape the tcgen05 kernel cannot take is an error instead of an FFMA run."""
+        self.lib.csi_set_strict_tc(C.c_int(1 if on else 0))
+
+    def dispatch_counts(self, reset: bool = False):
+        """{"tcgen05": n, "ffma_fallback": n, "mma_sync": n}: bf16 contraction / attention calls by the kernel class that served them."""
+        a, b, c = C.c_longlong(0), C.c_longlong(0), C.c_longlong(0)
+        self.lib.csi_dispatch_counts(C.byref(a), C.byref(b), C.byref(c), C.c_int(1 if reset else 0))
+        return {"tcgen05": a.value, "ffma_fallback": b.value, "mma_sync": c.value}
+
+    def set_attn_impl(self, fwd_mode: int = 0, bwd_mode: int = 0):
+        """0 = measured-best per shape, 1 = tcgen05/TMEM attention wherever eligible, 2 = mma.sync only."""
+        self.lib.csi_set_attn_impl(C.c_int(fwd_mode), C.c_int(bwd_mode))
+
     def make_pack_table(self, entries, device):
         arr = (PackEntry * len(entries))()
         for i, e in enumerate(entries):
@@ -170,17 +185,22 @@ class NativeOps:
 
     # -------------------------------------------------------------- algorithmic work per launch (roofline numerators)
     alg_scale = 1.0     # set by the engine: (valid tokens / padded rows) * (true channels / padded channels)
+    alg_flops = None    # set by the engine before a contraction call: its algorithmic FLOPs (true dims, no padding)
 
     def _work(self, name, a):
         """Algorithmic FLOPs / minimum HBM bytes of one launch (DESIGN.md lists the formulas)."""
         es = lambda t: 0 if t is None else t.element_size()
+        if name in ("gemm_nt", "gemm_tn") and self.alg_flops is not None:
+            fl, self.alg_flops = self.alg_flops, None
+        else:
+            fl = None
         if name == "gemm_nt":
             k = sum(s[3] for s in a["segs"])
-            return {"flops": int(2 * a["M"] * a["N"] * k * self.alg_scale),
+            return {"flops": fl if fl is not None else int(2 * a["M"] * a["N"] * k * self.alg_scale),
                     "nbytes": a["M"] * k // max(1, len(a["segs"])) * es(a["A"]) + a["N"] * k * es(a["Bw"]) + a["M"] * a["N"] * es(a["Cm"])}
         if name == "gemm_tn":
             n = sum(s[3] for s in a["segs"])
-            return {"flops": int(2 * a["M"] * a["Na"] * n * (self.alg_scale if n > 16 else 1.0)), "nbytes": a["M"] * (a["Na"] + n // max(1, len(a["segs"]))) * es(a["A"])}
+            return {"flops": fl if fl is not None else int(2 * a["M"] * a["Na"] * n * (self.alg_scale if n > 16 else 1.0)), "nbytes": a["M"] * (a["Na"] + n // max(1, len(a["segs"]))) * es(a["A"])}
         if name == "attn_fwd":
             hd = a["d"] // a["H"]
             return {"flops": 4 * a["B"] * a["H"] * a["L"] * a["L"] * hd, "nbytes": a["B"] * a["L"] * a["d"] * 4 * es(a["qkv"])}

@@ -68,8 +68,23 @@ class GradSync:
             self._work = None
 
 
+def broadcast_buffers(model, src: int = 0):
+    """Rank ``src``'s BatchNorm running statistics on every rank (they are per rank during training: DDP semantics).
+    ``train()`` calls this before each evaluation so that metrics, best-weight selection and early stopping agree on all
+    ranks; one flattened broadcast instead of one per buffer."""
+    bufs = [b for b in model.buffers()]
+    if not bufs:
+        return
+    flat = torch.cat([b.detach().reshape(-1).to(torch.float64) for b in bufs])      # float64 holds the int64 batch counters exactly
+    dist.broadcast(flat, src)
+    pos = 0
+    for b in bufs:
+        n = b.numel()
+        b.copy_(flat[pos:pos + n].view(b.shape).to(b.dtype))
+        pos += n
+
+
 def broadcast_parameters(model, src: int = 0):
     """Make every rank start from rank ``src``'s weights and BatchNorm buffers."""
     dist.broadcast(model.flat_params, src)
-    for b in model.buffers():
-        dist.broadcast(b, src)
+    broadcast_buffers(model, src)

@@ -100,6 +100,7 @@ class _THATFunction(torch.autograd.Function):
         B = x.shape[0]
         eng = model._engine_for(B)
         eng.repack()
+        eng.begin_train_forward()
         logits = eng.forward(x, B, training=True, dropout=model.dropout_enabled, augment=False)
         ctx.model, ctx.B = model, B
         return logits.clone()
@@ -111,6 +112,7 @@ class _THATFunction(torch.autograd.Function):
         params = [p for p in model.parameters() if p.requires_grad]
         fresh = all(p.grad is None for p in params)
         eng.backward(dlogits.contiguous().float(), B, dropout=model.dropout_enabled, zero_grads=fresh)
+        eng.end_train_step()             # the dropout masks of this forward/backward pair are spent: next Philox step
         model._attach_grads()
         return None, None, None
 
@@ -130,7 +132,11 @@ class THAT(torch.nn.Module):
                           "fp32": torch.float32, "float32": torch.float32}[act_dtype]
         self.max_batch = max_batch
         self.dropout_enabled = True          # parity tests switch the Dropout layers off (p = 0)
-        self.rng_seed = int(torch.initial_seed() & 0x7FFFFFFF)
+        # Philox {seed, step} and the 1-based Adam step live on the MODEL (device tensors, created with the first
+        # engine): an engine rebuilt for a larger batch, or after .to() / configure(), keeps counting where the old one was
+        self._rng_seed = int(torch.initial_seed() & 0x7FFFFFFF)
+        self._rng = None
+        self._opt_step = None
         self._engine: Optional[THATEngine] = None
         self._ops_override = None            # tests only: inject the torch mirror of the kernels
         # fused_train_step replays forward+loss+backward as one CUDA graph (CSI_NO_GRAPH=1: eager launches, for profilers)
@@ -154,6 +160,24 @@ class THAT(torch.nn.Module):
             self._register(name, p, is_buffer=False)
         for name, val in bufs.items():
             self._register(name, val, is_buffer=True)
+
+    @property
+    def rng_seed(self) -> int:
+        return self._rng_seed
+
+    @rng_seed.setter
+    def rng_seed(self, seed: int):
+        self._rng_seed = int(seed)
+        if self._rng is not None:
+            self._rng[0] = self._rng_seed
+
+    def _counters(self, device):
+        if self._rng is None:
+            self._rng = torch.tensor([self._rng_seed, 0], dtype=torch.int64, device=device)
+            self._opt_step = torch.ones(1, dtype=torch.int64, device=device)
+        elif self._rng.device != device:
+            self._rng, self._opt_step = self._rng.to(device), self._opt_step.to(device)
+        return self._rng, self._opt_step
 
     # ------------------------------------------------------------------ module tree
     def _register(self, name, tensor, is_buffer):
@@ -235,8 +259,11 @@ class THAT(torch.nn.Module):
             mb = max(B, self.max_batch or 0)
             bn = OrderedDict((k, v) for k, v in self.named_buffers())
             frozen = {k: p.data.reshape(-1) for k, p in self.named_parameters() if k in LY.FROZEN}
+            rng, opt_step = self._counters(self._flat.device)
             eng = THATEngine(self.geom, mb, self._flat, self._gflat, self.arena, bn, frozen,
-                             act_dtype=self.act_dtype, ops=self._ops_override, seed=self.rng_seed)
+                             act_dtype=self.act_dtype, ops=self._ops_override, rng=rng, opt_step=opt_step)
+            if self._engine is not None:
+                eng.rng_used = self._engine.rng_used
             self._engine = eng
             self._eager_steps = 0
         return eng
@@ -264,6 +291,8 @@ class THAT(torch.nn.Module):
         outs = []
         for i in range(0, N, eng.B):
             xb = x[i:i + eng.B]
+            if training:
+                eng.begin_train_forward()
             outs.append(eng.forward(xb, xb.shape[0], training=training, dropout=self.dropout_enabled).clone())
         return outs[0] if len(outs) == 1 else torch.cat(outs, 0)
 
@@ -293,6 +322,7 @@ class THAT(torch.nn.Module):
         yf = y.reshape(B, -1)
         if yf.dtype != torch.float32:
             yf = yf.float()
+        eng.begin_train_forward()
         eng.forward_input(x, B, True, augment, offs, lens)
         eng.y_static[:B].copy_(yf)
         graph = self.use_cuda_graph if use_graph is None else use_graph
@@ -314,7 +344,7 @@ class THAT(torch.nn.Module):
         self._attach_grads()
         if grad_hook is not None and not overlap:
             grad_hook(eng)
-        optimizer.fused_step(eng)
+        optimizer.fused_step(eng, advance_rng=True)     # one launch advances the Adam step and the Philox step
         return loss, logits
 
 

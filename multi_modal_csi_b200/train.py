@@ -9,9 +9,13 @@ in one batch (:49,111-127), the wandb keys (:130-144), the selection rule f1 AND
 
 Changed underneath: when the model is a multi_modal_csi_b200.THAT on a CUDA device, the optimizer a FusedAdam and the
 loss a uniform-pos_weight BCEWithLogitsLoss, one step is ``model.fused_train_step`` (augmentation, forward, loss,
-backward and Adam in hand-written sm_100a kernels); otherwise the same loop runs through autograd on the model's
-kernels with torch's loss/optimizer.  Under ``torch.distributed`` the batches are sharded over ranks and gradients are
-all-reduced before the update.
+backward and Adam in hand-written sm_100a kernels) and the batches come from ``loader.CSIBatchSource``: the dataset
+(dense TensorDataset or the ragged ``PackedCSIDataset``) is either resident in HBM (a batch = offsets into it) or
+streamed from page-locked host memory, double-buffered on a copy stream, instead of the reference's per-batch host
+collate + pin + ``.to(device)`` (train.py:48,84-86).  Otherwise the same loop runs through autograd on the model's
+kernels with torch's loss/optimizer.  Under ``torch.distributed`` the batches are sharded over ranks, every rank starts
+from rank 0's weights, gradients are all-reduced before the update and BatchNorm running statistics are taken from rank 0
+before every evaluation, so that the selection / early-stopping decisions are identical on all ranks.
 """
 from __future__ import annotations
 
@@ -23,8 +27,9 @@ import torch.distributed as dist
 from torch.utils.data import DataLoader, TensorDataset
 from torch.utils.data.distributed import DistributedSampler
 
+from .loader import CSIBatchSource, PackedCSIDataset
 from .optim import FusedAdam
-from .parallel import GradSync
+from .parallel import GradSync, broadcast_buffers, broadcast_parameters
 from .that import PermutationMatchingLoss
 from .that import THAT
 from .utils import performance_metrics
@@ -72,12 +77,22 @@ def cosine_schedule_with_warmup(optimizer, num_warmup_steps, num_training_steps,
     return torch.optim.lr_scheduler.LambdaLR(optimizer, lr_lambda)
 
 
+def _epoch_index_batches(dataset, batch_size, sampler):
+    """The index lists a ``DataLoader(dataset, batch_size, shuffle=True)`` would collate this epoch (same RNG draws:
+    the loader iterator's base seed first, then the RandomSampler's seed), or the rank's shard under a DistributedSampler."""
+    if sampler is not None:
+        idx = list(iter(sampler))
+    else:
+        torch.empty((), dtype=torch.int64).random_()                     # _BaseDataLoaderIter draws its base seed first
+        idx = list(iter(torch.utils.data.RandomSampler(dataset)))
+    return [idx[i:i + batch_size] for i in range(0, len(idx), batch_size)]
+
+
 def train(model, optimizer, loss, data_train_set: TensorDataset, data_test_set: TensorDataset, var_threshold: float,
-          var_batch_size: int, var_epochs: int, device, var_mode: str, patience: int = 150):
+          var_batch_size: int, var_epochs: int, device, var_mode: str, patience: int = 150, loader_mode: str = "auto"):
     device = torch.device(device)
     distributed = dist.is_available() and dist.is_initialized() and dist.get_world_size() > 1
     sampler = DistributedSampler(data_train_set, shuffle=True, drop_last=False) if distributed else None
-    data_train_loader = DataLoader(data_train_set, var_batch_size, shuffle=sampler is None, sampler=sampler, pin_memory=True)
     data_test_loader = DataLoader(data_test_set, len(data_test_set))
     pos_weight = _uniform_pos_weight(loss)
     loss_kind = None                                    # which fused loss kernel implements ``loss``
@@ -91,6 +106,19 @@ def train(model, optimizer, loss, data_train_set: TensorDataset, data_test_set: 
     fused = (isinstance(model, THAT) and isinstance(optimizer, FusedAdam) and loss_kind is not None
              and device.type == "cuda")
     sync = GradSync(model, dist.get_world_size()) if distributed and isinstance(model, THAT) else None
+    if distributed and isinstance(model, THAT):
+        broadcast_parameters(model)                     # every rank starts from rank 0's weights and BatchNorm buffers
+        model.rng_seed = (model.rng_seed + 7919 * dist.get_rank()) & 0x7FFFFFFF      # decorrelated dropout / augmentation
+    source = data_train_loader = None
+    if fused:
+        source = CSIBatchSource(data_train_set, device, var_batch_size, mode=loader_mode)
+        n_train = len(sampler) if sampler is not None else len(data_train_set)
+        total_batches = (n_train + var_batch_size - 1) // var_batch_size
+    else:
+        if isinstance(data_train_set, PackedCSIDataset):
+            raise ValueError("PackedCSIDataset feeds the fused path (THAT + FusedAdam + a fused loss on a CUDA device)")
+        data_train_loader = DataLoader(data_train_set, var_batch_size, shuffle=sampler is None, sampler=sampler, pin_memory=True)
+        total_batches = len(data_train_loader)
 
     var_best_f1_score, var_best_PPP, var_best_weight, counter = 0, 0, None, 0
     var_epoch_saved = None
@@ -98,33 +126,42 @@ def train(model, optimizer, loss, data_train_set: TensorDataset, data_test_set: 
     if var_mode == "multi_head":                        # train.py:57-63: per-step cosine schedule with linear warm-up
         from .preset import preset
         sch = preset["nn"]["scheduler"]
-        scheduler = cosine_schedule_with_warmup(optimizer, sch["num_warmup_epochs"] * len(data_train_loader),
-                                                preset["nn"]["epoch"] * len(data_train_loader), sch["min_lr_ratio"])
+        scheduler = cosine_schedule_with_warmup(optimizer, sch["num_warmup_epochs"] * total_batches,
+                                                preset["nn"]["epoch"] * total_batches, sch["min_lr_ratio"])
     for var_epoch in range(var_epochs):
         var_time_e0 = time.time()
         model.train()
         if sampler is not None:
             sampler.set_epoch(var_epoch)
-        total_batches = len(data_train_loader)
         predict_train_y = data_batch_y = var_loss_train = None
-        for batch_idx, data_batch in enumerate(data_train_loader):
-            if batch_idx == total_batches - 1:
-                continue
-            data_batch_x, data_batch_y = data_batch
-            data_batch_x = data_batch_x.to(device, non_blocking=True)
-            data_batch_y = data_batch_y.to(device, non_blocking=True)
-            if var_mode == "count_classification":
-                data_batch_y = data_batch_y.sum(axis=1)                                  # train.py:91-92
-            if var_mode == "baseline":
-                data_batch_y = data_batch_y.reshape(data_batch_y.shape[0], -1)
-            if fused:
-                x = data_batch_x.reshape(data_batch_x.shape[0], data_batch_x.shape[1], -1).float()
+        if fused:
+            # the LAST batch of the epoch is skipped (train.py:81-82): it is never even copied
+            lists = _epoch_index_batches(data_train_set, var_batch_size, sampler)[:-1]
+            for batch in source.batches(lists):
+                data_batch_y = batch.y
+                if var_mode == "count_classification":
+                    data_batch_y = data_batch_y.sum(axis=1)                              # train.py:91-92
+                if var_mode == "baseline":
+                    data_batch_y = data_batch_y.reshape(data_batch_y.shape[0], -1)
                 var_loss_train, predict_train_y = model.fused_train_step(
-                    x, data_batch_y, optimizer, pos_weight=pos_weight, augment=True, grad_hook=sync, loss_kind=loss_kind)
-                var_loss_train, predict_train_y = var_loss_train.clone(), predict_train_y.clone()
+                    batch.x, data_batch_y, optimizer, pos_weight=pos_weight, augment=True, grad_hook=sync,
+                    loss_kind=loss_kind, offs=batch.offs, lens=batch.lens)
                 if scheduler is not None:
                     scheduler.step()
-            else:
+            if predict_train_y is not None:
+                var_loss_train, predict_train_y = var_loss_train.clone(), predict_train_y.clone()
+                data_batch_y = data_batch_y.clone()
+        else:
+            for batch_idx, data_batch in enumerate(data_train_loader):
+                if batch_idx == total_batches - 1:
+                    continue
+                data_batch_x, data_batch_y = data_batch
+                data_batch_x = data_batch_x.to(device, non_blocking=True)
+                data_batch_y = data_batch_y.to(device, non_blocking=True)
+                if var_mode == "count_classification":
+                    data_batch_y = data_batch_y.sum(axis=1)                              # train.py:91-92
+                if var_mode == "baseline":
+                    data_batch_y = data_batch_y.reshape(data_batch_y.shape[0], -1)
                 if model.training:
                     data_batch_x = apply_augmentation(data_batch_x)
                 predict_train_y = model(data_batch_x)
@@ -143,6 +180,8 @@ def train(model, optimizer, loss, data_train_set: TensorDataset, data_test_set: 
         dict_error_train = performance_metrics(data_batch_y.astype(int), predict_train_y.astype(int), var_mode=var_mode,
                                                var_threshold=var_threshold)
         model.eval()
+        if distributed and isinstance(model, THAT):
+            broadcast_buffers(model)                    # rank 0's BatchNorm running statistics: identical eval on every rank
         with torch.no_grad():
             data_test_x, data_test_y = next(iter(data_test_loader))
             data_test_x, data_test_y = data_test_x.to(device), data_test_y.to(device)
@@ -184,6 +223,8 @@ def train(model, optimizer, loss, data_train_set: TensorDataset, data_test_set: 
         if counter >= patience:
             print(f"Early stopping triggered at epoch {var_epoch}")
             break
+    if source is not None:
+        source.close()
     if var_best_weight is None:
         # the reference raises UnboundLocalError here (train.py:175); keep the last weights instead of crashing
         var_best_weight = deepcopy(model.state_dict())

@@ -1,11 +1,10 @@
-"""A few launches of one NT GEMM shape (for ncu): argv = M N Dp k v2 reps."""
+"""A few launches of one NT GEMM shape (for ncu): argv = M N Dp k reps."""
 import sys, os, math
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 import torch
 from multi_modal_csi_b200.ops import NativeOps
-M, N, Dp, k, v2, reps = [int(a) for a in sys.argv[1:7]]
+M, N, Dp, k, reps = [int(a) for a in sys.argv[1:6]]
 ops = NativeOps(torch.device("cuda", 0))
-ops.lib.csi_set_gemm_v2(v2)
 GUARD = 16
 full = torch.randn(M + 2 * GUARD, Dp, device="cuda").to(torch.bfloat16)
 A = full[GUARD:GUARD + M]

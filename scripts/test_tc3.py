@@ -46,18 +46,12 @@ for (M, N, Dp, k) in [(1024, 270, 272, 5), (1000, 150, 160, 2), (2048, 128, 272,
     full, A, W, Cm, segs, pl = make(M, N, Dp, k)
     r = ref(full, W, M, N, Dp, k, pl)
     for mode in (0, 1):
-        lib.csi_set_gemm_v2(0)
         lib.csi_set_gemm_desc_mode(mode)
         Cm.zero_()
         ops.gemm_nt(A, W, Cm, M, N, segs, None, None, 0.0, 0, None)
         torch.cuda.synchronize()
         err = ((Cm[:, :N].float() - r).norm() / r.norm()).item()
         print(f"M={M} N={N} k={k} desc_mode={mode}: rel err {err:.3e}", flush=True)
-    lib.csi_set_gemm_v2(1)
-    Cm.zero_()
-    ops.gemm_nt(A, W, Cm, M, N, segs, None, None, 0.0, 0, None)
-    torch.cuda.synchronize()
-    print(f"   tc2 rel err {((Cm[:, :N].float() - r).norm() / r.norm()).item():.3e}", flush=True)
 
 mode = int(sys.argv[1]) if len(sys.argv) > 1 else 0
 lib.csi_set_gemm_desc_mode(mode)
@@ -66,8 +60,6 @@ for (M, N, Dp, k) in [(39424, 960, 272, 1), (39424, 270, 272, 1), (39424, 270, 2
     full, A, W, Cm, segs, pl = make(M, N, Dp, k)
     fl = 2.0 * M * N * k * Dp
     res = []
-    for v2 in (1, 0):
-        lib.csi_set_gemm_v2(v2)
-        ms = timeit(lambda: ops.gemm_nt(A, W, Cm, M, N, segs, None, None, 0.0, 0, None))
-        res.append(f"{'tc2' if v2 else 'tc3'} {ms*1e3:7.1f} us {fl/ms/1e9:7.1f} TF/s")
+    ms = timeit(lambda: ops.gemm_nt(A, W, Cm, M, N, segs, None, None, 0.0, 0, None))
+    res.append(f"tc3 {ms*1e3:7.1f} us {fl/ms/1e9:7.1f} TF/s")
     print(f"M={M} N={N} K={k}x{Dp}: " + " | ".join(res), flush=True)

@@ -44,22 +44,18 @@ def timeit(fn, reps=10):
 for (M, Na, Dp, nlen, k) in [(4096, 270, 272, 270, 5), (3000, 150, 160, 150, 2), (4096, 128, 272, 270, 16), (4096, 270, 272, 270, 1)]:
     A, full, X, Cm, segs, pl = make(M, Na, Dp, nlen, k)
     r = ref(A, full, M, Na, nlen, k, pl)
-    for v1 in (0, 1):
-        lib.csi_set_gemm_tn_v1(v1)
-        Cm.zero_()
-        ops.gemm_tn(A, X, Cm, nlen * k, k, M, Na, segs)
-        torch.cuda.synchronize()
-        print(f"M={M} Na={Na} nlen={nlen} k={k} {'tc1' if v1 else 'tn3'}: rel err {((Cm - r).norm() / r.norm()).item():.3e}", flush=True)
+    Cm.zero_()
+    ops.gemm_tn(A, X, Cm, nlen * k, k, M, Na, segs)
+    torch.cuda.synchronize()
+    print(f"M={M} Na={Na} nlen={nlen} k={k} tn3: rel err {((Cm - r).norm() / r.norm()).item():.3e}", flush=True)
 
 for (M, Na, Dp, nlen, k) in [(39424, 270, 272, 270, 1), (39424, 270, 272, 270, 3), (39424, 270, 272, 270, 5), (39424, 960, 272, 270, 1),
                              (39424, 128, 272, 270, 8), (39424, 128, 272, 270, 16), (70144, 150, 160, 150, 3), (70144, 480, 160, 150, 1)]:
     A, full, X, Cm, segs, pl = make(M, Na, Dp, nlen, k)
     fl = 2.0 * M * Na * nlen * k
     res = []
-    for v1 in (1, 0):
-        lib.csi_set_gemm_tn_v1(v1)
-        ms = timeit(lambda: ops.gemm_tn(A, X, Cm, nlen * k, k, M, Na, segs))
-        res.append(f"{'tc1' if v1 else 'tn3'} {ms*1e3:7.1f} us {fl/ms/1e9:7.1f} TF/s")
+    ms = timeit(lambda: ops.gemm_tn(A, X, Cm, nlen * k, k, M, Na, segs))
+    res.append(f"tn3 {ms*1e3:7.1f} us {fl/ms/1e9:7.1f} TF/s")
     for dbg in (1, 2):
         lib.csi_set_tn_debug(dbg)
         ms = timeit(lambda: ops.gemm_tn(A, X, Cm, nlen * k, k, M, Na, segs))

@@ -367,8 +367,10 @@ class MirrorOps:
         p[:n].addcdiv_(m[:n], denom, value=-lr / bc1)
 
     def advance_counters(self, rng, step):
-        rng[1] += 1
-        step[0] += 1
+        if rng is not None:
+            rng[1] += 1
+        if step is not None:
+            step[0] += 1
 
     def fill_f32(self, t, v):
         t.fill_(v)

@@ -465,15 +465,16 @@ def test_bench_family_table_and_roofline_schema():
     import bench
     table = {"gemm_nt": (2.0, 48, {"flops": 2.0e12, "bytes": 1.0e9}), "layernorm_fwd": (0.25, 12, {"flops": 0, "bytes": 1.0e9}),
              "bn_finalize": (0.04, 5, {"flops": 0, "bytes": 0})}
-    peaks = {"hbm_gbs": 6547.5, "bf16_tflops_sustained": 1340.8}
+    peaks = {"hbm_gbs": 6547.5, "bf16_tflops": 1595.7, "bf16_tflops_sustained": 1340.8}
     fam = bench.family_table(table, peaks)
     assert list(fam) == ["gemm_nt", "layernorm_fwd", "bn_finalize"]                    # sorted by device time
     assert fam["gemm_nt"]["bound"] == "tensor" and abs(fam["gemm_nt"]["achieved"] - 1000.0) < 1e-6
-    assert abs(fam["gemm_nt"]["frac"] - round(1000.0 / 1340.8, 3)) < 1e-9
+    assert abs(fam["gemm_nt"]["frac"] - round(1000.0 / 1595.7, 3)) < 1e-9          # burst cuBLAS peak
     assert fam["layernorm_fwd"]["bound"] == "hbm" and abs(fam["layernorm_fwd"]["achieved"] - 4000.0) < 1e-6
     assert "bound" not in fam["bn_finalize"] and fam["bn_finalize"]["launches"] == 5
-    r = bench.roofline("gemm_nt", table, None, 256, peaks)
-    assert r["bound"] == "tensor" and r["unit"] == "TFLOP/s" and abs(r["frac"] - 1000.0 / 1340.8) < 1e-9
+    r = bench.roofline("gemm_nt", table, 256, peaks)
+    assert r["bound"] == "tensor" and r["unit"] == "TFLOP/s" and abs(r["frac"] - 1000.0 / 1595.7) < 1e-9
+    assert abs(r["frac_sustained"] - 1000.0 / 1340.8) < 1e-9 and r["peak"] == 1595.7
     assert set(r) >= {"kernel", "bound", "achieved", "peak", "unit", "frac", "traffic", "launches", "ms_per_launch"}
 
 
@@ -507,3 +508,90 @@ def test_cosine_schedule_with_warmup_matches_reference_formula():
             assert abs(opt2.param_groups[0]["lr"] - ours[s]) < 1e-15, s
             opt2.step()
             sch2.step()
+
+
+def test_counters_live_on_the_model_and_survive_an_engine_rebuild():
+    """the Adam step and the Philox {seed, step} belong to the model, not to the engine: an engine rebuilt for
+    a larger batch (epoch-0 evaluation of train()) continues them, and the Philox step advances once per
+    forward/backward pair whichever optimizer follows."""
+    from multi_modal_csi_b200 import FusedAdam
+    T, F, out = 400, 30, 12
+    torch.manual_seed(3)
+    m = _mirror_model(T, F, out)
+    m.rng_seed = 77
+    opt = FusedAdam(m.parameters(), lr=5e-4, weight_decay=2e-4)
+    x, y = torch.rand(2, T, F) * 20, (torch.rand(2, out) < 0.2).float()
+    m.train()
+    for _ in range(2):
+        m.fused_train_step(x, y, opt, augment=False)
+    e0 = m._engine
+    assert m._rng.tolist() == [77, 2] and int(m._opt_step) == 3 and e0.rng is m._rng
+    m.eval()
+    with torch.no_grad():
+        m(torch.rand(5, T, F))                                   # N=5 > engine batch 2: rebuild
+    assert m._engine is not e0 and m._engine.rng is m._rng and m._engine.opt_step is m._opt_step
+    m.train()
+    m.fused_train_step(x, y, opt, augment=False)
+    assert m._rng.tolist() == [77, 3] and int(m._opt_step) == 4
+    # autograd path with a torch optimizer: one Philox step per forward/backward pair, none from the optimizer
+    sgd = torch.optim.SGD(m.parameters(), lr=0.0)
+    for _ in range(2):
+        sgd.zero_grad()
+        m(x).sum().backward()
+        sgd.step()
+    assert m._rng.tolist() == [77, 5] and int(m._opt_step) == 4
+    m(x)
+    m(x)                                                         # two train forwards without backward: masks are not reused
+    assert int(m._rng[1]) == 6
+    m.rng_seed = 5
+    assert m._rng.tolist() == [5, 6]
+
+
+def test_fused_adam_keeps_omitted_parameters_fixed():
+    from multi_modal_csi_b200 import FusedAdam
+    T, F, out = 400, 30, 12
+    torch.manual_seed(3)
+    m = _mirror_model(T, F, out)
+    named = dict(m.named_parameters())
+    frozen = [k for k in named if k.startswith("layer_right_")]
+    for k in frozen:
+        named[k].requires_grad_(False)
+    with pytest.raises(ValueError):
+        FusedAdam(m.parameters(), lr=1e-3, weight_decay=2e-4)    # coupled L2 would move the frozen weights
+    opt = FusedAdam([p for p in m.parameters() if p.requires_grad], lr=1e-3, weight_decay=0)
+    before = {k: v.detach().clone() for k, v in named.items()}
+    x, y = torch.rand(2, T, F) * 20, (torch.rand(2, out) < 0.2).float()
+    m.train()
+    for _ in range(2):
+        m.fused_train_step(x, y, opt, augment=False)
+    for k in named:
+        if ".layer_cnn." in k and k.endswith(".0.bias"):
+            continue                                                 # conv bias in front of a train-mode BatchNorm: zero gradient
+        assert torch.equal(named[k].detach(), before[k]) == (k in frozen or k == "layer_left_gaussian.var_position"), k
+    sd = opt.state_dict()
+    assert sd["csi_flat"]["step"] == 3
+    opt2 = FusedAdam([p for p in m.parameters() if p.requires_grad], lr=1e-3, weight_decay=0)
+    opt2.load_state_dict(sd)
+    assert torch.equal(opt2._m, sd["csi_flat"]["exp_avg"])
+
+
+def test_epoch_index_batches_match_dataloader_and_packed_dataset_pads_in_front():
+    from torch.utils.data import DataLoader, TensorDataset
+    from multi_modal_csi_b200.loader import PackedCSIDataset
+    from multi_modal_csi_b200.train import _epoch_index_batches
+    ds = TensorDataset(torch.arange(23).float().reshape(23, 1), torch.arange(23))
+    torch.manual_seed(5)
+    a = [b[1].tolist() for b in DataLoader(ds, 4, shuffle=True)] + [b[1].tolist() for b in DataLoader(ds, 4, shuffle=True)]
+    torch.manual_seed(5)
+    b = _epoch_index_batches(ds, 4, None) + _epoch_index_batches(ds, 4, None)
+    assert a == b
+    T, F = 12, 3
+    lens = [12, 7, 1]
+    chunks = [torch.rand(n, F) for n in lens]
+    offs = [0, 12 * F, 19 * F]
+    p = PackedCSIDataset(torch.cat([c.reshape(-1) for c in chunks]), offs, lens, F, torch.arange(3), T)
+    for i, c in enumerate(chunks):
+        xi, yi = p[i]
+        assert xi.shape == (T, F) and torch.equal(xi[T - lens[i]:], c) and float(xi[:T - lens[i]].abs().sum()) == 0 and int(yi) == i
+    with pytest.raises(ValueError):
+        PackedCSIDataset(torch.zeros(13 * F), [0], [13], F, torch.zeros(1), T)
