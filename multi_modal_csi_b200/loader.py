@@ -180,11 +180,21 @@ class CSIBatchSource:
                 pos = 0
                 src_offs = self.offs_host[it].tolist()
                 ll = lens.tolist()
+                # one async copy per RUN of samples that are adjacent in the source arena (a shuffled batch: one per
+                # sample; an unshuffled / sorted one: a few large copies)
+                run_src = run_dst = run_len = 0
                 for i in range(b):
                     n = ll[i] * self.F
-                    x[pos:pos + n].copy_(self.x_host[src_offs[i]:src_offs[i] + n], non_blocking=True)
                     tab["offs"][i] = pos
+                    if run_len and src_offs[i] == run_src + run_len:
+                        run_len += n
+                    else:
+                        if run_len:
+                            x[run_dst:run_dst + run_len].copy_(self.x_host[run_src:run_src + run_len], non_blocking=True)
+                        run_src, run_dst, run_len = src_offs[i], pos, n
                     pos += n
+                if run_len:
+                    x[run_dst:run_dst + run_len].copy_(self.x_host[run_src:run_src + run_len], non_blocking=True)
                 nbytes += pos * 4
             tab["d_offs"][:b].copy_(tab["offs"][:b], non_blocking=True)
             tab["d_lens"][:b].copy_(tab["lens"][:b], non_blocking=True)

@@ -10,9 +10,11 @@ pytestmark = pytest.mark.gpu
 
 # Stated tolerances (normwise relative error  ||a-b|| / ||b||):
 #   fp32 mode : 1e-4 on logits and on the full gradient vector (north_star)
-#   bf16 mode : 2e-2 on logits, 5e-2 on the gradient vector; multi-label predictions must be identical wherever
+#   bf16 mode : 1e-2 on logits, 3e-2 on the gradient vector (SURVEY.md section 7 / BASELINE.md section 4); measured on
+#               B200 at the benchmarked batch (B=256, F=270; tests/test_gpu_round2.py prints them): 2.6e-3 / 2.9e-3, the
+#               reference's own bf16 autocast: 3.1e-3 / 9.3e-3.  Multi-label predictions must be identical wherever
 #               |logit_ref| exceeds the measured absolute logit error (SURVEY.md section 7 "hard parts")
-TOL = {"fp32": (1e-4, 1e-4), "bf16": (2e-2, 5e-2)}
+TOL = {"fp32": (1e-4, 1e-4), "bf16": (1e-2, 3e-2)}
 
 
 def nrel(a, b):
@@ -220,14 +222,18 @@ def test_backward_uses_the_forward_dropout_masks(mode):
     if mode == "bf16":                      # exercise the tensor-core epilogue's mask on the analytic side only
         m.configure(act_dtype="bf16")
     lossf = torch.nn.BCEWithLogitsLoss(pos_weight=torch.full((out,), 4.0, device="cuda"))
+    step0 = int(m._engine_for(B).rng[1].item())      # the Philox step the forward/backward pair below draws its masks from
     loss = lossf(m(x), y)
     loss.backward()
     g = m.flat_grads.clone()
     assert torch.isfinite(g).all()
-    eng = m._engine
-    step0 = int(eng.rng[1].item())
+    assert int(m._rng[1].item()) == step0 + 1       # backward closed the pair: the next forward gets new masks
     m.configure(act_dtype="fp32")           # finite differences always in fp32; same seed/step -> same masks
-    m._engine_for(B).rng.copy_(torch.tensor([m.rng_seed, step0], device="cuda"))
+
+    def pin_masks():
+        eng = m._engine_for(B)
+        eng.rng.copy_(torch.tensor([m.rng_seed, step0], device="cuda"))
+        eng.rng_used = False                # the next train-mode forward draws from step0 again
     gen = torch.Generator(device="cuda").manual_seed(3)
     worst = 0.0
     for trial in range(3):
@@ -239,6 +245,7 @@ def test_backward_uses_the_forward_dropout_masks(mode):
         for sgn in (1.0, -1.0):
             with torch.no_grad():
                 m.flat_params.add_(v, alpha=sgn * eps)
+                pin_masks()
                 vals.append(float(lossf(m._forward_nograd(x, True), y)))
                 m.flat_params.add_(v, alpha=-sgn * eps)
         fd = (vals[0] - vals[1]) / (2 * eps)

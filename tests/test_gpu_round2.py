@@ -32,7 +32,9 @@ def test_oracle_parity_at_benchmarked_batch(mode, B, capsys):
     x, y = bench_batch(B, F, out)
     m = build(T, F, out, mode)
     m.configure(max_batch=B)
-    m._engine_for(B).ops.set_strict_tc(mode == "bf16")
+    # strict: any bf16 contraction that cannot run on tcgen05 is an error (B=32: the output layer's weight gradient
+    # contracts over only 32 rows, below the 64-row minimum of the tcgen05 wgrad kernel, so strict applies at B=256)
+    m._engine_for(B).ops.set_strict_tc(mode == "bf16" and B >= 64)
     try:
         sd_cpu = copy.deepcopy({k: v.cpu() for k, v in m.state_dict().items()})
         m.train()
@@ -53,13 +55,16 @@ def test_oracle_parity_at_benchmarked_batch(mode, B, capsys):
         tg = 3e-4          # fp32 CPU reference vs fp32 GPU: summation order over 32 x 150 tokens (the B=4 test pins 1e-4 against fp64)
     assert el < tl and ge < tg, (el, ge, worst)
     assert abs(loss.item() - ref_loss.item()) < 10 * tl * abs(ref_loss.item())
-    # equal multi-label predictions (train-mode logits here; the eval-mode rule is covered by the B=4 fixture test)
-    mine, ref = O.predict_counts(logits.detach().cpu(), 6), O.predict_counts(ref_logits, 6)
-    margin = (logits.detach().cpu() - ref_logits).abs().max().item()
-    p = torch.sigmoid(ref_logits.double()).reshape(B, 6, -1)
-    top2 = p.topk(2, dim=2).values
-    ok = (((top2[..., 0] - 0.5).abs() > margin) & ((top2[..., 0] - top2[..., 1]) > margin)).all(dim=1)
-    assert torch.equal(mine[ok], ref[ok]) and int(ok.sum()) > B // 2
+    # equal multi-label decisions (utils.py:147-183: per user the arg-max class, kept iff sigmoid > 0.5 <=> logit > 0)
+    # wherever the reference decision is outside the measured logit error
+    mine, ref = logits.detach().cpu().reshape(B, 6, -1), ref_logits.reshape(B, 6, -1)
+    margin = (mine - ref).abs().max().item()
+    top2 = ref.topk(2, dim=2).values
+    decisive = (top2[..., 0].abs() > margin) & ((top2[..., 0] - top2[..., 1]) > 2 * margin)
+    assert int(decisive.sum()) > B * 6 // 2
+    assert torch.equal(mine.argmax(2)[decisive], ref.argmax(2)[decisive])
+    assert torch.equal((mine.max(2).values > 0)[decisive], (ref.max(2).values > 0)[decisive])
+    assert torch.equal(O.predict_counts(logits.detach().cpu(), 6)[decisive.all(1)], O.predict_counts(ref_logits, 6)[decisive.all(1)])
 
 
 # ------------------------------------------------------------------------------------------- loader
@@ -256,13 +261,14 @@ def test_bf16_dispatch_is_counted_and_strict_mode_raises():
     Cm = torch.zeros(256, 32, dtype=torch.bfloat16, device="cuda")
     ops.gemm_nt(A, W, Cm, 256, 32, [(0, 0, 0, 64)], None, None, 0.0, 0, None)
     assert ops.dispatch_counts() == {"tcgen05": 1, "ffma_fallback": 0, "mma_sync": 0}
-    # K segment of 24 is not a multiple of 16: the tcgen05 kernel cannot take it
-    ops.gemm_nt(A, W, Cm, 256, 32, [(0, 0, 0, 24)], None, None, 0.0, 0, None)
+    # a weight gradient that contracts over fewer than 64 rows: the tcgen05 wgrad kernel cannot take it
+    G = torch.zeros(32, 64, device="cuda")
+    ops.gemm_tn(A[:32, :32].contiguous(), A[:32], G, 64, 1, 32, 32, [(0, 0, 0, 64)])
     assert ops.dispatch_counts()["ffma_fallback"] == 1
     ops.set_strict_tc(True)
     try:
         with pytest.raises(RuntimeError, match="strict"):
-            ops.gemm_nt(A, W, Cm, 256, 32, [(0, 0, 0, 24)], None, None, 0.0, 0, None)
+            ops.gemm_tn(A[:32, :32].contiguous(), A[:32], G, 64, 1, 32, 32, [(0, 0, 0, 64)])
     finally:
         ops.set_strict_tc(False)
     torch.cuda.synchronize()
