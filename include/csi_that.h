@@ -233,6 +233,56 @@ int csi_predict_counts(const float* logits, int ldz, int rows, int users, int cl
 
 /* Generic helpers */
 int csi_fill_f32(float* p, long long n, float v, void* stream);
+int csi_fill_f64(double* p, long long n, double v, void* stream);
+int csi_copy_f32(float* dst, const float* src, long long n, void* stream);
+
+/* ---- (f)3 CSI-as-image path: model/cnn_2d.py:23-99 (CNN_2D: BatchNorm2d -> Conv2d -> LeakyReLU -> Dropout(0.2) three
+ * times, BatchNorm2d, mean over the image, Linear).  Activations are NHWC matrices [B*H*W, C] (C = 1 for the raw fp32 CSI
+ * image, then 32 / 64 / 128, stored in the activation dtype).  A Conv2d(k, stride s) is csi_im2col_bn (the preceding
+ * BatchNorm2d applied on the fly) + csi_gemm_nt; its weight gradient csi_gemm_tn over (dZ, patches); its data gradient
+ * csi_gemm_nt against the transposed weights + csi_col2im. */
+/* load_data.py:66-72 + train.py:65-73 for the image path: the dense FRONT-padded batch out [B,T,F] gathered from a packed
+ * arena (offs / lens as in csi_pool_dual; NULL = x is dense already), optionally augmented
+ * ((x + 0.1 N(0,1)) * U[0.9,1.1)_b * Bernoulli(0.96)). */
+int csi_gather_aug(const float* x, const long long* offs, const int* lens, int B, int T, int F, float* out, int augment,
+                   const unsigned long long* rng, void* stream);
+/* cnn_2d.py:75,80,85,90 BatchNorm2d statistics: sums[c] += sum x, sums[C + c] += sum x^2 over x [rows, C] contiguous
+ * (C = 1, or a multiple of 8 dividing 2048). */
+int csi_nhwc_stats(const void* x, int dtype, long long rows, int C, double* sums, void* stream);
+/* train (training != 0): batch statistics from sums, running statistics / num_batches_tracked updated (momentum 0.1,
+ * unbiased variance); eval: running statistics.  scale = gamma*invstd, shift = beta - mean*scale. */
+int csi_bn2d_finalize(const double* sums, int C, long long count, const float* gamma, const float* beta, float* run_mean,
+                      float* run_var, long long* nbt, float momentum, float eps, int training, float* mean, float* invstd,
+                      float* scale, float* shift, void* stream);
+/* cnn_2d.py:76,81,86 patch matrix of Conv2d(k, stride s, no padding) over x [B,H,W,C] with BatchNorm applied:
+ * col[(b,oh,ow), (kh*k+kw)*C + c] = x[b, oh*s+kh, ow*s+kw, c]*scale[c] + shift[c]; columns [k*k*C, Kp) are zero. */
+int csi_im2col_bn(const void* x, int x_dtype, int B, int H, int W, int C, int k, int s, const float* scale, const float* shift,
+                  void* col, int col_dtype, int Kp, void* stream);
+/* data gradient: g[b,h,w,c] (fp32) = sum of gcol over the patches covering the pixel (gather, no atomics). */
+int csi_col2im(const void* gcol, int dtype, int B, int H, int W, int C, int k, int s, int Kp, float* g, void* stream);
+/* cnn_2d.py:77-78: y = Dropout_p(LeakyReLU(z)) over n elements; the keep bits of every 8 elements are stored (1 byte). */
+int csi_act_drop_fwd(const void* z, void* y, int dtype, long long n, float p, unsigned site, const unsigned long long* rng,
+                     unsigned char* mask, void* stream);
+/* BatchNorm2d backward, pass 1: sums[c] += sum g', sums[C+c] += sum g'*(x-mean)*invstd with g' = g_scale * g (row r of g is
+ * row r / g_div: the gradient of the spatial mean, cnn_2d.py:91, is shared by the g_div positions it averages). */
+int csi_bn2d_bwd_reduce(const void* g, int g_dtype, long long g_div, float g_scale, const void* x, int x_dtype, long long rows, int C,
+                        const float* mean, const float* invstd, double* sums, void* stream);
+/* pass 2, fused with the Dropout + LeakyReLU backward of the block that produced x = Dropout(LeakyReLU(zprev)):
+ * gz = gamma*invstd*(g' - sum_g/n - xhat*sum_gxhat/n) * keep/(1-p) * leaky'(zprev); dgamma += sum_gxhat, dbeta += sum_g. */
+int csi_bn2d_bwd_apply(const float* g, long long g_div, float g_scale, const void* x, const void* zprev, int dtype, const unsigned char* mask,
+                       float drop_p, long long rows, int C, const float* mean, const float* invstd, const float* gamma,
+                       const double* sums, void* gz, float* dgamma, float* dbeta, void* stream);
+/* cnn_2d.py:90-91: feat[b,c] = scale[c] * mean_p y[b,p,c] + shift[c] (fp32) and the same in the activation dtype. */
+int csi_pool_bn_fwd(const void* y, int dtype, int B, int P, int C, const float* scale, const float* shift, float* feat,
+                    void* featd, void* stream);
+/* Conv2d / Linear weights: reference layout [N,C,k,k] fp32 -> forward operand wf [N,Kp] ((kh,kw,c) order) and
+ * data-gradient operand wb [Kp,Np] (may be NULL); and the weight gradient back: gw[n,c,kh,kw] += gs[n,(kh*k+kw)*C+c]. */
+int csi_conv2d_pack(const float* w, int N, int C, int k, void* wf, int Kp, void* wb, int Np, int dtype, void* stream);
+int csi_conv2d_unpack_grad(const float* gs, int N, int C, int k, int Kp, float* gw, void* stream);
+/* Affine gradients of the single-channel BatchNorm2d in front of conv 0 and the conv-0 bias gradient from the column sums
+ * sums = [sum_m gz0, sum_m gz0*z0] (cnn2d.cu explains the identity). */
+int csi_bn0_grads(const double* sums, const void* wf, int ldw, int dtype, int N, int K, const float* bias, const float* gamma0,
+                  const float* beta0, float* dgamma0, float* dbeta0, float* dbias, void* stream);
 
 #ifdef __cplusplus
 }

@@ -36,7 +36,39 @@ class _TokBuf:
         self.t = self.full[GUARD:GUARD + rows]
 
 
-class THATEngine:
+class StepCounters:
+    """Philox / Adam step bookkeeping shared by the engines of this package (``rng``, ``opt_step``, ``rng_used``, ``ops``,
+    ``params`` and ``grads`` are set by the engine)."""
+
+    # The Philox step is a property of the forward/backward pair, not of the optimizer: backward regenerates the masks
+    # its forward drew, then the step moves on -- whichever optimizer (or none) follows.
+    def begin_train_forward(self):
+        """Call before a train-mode forward: if the previous train forward never reached ``end_train_step`` (no
+        backward, e.g. two forwards in a row) its masks must not be reused."""
+        if self.rng_used:
+            self.ops.advance_counters(self.rng, None)
+        self.rng_used = True
+
+    def end_train_step(self):
+        """Call after the backward that belongs to the last train forward (autograd path)."""
+        if self.rng_used:
+            self.ops.advance_counters(self.rng, None)
+        self.rng_used = False
+
+    def adam(self, m: torch.Tensor, v: torch.Tensor, lr: float, betas=(0.9, 0.999), eps: float = 1e-8,
+             weight_decay: float = 0.0, grad_scale: float = 1.0, advance_rng: bool = False):
+        """One fused Adam launch over the arena; advances the Adam step and, on the fused train step
+        (``advance_rng``), the Philox step in the same tiny launch."""
+        self.ops.adam_flat(self.params, self.grads, m, v, self.params.numel(), lr, betas[0], betas[1], eps,
+                           weight_decay, self.opt_step, grad_scale)
+        adv = advance_rng and self.rng_used
+        self.ops.advance_counters(self.rng if adv else None, self.opt_step)
+        if adv:
+            self.rng_used = False
+        self.weights_dirty = True
+
+
+class THATEngine(StepCounters):
     def __init__(self, geom: ModelGeom, max_batch: int, params: torch.Tensor, grads: torch.Tensor,
                  arena: LY.Arena, buffers: Dict[str, torch.Tensor], frozen: Dict[str, torch.Tensor],
                  act_dtype: torch.dtype = torch.bfloat16, ops=None, seed: int = 0, rng: Optional[torch.Tensor] = None,
@@ -242,7 +274,7 @@ class THATEngine:
         pd = P_DROP if (training and dropout) else 0.0
         pf = P_FEAT if (training and dropout) else 0.0
         if training:
-            self.stat_pool.zero_()
+            ops.fill_f64(self.stat_pool, 0.0)
         join = self._fork(lambda: self._forward_stream(1, B, training, pd))
         self._forward_stream(0, B, training, pd)
         join()
@@ -338,8 +370,8 @@ class THATEngine:
         if part == 2:
             return self._backward_stream(0, B, pd, range(0, 1), head=False) if nl > 1 else None
         if zero_grads:
-            self.grads.zero_()
-        self.red_pool.zero_()                             # parts 1 and 2 use disjoint slices: zeroed once, here
+            ops.fill_f32(self.grads, 0.0)
+        ops.fill_f64(self.red_pool, 0.0)                  # parts 1 and 2 use disjoint slices: zeroed once, here
         if dlogits is not None:
             if g.heads == 1:
                 self.dlogits[:B, :g.out].copy_(dlogits)
@@ -507,30 +539,3 @@ class THATEngine:
             self.ops.bce_logits(self.logits, y, B, self.g.out, pos_weight, grad_scale, self.loss,
                                 self.dlogits if want_grad else None)
         return self.loss
-
-    # The Philox step is a property of the forward/backward pair, not of the optimizer: backward regenerates the masks
-    # its forward drew, then the step moves on -- whichever optimizer (or none) follows.
-    def begin_train_forward(self):
-        """Call before a train-mode forward: if the previous train forward never reached ``end_train_step`` (no
-        backward, e.g. two forwards in a row) its masks must not be reused."""
-        if self.rng_used:
-            self.ops.advance_counters(self.rng, None)
-        self.rng_used = True
-
-    def end_train_step(self):
-        """Call after the backward that belongs to the last train forward (autograd path)."""
-        if self.rng_used:
-            self.ops.advance_counters(self.rng, None)
-        self.rng_used = False
-
-    def adam(self, m: torch.Tensor, v: torch.Tensor, lr: float, betas=(0.9, 0.999), eps: float = 1e-8,
-             weight_decay: float = 0.0, grad_scale: float = 1.0, advance_rng: bool = False):
-        """One fused Adam launch over the arena; advances the Adam step and, on the fused train step
-        (``advance_rng``), the Philox step in the same tiny launch."""
-        self.ops.adam_flat(self.params, self.grads, m, v, self.params.numel(), lr, betas[0], betas[1], eps,
-                           weight_decay, self.opt_step, grad_scale)
-        adv = advance_rng and self.rng_used
-        self.ops.advance_counters(self.rng if adv else None, self.opt_step)
-        if adv:
-            self.rng_used = False
-        self.weights_dirty = True

@@ -68,6 +68,9 @@ EXPORTS = [
     "csi_bn_act_bwd_reduce", "csi_bn_act_bwd_dz", "csi_head_reduce_fwd", "csi_head_reduce_bwd", "csi_dropout_rows",
     "csi_bce_logits", "csi_smooth_l1", "csi_perm_ce", "csi_predict_counts", "csi_adam_flat", "csi_advance_counters", "csi_pack_weights", "csi_fill_f32",
     "csi_set_force_simt", "csi_set_strict_tc", "csi_dispatch_counts", "csi_set_attn_impl",
+    "csi_fill_f64", "csi_copy_f32", "csi_nhwc_stats", "csi_bn2d_finalize", "csi_im2col_bn", "csi_col2im", "csi_act_drop_fwd",
+    "csi_bn2d_bwd_reduce", "csi_bn2d_bwd_apply", "csi_pool_bn_fwd", "csi_conv2d_pack", "csi_conv2d_unpack_grad", "csi_bn0_grads",
+    "csi_gather_aug",
 ]
 
 
@@ -374,3 +377,56 @@ class NativeOps:
     def fill_f32(self, t, v):
         wk = self._work("fill_f32", locals())
         self._call("csi_fill_f32", _p(t), C.c_longlong(t.numel()), C.c_float(v), **wk)
+
+    def fill_f64(self, t, v=0.0):
+        self._call("csi_fill_f64", _p(t), C.c_longlong(t.numel()), C.c_double(v))
+
+    def copy_f32(self, dst, src, n):
+        self._call("csi_copy_f32", _p(dst), _p(src), C.c_longlong(n))
+
+    # -------------------------------------------------------------- CSI-as-image path (cnn2d.cu)
+    def nhwc_stats(self, x, rows, Cc, sums):
+        self._call("csi_nhwc_stats", _p(x), _dt(x), C.c_longlong(rows), Cc, _p(sums), nbytes=rows * Cc * x.element_size())
+
+    def bn2d_finalize(self, sums, Cc, count, gamma, beta, run_mean, run_var, nbt, momentum, eps, training, mean, invstd, scale, shift):
+        self._call("csi_bn2d_finalize", _p(sums), Cc, C.c_longlong(count), _p(gamma), _p(beta), _p(run_mean), _p(run_var), _p(nbt),
+                   C.c_float(momentum), C.c_float(eps), int(training), _p(mean), _p(invstd), _p(scale), _p(shift))
+
+    def im2col_bn(self, x, B, H, W, Cc, k, s, scale, shift, col, Kp):
+        OH, OW = (H - k) // s + 1, (W - k) // s + 1
+        self._call("csi_im2col_bn", _p(x), _dt(x), B, H, W, Cc, k, s, _p(scale), _p(shift), _p(col), _dt(col), Kp,
+                   nbytes=B * OH * OW * Kp * col.element_size() + B * H * W * Cc * x.element_size())
+
+    def col2im(self, gcol, B, H, W, Cc, k, s, Kp, g):
+        OH, OW = (H - k) // s + 1, (W - k) // s + 1
+        self._call("csi_col2im", _p(gcol), _dt(gcol), B, H, W, Cc, k, s, Kp, _p(g),
+                   nbytes=B * OH * OW * Kp * gcol.element_size() + B * H * W * Cc * 4)
+
+    def act_drop_fwd(self, z, y, n, p, site, rng, mask):
+        self._call("csi_act_drop_fwd", _p(z), _p(y), _dt(z), C.c_longlong(n), C.c_float(p), C.c_uint(site), _p(rng), _p(mask),
+                   nbytes=2 * n * z.element_size())
+
+    def bn2d_bwd_reduce(self, g, g_div, g_scale, x, rows, Cc, mean, invstd, sums):
+        self._call("csi_bn2d_bwd_reduce", _p(g), _dt(g), C.c_longlong(g_div), C.c_float(g_scale), _p(x), _dt(x), C.c_longlong(rows), Cc, _p(mean),
+                   _p(invstd), _p(sums), nbytes=rows * Cc * x.element_size() + (rows // g_div) * Cc * g.element_size())
+
+    def bn2d_bwd_apply(self, g, g_div, g_scale, x, zprev, mask, drop_p, rows, Cc, mean, invstd, gamma, sums, gz, dgamma, dbeta):
+        self._call("csi_bn2d_bwd_apply", _p(g), C.c_longlong(g_div), C.c_float(g_scale), _p(x), _p(zprev), _dt(x), _p(mask), C.c_float(drop_p),
+                   C.c_longlong(rows), Cc, _p(mean), _p(invstd), _p(gamma), _p(sums), _p(gz), _p(dgamma), _p(dbeta),
+                   nbytes=rows * Cc * 3 * x.element_size() + (rows // g_div) * Cc * 4)
+
+    def pool_bn_fwd(self, y, B, P, Cc, scale, shift, feat, featd):
+        self._call("csi_pool_bn_fwd", _p(y), _dt(y), B, P, Cc, _p(scale), _p(shift), _p(feat), _p(featd))
+
+    def conv2d_pack(self, w, N, Cc, k, wf, Kp, wb, Np):
+        self._call("csi_conv2d_pack", _p(w), N, Cc, k, _p(wf), Kp, _p(wb), Np, _dt(wf))
+
+    def conv2d_unpack_grad(self, gs, N, Cc, k, Kp, gw):
+        self._call("csi_conv2d_unpack_grad", _p(gs), N, Cc, k, Kp, _p(gw))
+
+    def bn0_grads(self, sums, wf, ldw, N, K, bias, gamma0, beta0, dgamma0, dbeta0, dbias):
+        self._call("csi_bn0_grads", _p(sums), _p(wf), ldw, _dt(wf), N, K, _p(bias), _p(gamma0), _p(beta0), _p(dgamma0), _p(dbeta0),
+                   _p(dbias))
+
+    def gather_aug(self, x, offs, lens, B, T, F, out, augment, rng):
+        self._call("csi_gather_aug", _p(x), _p(offs), _p(lens), B, T, F, _p(out), int(augment), _p(rng), nbytes=2 * B * T * F * 4)

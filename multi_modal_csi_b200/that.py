@@ -20,11 +20,8 @@ from typing import Optional
 import torch
 
 from . import layout as LY
+from .arena_module import ArenaModule, _Node
 from .engine import THATEngine
-
-
-class _Node(torch.nn.Module):
-    """Parameter container; the module tree only exists to reproduce the reference's state_dict keys."""
 
 
 def _kaiming_conv(shape):
@@ -117,10 +114,11 @@ class _THATFunction(torch.autograd.Function):
         return None, None, None
 
 
-class THAT(torch.nn.Module):
+class THAT(ArenaModule):
     """``THAT(var_x_shape, var_y_shape)``: var_x_shape[-2:] = (T, F), var_y_shape[-1] = out (that.py:183-192)."""
 
     NUM_OUTPUT_HEADS = 1
+    FROZEN_PARAMS = LY.FROZEN
 
     def __init__(self, var_x_shape, var_y_shape, act_dtype: Optional[str] = None, max_batch: Optional[int] = None):
         super().__init__()
@@ -160,85 +158,6 @@ class THAT(torch.nn.Module):
             self._register(name, p, is_buffer=False)
         for name, val in bufs.items():
             self._register(name, val, is_buffer=True)
-
-    @property
-    def rng_seed(self) -> int:
-        return self._rng_seed
-
-    @rng_seed.setter
-    def rng_seed(self, seed: int):
-        self._rng_seed = int(seed)
-        if self._rng is not None:
-            self._rng[0] = self._rng_seed
-
-    def _counters(self, device):
-        if self._rng is None:
-            self._rng = torch.tensor([self._rng_seed, 0], dtype=torch.int64, device=device)
-            self._opt_step = torch.ones(1, dtype=torch.int64, device=device)
-        elif self._rng.device != device:
-            self._rng, self._opt_step = self._rng.to(device), self._opt_step.to(device)
-        return self._rng, self._opt_step
-
-    # ------------------------------------------------------------------ module tree
-    def _register(self, name, tensor, is_buffer):
-        parts = name.split(".")
-        node = self
-        for i, part in enumerate(parts[:-1]):
-            nxt = parts[i + 1]
-            if part.isdigit():
-                idx = int(part)
-                assert isinstance(node, torch.nn.ModuleList)
-                while len(node) <= idx:
-                    node.append(torch.nn.ModuleList() if nxt.isdigit() else _Node())
-                node = node[idx]
-            else:
-                if part not in node._modules:
-                    node.add_module(part, torch.nn.ModuleList() if nxt.isdigit() else _Node())
-                node = node._modules[part]
-        if is_buffer:
-            node.register_buffer(parts[-1], tensor)
-        else:
-            node.register_parameter(parts[-1], tensor)
-
-    def _named(self):
-        return OrderedDict(self.named_parameters())
-
-    def _apply(self, fn, recurse=True):
-        """``.to(device)`` / ``.cuda()``: move the two flat arenas and re-create the parameter views."""
-        new_flat = fn(self._flat)
-        if new_flat.dtype != torch.float32:
-            raise TypeError("THAT master weights are fp32; choose the compute type with act_dtype")
-        new_g = fn(self._gflat)
-        object.__setattr__(self, "_flat", new_flat)
-        object.__setattr__(self, "_gflat", new_g)
-        for name, p in self._named().items():
-            had_grad = p.grad is not None
-            if name in LY.FROZEN:
-                p.data = fn(p.data)
-            else:
-                off, shape = self.arena.offsets[name], self.arena.shapes[name]
-                p.data = new_flat[off:off + LY.numel(shape)].view(shape)
-                p.grad = new_g[off:off + LY.numel(shape)].view(shape) if had_grad else None
-        for mod in self.modules():
-            for k, b in mod._buffers.items():
-                if b is not None:
-                    mod._buffers[k] = fn(b)
-        self._engine = None
-        return self
-
-    def _attach_grads(self):
-        for name, p in self.named_parameters():
-            if p.requires_grad and p.grad is None:
-                off, shape = self.arena.offsets[name], self.arena.shapes[name]
-                p.grad = self._gflat[off:off + LY.numel(shape)].view(shape)
-
-    @property
-    def flat_params(self) -> torch.Tensor:
-        return self._flat
-
-    @property
-    def flat_grads(self) -> torch.Tensor:
-        return self._gflat
 
     # ------------------------------------------------------------------ engine
     def configure(self, act_dtype: Optional[str] = None, max_batch: Optional[int] = None):
@@ -324,7 +243,7 @@ class THAT(torch.nn.Module):
             yf = yf.float()
         eng.begin_train_forward()
         eng.forward_input(x, B, True, augment, offs, lens)
-        eng.y_static[:B].copy_(yf)
+        eng.ops.copy_f32(eng.y_static, yf.contiguous(), yf.numel())     # rows of y_static and yf have the same pitch
         graph = self.use_cuda_graph if use_graph is None else use_graph
         run = eng.train_body_graph if (graph and x.is_cuda and self._eager_steps >= 1) else eng.train_body
         overlap = grad_hook is not None and hasattr(grad_hook, "start_bucket")

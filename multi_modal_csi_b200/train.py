@@ -30,6 +30,8 @@ from torch.utils.data.distributed import DistributedSampler
 from .loader import CSIBatchSource, PackedCSIDataset
 from .optim import FusedAdam
 from .parallel import GradSync, broadcast_buffers, broadcast_parameters
+from .arena_module import ArenaModule
+from .cnn2d import CNN_2D
 from .that import PermutationMatchingLoss
 from .that import THAT
 from .utils import performance_metrics
@@ -103,10 +105,10 @@ def train(model, optimizer, loss, data_train_set: TensorDataset, data_test_set: 
         loss_kind, pos_weight = "smooth_l1", 1.0
     elif isinstance(loss, PermutationMatchingLoss) and var_mode == "multi_head":
         loss_kind, pos_weight = "perm_ce", 1.0
-    fused = (isinstance(model, THAT) and isinstance(optimizer, FusedAdam) and loss_kind is not None
-             and device.type == "cuda")
-    sync = GradSync(model, dist.get_world_size()) if distributed and isinstance(model, THAT) else None
-    if distributed and isinstance(model, THAT):
+    fused = (isinstance(model, (THAT, CNN_2D)) and isinstance(optimizer, FusedAdam) and loss_kind is not None
+             and device.type == "cuda" and (loss_kind == "bce" or isinstance(model, THAT)))
+    sync = GradSync(model, dist.get_world_size()) if distributed and isinstance(model, ArenaModule) else None
+    if distributed and isinstance(model, ArenaModule):
         broadcast_parameters(model)                     # every rank starts from rank 0's weights and BatchNorm buffers
         model.rng_seed = (model.rng_seed + 7919 * dist.get_rank()) & 0x7FFFFFFF      # decorrelated dropout / augmentation
     source = data_train_loader = None
@@ -180,7 +182,7 @@ def train(model, optimizer, loss, data_train_set: TensorDataset, data_test_set: 
         dict_error_train = performance_metrics(data_batch_y.astype(int), predict_train_y.astype(int), var_mode=var_mode,
                                                var_threshold=var_threshold)
         model.eval()
-        if distributed and isinstance(model, THAT):
+        if distributed and isinstance(model, ArenaModule):
             broadcast_buffers(model)                    # rank 0's BatchNorm running statistics: identical eval on every rank
         with torch.no_grad():
             data_test_x, data_test_y = next(iter(data_test_loader))

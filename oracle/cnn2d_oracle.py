@@ -1,7 +1,7 @@
 """TEST INFRASTRUCTURE ONLY -- CPU restatement of the reference CNN_2D (CSI-as-image) path, SURVEY.md section 8(f)-3.
 
-Groundwork for BASELINE config 4: the oracle and its fixture exist, the CUDA path does not yet.
-Nothing in the product package imports this file.
+The oracle of BASELINE config 4 (product: multi_modal_csi_b200/cnn2d.py + csrc/cnn2d.cu).  Nothing in the product package
+imports this file.
 
 Restates, as pure functions over a ``state_dict`` (plain torch CPU ops):
 
@@ -73,17 +73,38 @@ def _bn2d(sd, prefix, x, training, update_stats):
     return xh * sd[prefix + "weight"][None, :, None, None] + sd[prefix + "bias"][None, :, None, None]
 
 
-def cnn2d_forward(sd, x: torch.Tensor, training: bool = False, update_stats: bool = True, drop=None) -> torch.Tensor:
+class _RoundBF16(torch.autograd.Function):
+    """x -> bf16(x) with a straight-through gradient (optionally rounded to bf16 as well): restates WHERE the bf16 mode of
+    the CUDA path stores a tensor in bf16, so that "bf16 parity" can be stated against the reference ALGORITHM evaluated
+    with bf16-rounded operands instead of only against a loose tolerance."""
+
+    @staticmethod
+    def forward(ctx, x, round_grad):
+        ctx.round_grad = round_grad
+        return x.bfloat16().to(x.dtype)
+
+    @staticmethod
+    def backward(ctx, g):
+        return (g.bfloat16().to(g.dtype) if ctx.round_grad else g), None
+
+
+def cnn2d_forward(sd, x: torch.Tensor, training: bool = False, update_stats: bool = True, drop=None,
+                  emulate_bf16: bool = False) -> torch.Tensor:
     """cnn_2d.py:70-99.  x: [B, T, F] -> logits [B, out]; BatchNorm2d -> Conv2d -> LeakyReLU -> Dropout(0.2), three
-    times, then BatchNorm2d, mean over the image and the Linear layer."""
+    times, then BatchNorm2d, mean over the image and the Linear layer.
+
+    emulate_bf16: round to bf16 wherever the bf16 mode of the CUDA path stores bf16 -- the normalised conv inputs (patch
+    matrix), the weights, the conv outputs, the activations, the pooled features -- and, in backward, the gradients of
+    the conv outputs and of the patch matrices.  Arithmetic stays fp32 (the tensor cores accumulate in fp32)."""
     drop = drop or (lambda t, p: t)
+    r = (lambda t, g=False: _RoundBF16.apply(t, g)) if emulate_bf16 else (lambda t, g=False: t)
     t = x.unsqueeze(1)
     for i, (_ci, _co, _k, s) in enumerate(CONVS):
-        t = _bn2d(sd, f"layer_norm_{i}.", t, training, update_stats)
-        t = Fn.conv2d(t, sd[f"layer_cnn_2d_{i}.weight"], sd[f"layer_cnn_2d_{i}.bias"], stride=s)
-        t = drop(Fn.leaky_relu(t, LEAKY), P_DROP)
+        t = r(_bn2d(sd, f"layer_norm_{i}.", t, training, update_stats), i > 0)
+        t = r(Fn.conv2d(t, r(sd[f"layer_cnn_2d_{i}.weight"]), sd[f"layer_cnn_2d_{i}.bias"], stride=s), True)
+        t = r(drop(Fn.leaky_relu(t, LEAKY), P_DROP))
     t = _bn2d(sd, "layer_norm_3.", t, training, update_stats)
-    return Fn.linear(t.mean(dim=(-2, -1)), sd["layer_linear.weight"], sd["layer_linear.bias"])
+    return Fn.linear(r(t.mean(dim=(-2, -1))), r(sd["layer_linear.weight"]), sd["layer_linear.bias"])
 
 
 def bce_with_logits(z, y, pos_weight: float = 6.0):
@@ -91,12 +112,12 @@ def bce_with_logits(z, y, pos_weight: float = 6.0):
     return -(pos_weight * y * Fn.logsigmoid(z) + (1 - y) * Fn.logsigmoid(-z)).mean()
 
 
-def loss_and_grads(sd, x, y, pos_weight: float = 6.0):
+def loss_and_grads(sd, x, y, pos_weight: float = 6.0, emulate_bf16: bool = False):
     names = [k for k, v in sd.items() if v.is_floating_point() and "running" not in k]
     work = OrderedDict(sd)
     leaves = {k: sd[k].detach().clone().requires_grad_(True) for k in names}
     work.update(leaves)
-    logits = cnn2d_forward(work, x, training=True, update_stats=False)
+    logits = cnn2d_forward(work, x, training=True, update_stats=False, emulate_bf16=emulate_bf16)
     loss = bce_with_logits(logits, y, pos_weight)
     grads = torch.autograd.grad(loss, [leaves[k] for k in names])
     return logits.detach(), loss.detach(), dict(zip(names, grads))

@@ -374,3 +374,9 @@ class MirrorOps:
 
     def fill_f32(self, t, v):
         t.fill_(v)
+
+    def fill_f64(self, t, v=0.0):
+        t.fill_(v)
+
+    def copy_f32(self, dst, src, n):
+        dst.reshape(-1)[:n].copy_(src.reshape(-1)[:n])

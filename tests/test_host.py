@@ -595,3 +595,31 @@ def test_epoch_index_batches_match_dataloader_and_packed_dataset_pads_in_front()
         assert xi.shape == (T, F) and torch.equal(xi[T - lens[i]:], c) and float(xi[:T - lens[i]].abs().sum()) == 0 and int(yi) == i
     with pytest.raises(ValueError):
         PackedCSIDataset(torch.zeros(13 * F), [0], [13], F, torch.zeros(1), T)
+
+
+def test_cnn2d_module_contract_matches_reference_fixture(gold):
+    """multi_modal_csi_b200.CNN_2D (the product module of the CSI-as-image path): the reference's 28 state_dict keys in
+    its order, bit-identical initial weights under its seed, fp32 arena views, and no CPU path."""
+    from multi_modal_csi_b200 import CNN_2D
+    g = gold("cnn2d_anchor.npz")
+    T, F, out, B = [int(v) for v in g["dims"]]
+    torch.manual_seed(39)
+    m = CNN_2D((T, F), (out,))
+    sd = m.state_dict()
+    assert list(sd.keys()) == [str(k) for k in g["keys"]]
+    for k, v in sd.items():
+        assert abs(v.double().sum().item() - float(g["init_sum/" + k])) <= 1e-6 * max(1.0, float(g["init_abs/" + k])), k
+    assert m.geom.H == [300, 40, 9, 3] and m.geom.W == [270, 35, 7, 1] and m.geom.Kp == [736, 7200, 3136]
+    assert sum(p.numel() for p in m.parameters()) == m.flat_params.numel() - sum(
+        (-LY_numel(s)) % 4 for s in m.arena.shapes.values())
+    with pytest.raises(RuntimeError, match="no CPU path"):
+        m(torch.zeros(1, T, F))
+    with pytest.raises(ValueError):
+        CNN_2D((20, 270), (54,))
+
+
+def LY_numel(shape):
+    n = 1
+    for s in shape:
+        n *= s
+    return n
