@@ -37,6 +37,8 @@ def parse():
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-e2e", action="store_true")
     ap.add_argument("--profile-ops", action="store_true", help="print the per-op device-time table (stderr)")
+    ap.add_argument("--no-config4", action="store_true", help="skip the CSI-as-image (CNN_2D) line")
+    ap.add_argument("--cnn-batch", type=int, default=128, help="samples per GPU of the CSI-as-image line (BASELINE config 4: 128)")
     ap.add_argument("--config3", action="store_true", help="also measure BASELINE config 3 (F=540, out=90) at N=1 (always on for N>1)")
     return ap.parse_args()
 
@@ -365,6 +367,92 @@ def measure(F, out, B, K, W, dtype, dev, world, rank, full, no_e2e=False, profil
     return res
 
 
+def measure_cnn2d(B, K, W, dtype, dev, world, rank, no_e2e=False):
+    """BASELINE config 4, the CSI-as-image model (the in-reference CNN_2D, model/cnn_2d.py) on [B,3000,270] images through the
+    same loader / loss / Adam / data-parallel layers: `value` with the batches resident in HBM, `e2e` through
+    CSIBatchSource(stream) with the loss read back every step."""
+    import torch
+    import torch.distributed as dist
+    from torch.utils.data import TensorDataset
+    from multi_modal_csi_b200 import CNN_2D, FusedAdam
+    from multi_modal_csi_b200.loader import CSIBatchSource
+    from multi_modal_csi_b200.parallel import GradSync
+    F, out = 270, 54
+    torch.manual_seed(39)
+    model = CNN_2D((T_LEN, F), (out,), act_dtype=dtype, max_batch=B).to(dev)
+    model.rng_seed = 2000 + rank
+    model.train()
+    opt = FusedAdam(model.parameters(), lr=1e-3, weight_decay=1e-4)            # cnn_2d.py:162-164
+    hook = GradSync(model, world) if world > 1 else None
+    hx, hy = zip(*[synth_batch(B, F, out, 4321 + rank + 100 * i) for i in range(2)])
+    host_x, host_y = torch.cat(hx), torch.cat(hy)
+    resident = [(host_x[i * B:(i + 1) * B].to(dev), host_y[i * B:(i + 1) * B].to(dev)) for i in range(2)]
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize(dev)
+
+    def max_over_ranks(ms):
+        t = torch.tensor([ms], device=dev)
+        if world > 1:
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        return float(t.item())
+
+    def step(i):
+        x, y = resident[i % 2]
+        return model.fused_train_step(x, y, opt, pos_weight=6.0, augment=True, grad_hook=hook)
+
+    for i in range(W):
+        step(i)
+    barrier()
+    ops = model._engine.ops
+    if dtype == "bf16":
+        ops.set_strict_tc(True)
+    ops.dispatch_counts(reset=True)
+    ops.start_profile()
+    step(0)
+    table = ops.stop_profile()
+    launches0 = ops.launches
+    ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    barrier()
+    ev0.record()
+    for i in range(K):
+        step(i)
+    ev1.record()
+    barrier()
+    ms = max_over_ranks(ev0.elapsed_time(ev1) / K)
+    res = {"workload": f"CNN_2D (model/cnn_2d.py) train step on CSI-as-image [B={B}/GPU,3000,{F}], out={out}, {dtype} "
+                       f"(BASELINE config 4; the reference has no ResNet-18: CNN_2D is its CSI-as-image model)",
+           "value": world * B / (ms / 1e3), "unit": "samples/s", "ms_per_step": ms, "gpu_launches": (ops.launches - launches0),
+           "families": family_table(table, PEAKS()), "e2e": None}
+    if not no_e2e:
+        src = CSIBatchSource(TensorDataset(host_x, host_y), dev, B, mode="stream")
+        h2d = [0]
+
+        def run_e2e(n):
+            for batch in src.batches([range((i % 2) * B, (i % 2 + 1) * B) for i in range(n)]):
+                loss, _ = model.fused_train_step(batch.x, batch.y, opt, pos_weight=6.0, augment=True, grad_hook=hook,
+                                                 offs=batch.offs, lens=batch.lens)
+                h2d[0] = batch.h2d_bytes
+                float(loss.item())
+
+        run_e2e(2)
+        barrier()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        run_e2e(K)
+        e1.record()
+        barrier()
+        ems = max_over_ranks(e0.elapsed_time(e1) / K)
+        res["e2e"] = {"value": world * B / (ems / 1e3), "unit": "samples/s", "h2d_bytes_per_step": int(h2d[0]),
+                      "d2h_bytes_per_step": 4, "ms_per_step": ems}
+        src.close()
+    res["dispatch"] = ops.dispatch_counts()
+    ops.set_strict_tc(False)
+    return res
+
+
 def run_b200(args):
     import torch
     import torch.distributed as dist
@@ -385,12 +473,11 @@ def run_b200(args):
     clk.__enter__()
     main = measure(F, out, B, K, W, args.dtype, dev, world, rank, full=True, no_e2e=args.no_e2e, profile_ops=args.profile_ops)
     clk.__exit__()
-    eng = main.pop("engine")
+    main.pop("engine")                                 # (its ~1.5 GB of activation buffers are freed before the next configuration)
     # BASELINE config 3 (dual band: 540 features, identity+location+activity = 90 outputs, B=256 per GPU) is quoted at
     # 2/4/8 GPUs: measured in the same launch and reported under "config3" so that the headline config stays config 2
     cfg3 = None
     if (world > 1 or args.config3) and F != 540:
-        del eng
         torch.cuda.empty_cache()
         c3 = measure(540, 90, B, K, W, args.dtype, dev, world, rank, full=False, no_e2e=args.no_e2e)
         c3.pop("engine")
@@ -398,6 +485,10 @@ def run_b200(args):
                 "unit": "samples/s", "ms_per_step": c3["ms_per_step"], "e2e": c3["e2e"], "allreduce": c3.get("allreduce"),
                 "gpu_launches": c3["gpu_launches"], "dispatch": c3["dispatch"],
                 "tensor_frac_step": TRAIN_FLOP[540] * c3["value"] / world / 1e12 / None_or(PEAKS().get("bf16_tflops"), 1595.7)}
+    cfg4 = None
+    if not args.no_config4:
+        torch.cuda.empty_cache()
+        cfg4 = measure_cnn2d(args.cnn_batch, max(3, K // 2), 3, args.dtype, dev, world, rank, no_e2e=args.no_e2e)
     if rank == 0:
         peaks = PEAKS()
         roof = roofline(main["dominant"], main["dom"], B, peaks)
@@ -421,7 +512,7 @@ def run_b200(args):
             # whole step against the tensor roofline: BASELINE.md section 3 formula, burst cuBLAS peak (sub-second timed region at full clocks)
             "tensor_frac_step": step_tf / burst,
             "tensor_frac_step_sustained": step_tf / None_or(peaks.get("bf16_tflops_sustained"), 1340.8),
-            "config3": cfg3,
+            "config3": cfg3, "config4": cfg4,
         }
         print(json.dumps(line), flush=True)
     if world > 1:

@@ -69,7 +69,23 @@ __global__ void __launch_bounds__(C2_THREADS) nhwc_sums_kernel(const T* __restri
     float s[8], q[8];
 #pragma unroll
     for (int j = 0; j < 8; ++j) s[j] = q[j] = 0.f;
-    for (long long v = v0; v < nv; v += stride) {
+    long long v = v0;
+    if (MODE == 0) {
+        // four independent 16/32-byte loads in flight per thread before the first use
+        for (; v + 3 * stride < nv; v += 4 * stride) {
+            float a0[8], a1[8], a2[8], a3[8];
+            load8<T>(x + v * 8, a0);
+            load8<T>(x + (v + stride) * 8, a1);
+            load8<T>(x + (v + 2 * stride) * 8, a2);
+            load8<T>(x + (v + 3 * stride) * 8, a3);
+#pragma unroll
+            for (int j = 0; j < 8; ++j) {
+                s[j] += (a0[j] + a1[j]) + (a2[j] + a3[j]);
+                q[j] = fmaf(a0[j], a0[j], fmaf(a1[j], a1[j], fmaf(a2[j], a2[j], fmaf(a3[j], a3[j], q[j]))));
+            }
+        }
+    }
+    for (; v < nv; v += stride) {
         float a[8];
         load8<T>(x + v * 8, a);
         if (MODE == 0) {
@@ -191,15 +207,16 @@ __global__ void __launch_bounds__(C2_THREADS) im2col_vec_kernel(const T* __restr
     const int K = k * k * C, cpr = Kp >> 3, kc8 = (k * C) >> 3;
     const long long items = M * cpr;
     for (long long it = (long long)blockIdx.x * C2_THREADS + threadIdx.x; it < items; it += (long long)gridDim.x * C2_THREADS) {
-        const long long m = it / cpr;
-        const int ch = (int)(it - m * cpr);
+        // M < 2^31 patch rows: 64-bit only for the item index and the final addresses
+        const unsigned m = (unsigned)(it / (unsigned)cpr);
+        const int ch = (int)(it - (long long)m * cpr);
         float v[8];
         if (ch * 8 < K) {
             const int kh = ch / kc8, r = ch - kh * kc8;              // r: 8-element chunk inside the k*C run of this kernel row
-            const int ow = (int)(m % OW);
-            const long long t = m / OW;
-            const int oh = (int)(t % OH);
-            const long long b = t / OH;
+            const unsigned t = m / (unsigned)OW;
+            const int ow = (int)(m - t * (unsigned)OW);
+            const long long b = t / (unsigned)OH;
+            const int oh = (int)(t - (unsigned)b * (unsigned)OH);
             const T* src = x + ((b * H + (long long)oh * s + kh) * W + (long long)ow * s) * C + r * 8;
             load8<T>(src, v);
             const int c0 = (r * 8) % C;
@@ -209,7 +226,7 @@ __global__ void __launch_bounds__(C2_THREADS) im2col_vec_kernel(const T* __restr
 #pragma unroll
             for (int j = 0; j < 8; ++j) v[j] = 0.f;
         }
-        store8<T>(col + m * Kp + ch * 8, v);
+        store8<T>(col + (long long)m * Kp + ch * 8, v);
     }
 }
 
@@ -235,6 +252,44 @@ __global__ void __launch_bounds__(C2_THREADS) im2col_c1_kernel(const TI* __restr
     }
 }
 
+// Single-channel image, compile-time kernel size / stride (conv 0 is 27x27 / 7): one CTA per (sample, output row).  The K
+// input rows the output row reads are ONE contiguous run of K*W floats: they are normalised into shared memory once
+// (each input pixel is fetched K/S = 3.9 times overall instead of once per patch that covers it), then the OW patch rows
+// are written as whole 16/32-byte chunks.
+template <typename T, int K, int S>
+__global__ void __launch_bounds__(C2_THREADS) im2col_c1_tile_kernel(const float* __restrict__ x, int H, int W, int OH, int OW,
+                                                                    const float* __restrict__ scale, const float* __restrict__ shift,
+                                                                    T* __restrict__ col, int Kp) {
+    extern __shared__ float c1_tile[];                                  // [K][W]
+    const int boh = blockIdx.x, b = boh / OH, oh = boh - b * OH;
+    const float sc = scale[0], sh = shift[0];
+    const float* src = x + ((long long)b * H + (long long)oh * S) * W;
+    const int n = K * W;
+    if ((reinterpret_cast<uintptr_t>(src) & 7) == 0 && (n & 1) == 0) {
+        for (int i = threadIdx.x; i < (n >> 1); i += C2_THREADS) {
+            const float2 v = reinterpret_cast<const float2*>(src)[i];
+            c1_tile[2 * i] = fmaf(v.x, sc, sh);
+            c1_tile[2 * i + 1] = fmaf(v.y, sc, sh);
+        }
+    } else {
+        for (int i = threadIdx.x; i < n; i += C2_THREADS) c1_tile[i] = fmaf(src[i], sc, sh);
+    }
+    __syncthreads();
+    const int cpr = Kp >> 3;
+    T* dst = col + (long long)boh * OW * Kp;
+    for (int c = threadIdx.x; c < OW * cpr; c += C2_THREADS) {
+        const int ow = c / cpr, j0 = (c - ow * cpr) * 8;
+        const float* base = c1_tile + ow * S;
+        float v[8];
+#pragma unroll
+        for (int j = 0; j < 8; ++j) {
+            const int jj = j0 + j, kh = jj / K, kw = jj - kh * K;
+            v[j] = jj < K * K ? base[kh * W + kw] : 0.f;
+        }
+        store8<T>(dst + (long long)ow * Kp + j0, v);
+    }
+}
+
 extern "C" int csi_im2col_bn(const void* x, int x_dtype, int B, int H, int W, int C, int k, int s, const float* scale,
                              const float* shift, void* col, int col_dtype, int Kp, void* stream) {
     CSI_CHECK_ARG(x && scale && shift && col && B >= 0 && k >= 1 && s >= 1 && H >= k && W >= k, "bad argument");
@@ -242,7 +297,13 @@ extern "C" int csi_im2col_bn(const void* x, int x_dtype, int B, int H, int W, in
     const int OH = (H - k) / s + 1, OW = (W - k) / s + 1;
     const long long M = (long long)B * OH * OW;
     if (M == 0) return CSI_OK;
-    if (C == 1) {
+    if (C == 1 && k == 27 && s == 7 && x_dtype == CSI_F32 && (size_t)k * W * sizeof(float) <= 48 * 1024) {
+        const size_t smem = (size_t)k * W * sizeof(float);
+        if (col_dtype == CSI_BF16)
+            im2col_c1_tile_kernel<bf16, 27, 7><<<B * OH, C2_THREADS, smem, ST(stream)>>>((const float*)x, H, W, OH, OW, scale, shift, (bf16*)col, Kp);
+        else
+            im2col_c1_tile_kernel<float, 27, 7><<<B * OH, C2_THREADS, smem, ST(stream)>>>((const float*)x, H, W, OH, OW, scale, shift, (float*)col, Kp);
+    } else if (C == 1) {
         const int grid = c2_grid(M * (Kp >> 1));
         if (x_dtype == CSI_F32 && col_dtype == CSI_BF16)
             im2col_c1_kernel<float, bf16><<<grid, C2_THREADS, 0, ST(stream)>>>((const float*)x, H, W, k, s, OH, OW, scale, shift, (bf16*)col, Kp, M);

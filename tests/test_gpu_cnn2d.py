@@ -227,38 +227,39 @@ def test_cnn2d_fused_step_trajectory_and_train_loop(gold, monkeypatch):
     assert int(m2._opt_step.item()) == 1 + 2 * 2 and int(m2.state_dict()["layer_norm_2.num_batches_tracked"]) == 4
 
 
-def test_cnn2d_backward_uses_the_forward_dropout_masks():
-    """Dropout(0.2) on: analytic gradient == finite-difference directional derivative of the same masked network."""
+def test_cnn2d_dropout_masks_forward_and_backward_agree_with_the_oracle(gold):
+    """Dropout(0.2) on: the keep bits the forward kernel stored are read back and handed to the oracle as ITS dropout
+    masks; logits and every gradient must then match to fp32 accuracy -- i.e. forward and backward used the same masks, with
+    the 1/(1-p) scaling, and the keep rate is 0.8."""
     from multi_modal_csi_b200 import CNN_2D
-    T, F, out, B = 300, 270, 12, 2
-    gen = torch.Generator().manual_seed(7)
-    x = (torch.rand(B, T, F, generator=gen) * 20).cuda()
-    y = (torch.rand(B, out, generator=gen) < 0.2).float().cuda()
+    from oracle import cnn2d_oracle as C
+    g = gold("cnn2d_anchor.npz")
+    T, F, out, B, x, y = data(g)
     torch.manual_seed(39)
-    m = CNN_2D((T, F), (out,), act_dtype="fp32").to("cuda").train()
-    lossf = torch.nn.BCEWithLogitsLoss(pos_weight=torch.full((out,), 6.0, device="cuda"))
-    step0 = int(m._engine_for(B).rng[1].item())
-    lossf(m(x), y).backward()
-    gflat = m.flat_grads.clone()
-
-    def pin():
-        eng = m._engine_for(B)
-        eng.rng.copy_(torch.tensor([m.rng_seed, step0], device="cuda"))
-        eng.rng_used = False
-
-    gen2 = torch.Generator(device="cuda").manual_seed(3)
-    worst = 0.0
-    for _ in range(3):
-        v = torch.randn(gflat.numel(), device="cuda", generator=gen2)
-        v = v / v.norm()
-        analytic = float((gflat.double() * v.double()).sum())
-        vals = []
-        for sgn in (1.0, -1.0):
-            with torch.no_grad():
-                m.flat_params.add_(v, alpha=sgn * 2e-3)
-                pin()
-                vals.append(float(lossf(m(x), y)))
-                m.flat_params.add_(v, alpha=-sgn * 2e-3)
-        fd = (vals[0] - vals[1]) / 4e-3
-        worst = max(worst, abs(fd - analytic) / (abs(fd) + 1e-3))
-    assert worst < 3e-2, worst
+    m = CNN_2D((T, F), (out,), act_dtype="fp32")
+    sd_cpu = copy.deepcopy(m.state_dict())
+    m = m.to("cuda").train()
+    logits = m(x.cuda())
+    torch.nn.BCEWithLogitsLoss(pos_weight=torch.full((out,), 6.0, device="cuda"))(logits, y.cuda()).backward()
+    eng, geo = m._engine, m.geom
+    masks, kept = [], []
+    for i in range(3):
+        M, co = geo.rows(i + 1, B), geo.C[i + 1]
+        bits = eng.L[i]["mask"][:M * co // 8].cpu().to(torch.int64)
+        keep = ((bits[:, None] >> torch.arange(8)) & 1).reshape(B, geo.H[i + 1], geo.W[i + 1], co).permute(0, 3, 1, 2).float()
+        masks.append(keep)
+        kept.append(keep.mean().item())
+    assert abs(kept[0] - 0.8) < 0.01 and abs(kept[1] - 0.8) < 0.02, kept
+    it = iter(masks)
+    names = [k for k, v in sd_cpu.items() if v.is_floating_point() and "running" not in k]
+    leaves = {k: sd_cpu[k].clone().requires_grad_(True) for k in names}
+    work = dict(sd_cpu)
+    work.update(leaves)
+    ref_logits = C.cnn2d_forward(work, x, training=True, update_stats=False, drop=lambda t, p: t * next(it) / (1.0 - p))
+    ref_loss = C.bce_with_logits(ref_logits, y, 6.0)
+    ref_grads = dict(zip(names, torch.autograd.grad(ref_loss, [leaves[k] for k in names])))
+    ge, worst = grad_err(m, ref_grads)
+    assert nrel(logits, ref_logits) < 1e-4 and ge < 1e-4, (nrel(logits, ref_logits), ge, worst)
+    # a second forward/backward pair draws new masks
+    m(x.cuda()).sum().backward()
+    assert not torch.equal(bits, eng.L[2]["mask"][:bits.numel()].cpu().to(torch.int64))
