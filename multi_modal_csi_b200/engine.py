@@ -103,6 +103,10 @@ class THATEngine(StepCounters):
         # left / right streams on two CUDA streams (see _fork); CSI_NO_CONCURRENT=1 for A/B runs
         self.concurrent = os.environ.get("CSI_NO_CONCURRENT", "0") != "1"
         self._side = None
+        # weight gradients on a third stream (see _wgrad); CSI_NO_WGRAD_STREAM=1 for A/B runs
+        self.wgrad_stream_on = os.environ.get("CSI_NO_WGRAD_STREAM", "0") != "1"
+        self._wside = None
+        self._wgrad_pending = []
         self.weights_dirty = True
 
     # ------------------------------------------------------------------ views
@@ -161,12 +165,15 @@ class THATEngine(StepCounters):
             st["p"] = _TokBuf(rows, 2 * sg.head_np, adt, dev)
             # backward scratch (shared by the encoders of the stream)
             st["dout"] = [_TokBuf(rows, Dp, f32, dev), _TokBuf(rows, Dp, f32, dev)]
-            st["dz"] = _TokBuf(rows, 3 * Dp, adt, dev)
+            # dz / dtm / dqkv are read by the weight-gradient GEMMs, which run on their own CUDA stream behind the
+            # data-gradient chain (see _wgrad): one buffer per encoder, so the next encoder's backward never overwrites
+            # an operand a weight gradient is still reading (0.65 GB at B=256, F=270)
+            st["dz"] = [_TokBuf(rows, 3 * Dp, adt, dev) for _ in range(sg.n_enc)]
             st["ds"] = _TokBuf(rows, Dp, adt, dev)
             st["dt"] = _TokBuf(rows, Dp, f32, dev)
-            st["dtm"] = _TokBuf(rows, Dp, adt, dev)
+            st["dtm"] = [_TokBuf(rows, Dp, adt, dev) for _ in range(sg.n_enc)]
             st["do"] = _TokBuf(rows, sg.dh, adt, dev)
-            st["dqkv"] = _TokBuf(rows, sg.ld3, adt, dev)
+            st["dqkv"] = [_TokBuf(rows, sg.ld3, adt, dev) for _ in range(sg.n_enc)]
             st["dt0"] = _TokBuf(rows, Dp, adt, dev)
             st["dp"] = _TokBuf(rows, 2 * sg.head_np, adt, dev)
             st["dhn"] = _TokBuf(rows, Dp, adt, dev)
@@ -269,6 +276,38 @@ class THATEngine(StepCounters):
             fn()
         return lambda: cur.wait_stream(side)
 
+    def _wgrad(self, fn):
+        """Issue the weight-gradient work ``fn()`` (wgrad GEMMs, bias column sums) on the engine's weight-gradient stream,
+        ordered after everything already on the current stream.
+
+        Nothing in the backward chain depends on a weight gradient -- only the optimizer / the gradient all-reduce do --
+        so these launches leave the critical path (per encoder: 6 GEMMs + 2 column sums, ~0.22 ms of 0.73 ms): they fill
+        the SMs whenever the data-gradient chain runs a bandwidth-bound kernel or a tail wave.  ``_wgrad_join`` makes the
+        current stream wait for all of them.  Inline when concurrency is off / while per-launch timing is recorded."""
+        if not (self.wgrad_stream_on and self.concurrent and self.dev.type == "cuda") or getattr(self.ops, "_prof", None) is not None:
+            fn()
+            return
+        cur = torch.cuda.current_stream(self.dev)
+        if self._wside is None:
+            self._wside = {}
+        ws = self._wside.get(cur.cuda_stream)                   # one weight-gradient stream per issuing (left / right) stream
+        if ws is None:
+            ws = self._wside[cur.cuda_stream] = torch.cuda.Stream(self.dev)
+        ws.wait_stream(cur)
+        with torch.cuda.stream(ws):
+            fn()
+        if ws not in self._wgrad_pending:
+            self._wgrad_pending.append(ws)
+
+    def _wgrad_join(self):
+        """The current stream waits for every weight gradient issued so far (end of a backward part)."""
+        if not self._wgrad_pending:
+            return
+        cur = torch.cuda.current_stream(self.dev)
+        for ws in self._wgrad_pending:
+            cur.wait_stream(ws)
+        self._wgrad_pending = []
+
     def forward_body(self, B: int, training: bool, dropout: bool = True) -> torch.Tensor:
         ops, g = self.ops, self.g
         pd = P_DROP if (training and dropout) else 0.0
@@ -368,7 +407,10 @@ class THATEngine(StepCounters):
         pf = P_FEAT if dropout else 0.0
         nl = g.left.n_enc
         if part == 2:
-            return self._backward_stream(0, B, pd, range(0, 1), head=False) if nl > 1 else None
+            if nl > 1:
+                self._backward_stream(0, B, pd, range(0, 1), head=False)
+                self._wgrad_join()
+            return None
         if zero_grads:
             ops.fill_f32(self.grads, 0.0)
         ops.fill_f64(self.red_pool, 0.0)                  # parts 1 and 2 use disjoint slices: zeroed once, here
@@ -379,11 +421,13 @@ class THATEngine(StepCounters):
                 self.dlogits[:B].view(B, g.heads, g.cp)[:, :, :g.out].copy_(dlogits.reshape(B, g.heads, g.out))
         ops.alg_scale = 1.0
         ops.dropout_rows(self.dlogits, self.dlogits_a, B, g.ld_out, 0.0, 0, self.rng)      # cast to act dtype
-        for h, (wn, bn) in enumerate(g.output_names()):
-            dl = self.dlogits_a[:, h * g.cp:]
-            self._alg(2 * B * LY.FEAT * g.out)
-            ops.gemm_tn(dl, self.featd, self.G(wn), LY.FEAT, 1, B, g.out, [(0, 0, 0, LY.FEAT)])
-            ops.colsum_tokens(dl, B, 1, 0, g.out, self.G(bn))
+        def w_out():
+            for h, (wn, bn) in enumerate(g.output_names()):
+                dl = self.dlogits_a[:, h * g.cp:]
+                self._alg(2 * B * LY.FEAT * g.out)
+                ops.gemm_tn(dl, self.featd, self.G(wn), LY.FEAT, 1, B, g.out, [(0, 0, 0, LY.FEAT)])
+                ops.colsum_tokens(dl, B, 1, 0, g.out, self.G(bn))
+        self._wgrad(w_out)
         self._alg(2 * B * LY.FEAT * g.out * g.heads)
         ops.gemm_nt(self.dlogits_a, self.W("b:layer_output.weight"), self.dfeatd, B, LY.FEAT,
                     [(0, 0, 0, g.ld_out)], None, None, 0.0, 0, self.rng)
@@ -391,6 +435,7 @@ class THATEngine(StepCounters):
         join = self._fork(lambda: self._backward_stream(1, B, pd, range(0, g.right.n_enc), head=True))
         self._backward_stream(0, B, pd, range(1 if (part == 1 and nl > 1) else 0, nl), head=True)
         join()
+        self._wgrad_join()
 
     @property
     def bucket_split(self) -> int:
@@ -426,13 +471,16 @@ class THATEngine(StepCounters):
         if head:
             ops.head_reduce_bwd(self.dfeat[:, sg.feat_off:], st["p"].t, B, L, HALO, 2 * sg.head_n, sg.head_n,
                                 sg.head_k[0], sg.head_k[1], st["dp"].t)
+            def w_head():
+                for j, k in enumerate(sg.head_k):
+                    w = f"layer_{sg.name}_cnn_{j}"
+                    self._alg(2 * B * (L - k + 1) * d * sg.head_n * k)
+                    ops.gemm_tn(st["dp"].t[:, j * Np:], st["hn"].t, self.G(w + ".weight"), d * k, k, rows, sg.head_n,
+                                [(t, 0, t, d) for t in range(k)])
+                    ops.colsum_tokens(st["dp"].t[:, j * Np:], B, L, HALO, sg.head_n, self.G(w + ".bias"))
+            self._wgrad(w_head)
             dsegs, seg = [], 0
             for j, k in enumerate(sg.head_k):
-                w = f"layer_{sg.name}_cnn_{j}"
-                self._alg(2 * B * (L - k + 1) * d * sg.head_n * k)
-                ops.gemm_tn(st["dp"].t[:, j * Np:], st["hn"].t, self.G(w + ".weight"), d * k, k, rows, sg.head_n,
-                            [(t, 0, t, d) for t in range(k)])
-                ops.colsum_tokens(st["dp"].t[:, j * Np:], B, L, HALO, sg.head_n, self.G(w + ".bias"))
                 dsegs += [(-t, j * Np, (seg + t) * Np, Np) for t in range(k)]
                 seg += k
             self._alg(sum(2 * B * (L - k + 1) * d * sg.head_n * k for k in sg.head_k))
@@ -445,46 +493,57 @@ class THATEngine(StepCounters):
         for e in reversed(encs):
             a, p = st["enc"][e], sg.prefix(e)
             x_in = st["enc"][e - 1]["out"] if e > 0 else st["x0"]
+            dz, dtm, dqkv = st["dz"][e], st["dtm"][e], st["dqkv"][e]
             gam, bet = self._bn3(sg, e, "1.weight"), self._bn3(sg, e, "1.bias")
             sb, so = site(si, e, LY.SITE_BRANCH), site(si, e, LY.SITE_SUM)
             ops.bn_act_bwd_reduce(dout.t, a["z"].t, a["bn_mean"], a["bn_invstd"], gam, bet, B, L, d, HALO, 3,
                                   pd, sb, pd, so, self.rng, a["red"], a["dmask"] if pd > 0.0 else None)
             ops.bn_act_bwd_dz(dout.t, a["z"].t, a["bn_mean"], a["bn_invstd"], gam, bet, a["red"], B, L, d,
-                              HALO, 3, pd, sb, pd, so, self.rng, st["dz"].t,
+                              HALO, 3, pd, sb, pd, so, self.rng, dz.t,
                               self._bn3(sg, e, "1.weight", grad=True), self._bn3(sg, e, "1.bias", grad=True),
                               a["dmask"] if pd > 0.0 else None)
+
+            def w_conv(a=a, p=p, dz=dz):
+                for j, k in enumerate(sg.kernels):
+                    pl = (k - 1) // 2
+                    self._alg(2 * B * L * d * d * k)
+                    ops.gemm_tn(dz.t[:, j * Dp:], a["s"].t, self.G(f"{p}layer_cnn.{j}.0.weight"), d * k, k,
+                                rows, d, [(t - pl, 0, t, d) for t in range(k)])
+            self._wgrad(w_conv)
             dsegs, seg = [], 0
             for j, k in enumerate(sg.kernels):
                 pl = (k - 1) // 2
-                self._alg(2 * B * L * d * d * k)
-                ops.gemm_tn(st["dz"].t[:, j * Dp:], a["s"].t, self.G(f"{p}layer_cnn.{j}.0.weight"), d * k, k,
-                            rows, d, [(t - pl, 0, t, d) for t in range(k)])
                 dsegs += [(pl - t, j * Dp, (seg + t) * Dp, Dp) for t in range(k)]
                 seg += k
             # the Conv1d biases feed a train-mode BatchNorm: their gradient is identically zero
             self._alg(2 * B * L * d * d * sum(sg.kernels))
-            ops.gemm_nt(st["dz"].t, self.W("b:" + p + "layer_cnn"), st["ds"].t, rows, d, dsegs, None, None,
+            ops.gemm_nt(dz.t, self.W("b:" + p + "layer_cnn"), st["ds"].t, rows, d, dsegs, None, None,
                         0.0, 0, self.rng)
             ops.layernorm_bwd(st["ds"].t, a["t"].t, self.P(p + "layer_norm_1.weight"), a["mean1"], a["rstd1"],
-                              dout.t, st["dt"].t, st["dtm"].t, pd, site(si, e, LY.SITE_ATTN), self.rng,
+                              dout.t, st["dt"].t, dtm.t, pd, site(si, e, LY.SITE_ATTN), self.rng,
                               self.G(p + "layer_norm_1.weight"), self.G(p + "layer_norm_1.bias"), B, L, d, HALO)
             one = [(0, 0, 0, d)]
             w = p + "layer_attention.out_proj."
+
+            def w_out_proj(a=a, w=w, dtm=dtm):
+                self._alg(2 * B * L * d * d)
+                ops.gemm_tn(dtm.t, a["o"].t, self.G(w + "weight"), d, 1, rows, d, [(0, 0, 0, sg.dh)], (0, 0), sg.grp)
+                ops.colsum_tokens(dtm.t, B, L, HALO, d, self.G(w + "bias"))
+            self._wgrad(w_out_proj)
             self._alg(2 * B * L * d * d)
-            ops.gemm_tn(st["dtm"].t, a["o"].t, self.G(w + "weight"), d, 1, rows, d, [(0, 0, 0, sg.dh)],
-                        (0, 0), sg.grp)
-            ops.colsum_tokens(st["dtm"].t, B, L, HALO, d, self.G(w + "bias"))
-            self._alg(2 * B * L * d * d)
-            ops.gemm_nt(st["dtm"].t, self.W("b:" + w + "weight"), st["do"].t, rows, sg.dh, [(0, 0, 0, Dp)], None,
+            ops.gemm_nt(dtm.t, self.W("b:" + w + "weight"), st["do"].t, rows, sg.dh, [(0, 0, 0, Dp)], None,
                         None, 0.0, 0, self.rng)
             w = p + "layer_attention.in_proj_"
             # the in_proj bias gradient (column sums of dqkv) is accumulated by the attention backward kernel itself
-            ops.attn_bwd(a["qkv"].t, a["o"].t, st["do"].t, st["dqkv"].t, a["lse"], B, L, d, sg.H, sg.hp, HALO,
+            ops.attn_bwd(a["qkv"].t, a["o"].t, st["do"].t, dqkv.t, a["lse"], B, L, d, sg.H, sg.hp, HALO,
                          self.G(w + "bias"))
+
+            def w_in_proj(a=a, w=w, dqkv=dqkv):
+                self._alg(2 * B * L * d * 3 * d)
+                ops.gemm_tn(dqkv.t, a["t0"].t, self.G(w + "weight"), d, 1, rows, sg.ld3, one, sg.grp, (0, 0))
+            self._wgrad(w_in_proj)
             self._alg(2 * B * L * d * 3 * d)
-            ops.gemm_tn(st["dqkv"].t, a["t0"].t, self.G(w + "weight"), d, 1, rows, sg.ld3, one, sg.grp, (0, 0))
-            self._alg(2 * B * L * d * 3 * d)
-            ops.gemm_nt(st["dqkv"].t, self.W("b:" + w + "weight"), st["dt0"].t, rows, d, [(0, 0, 0, sg.ld3)],
+            ops.gemm_nt(dqkv.t, self.W("b:" + w + "weight"), st["dt0"].t, rows, d, [(0, 0, 0, sg.ld3)],
                         None, None, 0.0, 0, self.rng)
             ops.layernorm_bwd(st["dt0"].t, x_in.t, self.P(p + "layer_norm_0.weight"), a["mean0"], a["rstd0"],
                               st["dt"].t, dnext.t, None, 0.0, 0, self.rng,
