@@ -37,6 +37,7 @@ def parse():
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-e2e", action="store_true")
     ap.add_argument("--profile-ops", action="store_true", help="print the per-op device-time table (stderr)")
+    ap.add_argument("--no-numa-bind", action="store_true", help="N>1: do not bind each rank to its GPU's NUMA node (A/B runs)")
     ap.add_argument("--no-config4", action="store_true", help="skip the CSI-as-image (CNN_2D) line")
     ap.add_argument("--cnn-batch", type=int, default=128, help="samples per GPU of the CSI-as-image line (BASELINE config 4: 128)")
     ap.add_argument("--config3", action="store_true", help="also measure BASELINE config 3 (F=540, out=90) at N=1 (always on for N>1)")
@@ -464,6 +465,10 @@ def run_b200(args):
         raise SystemExit("bench.py --impl b200 needs a CUDA device (no CPU fallback)")
     torch.cuda.set_device(local)
     dev = torch.device("cuda", local)
+    numa = None
+    if world > 1 and not args.no_numa_bind:
+        from multi_modal_csi_b200.parallel import bind_to_gpu_numa_node
+        numa = bind_to_gpu_numa_node(dev)                # before any pinned host memory exists (what train() does too)
     if world > 1:
         dist.init_process_group("nccl", device_id=dev)
     F, out, B = args.features, out_dim(args.features), args.batch
@@ -512,7 +517,7 @@ def run_b200(args):
             # whole step against the tensor roofline: BASELINE.md section 3 formula, burst cuBLAS peak (sub-second timed region at full clocks)
             "tensor_frac_step": step_tf / burst,
             "tensor_frac_step_sustained": step_tf / None_or(peaks.get("bf16_tflops_sustained"), 1340.8),
-            "config3": cfg3, "config4": cfg4,
+            "config3": cfg3, "config4": cfg4, "numa_binding_rank0": numa,
         }
         print(json.dumps(line), flush=True)
     if world > 1:

@@ -29,7 +29,7 @@ from torch.utils.data.distributed import DistributedSampler
 
 from .loader import CSIBatchSource, PackedCSIDataset
 from .optim import FusedAdam
-from .parallel import GradSync, broadcast_buffers, broadcast_parameters
+from .parallel import GradSync, bind_to_gpu_numa_node, broadcast_buffers, broadcast_parameters
 from .arena_module import ArenaModule
 from .cnn2d import CNN_2D
 from .that import PermutationMatchingLoss
@@ -109,6 +109,8 @@ def train(model, optimizer, loss, data_train_set: TensorDataset, data_test_set: 
              and device.type == "cuda" and (loss_kind == "bce" or isinstance(model, THAT)))
     sync = GradSync(model, dist.get_world_size()) if distributed and isinstance(model, ArenaModule) else None
     if distributed and isinstance(model, ArenaModule):
+        if device.type == "cuda":
+            bind_to_gpu_numa_node(device)               # before the loader page-locks the dataset: node-local host memory
         broadcast_parameters(model)                     # every rank starts from rank 0's weights and BatchNorm buffers
         model.rng_seed = (model.rng_seed + 7919 * dist.get_rank()) & 0x7FFFFFFF      # decorrelated dropout / augmentation
     source = data_train_loader = None
