@@ -36,6 +36,23 @@ class _TokBuf:
         self.t = self.full[GUARD:GUARD + rows]
 
 
+class _Range:
+    """NVTX range (nsys / ncu --nvtx timelines): per encoder block and pass, only with CSI_NVTX=1 (push/pop cost ~1 us each,
+    and they must not be recorded while a CUDA graph is being captured)."""
+    ON = os.environ.get("CSI_NVTX", "0") == "1"
+
+    def __init__(self, name):
+        self.name = name
+
+    def __enter__(self):
+        if _Range.ON:
+            torch.cuda.nvtx.range_push(self.name)
+
+    def __exit__(self, *a):
+        if _Range.ON:
+            torch.cuda.nvtx.range_pop()
+
+
 class StepCounters:
     """Philox / Adam step bookkeeping shared by the engines of this package (``rng``, ``opt_step``, ``rng_used``, ``ops``,
     ``params`` and ``grads`` are set by the engine)."""
@@ -345,6 +362,7 @@ class THATEngine(StepCounters):
         x_in = st["x0"]
         one = [(0, 0, 0, Dp)]
         for e in range(sg.n_enc):
+          with _Range(f"fwd/{sg.name}/encoder{e}"):
             a, p = st["enc"][e], sg.prefix(e)
             ops.layernorm_fwd(x_in.t, self.P(p + "layer_norm_0.weight"), self.P(p + "layer_norm_0.bias"),
                               a["t0"].t, a["mean0"], a["rstd0"], B, L, d, HALO, LN_EPS)
@@ -491,6 +509,7 @@ class THATEngine(StepCounters):
                               dout.t, None, 0.0, 0, self.rng, self.G(nm + "weight"), self.G(nm + "bias"),
                               B, L, d, HALO)
         for e in reversed(encs):
+          with _Range(f"bwd/{sg.name}/encoder{e}"):
             a, p = st["enc"][e], sg.prefix(e)
             x_in = st["enc"][e - 1]["out"] if e > 0 else st["x0"]
             dz, dtm, dqkv = st["dz"][e], st["dtm"][e], st["dqkv"][e]
