@@ -42,7 +42,7 @@ def rel(a, b):
 
 
 def run_fwd(kind, qkv, o, lse, B, L, d, H, hp):
-    fn = lib.csi_attn_fwd_tc if kind == "tc" else lib.csi_attn_fwd_mma
+    fn = {"tc": lib.csi_attn_fwd_tc, "tc2": lib.csi_attn_fwd_tc2, "mma": lib.csi_attn_fwd_mma}[kind]
     rc = fn(_p(qkv), _ld(qkv), _p(o), _ld(o), _p(lse), B, L, d, H, hp, HALO, st())
     if rc:
         raise RuntimeError(lib.csi_last_error().decode())
@@ -71,7 +71,9 @@ def check(B, L, d, H=10, bwd=True):
     ref_o = ref.transpose(1, 2)
     ref_lse = torch.logsumexp((q @ k.transpose(-1, -2)) / hd ** 0.5, dim=-1)       # [B,H,L]
     out = {}
-    for kind in ("mma", "tc"):
+    for kind in ("mma", "tc", "tc2"):
+        if kind == "tc2" and not lib.csi_attn_tc2_ok(L, d, H, hp):
+            continue
         fo, o = mk(B, L, H, hd, hp, 1, 0, 0.0)
         lse = torch.zeros(B * H * L, device="cuda")
         try:
@@ -86,7 +88,7 @@ def check(B, L, d, H=10, bwd=True):
         halo = float(o.view(B, L + 2 * HALO, -1)[:, :HALO].float().abs().max())
         guard = float(fo[:GUARD].float().abs().max() + fo[-GUARD:].float().abs().max())
         msg = f"fwd {kind:3s} B={B} L={L} d={d} hp={hp}: o {eo:.2e} lse {el:.2e} pad {pad} halo {halo} guard {guard}"
-        if bwd and (kind == "mma" or hasattr(lib, "csi_attn_bwd_tc")):
+        if bwd and kind != "tc2" and (kind == "mma" or hasattr(lib, "csi_attn_bwd_tc")):
             _, dqkv = mk(B, L, H, hd, hp, 3, 0, 0.0)
             dbias = torch.full((3 * d,), 0.5, device="cuda")
             try:
@@ -114,10 +116,12 @@ def timeit(B, L, d, H=10):
     lse = torch.zeros(B * H * L, device="cuda")
     dbias = torch.zeros(3 * d, device="cuda")
     line = f"time B={B} L={L} d={d} hp={hp}:"
-    for kind in ("mma", "tc"):
+    for kind in ("mma", "tc", "tc2"):
         for name, fn in (("fwd", lambda: run_fwd(kind, qkv, o, lse, B, L, d, H, hp)),
                          ("bwd", lambda: run_bwd(kind, qkv, o, do, dqkv, lse, B, L, d, H, hp, dbias))):
             try:
+                if kind == "tc2" and (name == "bwd" or not lib.csi_attn_tc2_ok(L, d, H, hp)):
+                    continue
                 if kind == "tc" and (not lib.csi_attn_tc_ok(L, d, H, hp) or (name == "bwd" and not lib.csi_attn_bwd_tc_ok(L, d, H, hp))):
                     continue
                 for _ in range(3):
@@ -190,7 +194,36 @@ def phases_bwd(B, L, d, H=10):
         print(f"  wrk kt {j}: waitS {v[1] - v[0]} compute {v[2] - v[1]} waitG {v[3] - v[2]} drain {v[4] - v[3]}", flush=True)
 
 
+def phases2(B, L, d, H=10):
+    """attention_tc2.cu: clocks of warpgroup 0 / 1 (quarter 0) and of the MMA warp of one mid-grid CTA."""
+    hd = d // H
+    hp = 16 if hd <= 16 else 32 if hd <= 32 else 64
+    _, qkv = mk(B, L, H, hd, hp, 3, 1, 0.5)
+    _, o = mk(B, L, H, hd, hp, 1, 0, 0.0)
+    lse = torch.zeros(B * H * L, device="cuda")
+    dbg = torch.zeros(2048, dtype=torch.int64, device="cuda")
+    run_fwd("tc2", qkv, o, lse, B, L, d, H, hp)
+    lib.csi_set_attn2_debug(C.c_void_p(dbg.data_ptr()))
+    run_fwd("tc2", qkv, o, lse, B, L, d, H, hp)
+    torch.cuda.synchronize()
+    lib.csi_set_attn2_debug(C.c_void_p(0))
+    t = dbg.cpu().tolist()
+    t0 = min(v for v in t if v)
+    print(f"phases2 L={L} d={d}: job: WG [wait S | softmax | wait O | drain]   MMA [S issued at | P seen | PV issued]", flush=True)
+    for n in range(14):
+        w = t[8 * n: 8 * n + 5]
+        m = t[1000 + 8 * n: 1000 + 8 * n + 6]
+        if not w[4]:
+            break
+        print(f"  job {n:2d} wg{n & 1}: start {w[0] - t0:6d} waitS {w[1] - w[0]:5d} softmax {w[2] - w[1]:5d} waitO {w[3] - w[2]:5d} drain {w[4] - w[3]:5d}"
+              f" | mma: loop {m[1] - t0:6d} S-issued {m[2] - t0:6d} P-seen {m[3] - t0 if m[3] else 0:6d} PV-issued {m[5] - t0 if m[5] else 0:6d}", flush=True)
+
+
 if __name__ == "__main__":
+    if len(sys.argv) > 2 and sys.argv[2] == "phases2":
+        for (L, d) in [(150, 270), (150, 540)]:
+            phases2(BT, L, d)
+        sys.exit(0)
     if len(sys.argv) > 2 and sys.argv[2] == "phases_bwd":
         for (L, d) in [(150, 270), (270, 150), (150, 540)]:
             phases_bwd(BT, L, d)
