@@ -1,0 +1,91 @@
+"""CTA-pair (cta_group::2) NT GEMM against the single-CTA kernel: the K order of every output element is the same, so the
+results must be bit-identical (bias / dropout / fp32 residual epilogues included); then timing of the model's shapes."""
+import sys, os, math, ctypes as C
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+import torch
+from multi_modal_csi_b200.ops import NativeOps
+
+ops = NativeOps(torch.device("cuda", 0))
+lib = ops.lib
+GUARD = 16
+
+
+def make(M, N, Dp, k, out_dtype=torch.bfloat16):
+    torch.manual_seed(1)
+    full = torch.randn(M + 2 * GUARD, Dp, device="cuda").to(torch.bfloat16)
+    A = full[GUARD:GUARD + M]
+    W = (torch.randn(N, k * Dp, device="cuda") / math.sqrt(k * Dp)).to(torch.bfloat16)
+    ldc = (N + 15) // 16 * 16
+    Cm = torch.zeros(M, ldc, dtype=out_dtype, device="cuda")
+    pl = (k - 1) // 2
+    segs = [(j - pl, 0, j * Dp, Dp) for j in range(k)]
+    return full, A, W, Cm, segs, pl
+
+
+def ref(full, W, M, N, Dp, k, pl):
+    out = torch.zeros(M, N, device="cuda")
+    for j in range(k):
+        a = full[GUARD + j - pl: GUARD + j - pl + M].float()
+        out += a @ W[:, j * Dp:(j + 1) * Dp].float().t()
+    return out
+
+
+def timeit(fn, reps=20):
+    for _ in range(3):
+        fn()
+    torch.cuda.synchronize()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for _ in range(reps):
+        fn()
+    e1.record()
+    torch.cuda.synchronize()
+    return e0.elapsed_time(e1) / reps
+
+
+what = sys.argv[1] if len(sys.argv) > 1 else "all"
+if what in ("all", "check"):
+    rng = torch.tensor([1234, 7], dtype=torch.int64, device="cuda")
+    bad = 0
+    for (M, N, Dp, k) in [(1024, 270, 272, 5), (1000, 150, 160, 2), (2048, 128, 272, 16), (100, 54, 288, 1), (300, 16, 160, 4),
+                          (39424, 270, 272, 5), (39424, 960, 272, 1), (70144, 150, 160, 3), (5000, 540, 544, 3), (39424, 128, 272, 16)]:
+        for variant in ("plain", "bias", "res+drop"):
+            od = torch.float32 if variant == "res+drop" else torch.bfloat16
+            full, A, W, Cm, segs, pl = make(M, N, Dp, k, od)
+            bias = torch.randn(N, device="cuda") if variant != "plain" else None
+            res = torch.randn(M, Cm.shape[1], device="cuda") if variant == "res+drop" else None
+            dp = 0.1 if variant == "res+drop" else 0.0
+            outs = []
+            for pair in (0, 1, 2):                              # single CTA | forced pairs | default (pairs + weight-stationary)
+                lib.csi_set_gemm_pair((0, 2, 1)[pair])
+                lib.csi_set_gemm_resident(1 if pair == 2 else 0)
+                Cm.fill_(7.0)
+                ops.gemm_nt(A, W, Cm, M, N, segs, bias, res, dp, 3, rng if dp else None)
+                torch.cuda.synchronize()
+                outs.append(Cm.clone())
+            same = torch.equal(outs[0], outs[1]) and torch.equal(outs[0], outs[2])
+            msg = ""
+            if variant == "plain":
+                r = ref(full, W, M, N, Dp, k, pl)
+                msg = f" rel err vs torch {((outs[1][:, :N].float() - r).norm() / r.norm()).item():.2e}"
+            if not same:
+                bad += 1
+                d = (outs[0].float() - outs[1].float()).abs() + (outs[0].float() - outs[2].float()).abs()
+                rows = (d.amax(dim=1) > 0).nonzero().flatten()
+                msg += f"  MISMATCH max {d.max().item():.3e} rows {rows[:6].tolist()}..{rows[-3:].tolist()} n={rows.numel()}"
+            print(f"M={M} N={N} K={k}x{Dp} {variant:9s}: pair == single: {same}{msg}", flush=True)
+    print("MISMATCHES", bad, flush=True)
+
+if what in ("all", "time"):
+    for (M, N, Dp, k) in [(39424, 960, 272, 1), (39424, 270, 272, 1), (39424, 270, 272, 3), (39424, 270, 272, 5), (39424, 270, 272, 9),
+                          (39424, 128, 272, 8), (39424, 128, 272, 16), (70144, 480, 160, 1), (70144, 150, 160, 1), (70144, 150, 160, 3),
+                          (39424, 270, 320, 1), (39424, 320, 272, 1), (70144, 150, 160, 2), (70144, 16, 160, 4)]:
+        full, A, W, Cm, segs, pl = make(M, N, Dp, k)
+        fl = 2.0 * M * N * k * Dp
+        res = []
+        for pair in (0, 1, 2):
+            lib.csi_set_gemm_pair((0, 2, 1)[pair])
+            lib.csi_set_gemm_resident(1 if pair == 2 else 0)
+            ms = timeit(lambda: ops.gemm_nt(A, W, Cm, M, N, segs, None, None, 0.0, 0, None))
+            res.append(f"{('single', 'pair', 'default')[pair]} {ms*1e3:7.1f} us {fl/ms/1e9:7.1f} TF/s")
+        print(f"M={M} N={N} K={k}x{Dp}: " + " | ".join(res), flush=True)
