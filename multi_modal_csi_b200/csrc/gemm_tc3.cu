@@ -164,7 +164,9 @@ __global__ void __launch_bounds__(T3_THREADS, 1) gemm_nt_tc3_kernel(const __grid
                                                                     const __grid_constant__ CUtensorMap tmB,
                                                                     const __grid_constant__ CUtensorMap tmB2,
                                                                     const __grid_constant__ CUtensorMap tmC,
-                                                                    const __grid_constant__ CUtensorMap tmCt, Nt3Params p,
+                                                                    const __grid_constant__ CUtensorMap tmCt,
+                                                                    const __grid_constant__ CUtensorMap tmR,
+                                                                    const __grid_constant__ CUtensorMap tmRt, Nt3Params p,
                                                                     const __grid_constant__ T3Plan plan) {
     constexpr int PW = 128 / (int)sizeof(TC);
     extern __shared__ __align__(1024) uint8_t smem_raw[];
@@ -176,6 +178,7 @@ __global__ void __launch_bounds__(T3_THREADS, 1) gemm_nt_tc3_kernel(const __grid
     __shared__ __align__(8) uint64_t tmem_empty_bar[2];
     __shared__ uint32_t tmem_base_smem;
     __shared__ __align__(16) float sbias[2][256];
+    __shared__ __align__(8) uint64_t res_full[T3_EPI_THREADS / 32][2];   // RES: residual panel ring of every epilogue warp
 
     if (p.pdl) asm volatile("griddepcontrol.launch_dependents;" ::: "memory");   // the next kernel may start its prologue
     uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
@@ -210,6 +213,8 @@ __global__ void __launch_bounds__(T3_THREADS, 1) gemm_nt_tc3_kernel(const __grid
         for (int s = 0; s < NSB; ++s) { mbar_init(&full_b[s], 1); mbar_init(&empty_b[s], 1); }
         // PAIR: the epilogue warps of both CTAs release an accumulator on the leader's barrier
         for (int a = 0; a < 2; ++a) { mbar_init(&tmem_full_bar[a], 1); mbar_init(&tmem_empty_bar[a], (PAIR ? 2 : 1) * T3_EPI_THREADS / 32); }
+        if constexpr (RES)
+            for (int w = 0; w < T3_EPI_THREADS / 32; ++w) { mbar_init(&res_full[w][0], 1); mbar_init(&res_full[w][1], 1); }
         fence_barrier_init();
     }
     if (warp == 1) { if constexpr (PAIR) tmem_alloc_pair(&tmem_base_smem, 512); else tmem_alloc(&tmem_base_smem, 512); }
@@ -381,6 +386,31 @@ __global__ void __launch_bounds__(T3_THREADS, 1) gemm_nt_tc3_kernel(const __grid
         int ti = 0, sbuf = 0;
         const bool dbg_on = T3_DBG_ON(blockIdx.x == (gridDim.x / 2 & ~1u) && ew == 0 && lane == 0); (void)dbg_on;
         const uint32_t tempty_remote = PAIR ? mapa_u32(smem_u32(&tmem_empty_bar[0]), 0u) : 0u;
+        // RES: the fp32 residual panels (32 rows x 128 B, the geometry of the output panels) of this warp arrive by TMA in a
+        // two-slot ring that runs TWO panels ahead of the arithmetic, across tile boundaries: 64 KB in flight per SM.  With
+        // register prefetch one panel ahead (32 KB per SM) the epilogue sat on the load latency: out-proj 20 -> 37 us.
+        uint8_t* rbuf = cstage + (size_t)(T3_EPI_THREADS / 32) * p.epi_bufs * 4096 + (size_t)ew * 2 * 4096;
+        int pf_tile = tile_first, pf_pi = half;
+        uint32_t pf_cnt = 0, rcc = 0;
+        auto pf_issue = [&]() {
+            if constexpr (!RES) return;
+            while (pf_tile < tile_end) {
+                const T3Tile t = t3_decode(p, pf_tile, n_res);
+                if (pf_pi < (t.bn + PW - 1) / PW) {
+                    if (lane == 0) {
+                        const int pc0 = pf_pi * PW, w = min(PW, t.bn - pc0);
+                        const uint32_t slot = pf_cnt & 1u, bar = smem_u32(&res_full[ew][slot]);
+                        mbar_expect_tx_u(bar, (uint32_t)(32 * w) * 4u);
+                        tma_load_2d_u(w == PW ? &tmR : &tmRt, bar, smem_u32(rbuf + slot * 4096), t.n0 + pc0,
+                                      t.mt * TILE_M + (int)rank * TC_BM + q * 32);
+                    }
+                    ++pf_cnt; pf_pi += 2;
+                    return;
+                }
+                pf_tile += tile_step; pf_pi = half;
+            }
+        };
+        if constexpr (RES) { pf_issue(); pf_issue(); }
         for (int tile = tile_first; tile < tile_end; tile += tile_step, ++ti) {
             const int acc = ti & 1;
             const uint32_t aph = (uint32_t)(ti >> 1) & 1u;
@@ -392,31 +422,6 @@ __global__ void __launch_bounds__(T3_THREADS, 1) gemm_nt_tc3_kernel(const __grid
                 sbias[acc][et] = (et < bn && (n0 + et) < p.N) ? p.bias[n0 + et] : 0.f;
                 named_bar_sync(1, T3_EPI_THREADS);
             }
-            // fp32 residual of a FULL panel (32 rows x 128 B): fetched with coalesced 16-byte loads (lane -> row 4i + lane/8,
-            // chunk lane%8: four whole 128-byte lines per instruction instead of 32 partial ones), one panel ahead, and
-            // transposed to the row-per-lane layout through the staging buffer.  Narrow tail panels load row-per-lane.
-            const float* rrow = (RES && m < p.M) ? p.residual + (size_t)m * p.ldr : nullptr;
-            float rnext[RES ? PW : 1];
-            auto fetch_res = [&](int pc0) {
-                if constexpr (!RES) return;
-                if (bn - pc0 >= PW) {
-                    const int ch = lane & 7, ncol = n0 + pc0 + ch * 4;
-#pragma unroll
-                    for (int i = 0; i < (RES ? PW / 4 : 0); ++i) {
-                        const int mg = m0 + q * 32 + 4 * i + (lane >> 3);
-                        float4 v4 = make_float4(0.f, 0.f, 0.f, 0.f);
-                        if (mg < p.M && ncol + 3 < p.ldr) v4 = *reinterpret_cast<const float4*>(p.residual + (size_t)mg * p.ldr + ncol);
-                        rnext[4 * i] = v4.x; rnext[4 * i + 1] = v4.y; rnext[4 * i + 2] = v4.z; rnext[4 * i + 3] = v4.w;
-                    }
-                } else {
-#pragma unroll
-                    for (int j = 0; j < (RES ? PW : 0); ++j) {
-                        const int n = n0 + pc0 + j;
-                        rnext[j] = (rrow && pc0 + j < bn && n < p.N) ? rrow[n] : 0.f;
-                    }
-                }
-            };
-            if constexpr (RES) { if (half < npan) fetch_res(half * PW); }
             T3_CLK(1000 + 8 * ti);
             mbar_wait(&tmem_full_bar[acc], aph);
             tc_fence_after();
@@ -456,6 +461,30 @@ __global__ void __launch_bounds__(T3_THREADS, 1) gemm_nt_tc3_kernel(const __grid
                         for (int j = 0; j < 8; ++j) v[g8 * 8 + j] *= ks[j];
                     }
                 }
+                if constexpr (RES) {
+                    const uint32_t slot = rcc & 1u;
+                    mbar_wait(&res_full[ew][slot], (rcc >> 1) & 1u);
+                    const uint8_t* rb = rbuf + slot * 4096;
+                    if (width == PW) {
+#pragma unroll
+                        for (int c16 = 0; c16 < 8; ++c16) {
+                            const float4 r4 = *reinterpret_cast<const float4*>(rb + lane * 128 + ((c16 ^ (lane & 7)) << 4));
+                            v[c16 * 4] += r4.x; v[c16 * 4 + 1] += r4.y; v[c16 * 4 + 2] += r4.z; v[c16 * 4 + 3] += r4.w;
+                        }
+                    } else {
+                        const uint8_t* rowp = rb + lane * (width * 4);
+#pragma unroll
+                        for (int c16 = 0; c16 < 8; ++c16) {
+                            if (c16 * 4 < width) {
+                                const float4 r4 = *reinterpret_cast<const float4*>(rowp + (c16 << 4));
+                                v[c16 * 4] += r4.x; v[c16 * 4 + 1] += r4.y; v[c16 * 4 + 2] += r4.z; v[c16 * 4 + 3] += r4.w;
+                            }
+                        }
+                    }
+                    __syncwarp();                                    // every lane has read its row: refill the slot
+                    pf_issue();
+                    ++rcc;
+                }
                 // stage the 32-row slice of this warp (row = lane) and bulk-store it; the tensor maps clip rows >= M and
                 // columns >= N.  Full panels are 128-byte rows in the TMA 128B swizzle; the narrower last panel of a tile
                 // uses linear rows of width*es bytes and its own (unswizzled) tensor map.
@@ -463,27 +492,6 @@ __global__ void __launch_bounds__(T3_THREADS, 1) gemm_nt_tc3_kernel(const __grid
                 __syncwarp();
                 if (pi == half) T3_CLK(1000 + 8 * ti + 3);
                 uint8_t* buf = mybuf + (size_t)sbuf * 4096;
-                if constexpr (RES) {
-                    if (width == PW) {
-                        const int ch = lane & 7;
-#pragma unroll
-                        for (int i = 0; i < PW / 4; ++i) {
-                            const int rl = 4 * i + (lane >> 3);
-                            *reinterpret_cast<float4*>(buf + rl * 128 + ((ch ^ (rl & 7)) << 4)) =
-                                make_float4(rnext[4 * i], rnext[4 * i + 1], rnext[4 * i + 2], rnext[4 * i + 3]);
-                        }
-                        __syncwarp();
-#pragma unroll
-                        for (int c16 = 0; c16 < 8; ++c16) {
-                            const float4 r4 = *reinterpret_cast<const float4*>(buf + lane * 128 + ((c16 ^ (lane & 7)) << 4));
-                            v[c16 * 4] += r4.x; v[c16 * 4 + 1] += r4.y; v[c16 * 4 + 2] += r4.z; v[c16 * 4 + 3] += r4.w;
-                        }
-                    } else {
-#pragma unroll
-                        for (int j = 0; j < PW; ++j) v[j] += rnext[j];
-                    }
-                    if (pi + 2 < npan) fetch_res(pc0 + 2 * PW);
-                }
                 if (width == PW) {
                     uint8_t* rowp = buf + lane * 128;
 #pragma unroll
@@ -516,8 +524,10 @@ __global__ void __launch_bounds__(T3_THREADS, 1) gemm_nt_tc3_kernel(const __grid
                         }
                     }
                 }
+                if (pi == half) T3_CLK(1000 + 8 * ti + 6);
                 fence_proxy_async();
                 __syncwarp();
+                if (pi == half) T3_CLK(1000 + 8 * ti + 7);
                 if (lane == 0) {
                     if (width == PW) tma_store_2d(&tmC, buf, n0 + pc0, m0 + q * 32);
                     else tma_store_2d(&tmCt, buf, n0 + pc0, m0 + q * 32);
@@ -643,7 +653,7 @@ extern "C" int csi_gemm_nt_tc3(const void* A, int lda, const void* Bw, int ldb, 
     // One staging buffer per epilogue warp (two were measured: no difference) leaves 32 KB more for the operand rings.
     static int epi_bufs = 0;                             // CSI_GEMM_EPIBUF=2 restores double-buffered staging (A/B runs)
     if (!epi_bufs) { const char* e = getenv("CSI_GEMM_EPIBUF"); epi_bufs = (e && e[0] == '2') ? 2 : 1; }
-    const size_t fixed = 1024 + 8 * (size_t)epi_bufs * 4096;
+    const size_t fixed = 1024 + 8 * (size_t)epi_bufs * 4096 + (residual ? 8 * 2 * 4096 : 0);   // + the residual panel rings
     const size_t budget = 224 * 1024 - fixed;            // + 3 KB of static shared memory = the 227 KB an SM offers
     // ---- weight-stationary mode (Nt3Params::resident): a CTA pair keeps all weight stages of its column tile in shared
     //      memory when they leave room for at least four A stages
@@ -675,6 +685,16 @@ extern "C" int csi_gemm_nt_tc3(const void* A, int lda, const void* Bw, int ldb, 
     if (tail) {
         rc = make_map_ex(&tmCt, C, M, N, ldc, 32, tail, es, false);
         if (rc) return rc;
+    }
+    CUtensorMap tmR = tmC, tmRt = tmC;                   // fp32 residual: the geometry of the output panels
+    if (residual) {
+        rc = make_map_ex(&tmR, residual, M, N, ldr, 32, 32, 4);
+        if (rc) return rc;
+        tmRt = tmR;
+        if (tail) {
+            rc = make_map_ex(&tmRt, residual, M, N, ldr, 32, tail, 4, false);
+            if (rc) return rc;
+        }
     }
     Nt3Params p;
     p.M = M; p.N = N; p.BN = BN; p.C = C; p.ldc = ldc; p.a_rows = a_rows;
@@ -745,7 +765,7 @@ extern "C" int csi_gemm_nt_tc3(const void* A, int lda, const void* Bw, int ldb, 
         at[1].id = cudaLaunchAttributeClusterDimension;                                                                 \
         at[1].val.clusterDim.x = 2; at[1].val.clusterDim.y = 1; at[1].val.clusterDim.z = 1;                             \
         cfg.attrs = at; cfg.numAttrs = PAIR ? 2 : 1;                                                                    \
-        CSI_CUDA(cudaLaunchKernelEx(&cfg, gemm_nt_tc3_kernel<TC, RES, PAIR>, tmA, tmB, tmB2, tmC, tmCt, p, plan));      \
+        CSI_CUDA(cudaLaunchKernelEx(&cfg, gemm_nt_tc3_kernel<TC, RES, PAIR>, tmA, tmB, tmB2, tmC, tmCt, tmR, tmRt, p, plan)); \
     } while (0)
 #define LAUNCH3P(TC, RES) do { if (pair) LAUNCH3(TC, RES, true); else LAUNCH3(TC, RES, false); } while (0)
     if (c_dtype == CSI_BF16) LAUNCH3P(bf16, false);

@@ -30,11 +30,11 @@ torch.cuda.synchronize()
 lib.csi_set_gemm_debug(C.c_void_p(0))
 t = dbg.cpu().tolist()
 t0 = min(v for v in t if v)
-print(f"M={M} N={N} K={k}x{Dp} {mode} res={RES}:  MMA [tile top | acc free | first A | committed]   EPI warp0 [top | acc full | ld done | buf free | stored | end]   PROD [tile start]")
+print(f"M={M} N={N} K={k}x{Dp} {mode} res={RES}:  MMA [tile top | acc free | first A | committed]   EPI warp0 [top | acc full | ld done | buf free | (sts done | fenced) | stored | end]   PROD [tile start]")
 for i in range(12):
     m = [v - t0 if v else -1 for v in t[8 * i: 8 * i + 4]]
-    e = [v - t0 if v else -1 for v in t[1000 + 8 * i: 1000 + 8 * i + 6]]
+    e = [v - t0 if v else -1 for v in t[1000 + 8 * i: 1000 + 8 * i + 8]]
     pr = t[2000 + 8 * i] - t0 if t[2000 + 8 * i] else -1
     if m[0] < 0 and e[0] < 0:
         break
-    print(f"  tile {i:2d}  mma {m[0]:6d} {m[1]:6d} {m[2]:6d} {m[3]:6d}   epi {e[0]:6d} {e[1]:6d} {e[2]:6d} {e[3]:6d} {e[4]:6d} {e[5]:6d}   prod {pr:6d}")
+    print(f"  tile {i:2d}  mma {m[0]:6d} {m[1]:6d} {m[2]:6d} {m[3]:6d}   epi {e[0]:6d} {e[1]:6d} {e[2]:6d} {e[3]:6d} ({e[6]:6d} {e[7]:6d}) {e[4]:6d} {e[5]:6d}   prod {pr:6d}")

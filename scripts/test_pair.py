@@ -49,11 +49,11 @@ if what in ("all", "check"):
     bad = 0
     for (M, N, Dp, k) in [(1024, 270, 272, 5), (1000, 150, 160, 2), (2048, 128, 272, 16), (100, 54, 288, 1), (300, 16, 160, 4),
                           (39424, 270, 272, 5), (39424, 960, 272, 1), (70144, 150, 160, 3), (5000, 540, 544, 3), (39424, 128, 272, 16)]:
-        for variant in ("plain", "bias", "res+drop"):
-            od = torch.float32 if variant == "res+drop" else torch.bfloat16
+        for variant in ("plain", "bias", "res", "res+drop"):
+            od = torch.float32 if variant.startswith("res") else torch.bfloat16
             full, A, W, Cm, segs, pl = make(M, N, Dp, k, od)
             bias = torch.randn(N, device="cuda") if variant != "plain" else None
-            res = torch.randn(M, Cm.shape[1], device="cuda") if variant == "res+drop" else None
+            res = torch.randn(M, Cm.shape[1], device="cuda") if variant.startswith("res") else None
             dp = 0.1 if variant == "res+drop" else 0.0
             outs = []
             for pair in (0, 1, 2):                              # single CTA | forced pairs | default (pairs + weight-stationary)
@@ -64,10 +64,17 @@ if what in ("all", "check"):
                 torch.cuda.synchronize()
                 outs.append(Cm.clone())
             same = torch.equal(outs[0], outs[1]) and torch.equal(outs[0], outs[2])
+            if not same:                                          # a different smem budget can change blocks-per-stage, i.e. the K order
+                dmax = max((outs[0].float() - outs[i].float()).abs().max().item() for i in (1, 2))
+                if dmax <= 1e-4 * outs[0].float().abs().max().item():
+                    same = True
+                    print(f"    (fp32 rounding-order difference between modes, max {dmax:.2e})")
             msg = ""
-            if variant == "plain":
+            if variant in ("plain", "res"):
                 r = ref(full, W, M, N, Dp, k, pl)
-                msg = f" rel err vs torch {((outs[1][:, :N].float() - r).norm() / r.norm()).item():.2e}"
+                if variant == "res":
+                    r = r + bias + res[:, :N]
+                msg = f" rel err vs torch {((outs[2][:, :N].float() - r).norm() / r.norm()).item():.2e}"
             if not same:
                 bad += 1
                 d = (outs[0].float() - outs[1].float()).abs() + (outs[0].float() - outs[2].float()).abs()
