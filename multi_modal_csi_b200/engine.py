@@ -83,6 +83,8 @@ class StepCounters:
         if adv:
             self.rng_used = False
         self.weights_dirty = True
+        if advance_rng and hasattr(self, "repack_ahead"):
+            self.repack_ahead()                 # fused train step: the operand copies for the next step, off the critical path
 
 
 class THATEngine(StepCounters):
@@ -120,6 +122,11 @@ class THATEngine(StepCounters):
         # left / right streams on two CUDA streams (see _fork); CSI_NO_CONCURRENT=1 for A/B runs
         self.concurrent = os.environ.get("CSI_NO_CONCURRENT", "0") != "1"
         self._side = None
+        self._pack_stream = None                   # repack_ahead: packing stream and the not yet awaited pack on it
+        self._pack_pending = None
+        # A/B switches of the round-2 scheduling changes
+        self.pack_ahead_on = os.environ.get("CSI_NO_PACK_AHEAD", "0") != "1"
+        self.prefill_on = os.environ.get("CSI_NO_PREFILL", "0") != "1"
         # weight gradients on a third stream (see _wgrad); CSI_NO_WGRAD_STREAM=1 for A/B runs
         self.wgrad_stream_on = os.environ.get("CSI_NO_WGRAD_STREAM", "0") != "1"
         self._wside = None
@@ -234,8 +241,38 @@ class THATEngine(StepCounters):
         self.ops.alg_flops = int(flops)
 
     # ------------------------------------------------------------------ weights
+    def _sync_pack(self):
+        """The current stream waits for a ``repack_ahead`` still running on the packing stream."""
+        ps = self._pack_pending
+        if ps is not None:
+            torch.cuda.current_stream(self.dev).wait_stream(ps)
+            self._pack_pending = None
+
+    def ensure_packed(self):
+        """Operand copies are current (and visible to the current stream) on return."""
+        self._sync_pack()
+        if self.weights_dirty:
+            self.repack()
+
+    def repack_ahead(self):
+        """Right after the optimizer: repack on a side stream.  The two pack launches (~50 us) then overlap the next step's
+        input stage (pool_dual, HBM-bound, outside the step graph) instead of heading the graph's critical path.  Inline
+        packing stays the rule when concurrency is off, on the CPU mirror and while per-launch timing is recorded."""
+        if not (self.pack_ahead_on and self.concurrent and self.dev.type == "cuda") or getattr(self.ops, "_prof", None) is not None:
+            return
+        cur = torch.cuda.current_stream(self.dev)
+        if self._pack_stream is None:
+            self._pack_stream = torch.cuda.Stream(self.dev)
+        ps = self._pack_stream
+        ps.wait_stream(cur)
+        with torch.cuda.stream(ps):
+            self.repack()
+        self._pack_pending = ps
+
     def repack(self):
         """fp32 master weights -> GEMM operand copies (forward + data-gradient layouts) in the act dtype."""
+        if self._pack_pending is not None and torch.cuda.current_stream(self.dev) != self._pack_pending:
+            self._sync_pack()
         self.ops.pack_weights(self.params, self.packed, self.pack_table, len(self.pack.entries),
                               self.pack.max_elems)
         self.ops.pack_weights(self.params, self.packed_bias, self.bias_table, len(self.pack.bias_entries),
@@ -255,8 +292,7 @@ class THATEngine(StepCounters):
                 offs=None, lens=None) -> torch.Tensor:
         """x: fp32 [B,T,F] (or a packed ragged arena with offs/lens).  Returns logits [B, out] (a view of
         the engine's static logits buffer)."""
-        if self.weights_dirty:
-            self.repack()
+        self.ensure_packed()
         self.forward_input(x, B, training, augment, offs, lens)
         return self.forward_body(B, training, dropout)
 
@@ -325,13 +361,21 @@ class THATEngine(StepCounters):
             cur.wait_stream(ws)
         self._wgrad_pending = []
 
-    def forward_body(self, B: int, training: bool, dropout: bool = True) -> torch.Tensor:
+    def forward_body(self, B: int, training: bool, dropout: bool = True, prefill: bool = False) -> torch.Tensor:
+        """``prefill`` (fused train step): the gradient arena and the backward reduction pool are zeroed here, at the head
+        of the second CUDA stream, instead of between the loss and the backward on the critical path."""
         ops, g = self.ops, self.g
         pd = P_DROP if (training and dropout) else 0.0
         pf = P_FEAT if (training and dropout) else 0.0
         if training:
             ops.fill_f64(self.stat_pool, 0.0)
-        join = self._fork(lambda: self._forward_stream(1, B, training, pd))
+
+        def right():
+            if prefill:
+                ops.fill_f32(self.grads, 0.0)
+                ops.fill_f64(self.red_pool, 0.0)
+            self._forward_stream(1, B, training, pd)
+        join = self._fork(right)
         self._forward_stream(0, B, training, pd)
         join()
         ops.alg_scale = 1.0
@@ -412,7 +456,7 @@ class THATEngine(StepCounters):
 
     # ------------------------------------------------------------------ backward
     def backward(self, dlogits: Optional[torch.Tensor], B: int, dropout: bool = True, zero_grads: bool = True,
-                 part: int = 0):
+                 part: int = 0, prefilled: bool = False):
         """Gradient of every parameter into ``self.grads`` given dL/dlogits ([B,out] fp32; None = use the
         engine's own ``dlogits`` buffer written by ``loss_fwd_bwd``).
 
@@ -429,9 +473,10 @@ class THATEngine(StepCounters):
                 self._backward_stream(0, B, pd, range(0, 1), head=False)
                 self._wgrad_join()
             return None
-        if zero_grads:
-            ops.fill_f32(self.grads, 0.0)
-        ops.fill_f64(self.red_pool, 0.0)                  # parts 1 and 2 use disjoint slices: zeroed once, here
+        if not prefilled:                                 # (prefilled: ``forward_body(prefill=True)`` has zeroed both)
+            if zero_grads:
+                ops.fill_f32(self.grads, 0.0)
+            ops.fill_f64(self.red_pool, 0.0)              # parts 1 and 2 use disjoint slices: zeroed once, here
         if dlogits is not None:
             if g.heads == 1:
                 self.dlogits[:B, :g.out].copy_(dlogits)
@@ -580,10 +625,12 @@ class THATEngine(StepCounters):
         """repack + forward body + BCE + backward: a fixed launch sequence over static buffers.
         part 1 stops before the left stream's encoder 0 backward, part 2 is that remainder (see ``backward``)."""
         if part != 2:
-            self.repack()
-            self.forward_body(B, True, dropout)
+            # (the operand copies are packed outside: ``ensure_packed`` before the step, ``repack_ahead`` after the optimizer)
+            if self.dev.type != "cuda" or not torch.cuda.is_current_stream_capturing():
+                self.ensure_packed()
+            self.forward_body(B, True, dropout, prefill=self.prefill_on)
             self.loss_fwd_bwd(self.y_static, B, pos_weight)
-        self.backward(None, B, dropout=dropout, zero_grads=True, part=part)
+        self.backward(None, B, dropout=dropout, zero_grads=True, part=part, prefilled=self.prefill_on)
 
     def train_body_graph(self, B: int, pos_weight: float, dropout: bool, part: int = 0):
         """Replays train_body as one CUDA graph (captured on first use for this (B, pos_weight, dropout, part))."""

@@ -244,6 +244,7 @@ class THAT(ArenaModule):
         eng.begin_train_forward()
         eng.forward_input(x, B, True, augment, offs, lens)
         eng.ops.copy_f32(eng.y_static, yf.contiguous(), yf.numel())     # rows of y_static and yf have the same pitch
+        eng.ensure_packed()                             # operand copies: packed after the previous optimizer step (side stream)
         graph = self.use_cuda_graph if use_graph is None else use_graph
         run = eng.train_body_graph if (graph and x.is_cuda and self._eager_steps >= 1) else eng.train_body
         overlap = grad_hook is not None and hasattr(grad_hook, "start_bucket")
