@@ -128,6 +128,13 @@ int csi_gemm_tn(const void* A, int lda, const void* Bv, int ldb, int ab_dtype, f
 /* i_grp / q_grp: A's columns (i) / Bv's columns (q) are head-padded; C is indexed with the compact indices and the
  * padding entries are skipped (in-projection and out-projection weight gradients). */
 
+/* Two-stage reduction for csi_gemm_tn (bf16): after this call every csi_gemm_tn issued on `stream` of the current device
+ * stores the partial sums of its token chunks in `ws` and adds them to C with a second, fixed-order kernel instead of fp32
+ * atomics from every CTA (faster, and the gradient is bit-reproducible).  nfloats >= SMs * 128 * 512 covers every shape;
+ * a call that needs more falls back to atomics.  The caller owns `ws` (128-byte aligned) and must keep it alive and use it
+ * for one stream only; ws = NULL unregisters.  Replaces nothing in the reference: torch.autograd reduces inside cuBLAS. */
+int csi_gemm_tn_workspace(void* stream, float* ws, long long nfloats);
+
 /* Column sums over the valid token rows: out[compact(c)] += sum_{b,l} A[row(b,l), c]  (bias gradients). */
 int csi_colsum_tokens(const void* A, int lda, int dtype, int B, int L, int halo, int ncols, csi_grp grp, float* out,
                       void* stream);

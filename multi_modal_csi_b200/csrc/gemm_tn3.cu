@@ -34,6 +34,9 @@ struct Tn3Params {
     uint32_t tmem_cols;
     csi_grp ig, qg;
     int dbg;
+    // two-stage reduction (csi_gemm_tn_workspace): every CTA stores its raw accumulators as
+    // ws[((tile * zs + z) * 128 + row) * ws_w + tmem column]; tn3_reduce_kernel sums the zs token chunks in a fixed order
+    float* ws; int ws_w;
 };
 
 __device__ __forceinline__ bool elect_one_tn() {
@@ -92,9 +95,14 @@ __device__ __forceinline__ void tn3_epilogue(const Tn3Params& p, const Tn3Plan& 
     const int irow = i0 + q * 32 + lane;
     const int my_ic = irow < p.Na ? grp_to_compact(irow, p.ig) : -1;
     const int npass = (p.BN + NQ - 1) / NQ;
-    for (int ps = half; ps < npass; ps += 2) {
+    // dbg 8 / 16 (A/B): token chunks start at different column passes / rows, so that the CTAs of one output tile (which all
+    // finish their mainloop together) do not queue on the same L2 lines
+    const int prot = (p.dbg & 8) ? (int)(blockIdx.z % (unsigned)npass) : 0, rrot = (p.dbg & 16) ? (int)((blockIdx.z * 5u) & 31u) : 0;
+    for (int pn = half; pn < npass; pn += 2) {
+        int ps = pn + prot;
+        if (ps >= npass) ps -= npass;
         const int c0 = ps * NQ;
-        if (q0 + c0 >= g_nlen) break;                              // warp-uniform
+        if (q0 + c0 >= g_nlen) continue;                           // warp-uniform
         uint32_t r[NT][NQ];
 #pragma unroll
         for (int t = 0; t < NT; ++t)
@@ -128,7 +136,8 @@ __device__ __forceinline__ void tn3_epilogue(const Tn3Params& p, const Tn3Plan& 
         __syncwarp();
         if (p.dbg & 1) continue;
 #pragma unroll 4
-        for (int rr = 0; rr < 32; ++rr) {
+        for (int r0 = 0; r0 < 32; ++r0) {
+            const int rr = (r0 + rrot) & 31;
             const int ic = __shfl_sync(0xffffffffu, my_ic, rr);
             if (ic < 0) continue;                                  // warp-uniform
             float* crow = p.C + (size_t)ic * p.ldc;
@@ -137,6 +146,82 @@ __device__ __forceinline__ void tn3_epilogue(const Tn3Params& p, const Tn3Plan& 
                 if (off[u] >= 0) atomicAdd(crow + off[u], tbuf[rr * N3_TPITCH + u * 32 + lane]);
         }
     }
+}
+
+// Two-stage epilogue: the lane (= row i of the tile) copies its TMEM columns [0, ncols) to the workspace slab of this CTA,
+// stored COLUMN-major (ws[slab][column][128 rows]): the 32 lanes of a warp hold 32 consecutive rows of one column, so every
+// store instruction writes one whole 128-byte line.  The two warps of a lane quarter take alternate 32-column groups.
+// No atomics: the token chunks are summed afterwards by tn3_reduce_kernel in a fixed order, so the weight gradient is
+// bit-reproducible from run to run.
+__device__ __forceinline__ void tn3_epilogue_ws(const Tn3Params& p, int ncols, int i0, uint32_t tmem_base, int warp, int lane) {
+    const int q = warp & 3, half = (warp - 2) >> 2;
+    const int irow = i0 + q * 32 + lane;
+    const size_t slab = ((size_t)blockIdx.y * gridDim.x + blockIdx.x) * gridDim.z + blockIdx.z;
+    float* dst = p.ws + slab * (size_t)(TC_BM * p.ws_w) + (size_t)(q * 32 + lane);
+    const bool ok = irow < p.Na;
+    for (int c = half * 32; c < ncols; c += 64) {
+        uint32_t r[32];
+        tmem_ld16(tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)c, r);
+        tmem_ld16(tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(c + 16), r + 16);
+        tmem_ld_wait();
+        if (ok) {
+#pragma unroll
+            for (int j = 0; j < 32; ++j) __stcg(dst + (size_t)(c + j) * TC_BM, __uint_as_float(r[j]));
+        }
+    }
+}
+
+// Stage two: C[ic, c_off_t + qc * cs] += sum_z ws[tile, z, t * pitch + j, row].  One CTA = (tile, 32 rows, 8 workspace columns);
+// warp w sums the token chunks z = w, w + 8, ... of those 8 columns (lane = row: every load instruction is one 128-byte line,
+// 8-16 in flight per thread; the partial sums are L2-resident, written microseconds earlier), the eight per-warp sums are
+// combined through shared memory in warp order, and thread (row, column) adds the result to C.  The order of every sum is
+// fixed, so the gradient is bit-reproducible.  Grid = (row quarters, 8-column blocks, tiles).
+__global__ void __launch_bounds__(256) tn3_reduce_kernel(Tn3Params p, const __grid_constant__ Tn3Plan plan, int zs, int itiles) {
+    __shared__ float sm[8][8][33];
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int tile = blockIdx.z, ty = tile / itiles, it = tile - ty * itiles;        // slab order of the main kernel: (y, x, z)
+    const int gi = ty / p.qtiles, qt = ty - gi * p.qtiles;
+    const int q0 = qt * p.BN, g_nlen = plan.g[gi].nlen, tap0 = plan.g[gi].tap0, ntaps = plan.g[gi].ntaps;
+    const int r0 = it * TC_BM + blockIdx.x * 32, c0 = blockIdx.y * 8;
+    if (q0 >= g_nlen || r0 >= p.Na || c0 >= ntaps * p.pitch) return;                 // uniform per CTA
+    {
+        const int t0 = c0 / p.pitch, j0 = c0 - t0 * p.pitch;                         // 8 | pitch: the block lies inside one tap
+        if (j0 >= p.BN || q0 + j0 >= g_nlen) return;
+    }
+    const size_t zstride = (size_t)TC_BM * p.ws_w;
+    const float* src = p.ws + (size_t)tile * zs * zstride + (size_t)c0 * TC_BM + blockIdx.x * 32 + lane;
+    float a[8] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
+    if (r0 + lane < p.Na) {
+        int z = warp;
+        for (; z + 8 < zs; z += 16) {
+            float v0[8], v1[8];
+#pragma unroll
+            for (int u = 0; u < 8; ++u) v0[u] = __ldcg(src + (size_t)z * zstride + u * TC_BM);
+#pragma unroll
+            for (int u = 0; u < 8; ++u) v1[u] = __ldcg(src + (size_t)(z + 8) * zstride + u * TC_BM);
+#pragma unroll
+            for (int u = 0; u < 8; ++u) a[u] += v0[u];
+#pragma unroll
+            for (int u = 0; u < 8; ++u) a[u] += v1[u];
+        }
+        if (z < zs) {
+#pragma unroll
+            for (int u = 0; u < 8; ++u) a[u] += __ldcg(src + (size_t)z * zstride + u * TC_BM);
+        }
+    }
+#pragma unroll
+    for (int u = 0; u < 8; ++u) sm[warp][u][lane] = a[u];
+    __syncthreads();
+    const int row = threadIdx.x >> 3, u = threadIdx.x & 7;
+    const int c = c0 + u, t = c / p.pitch, j = c - t * p.pitch, qq = q0 + j, irow = r0 + row;
+    if (irow >= p.Na || j >= p.BN || qq >= g_nlen) return;
+    const int ic = grp_to_compact(irow, p.ig), qc = grp_to_compact(qq, p.qg);
+    if (ic < 0 || qc < 0) return;
+    float v = 0.f;
+#pragma unroll
+    for (int w = 0; w < 8; ++w) v += sm[w][u][row];
+    // one add per address and launch (segments with disjoint outputs): the result does not depend on any ordering
+    atomicAdd(p.C + (size_t)ic * p.ldc + plan.t[tap0 + t].c_off + qc * p.cs, v);
 }
 
 __global__ void __launch_bounds__(N3_THREADS, 1) gemm_tn_tc3_kernel(const __grid_constant__ CUtensorMap tmA,
@@ -229,7 +314,8 @@ __global__ void __launch_bounds__(N3_THREADS, 1) gemm_tn_tc3_kernel(const __grid
         mbar_wait(&tmem_full_bar, 0);                              // every UMMA has completed: the stage ring is free
         tc_fence_after();
         float* tbuf = reinterpret_cast<float*>(smem) + (size_t)(warp - 2) * (32 * N3_TPITCH);
-        if (!(p.dbg & 2)) switch (ntaps) {
+        if (p.ws) { if (!(p.dbg & 2)) tn3_epilogue_ws(p, ntaps * p.pitch, i0, tmem_base, warp, lane); }
+        else if (!(p.dbg & 2)) switch (ntaps) {
             case 1: tn3_epilogue<1>(p, plan, tap0, g_nlen, i0, q0, tmem_base, tbuf, warp, lane); break;
             case 2: tn3_epilogue<2>(p, plan, tap0, g_nlen, i0, q0, tmem_base, tbuf, warp, lane); break;
             case 3: tn3_epilogue<3>(p, plan, tap0, g_nlen, i0, q0, tmem_base, tbuf, warp, lane); break;
@@ -250,6 +336,37 @@ static int g_tn_dbg = 0;
 static int g_tn_pdl = -1;           // programmatic dependent launch (CSI_PDL=0 disables)
 extern "C" int csi_set_gemm_tn_pdl(int on) { g_tn_pdl = on ? 1 : 0; return CSI_OK; }
 extern "C" int csi_set_tn_debug(int v) { g_tn_dbg = v; return CSI_OK; }
+
+// ---- workspaces of the two-stage reduction, registered per (device, stream) by the caller that owns the memory
+struct TnWorkspace { int dev; void* stream; float* ws; long long nfloats; };
+static TnWorkspace g_tn_ws[32];
+static int g_tn_nws = 0;
+static std::mutex g_tn_ws_mu;
+extern "C" int csi_gemm_tn_workspace(void* stream, float* ws, long long nfloats) {
+    int dev = 0;
+    CSI_CUDA(cudaGetDevice(&dev));
+    CSI_CHECK_ARG(!ws || ((reinterpret_cast<uintptr_t>(ws) & 127) == 0 && nfloats > 0), "workspace must be 128-byte aligned");
+    std::lock_guard<std::mutex> lk(g_tn_ws_mu);
+    for (int i = 0; i < g_tn_nws; ++i)
+        if (g_tn_ws[i].dev == dev && g_tn_ws[i].stream == stream) {
+            if (ws) { g_tn_ws[i].ws = ws; g_tn_ws[i].nfloats = nfloats; }
+            else g_tn_ws[i] = g_tn_ws[--g_tn_nws];
+            return CSI_OK;
+        }
+    if (!ws) return CSI_OK;
+    CSI_CHECK_ARG(g_tn_nws < 32, "too many registered streams");
+    g_tn_ws[g_tn_nws++] = TnWorkspace{dev, stream, ws, nfloats};
+    return CSI_OK;
+}
+static float* tn_workspace_for(void* stream, long long need) {
+    if (g_tn_nws == 0) return nullptr;
+    int dev = 0;
+    if (cudaGetDevice(&dev) != cudaSuccess) return nullptr;
+    std::lock_guard<std::mutex> lk(g_tn_ws_mu);
+    for (int i = 0; i < g_tn_nws; ++i)
+        if (g_tn_ws[i].dev == dev && g_tn_ws[i].stream == stream) return g_tn_ws[i].nfloats >= need ? g_tn_ws[i].ws : nullptr;
+    return nullptr;
+}
 
 extern "C" int csi_gemm_tn_tc3(const void* A, int lda, const void* Bv, int ldb, float* C, int ldc, int c_col_stride, int M,
                                int Na, const csi_seg_tn* segs, int nseg, csi_grp ig, csi_grp qg, void* stream) {
@@ -344,6 +461,8 @@ extern "C" int csi_gemm_tn_tc3(const void* A, int lda, const void* Bv, int ldb, 
     uint32_t cols = 32;
     while ((int)cols < gtaps * pitch) cols <<= 1;
     p.tmem_cols = cols;
+    p.ws_w = gtaps * pitch;
+    p.ws = tn_workspace_for(stream, (long long)tiles * zs * TC_BM * p.ws_w);
     const size_t smem = (size_t)N3_STAGES * (2 * N3_BKM * 128 + (size_t)nbox_b * rows_b * 128) + 1024;
     CSI_CHECK_ARG(smem <= 227 * 1024, "stage does not fit in shared memory");
     CSI_CUDA(cudaFuncSetAttribute(gemm_tn_tc3_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
@@ -354,7 +473,12 @@ extern "C" int csi_gemm_tn_tc3(const void* A, int lda, const void* Bv, int ldb, 
     at[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
     at[0].val.programmaticStreamSerializationAllowed = g_tn_pdl;
     cfg.attrs = at; cfg.numAttrs = 1;
-    CSI_CUDA(cudaLaunchKernelEx(&cfg, gemm_tn_tc3_kernel, tmA, tmB, p, plan));
+    if (!(g_tn_dbg & 64)) CSI_CUDA(cudaLaunchKernelEx(&cfg, gemm_tn_tc3_kernel, tmA, tmB, p, plan));
     CSI_LAUNCH_CHECK();
+    if (p.ws && !(g_tn_dbg & 32)) {
+        // stage two (plain stream order: it starts once every partial sum is in memory)
+        tn3_reduce_kernel<<<dim3(TC_BM / 32, p.ws_w / 8, (unsigned)tiles), 256, 0, ST(stream)>>>(p, plan, zs, itiles);
+        CSI_LAUNCH_CHECK();
+    }
     return CSI_OK;
 }

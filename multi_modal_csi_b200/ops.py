@@ -70,8 +70,14 @@ EXPORTS = [
     "csi_set_force_simt", "csi_set_strict_tc", "csi_dispatch_counts", "csi_set_attn_impl",
     "csi_fill_f64", "csi_copy_f32", "csi_nhwc_stats", "csi_bn2d_finalize", "csi_im2col_bn", "csi_col2im", "csi_act_drop_fwd",
     "csi_bn2d_bwd_reduce", "csi_bn2d_bwd_apply", "csi_pool_bn_fwd", "csi_conv2d_pack", "csi_conv2d_unpack_grad", "csi_bn0_grads",
-    "csi_gather_aug",
+    "csi_gather_aug", "csi_gemm_tn_workspace",
 ]
+
+# Workspaces of the two-stage weight-gradient reduction (csi_gemm_tn_workspace), one per (device, stream) that ever issued a
+# weight gradient; they live as long as the process, so the library never holds a pointer to freed memory.
+# Largest need: one wave of CTAs x 128 rows x 512 TMEM columns of fp32 = 38.8 MB on a 148-SM part.
+TN_TWO_STAGE = os.environ.get("CSI_TN_TWO_STAGE", "1") != "0"
+_TN_WS = {}
 
 
 def _dt(t: torch.Tensor) -> int:
@@ -274,8 +280,26 @@ class NativeOps:
                                       len(segs), _p(bias), _p(residual), _ld(residual), C.c_float(drop_p),
                                       C.c_uint(drop_site), _p(rng), **wk)
 
+    def tn_workspace(self):
+        """Registers (once per device and stream) the workspace that makes csi_gemm_tn on the current stream reduce its token
+        chunks in two stages (partial sums + one fixed-order reduce) instead of with fp32 atomics: faster and bit-reproducible."""
+        if not TN_TWO_STAGE:
+            return
+        st = torch.cuda.current_stream(self.device).cuda_stream
+        key = (self.device.index or 0, st)
+        if key not in _TN_WS:
+            sms = torch.cuda.get_device_properties(self.device).multi_processor_count
+            ws = torch.empty(sms * 128 * 512, dtype=torch.float32, device=self.device)
+            with torch.cuda.device(self.device):
+                rc = self.lib.csi_gemm_tn_workspace(C.c_void_p(st), _p(ws), C.c_longlong(ws.numel()))
+            if rc != 0:
+                raise RuntimeError(f"csi_gemm_tn_workspace failed ({rc}): {self.lib.csi_last_error().decode()}")
+            _TN_WS[key] = ws
+
     def gemm_tn(self, A, Bv, Cm, ldc, c_col_stride, M, Na, segs, i_grp=NO_GRP, q_grp=NO_GRP):
         wk = self._work("gemm_tn", locals())
+        if A.dtype == torch.bfloat16:
+            self.tn_workspace()
         if self._prof is not None:
             self._tag = f"M={M} Na={Na} nlen={sum(s[3] for s in segs)} nseg={len(segs)} cs={c_col_stride}"
         arr = (SegTN * len(segs))(*[SegTN(*s) for s in segs])

@@ -323,3 +323,49 @@ def test_attention_tcgen05_kernels(B, L, d):
     assert nrel(dbias, cs) < 1e-5
     if hp > hd:
         assert float(dqkv.view(B, Lp, 3 * H, hp)[:, :, :, hd:].float().abs().max()) == 0.0
+
+
+# ------------------------------------------------------------------------------------------- weight-gradient reduction modes
+@pytest.mark.parametrize("M,Na,Dp,nlen,k", [(39424, 270, 272, 270, 5), (70144, 150, 160, 150, 3), (4096, 128, 272, 270, 16),
+                                             (1000, 54, 288, 288, 1)])
+def test_wgrad_two_stage_reduction_is_reproducible(M, Na, Dp, nlen, k):
+    """csi_gemm_tn with a registered workspace (csi_gemm_tn_workspace: partial sums of the token chunks + one fixed-order
+    reduce) against the fp32 product on the bf16 operands and against the atomics mode; reruns are bit-identical, and the
+    call ACCUMULATES into C like the atomics mode does."""
+    import ctypes as C
+    from multi_modal_csi_b200 import ops as OPS
+    ops = OPS.NativeOps(torch.device("cuda", 0))
+    GUARD = 16
+    g = torch.Generator(device="cuda").manual_seed(5)
+    A = (torch.randn(M, (Na + 15) // 16 * 16, device="cuda", generator=g) * 0.1).to(torch.bfloat16)
+    full = torch.randn(M + 2 * GUARD, Dp, device="cuda", generator=g).to(torch.bfloat16)
+    X = full[GUARD:GUARD + M]
+    pl = (k - 1) // 2
+    segs = [(j - pl, 0, j, nlen) for j in range(k)]
+    ref = torch.zeros(Na, nlen, k, device="cuda")
+    for j in range(k):
+        ref[:, :, j] = A[:, :Na].float().t() @ full[GUARD + j - pl:GUARD + j - pl + M, :nlen].float()
+
+    def run(init):
+        out = torch.full((Na, nlen, k), init, device="cuda")
+        ops.gemm_tn(A, X, out, nlen * k, k, M, Na, segs)
+        torch.cuda.synchronize()
+        return out
+
+    assert OPS.TN_TWO_STAGE
+    a, b = run(0.0), run(0.0)
+    assert torch.equal(a, b)
+    assert nrel(a, ref) < 1e-5
+    assert nrel(run(0.25), ref + 0.25) < 1e-5
+    # atomics mode (no workspace registered for the stream)
+    st = torch.cuda.current_stream().cuda_stream
+    saved = OPS._TN_WS.pop((0, st))
+    ops.lib.csi_gemm_tn_workspace(C.c_void_p(st), C.c_void_p(0), C.c_longlong(0))
+    OPS.TN_TWO_STAGE = False
+    try:
+        c = run(0.0)
+    finally:
+        OPS.TN_TWO_STAGE = True
+        ops.lib.csi_gemm_tn_workspace(C.c_void_p(st), C.c_void_p(saved.data_ptr()), C.c_longlong(saved.numel()))
+        OPS._TN_WS[(0, st)] = saved
+    assert nrel(c, ref) < 1e-5 and nrel(a, c) < 1e-5
