@@ -1019,8 +1019,16 @@ extern "C" int csi_bn_act_fwd(const void* z, int ldz, int dtype, const float* me
 //   MODE 0: per-channel sums of dy and dy*zhat -> red (doubles, atomics)
 //   MODE 1: dz = gamma*invstd*(dy - s1/n - zhat*s2/n), plus dgamma/dbeta written once by CTA 0
 #define BNB_MAXT 224
+#ifndef BNB_ROWS_REDUCE
+#define BNB_ROWS_REDUCE 4
+#endif
+#ifndef BNB_ROWS_DZ
+#define BNB_ROWS_DZ 4
+#endif
 
-template <typename T, int MODE, int MINB>
+// REGEN: no stored keep bits, the dropout decisions are regenerated with Philox (tests / callers without a mask buffer); the
+// production path reads the bits bn_act_fwd stored and does not carry the generator state through the row loop.
+template <typename T, int MODE, int MINB, bool REGEN, int NR>
 __global__ void __launch_bounds__(BNB_MAXT, MINB) bn_act_bwd_kernel(
     const float* __restrict__ dout, int lddo, const T* __restrict__ z, int ldz, const float* __restrict__ mean,
     const float* __restrict__ invstd, csi_ptr3 gamma, csi_ptr3 beta, double* __restrict__ red, int B, int L, int d, int Dp,
@@ -1033,8 +1041,11 @@ __global__ void __launch_bounds__(BNB_MAXT, MINB) bn_act_bwd_kernel(
     const int total = B * L, ld8 = Dp >> 3, nc = nbr * Dp;
     const int r0 = blockIdx.x * rows_per_cta, r1 = min(total, r0 + rows_per_cta);
     const int q0 = br * Dp + ch * 8, c0 = ch * 8;
-    // y = zh*ga + be ; zh = (z - mu)*is ; MODE 1: dz = gi*dy - gk1 - zh*gk2
-    float mu[8], is[8], ga[8], be[8], gi[8], gk1[8], gk2[8], s1[8], s2[8];
+    // y = zh*ga + be with zh = (z - mu)*is, written as y = z*a + b (a = is*ga, b = be - mu*a).
+    //   MODE 0 accumulates s1 = sum dy and s2z = sum dy*z; sum dy*zh = is*(s2z - mu*s1) is formed once at the end.
+    //   MODE 1: dz = gi*dy - gk1 - zh*gk2 = a*dy - k1 - z*k2 with k1 = gk1 - mu*is*gk2, k2 = is*gk2.
+    // Two (three) per-channel vectors of state instead of four (seven): registers for more rows of loads in flight.
+    float a[8], b[8], k1[8], k2[8], s1[8], s2[8];
     {
         const float* gp = (const float*)gamma.p[br];
         const float* bp = (const float*)beta.p[br];
@@ -1042,71 +1053,78 @@ __global__ void __launch_bounds__(BNB_MAXT, MINB) bn_act_bwd_kernel(
 #pragma unroll
         for (int j = 0; j < 8; ++j) {
             const bool ok = (c0 + j) < d;
-            mu[j] = ok ? mean[q0 + j] : 0.f;
-            is[j] = ok ? invstd[q0 + j] : 0.f;
-            ga[j] = ok ? gp[c0 + j] : 0.f;
-            be[j] = ok ? bp[c0 + j] : 0.f;
+            const float mu = ok ? mean[q0 + j] : 0.f, is = ok ? invstd[q0 + j] : 0.f;
+            a[j] = ok ? is * gp[c0 + j] : 0.f;
+            b[j] = ok ? bp[c0 + j] - mu * a[j] : 0.f;
             s1[j] = s2[j] = 0.f;
             if (MODE == 1) {
-                gi[j] = ga[j] * is[j];
-                gk1[j] = ok ? gi[j] * (float)red[q0 + j] * invn : 0.f;
-                gk2[j] = ok ? gi[j] * (float)red[nc + q0 + j] * invn : 0.f;
+                const float gk1 = ok ? a[j] * (float)red[q0 + j] * invn : 0.f;
+                const float gk2 = ok ? a[j] * (float)red[nc + q0 + j] * invn : 0.f;
+                k2[j] = is * gk2;
+                k1[j] = gk1 - mu * k2[j];
             }
         }
     }
     const bool db = dcfg.p_branch > 0.f, dro = dcfg.p_out > 0.f;
     DropCtx cb, co;
-    if (db) cb = drop_ctx(rng, dcfg.p_branch);
-    if (dro) co = drop_ctx(rng, dcfg.p_out);
+    if (REGEN && db) cb = drop_ctx(rng, dcfg.p_branch);
+    if (REGEN && dro) co = drop_ctx(rng, dcfg.p_out);
     const float inv = 1.0f / nbr;
-    const float sc_o = inv * (dro ? co.inv_keep : 1.f), sc_b = db ? cb.inv_keep : 1.f;
+    const float sc = inv * (dro ? 1.f / (1.f - dcfg.p_out) : 1.f) * (db ? 1.f / (1.f - dcfg.p_branch) : 1.f);
     auto process = [&](size_t row, const Raw8<float>& gn, const Raw8<T>& zn, unsigned int word) {
         const unsigned long long idx8 = (unsigned long long)row * ld8 + ch;
         float g[8], zv[8], o[8];
         gn.get(g);
         zn.get(zv);
         unsigned int kb = 0xffu, ko = 0xffu;                      // keep bits of the branch / output dropout
-        if (masks) { kb = (word >> (8 * br)) & 0xffu; ko = word >> 24; }
+        if (!REGEN) { if (masks) { kb = (word >> (8 * br)) & 0xffu; ko = word >> 24; } }
         else {
             if (db) kb = drop_bits8(cb, dcfg.site_branch + br, idx8);
             if (dro) ko = drop_bits8(co, dcfg.site_out, idx8);
         }
 #pragma unroll
         for (int j = 0; j < 8; ++j) {
-            const float zh = (zv[j] - mu[j]) * is[j];
-            const float y = zh * ga[j] + be[j];                    // sign(y) is not changed by the (non-negative) keep scale
+            const float y = fmaf(zv[j], a[j], b[j]);               // sign(y) is not changed by the (non-negative) keep scale
             const bool keep = ((kb >> j) & (ko >> j) & 1u) != 0u;
-            const float dy = keep ? g[j] * sc_o * sc_b * leaky_grad(y) : 0.f;
-            if (MODE == 0) { s1[j] += dy; s2[j] += dy * zh; }
-            else o[j] = gi[j] * dy - gk1[j] - zh * gk2[j];
+            const float dy = keep ? g[j] * sc * leaky_grad(y) : 0.f;
+            if (MODE == 0) { s1[j] += dy; s2[j] = fmaf(dy, zv[j], s2[j]); }
+            else o[j] = fmaf(-zv[j], k2[j], fmaf(a[j], dy, -k1[j]));
         }
         if (MODE == 1) store8f<T>(dz + row * lddz + q0, o);
     };
+    // NR rows of loads in flight per thread: both passes are bound by load latency (ncu, reduce pass with two rows: 49 %
+    // long-scoreboard stalls at 52 % issue utilisation)
     RowWalk w;
     w.init(min(r0 + rl, total - 1), L, halo);
-    for (int r = r0 + rl; r < r1; r += 2 * RL) {
-        const size_t rowA = w.row();
-        w.advance(RL);
-        const bool hasB = r + RL < r1;
-        const size_t rowB = hasB ? w.row() : rowA;
-        w.advance(RL);
-        Raw8<float> gA, gB;
-        Raw8<T> zA, zB;
-        unsigned int wA = 0, wB = 0;
-        gA.load(dout + rowA * lddo + c0);
-        zA.load(z + rowA * ldz + q0);
-        if (masks) wA = masks[rowA * ld8 + ch];
-        gB.load(dout + rowB * lddo + c0);
-        zB.load(z + rowB * ldz + q0);
-        if (masks) wB = masks[rowB * ld8 + ch];
-        process(rowA, gA, zA, wA);
-        if (hasB) process(rowB, gB, zB, wB);
+    for (int r = r0 + rl; r < r1; r += NR * RL) {
+        size_t rows[NR];
+        bool has[NR];
+#pragma unroll
+        for (int i = 0; i < NR; ++i) {
+            has[i] = r + i * RL < r1;
+            rows[i] = has[i] ? w.row() : rows[0];
+            w.advance(RL);
+        }
+        Raw8<float> gR[NR];
+        Raw8<T> zR[NR];
+        unsigned int wR[NR];
+#pragma unroll
+        for (int i = 0; i < NR; ++i) {
+            gR[i].load(dout + rows[i] * lddo + c0);
+            zR[i].load(z + rows[i] * ldz + q0);
+            wR[i] = masks ? masks[rows[i] * ld8 + ch] : 0u;
+        }
+#pragma unroll
+        for (int i = 0; i < NR; ++i)
+            if (has[i]) process(rows[i], gR[i], zR[i], wR[i]);
     }
     if (MODE == 0) {
 #pragma unroll
         for (int j = 0; j < 8; ++j) {
+            const bool ok = (c0 + j) < d;
+            const float mu = ok ? mean[q0 + j] : 0.f, is = ok ? invstd[q0 + j] : 0.f;
             sred[((rl * ncombo + combo) * 2 + 0) * 8 + j] = s1[j];
-            sred[((rl * ncombo + combo) * 2 + 1) * 8 + j] = s2[j];
+            sred[((rl * ncombo + combo) * 2 + 1) * 8 + j] = is * (s2[j] - mu * s1[j]);       // sum dy * zhat of this thread's rows
         }
         __syncthreads();
         for (int e = threadIdx.x; e < ncombo * 16; e += blockDim.x) {
@@ -1143,10 +1161,23 @@ static int bn_bwd_launch(const float* dout, int lddo, const void* z, int ldz, in
     if (grid > cdiv(total, 2 * RL)) grid = cdiv(total, 2 * RL);
     const int rows_per_cta = cdiv(total, grid);
     grid = cdiv(total, rows_per_cta);
-#define BNB_GO(T, MINB) bn_act_bwd_kernel<T, MODE, MINB><<<grid, threads, smem, s>>>(dout, lddo, (const T*)z, ldz, mean, invstd, gamma, beta, \
+    const bool regen = !masks && (dc.p_branch > 0.f || dc.p_out > 0.f);
+    // rows of loads in flight per thread (A/B: CSI_BN_ROWS_REDUCE / CSI_BN_ROWS_DZ = 2 | 4 | 6); the Philox path keeps 2
+    static int nr_env[2] = {0, 0};
+    if (!nr_env[MODE]) {
+        const char* e = getenv(MODE == 0 ? "CSI_BN_ROWS_REDUCE" : "CSI_BN_ROWS_DZ");
+        const int v = e ? atoi(e) : 0;
+        nr_env[MODE] = (v == 2 || v == 4 || v == 6) ? v : (MODE == 0 ? BNB_ROWS_REDUCE : BNB_ROWS_DZ);
+    }
+    const int nr = regen ? 2 : nr_env[MODE];
+#define BNB_GO3(T, MINB, RG, NR) bn_act_bwd_kernel<T, MODE, MINB, RG, NR><<<grid, threads, smem, s>>>(dout, lddo, (const T*)z, ldz, mean, invstd, gamma, beta, \
         red, B, L, d, Dp, halo, nbr, dc, rng, (T*)dz, lddz, dgamma, dbeta, CH, RL, rows_per_cta, masks)
+#define BNB_GO2(T, MINB, RG) do { if (nr == 6) BNB_GO3(T, MINB, RG, 6); else if (nr == 4) BNB_GO3(T, MINB, RG, 4); else BNB_GO3(T, MINB, RG, 2); } while (0)
+#define BNB_GO(T, MINB) do { if (regen) BNB_GO3(T, MINB, true, 2); else BNB_GO2(T, MINB, false); } while (0)
     if (dtype == CSI_BF16) { if (ctas == 3) BNB_GO(bf16, 3); else BNB_GO(bf16, 2); }
     else { if (ctas == 3) BNB_GO(float, 3); else BNB_GO(float, 2); }
+#undef BNB_GO2
+#undef BNB_GO3
 #undef BNB_GO
     return CSI_OK;
 }
