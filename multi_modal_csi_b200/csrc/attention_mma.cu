@@ -8,9 +8,13 @@
 //             pass B (per 16-key tile)    S^T, dP^T -> dV = P^T dO, dK = dS^T Q     (no atomics, no cross-warp sums)
 //   dK/dV tiles are staged over the K/V rows they belong to once every warp has finished pass A (mbarrier split barrier).
 #include "common.cuh"
+#include <stdlib.h>
 
 #define ST(s) ((cudaStream_t)(s))
 #define AM_MAX_WARPS 5
+#ifndef AM_DIRECT_STORE
+#define AM_DIRECT_STORE 1
+#endif
 // occupancy: registers are the limit (3 CTAs/SM at ~103 regs).  CTAs have at most 5 warps; the (160 threads, 4 CTAs) bound
 // = 96 registers gives 20 resident warps per SM; the 64-wide heads need more accumulators and keep the loose bound
 template <int HDP> struct am_bounds { static constexpr int min_ctas = HDP <= 32 ? 4 : 2; };
@@ -355,10 +359,13 @@ __global__ void __launch_bounds__(AM_MAX_WARPS * 32, am_bounds_bwd<HDP>::min_cta
             float ds[2][4];
 #pragma unroll
             for (int nt = 0; nt < 2; ++nt) {
-                const int col = kp * 16 + nt * 8 + 2 * t;
-                const bool v0 = col < L, v1 = (col + 1) < L;
-                const float p0 = v0 ? fast_exp2(s[nt][0] * c - ls0) : 0.f, p1 = v1 ? fast_exp2(s[nt][1] * c - ls0) : 0.f;
-                const float p2 = v0 ? fast_exp2(s[nt][2] * c - ls1) : 0.f, p3 = v1 ? fast_exp2(s[nt][3] * c - ls1) : 0.f;
+                float p0 = fast_exp2(s[nt][0] * c - ls0), p1 = fast_exp2(s[nt][1] * c - ls0);
+                float p2 = fast_exp2(s[nt][2] * c - ls1), p3 = fast_exp2(s[nt][3] * c - ls1);
+                if (kp == ntile - 1) {                             // only the last key tile has columns >= L (warp-uniform)
+                    const int col = kp * 16 + nt * 8 + 2 * t;
+                    if (col >= L) p0 = p2 = 0.f;
+                    if (col + 1 >= L) p1 = p3 = 0.f;
+                }
                 ds[nt][0] = p0 * (dp[nt][0] - d0); ds[nt][1] = p1 * (dp[nt][1] - d0);
                 ds[nt][2] = p2 * (dp[nt][2] - d1); ds[nt][3] = p3 * (dp[nt][3] - d1);
             }
@@ -391,14 +398,16 @@ __global__ void __launch_bounds__(AM_MAX_WARPS * 32, am_bounds_bwd<HDP>::min_cta
         }
     }
     if (dbias) warp_colsum_flush<NTO>(cq, csum, g, t);
+#if !AM_DIRECT_STORE
     __syncwarp();
     if (lane == 0) am_mbar_arrive(abar);                          // this warp no longer reads K / V rows of other tiles
+#endif
     // ---------------- pass B: dK, dV (rows of the accumulators are keys, columns of S^T are queries)
     float ck[NTO][2], cv[NTO][2];
 #pragma unroll
     for (int no = 0; no < NTO; ++no) ck[no][0] = ck[no][1] = cv[no][0] = cv[no][1] = 0.f;
     // tiles are dealt in the opposite order to pass A, so a warp with one tile more there has one tile less here
-    bool passA_done = false;
+    bool passA_done = false; (void)passA_done;
     for (int kt = ntile - 1 - warp; kt >= 0; kt -= (int)(blockDim.x >> 5)) {
         uint32_t ka[KS][4], va[KS][4];
 #pragma unroll
@@ -425,11 +434,14 @@ __global__ void __launch_bounds__(AM_MAX_WARPS * 32, am_bounds_bwd<HDP>::min_cta
             float pt[2][4], dst_[2][4];
 #pragma unroll
             for (int nt = 0; nt < 2; ++nt) {
-                const int q0 = qp * 16 + nt * 8 + 2 * t, q1 = q0 + 1;
-                const bool v0 = q0 < L, v1 = q1 < L;
+                const int q0 = qp * 16 + nt * 8 + 2 * t;
                 const float2 lq = *reinterpret_cast<const float2*>(Ls + q0), dd = *reinterpret_cast<const float2*>(Ds + q0);
-                pt[nt][0] = v0 ? fast_exp2(st[nt][0] * c - lq.x) : 0.f; pt[nt][1] = v1 ? fast_exp2(st[nt][1] * c - lq.y) : 0.f;
-                pt[nt][2] = v0 ? fast_exp2(st[nt][2] * c - lq.x) : 0.f; pt[nt][3] = v1 ? fast_exp2(st[nt][3] * c - lq.y) : 0.f;
+                pt[nt][0] = fast_exp2(st[nt][0] * c - lq.x); pt[nt][1] = fast_exp2(st[nt][1] * c - lq.y);
+                pt[nt][2] = fast_exp2(st[nt][2] * c - lq.x); pt[nt][3] = fast_exp2(st[nt][3] * c - lq.y);
+                if (qp == ntile - 1) {                             // only the last query tile has columns >= L (warp-uniform)
+                    if (q0 >= L) pt[nt][0] = pt[nt][2] = 0.f;
+                    if (q0 + 1 >= L) pt[nt][1] = pt[nt][3] = 0.f;
+                }
                 dst_[nt][0] = pt[nt][0] * (dpt[nt][0] - dd.x); dst_[nt][1] = pt[nt][1] * (dpt[nt][1] - dd.y);
                 dst_[nt][2] = pt[nt][2] * (dpt[nt][2] - dd.x); dst_[nt][3] = pt[nt][3] * (dpt[nt][3] - dd.y);
             }
@@ -450,12 +462,35 @@ __global__ void __launch_bounds__(AM_MAX_WARPS * 32, am_bounds_bwd<HDP>::min_cta
         }
 #pragma unroll
         for (int no = 0; no < NTO; ++no) { dk[no][0] *= sc; dk[no][1] *= sc; dk[no][2] *= sc; dk[no][3] *= sc; }
+#if AM_DIRECT_STORE
+        // dK / dV: bf16x2 stores straight from the accumulator layout, like dQ (a quad of lanes writes 16 contiguous bytes of a
+        // row).  Nothing is staged over the K / V rows, so the two passes need no barrier between them and the kernel no
+        // store loop at its end (ncu: 8 % of the warp samples sat on that barrier).
+        {
+            const int k0 = kt * 16 + g, k1 = k0 + 8;
+            bf16* dkp = dqkv + row0 * lddqkv + H * HDP + h * HDP;
+            bf16* dvp = dkp + H * HDP;
+#pragma unroll
+            for (int no = 0; no < NTO; ++no) {
+                const int col = no * 8 + 2 * t;
+                if (k0 < L) {
+                    *reinterpret_cast<__nv_bfloat162*>(dkp + (size_t)k0 * lddqkv + col) = __floats2bfloat162_rn(dk[no][0], dk[no][1]);
+                    *reinterpret_cast<__nv_bfloat162*>(dvp + (size_t)k0 * lddqkv + col) = __floats2bfloat162_rn(dv[no][0], dv[no][1]);
+                }
+                if (k1 < L) {
+                    *reinterpret_cast<__nv_bfloat162*>(dkp + (size_t)k1 * lddqkv + col) = __floats2bfloat162_rn(dk[no][2], dk[no][3]);
+                    *reinterpret_cast<__nv_bfloat162*>(dvp + (size_t)k1 * lddqkv + col) = __floats2bfloat162_rn(dv[no][2], dv[no][3]);
+                }
+            }
+        }
+#else
         // K/V rows of this tile are otherwise only read as its own A fragments (held in registers by now) and by pass A
         // of the other warps: wait until every warp has left pass A (split barrier: arrived long ago, rarely blocks)
         if (!passA_done) { am_mbar_wait(abar, 0u); passA_done = true; }
         __syncwarp();
         stage_tile<LDS, NTO>(Ks, kt * 16, dk, 1.f, 1.f, g, t);
         stage_tile<LDS, NTO>(Vs, kt * 16, dv, 1.f, 1.f, g, t);
+#endif
         if (dbias) {
             const bool v0 = kt * 16 + g < L, v1 = kt * 16 + g + 8 < L;
 #pragma unroll
@@ -474,8 +509,10 @@ __global__ void __launch_bounds__(AM_MAX_WARPS * 32, am_bounds_bwd<HDP>::min_cta
         warp_colsum_flush<NTO>(cv, csum + 2 * HDP, g, t);
     }
     __syncthreads();
+#if !AM_DIRECT_STORE
     store_head_tile<HDP, LDS>(Ks, dqkv + row0 * lddqkv + H * HDP + h * HDP, lddqkv, L);
     store_head_tile<HDP, LDS>(Vs, dqkv + row0 * lddqkv + 2 * H * HDP + h * HDP, lddqkv, L);
+#endif
     if (dbias) {                                                   // one atomic per (q|k|v, channel) into the compact bias gradient
         for (int i = threadIdx.x; i < 3 * HDP; i += blockDim.x) {
             const int w = i / HDP, e = i - w * HDP;

@@ -333,7 +333,7 @@ __global__ void __launch_bounds__(N3_THREADS, 1) gemm_tn_tc3_kernel(const __grid
 
 static int g_num_sms_tn3 = 0;
 static int g_tn_dbg = 0;
-static int g_tn_pdl = -1;           // programmatic dependent launch (CSI_PDL=0 disables)
+static int g_tn_pdl = -1;           // programmatic dependent launch: off by default (measured in-step: 4.79 ms with, 4.78 ms without), CSI_PDL=1 enables
 extern "C" int csi_set_gemm_tn_pdl(int on) { g_tn_pdl = on ? 1 : 0; return CSI_OK; }
 extern "C" int csi_set_tn_debug(int v) { g_tn_dbg = v; return CSI_OK; }
 
@@ -456,7 +456,7 @@ extern "C" int csi_gemm_tn_tc3(const void* A, int lda, const void* Bv, int ldb, 
     Tn3Params p;
     p.C = C; p.ldc = ldc; p.cs = c_col_stride; p.M = M; p.Na = Na; p.BN = BN; p.pitch = pitch; p.chunk = chunk; p.qtiles = qtiles;
     p.row_base = -min_shift; p.rows_b = rows_b; p.nbox_b = nbox_b;
-    if (g_tn_pdl < 0) { const char* e = getenv("CSI_PDL"); g_tn_pdl = (e && e[0] == '0') ? 0 : 1; }
+    if (g_tn_pdl < 0) { const char* e = getenv("CSI_PDL"); g_tn_pdl = (e && e[0] == '1') ? 1 : 0; }
     p.ig = ig; p.qg = qg; p.dbg = g_tn_dbg | (g_tn_pdl ? 4 : 0);
     uint32_t cols = 32;
     while ((int)cols < gtaps * pitch) cols <<= 1;
