@@ -74,22 +74,30 @@ __device__ __forceinline__ void cp_async16(void* dst, const void* src) {
 __device__ __forceinline__ void cp_async_wait_all() { asm volatile("cp.async.commit_group;\ncp.async.wait_group 0;" ::: "memory"); }
 template <int HDP, int LDS>
 __device__ __forceinline__ void load_head_tile(const bf16* __restrict__ src, int ld, int L, int LP, bf16* __restrict__ dst) {
+    // a thread keeps one 16-byte chunk column and walks the rows with constant pointer strides: ~6 instructions per chunk
+    // (the index form -- row = i / CPR, column = i % CPR, 64-bit address per chunk -- was 30, 16 % of the forward kernel)
     constexpr int CPR = HDP / 8;                                   // 16-byte chunks per row
-    const int total = LP * CPR;
-    for (int i = threadIdx.x; i < total; i += blockDim.x) {
-        const int l = i / CPR, c = i % CPR;
-        if (l < L) cp_async16(dst + l * LDS + c * 8, src + (size_t)l * ld + c * 8);
-        else *reinterpret_cast<uint4*>(dst + l * LDS + c * 8) = make_uint4(0u, 0u, 0u, 0u);
-    }
+    const int c = threadIdx.x % CPR, r0 = threadIdx.x / CPR, rstep = (int)blockDim.x / CPR;   // blockDim is a multiple of 32
+    const bf16* s = src + (size_t)r0 * ld + c * 8;
+    const size_t sstep = (size_t)rstep * ld;
+    uint32_t d = (uint32_t)__cvta_generic_to_shared(dst + r0 * LDS + c * 8);
+    const uint32_t dstep = (uint32_t)(rstep * LDS * 2);
+    int l = r0;
+    for (; l < L; l += rstep, s += sstep, d += dstep)
+        asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(d), "l"(s) : "memory");
+    for (; l < LP; l += rstep, d += dstep)
+        asm volatile("st.shared.v4.b32 [%0], {%1, %1, %1, %1};" ::"r"(d), "r"(0u) : "memory");
 }
 // smem [L][LDS] -> global head tile (128-bit stores, padding columns included: they hold zeros)
 template <int HDP, int LDS>
 __device__ __forceinline__ void store_head_tile(const bf16* __restrict__ src, bf16* __restrict__ dst, int ld, int L) {
     constexpr int CPR = HDP / 8;
-    for (int i = threadIdx.x; i < L * CPR; i += blockDim.x) {
-        const int l = i / CPR, c = i % CPR;
-        *reinterpret_cast<uint4*>(dst + (size_t)l * ld + c * 8) = *reinterpret_cast<const uint4*>(src + l * LDS + c * 8);
-    }
+    const int c = threadIdx.x % CPR, r0 = threadIdx.x / CPR, rstep = (int)blockDim.x / CPR;
+    const bf16* s = src + r0 * LDS + c * 8;
+    bf16* d = dst + (size_t)r0 * ld + c * 8;
+    const size_t dstep = (size_t)rstep * ld;
+    const int sstep = rstep * LDS;
+    for (int l = r0; l < L; l += rstep, s += sstep, d += dstep) *reinterpret_cast<uint4*>(d) = *reinterpret_cast<const uint4*>(s);
 }
 // accumulator tile (16 rows x NTO*8 cols, mma C layout) -> bf16 smem rows [row0, row0+16)
 template <int LDS, int NTO>
