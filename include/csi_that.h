@@ -44,6 +44,9 @@ typedef enum {
  * are contracted with B columns [b_col_off, b_col_off+klen).  klen must be a multiple of 16. */
 typedef struct { int a_row_shift, a_col_off, b_col_off, klen; } csi_seg;
 
+/* Output-column band of one segment of csi_gemm_nt_banded: the segment contributes to columns [n_lo, n_hi) only. */
+typedef struct { int n_lo, n_hi; } csi_band;
+
 /* One output segment of the weight-gradient GEMM (see csi_gemm_tn). */
 typedef struct { int b_row_shift, b_col_off, c_off, nlen; } csi_seg_tn;
 
@@ -117,6 +120,17 @@ int csi_layernorm_bwd(const void* dy, int lddy, int dy_dtype, const float* x, in
 int csi_gemm_nt(const void* A, int lda, const void* Bw, int ldb, int ab_dtype, void* C, int ldc, int c_dtype,
                 int M, int N, const csi_seg* segs, int nseg, const float* bias, const float* residual,
                 int ldr, float drop_p, unsigned drop_site, const unsigned long long* rng, void* stream);
+
+/* The same contraction where segment s contributes to the output columns [bands[s].n_lo, bands[s].n_hi) only, i.e. the caller
+ * guarantees Bw[n, b_col_off_s ...] == 0 for n outside the band.  This is how the three parallel Conv1d branches of an encoder
+ * (kernel sizes 1/3/5 or 1/2/3 over the SAME input, that.py:122-135,158-162) run as ONE GEMM with N = 3*Dp: the weights of the
+ * branches are stacked along N with their taps aligned on the largest kernel, the taps a branch does not have are zero blocks,
+ * and the tcgen05 kernel skips them per column tile (column tiles are cut at the band boundaries).  bands == NULL is csi_gemm_nt.
+ * The FFMA kernel ignores the bands (the zero blocks make the result identical). */
+int csi_gemm_nt_banded(const void* A, int lda, const void* Bw, int ldb, int ab_dtype, void* C, int ldc, int c_dtype,
+                       int M, int N, const csi_seg* segs, const csi_band* bands, int nseg, const float* bias,
+                       const float* residual, int ldr, float drop_p, unsigned drop_site, const unsigned long long* rng,
+                       void* stream);
 
 /* ---- weight gradients (autograd of the same calls):
  * C[i*ldc + c_off_s + q*c_col_stride] += sum_{m<M} A[m*lda + i] * Bv[(m + b_row_shift_s)*ldb + b_col_off_s + q]

@@ -17,6 +17,8 @@ extern "C" int csi_attn_bwd_simt(const void*, int, const void*, int, const void*
                                  int, int, int, int, int, void*);
 extern "C" int csi_gemm_nt_tc3(const void*, int, const void*, int, void*, int, int, int, int, const csi_seg*, int,
                                const float*, const float*, int, float, unsigned, const unsigned long long*, void*);
+extern "C" int csi_gemm_nt_tc3_banded(const void*, int, const void*, int, void*, int, int, int, int, const csi_seg*, const csi_band*, int,
+                                      const float*, const float*, int, float, unsigned, const unsigned long long*, void*);
 extern "C" int csi_gemm_tn_tc3(const void*, int, const void*, int, float*, int, int, int, int, const csi_seg_tn*, int, csi_grp,
                                csi_grp, void*);
 extern "C" int csi_attn_mma_ok(int L, int d, int H, int hp);
@@ -76,14 +78,22 @@ extern "C" int csi_gemm_tn_tc_ok(int lda, int ldb, int M, int Na, const csi_seg_
 extern "C" int csi_gemm_nt(const void* A, int lda, const void* Bw, int ldb, int ab_dtype, void* C, int ldc, int c_dtype,
                            int M, int N, const csi_seg* segs, int nseg, const float* bias, const float* residual,
                            int ldr, float drop_p, unsigned drop_site, const unsigned long long* rng, void* stream) {
+    return csi_gemm_nt_banded(A, lda, Bw, ldb, ab_dtype, C, ldc, c_dtype, M, N, segs, nullptr, nseg, bias, residual, ldr, drop_p,
+                              drop_site, rng, stream);
+}
+
+extern "C" int csi_gemm_nt_banded(const void* A, int lda, const void* Bw, int ldb, int ab_dtype, void* C, int ldc, int c_dtype,
+                                  int M, int N, const csi_seg* segs, const csi_band* bands, int nseg, const float* bias,
+                                  const float* residual, int ldr, float drop_p, unsigned drop_site,
+                                  const unsigned long long* rng, void* stream) {
     if (ab_dtype == CSI_BF16) {
         const int es = c_dtype == CSI_BF16 ? 2 : 4;
         const bool aligned = ((long long)ldc * es) % 16 == 0 && (reinterpret_cast<uintptr_t>(C) & 15) == 0 &&
                              (!residual || (c_dtype != CSI_BF16 && ldr % 4 == 0 && (reinterpret_cast<uintptr_t>(residual) & 15) == 0));
         if (!force_simt() && aligned && csi_gemm_nt_tc_ok(lda, ldb, ldc, M, N, segs, nseg)) {
             ++g_counts[0];
-            return csi_gemm_nt_tc3(A, lda, Bw, ldb, C, ldc, c_dtype, M, N, segs, nseg, bias, residual, ldr, drop_p, drop_site,
-                                   rng, stream);
+            return csi_gemm_nt_tc3_banded(A, lda, Bw, ldb, C, ldc, c_dtype, M, N, segs, bands, nseg, bias, residual, ldr, drop_p,
+                                          drop_site, rng, stream);
         }
         CSI_FALLBACK("csi_gemm_nt");
     }

@@ -20,6 +20,7 @@
 #define T3_THREADS 320
 #define T3_EPI_THREADS 256
 #define T3_MAX_STAGES 16
+#define T3_MAX_NTAB 12
 
 __device__ __forceinline__ uint32_t pack2_bf16(float lo, float hi) {
     __nv_bfloat162 v = __floats2bfloat162_rn(lo, hi);
@@ -101,7 +102,7 @@ __device__ __forceinline__ void tmem_dealloc_pair(uint32_t taddr, uint32_t ncols
     asm volatile("tcgen05.dealloc.cta_group::2.sync.aligned.b32 %0, %1;" ::"r"(taddr), "r"(ncols) : "memory");
 }
 
-struct T3Tap { short a_row_off; short pad; int b_col_off; };
+struct T3Tap { short a_row_off; short pad; int b_col_off; int n_lo, n_hi; };       // [n_lo, n_hi): output columns the tap contributes to
 struct T3Group { int a_col_off, klen, min_shift, tap0, ntaps; };
 struct T3Plan {
     T3Group g[CSI_MAX_SEGS];
@@ -125,6 +126,10 @@ struct Nt3Params {
     // K = 272 call re-fetches 130 KB of weights per 70 KB of activations and is bound by the SM's share of L2 bandwidth.
     int resident, mtiles;
     long long* dbg;                   // optional phase clocks of one mid-grid CTA (scripts/gemm_phases.py), NULL in production
+    // banded calls (csi_gemm_nt_banded: the three Conv1d branches of an encoder as ONE GEMM): column tiles follow the band
+    // boundaries, so their widths differ (272 = 144 + 128); ntab > 0 replaces the uniform (tile % ntn) * BN rule
+    int ntab;
+    short tab_n0[T3_MAX_NTAB], tab_bn[T3_MAX_NTAB];
 };
 // The probes sit in the single-threaded issue loops, whose latency is the kernel's critical path: they are compiled in only
 // with -DCSI_T3_DEBUG (make EXTRA=-DCSI_T3_DEBUG).
@@ -139,7 +144,11 @@ struct Nt3Params {
 struct T3Tile { int mt, n0, bn; };
 __device__ __forceinline__ T3Tile t3_decode(const Nt3Params& p, int tile, int n_res) {
     T3Tile t;
-    if (p.resident) {
+    if (p.ntab) {
+        t.mt = tile / p.ntab;
+        const int nt = tile - t.mt * p.ntab;
+        t.n0 = p.tab_n0[nt]; t.bn = p.tab_bn[nt];
+    } else if (p.resident) {
         t.mt = tile; t.n0 = n_res * p.BN; t.bn = p.BN;
     } else if (tile < p.nfull) {
         t.mt = tile / p.ntn;
@@ -271,6 +280,7 @@ __global__ void __launch_bounds__(T3_THREADS, 1) gemm_nt_tc3_kernel(const __grid
                     }
                     if (++sa == NSA) { sa = 0; pa ^= 1u; }
                     for (int t = 0; t < ntaps; ++t) {
+                        if (tt.n0 >= plan.t[tap0 + t].n_hi || tt.n0 + tt.bn <= plan.t[tap0 + t].n_lo) continue;   // band: tap absent from these columns
                         if (resident) {                          // weights are loaded with the first tile only
                             if (tile != tile_first) continue;
                         } else mbar_wait_u(empty_b_u + 8u * sb, pb);
@@ -310,7 +320,8 @@ __global__ void __launch_bounds__(T3_THREADS, 1) gemm_nt_tc3_kernel(const __grid
         const bool leader = elect_one();
         const uint32_t dmode = (uint32_t)p.desc_mode;
         for (int tile = tile_first; tile < tile_end; tile += tile_step) {
-            const uint32_t idesc = make_idesc(TILE_M, t3_decode(p, tile, n_res).bn);
+            const T3Tile tt = t3_decode(p, tile, n_res);
+            const uint32_t idesc = make_idesc(TILE_M, tt.bn);
             T3_CLK(8 * dti);
             mbar_wait_u(tempty_u + 8u * acc, pacc);              // epilogue has drained this accumulator
             tc_fence_after();
@@ -333,6 +344,7 @@ __global__ void __launch_bounds__(T3_THREADS, 1) gemm_nt_tc3_kernel(const __grid
                     const bool last_full = rem_last >= TC_BK;
                     const int last_steps = last_full ? 4 : (rem_last >> 4);
                     for (int t = 0; t < ntaps; ++t) {
+                        if (tt.n0 >= plan.t[tap0 + t].n_hi || tt.n0 + tt.bn <= plan.t[tap0 + t].n_lo) continue;   // (same rule as the producer)
                         if (!resident || tile == tile_first) mbar_wait_u(full_b_u + 8u * sb, pb);
                         tc_fence_after();
                         if (leader) {
@@ -582,9 +594,22 @@ extern "C" int csi_set_gemm_pdl(int on) { g_pdl3 = on ? 1 : 0; return CSI_OK; }
 extern "C" int csi_set_gemm_desc_mode(int mode) { g_desc_mode = mode ? 1 : 0; return CSI_OK; }
 extern "C" int csi_set_gemm_tap_share(int on) { g_tap_share = on ? 1 : 0; return CSI_OK; }
 
+extern "C" int csi_gemm_nt_tc3_banded(const void* A, int lda, const void* Bw, int ldb, void* C, int ldc, int c_dtype, int M, int N,
+                               const csi_seg* segs, const csi_band* bands, int nseg, const float* bias, const float* residual, int ldr,
+                               float drop_p, unsigned drop_site, const unsigned long long* rng, void* stream);
+
 // row-box map for A: box = box_rows x 64 columns (box_rows <= 256)
 extern "C" int csi_gemm_nt_tc3(const void* A, int lda, const void* Bw, int ldb, void* C, int ldc, int c_dtype, int M, int N,
                                const csi_seg* segs, int nseg, const float* bias, const float* residual, int ldr,
+                               float drop_p, unsigned drop_site, const unsigned long long* rng, void* stream) {
+    return csi_gemm_nt_tc3_banded(A, lda, Bw, ldb, C, ldc, c_dtype, M, N, segs, nullptr, nseg, bias, residual, ldr, drop_p, drop_site,
+                                  rng, stream);
+}
+
+// bands[s] = {n_lo, n_hi}: segment s contributes to output columns [n_lo, n_hi) only (its weights are zero elsewhere).
+// NULL = every segment contributes everywhere.
+extern "C" int csi_gemm_nt_tc3_banded(const void* A, int lda, const void* Bw, int ldb, void* C, int ldc, int c_dtype, int M, int N,
+                               const csi_seg* segs, const csi_band* bands, int nseg, const float* bias, const float* residual, int ldr,
                                float drop_p, unsigned drop_site, const unsigned long long* rng, void* stream) {
     CSI_CHECK_ARG(A && Bw && C && segs, "null pointer");
     CSI_CHECK_ARG(!(drop_p > 0.f) || rng, "dropout needs rng");
@@ -620,6 +645,8 @@ extern "C" int csi_gemm_nt_tc3(const void* A, int lda, const void* Bw, int ldb, 
                     plan.t[g.tap0 + g.ntaps].a_row_off = (short)(s.a_row_shift - nlo);
                     plan.t[g.tap0 + g.ntaps].pad = 0;
                     plan.t[g.tap0 + g.ntaps].b_col_off = s.b_col_off;
+                    plan.t[g.tap0 + g.ntaps].n_lo = bands ? bands[i].n_lo : 0;
+                    plan.t[g.tap0 + g.ntaps].n_hi = bands ? bands[i].n_hi : 0x7fffffff;
                     ++g.ntaps;
                     if (nhi - nlo > span) span = nhi - nlo;
                     joined = true;
@@ -630,6 +657,8 @@ extern "C" int csi_gemm_nt_tc3(const void* A, int lda, const void* Bw, int ldb, 
             T3Group& g = plan.g[plan.ng];
             g.a_col_off = s.a_col_off; g.klen = s.klen; g.min_shift = s.a_row_shift; g.tap0 = i; g.ntaps = 1;
             plan.t[i].a_row_off = 0; plan.t[i].pad = 0; plan.t[i].b_col_off = s.b_col_off;
+            plan.t[i].n_lo = bands ? bands[i].n_lo : 0;
+            plan.t[i].n_hi = bands ? bands[i].n_hi : 0x7fffffff;
             ++plan.ng;
         }
     }
@@ -646,7 +675,46 @@ extern "C" int csi_gemm_nt_tc3(const void* A, int lda, const void* Bw, int ldb, 
     int ksum = 0;
     for (int i = 0; i < nseg; ++i) ksum += segs[i].klen;
     bool pair = g_num_sms3 >= 2 && (g_pair == 2 || (g_pair == 1 && ksum >= 512));
-    const int BN = pick_bn3(N, (M + TC_BM - 1) / TC_BM, g_num_sms3);
+    // ---- banded call: column tiles follow the band boundaries (each column group between two boundaries is cut like a GEMM
+    //      of its own), so that no tile mixes columns with different tap sets
+    int ntab = 0, tab_n0[T3_MAX_NTAB], tab_bn[T3_MAX_NTAB], bn_max = 0, tab_tail = 0;
+    if (bands) {
+        int cuts[2 * CSI_MAX_SEGS + 2], nc = 0;
+        cuts[nc++] = 0; cuts[nc++] = N;
+        bool ok = true;
+        for (int i = 0; i < nseg; ++i) {
+            CSI_CHECK_ARG(bands[i].n_lo >= 0 && bands[i].n_lo < bands[i].n_hi, "empty band");
+            const int lo = bands[i].n_lo, hi = bands[i].n_hi < N ? bands[i].n_hi : N;
+            if (lo % 16 || (hi % 16 && hi != N)) ok = false;
+            cuts[nc++] = lo; cuts[nc++] = hi;
+        }
+        for (int i = 1; i < nc; ++i)                          // insertion sort + unique
+            for (int j = i; j > 0 && cuts[j] < cuts[j - 1]; --j) { const int tmp = cuts[j]; cuts[j] = cuts[j - 1]; cuts[j - 1] = tmp; }
+        int nu = 1;
+        for (int i = 1; i < nc; ++i) if (cuts[i] != cuts[nu - 1]) cuts[nu++] = cuts[i];
+        for (int gI = 0; ok && gI + 1 < nu; ++gI) {
+            const int w = cuts[gI + 1] - cuts[gI], nt = (w + 255) / 256, bn = bn_for(w, nt);
+            for (int t = 0, n0 = cuts[gI]; t < nt; ++t, n0 += bn) {
+                if (ntab == T3_MAX_NTAB) { ok = false; break; }
+                int wt = cuts[gI + 1] - n0;
+                if (wt > bn) wt = bn;
+                tab_n0[ntab] = n0; tab_bn[ntab] = (wt + 15) & ~15;
+                if (tab_bn[ntab] > bn_max) bn_max = tab_bn[ntab];
+                ++ntab;
+            }
+        }
+        // the narrower last store panel of a tile goes through ONE extra tensor map: all tiles must agree on its width
+        const int pw = 128 / (c_dtype == CSI_BF16 ? 2 : 4);
+        int tailw = 0;
+        for (int i = 0; ok && i < ntab; ++i) {
+            const int tw = tab_bn[i] % pw;
+            if (tw && tailw && tw != tailw) ok = false;
+            if (tw) tailw = tw;
+        }
+        if (!ok) ntab = 0;                                     // boundaries off the 16-column grid: uniform tiles, taps still skipped per tile
+        else tab_tail = tailw;
+    }
+    const int BN = ntab ? bn_max : pick_bn3(N, (M + TC_BM - 1) / TC_BM, g_num_sms3);
     const int a_rows = TC_BM + ((span + 7) & ~7);
     static int ksub_env = -1;                            // CSI_GEMM_KSUB=1 forces one 64-channel block per stage (A/B runs)
     if (ksub_env < 0) { const char* e = getenv("CSI_GEMM_KSUB"); ksub_env = (e && e[0] == '1') ? 1 : 2; }
@@ -659,7 +727,7 @@ extern "C" int csi_gemm_nt_tc3(const void* A, int lda, const void* Bw, int ldb, 
     //      memory when they leave room for at least four A stages
     if (g_resident < 0) { const char* e = getenv("CSI_GEMM_RESIDENT"); g_resident = (e && e[0] == '0') ? 0 : 1; }
     int resident = 0, res_ksub = 1, res_nst = 0, res_nsa = 0;
-    if (g_resident && g_pair != 0 && g_num_sms3 >= 2) {
+    if (g_resident && g_pair != 0 && g_num_sms3 >= 2 && !bands) {
         res_ksub = (ksub_env == 2 && BN <= 160) ? 2 : 1;
         for (int gi = 0; gi < plan.ng; ++gi)
             res_nst += ((plan.g[gi].klen + res_ksub * TC_BK - 1) / (res_ksub * TC_BK)) * plan.g[gi].ntaps;
@@ -680,7 +748,7 @@ extern "C" int csi_gemm_nt_tc3(const void* A, int lda, const void* Bw, int ldb, 
     if (rc) return rc;
     rc = make_map_ex(&tmC, C, M, N, ldc, 32, 128 / es, es);
     if (rc) return rc;
-    const int tail = BN % (128 / es);                  // last panel of a tile when BN is not a whole number of panels
+    const int tail = ntab ? tab_tail : BN % (128 / es);   // last panel of a tile when its width is not a whole number of panels
     CUtensorMap tmCt = tmC;
     if (tail) {
         rc = make_map_ex(&tmCt, C, M, N, ldc, 32, tail, es, false);
@@ -698,7 +766,9 @@ extern "C" int csi_gemm_nt_tc3(const void* A, int lda, const void* Bw, int ldb, 
     }
     Nt3Params p;
     p.M = M; p.N = N; p.BN = BN; p.C = C; p.ldc = ldc; p.a_rows = a_rows;
-    p.ntn = (N + BN - 1) / BN;
+    p.ntn = ntab ? ntab : (N + BN - 1) / BN;
+    p.ntab = ntab;
+    for (int i = 0; i < ntab; ++i) { p.tab_n0[i] = (short)tab_n0[i]; p.tab_bn[i] = (short)tab_bn[i]; }
     const int mtiles = (M + tile_m - 1) / tile_m;
     p.ntiles = p.ntn * mtiles;
     // tail-wave split (see Nt3Params): 308 row tiles on 148 SMs are 2 full waves + 12 tiles; as 12 x 5 pieces of 64 columns
@@ -708,7 +778,7 @@ extern "C" int csi_gemm_nt_tc3(const void* A, int lda, const void* Bw, int ldb, 
     p.nfull = p.ntiles; p.npiece = 1; p.BN2 = BN; p.mt_tail = mtiles;
     CUtensorMap tmB2 = tmB;
     p.resident = resident; p.mtiles = mtiles; p.dbg = g_t3_dbg;
-    if (tail_split && !resident && p.ntn == 1 && mtiles > units && BN > 64) {
+    if (tail_split && !resident && !ntab && p.ntn == 1 && mtiles > units && BN > 64) {
         const int leftover = mtiles % units, npiece = (BN + 63) / 64;
         if (leftover > 0 && leftover * npiece <= units) {
             rc = make_map(&tmB2, Bw, N, b_cols, ldb, pair ? 32 : 64);

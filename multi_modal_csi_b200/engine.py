@@ -105,7 +105,9 @@ class THATEngine(StepCounters):
             from .ops import NativeOps    # raises if libcsi_that.so is missing or the device is not CUDA
             ops = NativeOps(self.dev)
         self.ops = ops
-        self.pack = LY.build_pack_plan(geom, arena)
+        # the three conv branches of an encoder as one banded GEMM (CSI_NO_FUSED_CONV=1: three launches, A/B runs)
+        self.fused_conv = os.environ.get("CSI_NO_FUSED_CONV", "0") != "1"
+        self.pack = LY.build_pack_plan(geom, arena, self.fused_conv)
         self.packed = torch.zeros(self.pack.size, dtype=act_dtype, device=self.dev)
         self.pack_table = ops.make_pack_table(self.pack.entries, self.dev)
         self.packed_bias = torch.zeros(max(self.pack.bias_size, 1), dtype=torch.float32, device=self.dev)
@@ -420,12 +422,20 @@ class THATEngine(StepCounters):
                         site(si, e, LY.SITE_ATTN), self.rng)
             ops.layernorm_fwd(a["t"].t, self.P(p + "layer_norm_1.weight"), self.P(p + "layer_norm_1.bias"),
                               a["s"].t, a["mean1"], a["rstd1"], B, L, d, HALO, LN_EPS)
-            for j, k in enumerate(sg.kernels):
-                pl = (k - 1) // 2
-                segs = [(t - pl, 0, t * Dp, Dp) for t in range(k)]
-                self._alg(2 * B * L * d * d * k)
-                ops.gemm_nt(a["s"].t, self.W(f"f:{p}layer_cnn.{j}.0.weight"), a["z"].t[:, j * Dp:], rows, d,
-                            segs, None, None, 0.0, 0, self.rng)
+            if self.fused_conv:
+                # the three Conv1d branches as ONE GEMM with N = 3*Dp over the shared input tile (taps a branch does not
+                # have are zero blocks of the fused operand, skipped per column tile)
+                segs, bands = sg.conv_bands()
+                self._alg(2 * B * L * d * d * sum(sg.kernels))
+                ops.gemm_nt_banded(a["s"].t, self.W("f:" + p + "layer_cnn"), a["z"].t, rows, len(sg.kernels) * Dp, segs, bands,
+                                   None, None, 0.0, 0, self.rng)
+            else:
+                for j, k in enumerate(sg.kernels):
+                    pl = (k - 1) // 2
+                    segs = [(t - pl, 0, t * Dp, Dp) for t in range(k)]
+                    self._alg(2 * B * L * d * d * k)
+                    ops.gemm_nt(a["s"].t, self.W(f"f:{p}layer_cnn.{j}.0.weight"), a["z"].t[:, j * Dp:], rows, d,
+                                segs, None, None, 0.0, 0, self.rng)
             cb = self._bn3(sg, e, "0.bias")
             rm = self._bn3(sg, e, "1.running_mean", buf=True)
             rv = self._bn3(sg, e, "1.running_var", buf=True)

@@ -81,6 +81,23 @@ class StreamGeom:
     def nseg_conv(self) -> int:
         return sum(self.kernels)
 
+    @property
+    def conv_shifts(self):
+        """Row shifts of the fused three-branch forward conv, ascending: the union of the branches' taps (tap t of a size-k
+        kernel reads row m + t - (k-1)//2, PyTorch's padding="same")."""
+        return sorted({t - (k - 1) // 2 for k in self.kernels for t in range(k)})
+
+    def conv_bands(self):
+        """(segments, bands) of csi_gemm_nt_banded for the fused forward conv: segment t = shift conv_shifts[t], contributing to
+        the columns of the branches that have that tap."""
+        Dp, segs, bands = self.Dp, [], []
+        for t, sh in enumerate(self.conv_shifts):
+            has = [j for j, k in enumerate(self.kernels) if -((k - 1) // 2) <= sh <= k - 1 - (k - 1) // 2]
+            assert has == list(range(has[0], has[-1] + 1)), "branches with a common tap must be adjacent"
+            segs.append((sh, 0, t * Dp, Dp))
+            bands.append((has[0] * Dp, (has[-1] + 1) * Dp))
+        return segs, bands
+
     def rows(self, B: int) -> int:
         return B * self.Lp
 
@@ -237,7 +254,7 @@ class PackPlan:
     max_elems: int
 
 
-def build_pack_plan(g: ModelGeom, arena: Arena) -> PackPlan:
+def build_pack_plan(g: ModelGeom, arena: Arena, fused_conv: bool = True) -> PackPlan:
     """Forward ("f:") and data-gradient ("b:") operand copies of every contraction weight.
 
     f:<w>   [N, k*Cp]        dst[n, j*Cp + c]              = W[n, c, j]
@@ -279,10 +296,17 @@ def build_pack_plan(g: ModelGeom, arena: Arena) -> PackPlan:
             add(w, d, d, 1, alloc("f:" + w, d, s.dh), 0, s.dh, 0, gc=s.grp)
             add(w, d, d, 1, alloc("b:" + w, s.dh, Dp), 1, Dp, 0, gc=s.grp)
             bmat = alloc("b:" + p + "layer_cnn", d, s.nseg_conv * Dp)
+            # fused forward operand of the three branches (csi_gemm_nt_banded): rows j*Dp.. = branch j, column block t =
+            # row shift conv_shifts[t]; the taps a branch does not have stay zero (the buffer is zero-initialised)
+            shifts = s.conv_shifts
+            fused = alloc("f:" + p + "layer_cnn", len(s.kernels) * Dp, len(shifts) * Dp)
             seg = 0
             for j, k in enumerate(s.kernels):
                 w = f"{p}layer_cnn.{j}.0.weight"
-                add(w, d, d, k, alloc("f:" + w, d, k * Dp), 0, Dp, 0)
+                if not fused_conv:                                         # per-branch operands: only the three-launch path reads them
+                    add(w, d, d, k, alloc("f:" + w, d, k * Dp), 0, Dp, 0)
+                first = shifts.index(-((k - 1) // 2))                      # column block of the branch's first tap
+                add(w, d, d, k, PackedMat(fused.off + j * Dp * fused.ld + first * Dp, d, fused.ld), 0, Dp, 0)
                 add(w, d, d, k, bmat, 1, Dp, seg)
                 seg += k
         Np = s.head_np

@@ -20,6 +20,11 @@ class Seg(C.Structure):
     _fields_ = [("a_row_shift", C.c_int), ("a_col_off", C.c_int), ("b_col_off", C.c_int), ("klen", C.c_int)]
 
 
+class Band(C.Structure):
+    """csi_band: output columns [n_lo, n_hi) a segment of csi_gemm_nt_banded contributes to."""
+    _fields_ = [("n_lo", C.c_int), ("n_hi", C.c_int)]
+
+
 class SegTN(C.Structure):
     _fields_ = [("b_row_shift", C.c_int), ("b_col_off", C.c_int), ("c_off", C.c_int), ("nlen", C.c_int)]
 
@@ -70,7 +75,7 @@ EXPORTS = [
     "csi_set_force_simt", "csi_set_strict_tc", "csi_dispatch_counts", "csi_set_attn_impl",
     "csi_fill_f64", "csi_copy_f32", "csi_nhwc_stats", "csi_bn2d_finalize", "csi_im2col_bn", "csi_col2im", "csi_act_drop_fwd",
     "csi_bn2d_bwd_reduce", "csi_bn2d_bwd_apply", "csi_pool_bn_fwd", "csi_conv2d_pack", "csi_conv2d_unpack_grad", "csi_bn0_grads",
-    "csi_gather_aug", "csi_gemm_tn_workspace",
+    "csi_gather_aug", "csi_gemm_tn_workspace", "csi_gemm_nt_banded",
 ]
 
 # Workspaces of the two-stage weight-gradient reduction (csi_gemm_tn_workspace), one per (device, stream) that ever issued a
@@ -135,6 +140,8 @@ class NativeOps:
     # -------------------------------------------------------------- launch + optional per-op device timing
     def _call(self, name, *args, flops=0, nbytes=0, launches=1):
         short = name[4:]
+        if short == "gemm_nt_banded":
+            short = "gemm_nt"                         # one op family in the profile tables
         prof = self._prof is not None and (self._only is None or short in self._only)
         if prof:
             e0 = torch.cuda.Event(enable_timing=True)
@@ -280,6 +287,16 @@ class NativeOps:
                                       len(segs), _p(bias), _p(residual), _ld(residual), C.c_float(drop_p),
                                       C.c_uint(drop_site), _p(rng), **wk)
 
+    def gemm_nt_banded(self, A, Bw, Cm, M, N, segs, bands, bias, residual, drop_p, drop_site, rng):
+        """csi_gemm_nt with per-segment output-column bands (the three Conv1d branches of an encoder as one GEMM)."""
+        wk = self._work("gemm_nt", locals())
+        if self._prof is not None:
+            self._tag = f"M={M} N={N} K={sum(s[3] for s in segs)} nseg={len(segs)} banded out={Cm.dtype}"
+        arr = (Seg * len(segs))(*[Seg(*s) for s in segs])
+        barr = (Band * len(bands))(*[Band(*b) for b in bands])
+        self._call("csi_gemm_nt_banded", _p(A), _ld(A), _p(Bw), _ld(Bw), _dt(A), _p(Cm), _ld(Cm), _dt(Cm), M, N, arr, barr,
+                   len(segs), _p(bias), _p(residual), _ld(residual), C.c_float(drop_p), C.c_uint(drop_site), _p(rng), **wk)
+
     def tn_workspace(self):
         """Registers (once per device and stream) the workspace that makes csi_gemm_tn on the current stream reduce its token
         chunks in two stages (partial sums + one fixed-order reduce) instead of with fp32 atomics: faster and bit-reproducible."""
@@ -303,8 +320,10 @@ class NativeOps:
         if self._prof is not None:
             self._tag = f"M={M} Na={Na} nlen={sum(s[3] for s in segs)} nseg={len(segs)} cs={c_col_stride}"
         arr = (SegTN * len(segs))(*[SegTN(*s) for s in segs])
+        # the tcgen05 path with a registered workspace is two kernels (partial sums + reduce): count both
+        two = A.dtype == torch.bfloat16 and TN_TWO_STAGE and M >= 64
         self._call("csi_gemm_tn", _p(A), _ld(A), _p(Bv), _ld(Bv), _dt(A), _p(Cm), ldc, c_col_stride, M, Na, arr,
-                   len(segs), Grp(*i_grp), Grp(*q_grp), **wk)
+                   len(segs), Grp(*i_grp), Grp(*q_grp), launches=2 if two else 1, **wk)
 
     def colsum_tokens(self, A, B, L, halo, ncols, out, grp=NO_GRP):
         wk = self._work("colsum_tokens", locals())

@@ -126,6 +126,13 @@ class MirrorOps:
         dbeta.add_(torch.where(v, dyv, torch.zeros_like(dyv)).sum(0))
 
     # ------------------------------------------------------------------ GEMMs
+    def gemm_nt_banded(self, A, Bw, C, M, N, segs, bands, bias, residual, drop_p, drop_site, rng):
+        # the weights are zero outside a segment's band, so the plain contraction is the banded one
+        for (shift, aoff, boff, klen), (lo, hi) in zip(segs, bands):
+            w = Bw[:N, boff:boff + klen].float()
+            assert float(w[:lo].abs().sum()) == 0.0 and float(w[hi:].abs().sum()) == 0.0
+        self.gemm_nt(A, Bw, C, M, N, segs, bias, residual, drop_p, drop_site, rng)
+
     def gemm_nt(self, A, Bw, C, M, N, segs, bias, residual, drop_p, drop_site, rng):
         assert drop_p == 0.0
         acc = torch.zeros(M, N, dtype=torch.float32, device=A.device)

@@ -536,12 +536,13 @@ def test_bce_and_dropout_and_adam(ops, mir):
     assert relerr(p, pt.detach()) < 1e-6
 
 
+@pytest.mark.parametrize("fused", [True, False])
 @pytest.mark.parametrize("dt", DT)
-def test_pack_weights(ops, mir, dt):
+def test_pack_weights(ops, mir, dt, fused):
     from multi_modal_csi_b200 import layout as LY
     g = LY.ModelGeom(400, 30, 12)
     arena = LY.build_arena(LY.parameter_specs(g))
-    plan = LY.build_pack_plan(g, arena)
+    plan = LY.build_pack_plan(g, arena, fused)
     params = torch.randn(arena.size, device="cuda", generator=gen(14))
     outs = []
     for o in (ops, mir):

@@ -369,3 +369,48 @@ def test_wgrad_two_stage_reduction_is_reproducible(M, Na, Dp, nlen, k):
         ops.lib.csi_gemm_tn_workspace(C.c_void_p(st), C.c_void_p(saved.data_ptr()), C.c_longlong(saved.numel()))
         OPS._TN_WS[(0, st)] = saved
     assert nrel(c, ref) < 1e-5 and nrel(a, c) < 1e-5
+
+
+# ------------------------------------------------------------------------------------------- fused three-branch conv
+@pytest.mark.parametrize("M,d,kernels", [(39424, 270, (1, 3, 5)), (70144, 150, (1, 2, 3)), (1200, 540, (1, 3, 5)), (300, 30, (1, 3, 5))])
+def test_banded_gemm_is_three_convs(M, d, kernels):
+    """csi_gemm_nt_banded on the stacked, tap-aligned weights of three Conv1d branches == three csi_gemm_nt calls (bit for bit:
+    the same taps in the same K order per output column) == conv1d of torch on the bf16 operands."""
+    from multi_modal_csi_b200.ops import NativeOps
+    ops = NativeOps(torch.device("cuda", 0))
+    GUARD, Dp = 16, (d + 15) // 16 * 16
+    g = torch.Generator(device="cuda").manual_seed(3)
+    full = torch.zeros(M + 2 * GUARD, Dp, dtype=torch.bfloat16, device="cuda")
+    full[GUARD:GUARD + M, :d] = torch.randn(M, d, device="cuda", generator=g).to(torch.bfloat16)
+    A = full[GUARD:GUARD + M]
+    shifts = sorted({t - (k - 1) // 2 for k in kernels for t in range(k)})
+    W = [(torch.randn(d, d, k, device="cuda", generator=g) / (d * k) ** 0.5).to(torch.bfloat16) for k in kernels]
+    fused = torch.zeros(3 * Dp, len(shifts) * Dp, dtype=torch.bfloat16, device="cuda")
+    sep = []
+    for j, (k, w) in enumerate(zip(kernels, W)):
+        pl = (k - 1) // 2
+        s = torch.zeros(d, k * Dp, dtype=torch.bfloat16, device="cuda")
+        for t in range(k):
+            s[:, t * Dp:t * Dp + d] = w[:, :, t]
+            c = shifts.index(t - pl)
+            fused[j * Dp:j * Dp + d, c * Dp:c * Dp + d] = w[:, :, t]
+        sep.append(s)
+    segs = [(sh, 0, t * Dp, Dp) for t, sh in enumerate(shifts)]
+    bands = []
+    for sh in shifts:
+        has = [j for j, k in enumerate(kernels) if -((k - 1) // 2) <= sh <= k - 1 - (k - 1) // 2]
+        bands.append((has[0] * Dp, (has[-1] + 1) * Dp))
+    z1 = torch.full((M, 3 * Dp), 7.0, dtype=torch.bfloat16, device="cuda")
+    ops.gemm_nt_banded(A, fused, z1, M, 3 * Dp, segs, bands, None, None, 0.0, 0, None)
+    z3 = torch.zeros(M, 3 * Dp, dtype=torch.bfloat16, device="cuda")
+    for j, k in enumerate(kernels):
+        pl = (k - 1) // 2
+        ops.gemm_nt(A, sep[j], z3[:, j * Dp:], M, d, [(t - pl, 0, t * Dp, Dp) for t in range(k)], None, None, 0.0, 0, None)
+    torch.cuda.synchronize()
+    assert torch.equal(z1, z3)
+    for j, (k, w) in enumerate(zip(kernels, W)):
+        pl = (k - 1) // 2
+        ref = torch.zeros(M, d, device="cuda")
+        for t in range(k):
+            ref += full[GUARD + t - pl:GUARD + t - pl + M, :d].float() @ w[:, :, t].float().t()
+        assert nrel(z1[:, j * Dp:j * Dp + d].float(), ref) < 4e-3, j
