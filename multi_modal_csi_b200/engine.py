@@ -354,6 +354,13 @@ class THATEngine(StepCounters):
         if ws not in self._wgrad_pending:
             self._wgrad_pending.append(ws)
 
+    def _busy_streams(self):
+        """Side streams that may still hold work feeding the gradient arena: the right-stream fork and the weight-gradient streams."""
+        out = list(self._wgrad_pending)
+        if self._side is not None and self.concurrent:
+            out.append(self._side)
+        return out
+
     def _wgrad_join(self):
         """The current stream waits for every weight gradient issued so far (end of a backward part)."""
         if not self._wgrad_pending:
@@ -466,7 +473,7 @@ class THATEngine(StepCounters):
 
     # ------------------------------------------------------------------ backward
     def backward(self, dlogits: Optional[torch.Tensor], B: int, dropout: bool = True, zero_grads: bool = True,
-                 part: int = 0, prefilled: bool = False):
+                 part: int = 0, prefilled: bool = False, bucket_hook=None):
         """Gradient of every parameter into ``self.grads`` given dL/dlogits ([B,out] fp32; None = use the
         engine's own ``dlogits`` buffer written by ``loss_fwd_bwd``).
 
@@ -506,6 +513,19 @@ class THATEngine(StepCounters):
                     [(0, 0, 0, g.ld_out)], None, None, 0.0, 0, self.rng)
         ops.dropout_rows(self.dfeatd, self.dfeat, B, LY.FEAT, pf, LY.SITE_FEAT, self.rng)
         join = self._fork(lambda: self._backward_stream(1, B, pd, range(0, g.right.n_enc), head=True))
+        if bucket_hook is not None and part == 0 and nl > 1:
+            # data parallel, ONE launch sequence (one CUDA graph with the all-reduces inside): when the left stream reaches
+            # encoder 0 the first gradient bucket is final as soon as the right stream and the weight-gradient streams have
+            # drained what they hold -- the all-reduce stream waits for exactly that (events), the data-gradient chain does
+            # not wait for anything and goes on into encoder 0
+            (lo1, hi1), (lo2, hi2) = self.buckets
+            self._backward_stream(0, B, pd, range(1, nl), head=True)
+            bucket_hook.start_bucket(self, lo1, hi1, extra_streams=self._busy_streams())
+            self._backward_stream(0, B, pd, range(0, 1), head=False)
+            join()
+            self._wgrad_join()
+            bucket_hook.finish(self, lo2, hi2)
+            return None
         self._backward_stream(0, B, pd, range(1 if (part == 1 and nl > 1) else 0, nl), head=True)
         join()
         self._wgrad_join()
@@ -631,7 +651,7 @@ class THATEngine(StepCounters):
                              self.G(gp + "var_sigma"))
 
     # ------------------------------------------------------------------ CUDA-graph train body
-    def train_body(self, B: int, pos_weight: float, dropout: bool, part: int = 0):
+    def train_body(self, B: int, pos_weight: float, dropout: bool, part: int = 0, bucket_hook=None):
         """repack + forward body + BCE + backward: a fixed launch sequence over static buffers.
         part 1 stops before the left stream's encoder 0 backward, part 2 is that remainder (see ``backward``)."""
         if part != 2:
@@ -640,18 +660,19 @@ class THATEngine(StepCounters):
                 self.ensure_packed()
             self.forward_body(B, True, dropout, prefill=self.prefill_on)
             self.loss_fwd_bwd(self.y_static, B, pos_weight)
-        self.backward(None, B, dropout=dropout, zero_grads=True, part=part, prefilled=self.prefill_on)
+        self.backward(None, B, dropout=dropout, zero_grads=True, part=part, prefilled=self.prefill_on, bucket_hook=bucket_hook)
 
-    def train_body_graph(self, B: int, pos_weight: float, dropout: bool, part: int = 0):
-        """Replays train_body as one CUDA graph (captured on first use for this (B, pos_weight, dropout, part))."""
-        key = (B, float(pos_weight), bool(dropout), part, self.loss_kind)
+    def train_body_graph(self, B: int, pos_weight: float, dropout: bool, part: int = 0, bucket_hook=None):
+        """Replays train_body as one CUDA graph (captured on first use for this (B, pos_weight, dropout, part)).  With a
+        ``bucket_hook`` the two gradient all-reduces are captured inside the graph (NCCL kernels as graph nodes)."""
+        key = (B, float(pos_weight), bool(dropout), part, self.loss_kind, bucket_hook is not None)
         g = self._graphs.get(key)
         if g is None:
             torch.cuda.synchronize(self.dev)
             g = torch.cuda.CUDAGraph()
             n0 = self.ops.launches
             with torch.cuda.graph(g):
-                self.train_body(B, pos_weight, dropout, part)
+                self.train_body(B, pos_weight, dropout, part, bucket_hook)
             self._graph_launches[key] = self.ops.launches - n0
             self._graphs[key] = g
         else:

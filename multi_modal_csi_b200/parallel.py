@@ -29,7 +29,10 @@ class GradSync:
         self.world = world_size
         self._side = None
         self._work = None
-        self._event = None
+        # the whole data-parallel step as ONE CUDA graph with the all-reduces captured inside (CSI_DP_ONE_GRAPH=0: two graphs with
+        # the first all-reduce issued between them)
+        import os
+        self.one_graph = os.environ.get("CSI_DP_ONE_GRAPH", "1") != "0"
 
     def _reduce(self, t, async_op=False):
         if t.is_cuda:
@@ -44,7 +47,9 @@ class GradSync:
 
     __call__ = hook
 
-    def start_bucket(self, engine, lo: int, hi: int):
+    def start_bucket(self, engine, lo: int, hi: int, extra_streams=()):
+        """All-reduce grads[lo:hi] on the side stream once the current stream AND every stream in ``extra_streams`` have
+        reached this point; the current stream itself does not wait (``finish`` does)."""
         if self.world <= 1:
             return
         g = engine.grads[lo:hi]
@@ -53,10 +58,10 @@ class GradSync:
             return
         if self._side is None:
             self._side = torch.cuda.Stream(g.device)
-            self._event = torch.cuda.Event()
-        self._event.record(torch.cuda.current_stream(g.device))
+        self._side.wait_stream(torch.cuda.current_stream(g.device))
+        for st in extra_streams:
+            self._side.wait_stream(st)
         with torch.cuda.stream(self._side):
-            self._side.wait_event(self._event)
             self._work = self._reduce(g, async_op=True)
 
     def finish(self, engine, lo: int, hi: int):
@@ -66,6 +71,7 @@ class GradSync:
         if self._work is not None:
             self._work.wait()                      # the compute stream waits for bucket 1's all-reduce
             self._work = None
+            torch.cuda.current_stream(engine.grads.device).wait_stream(self._side)      # (rejoins the side stream when captured)
 
 
 def bind_to_gpu_numa_node(device) -> dict:

@@ -248,7 +248,11 @@ class THAT(ArenaModule):
         graph = self.use_cuda_graph if use_graph is None else use_graph
         run = eng.train_body_graph if (graph and x.is_cuda and self._eager_steps >= 1) else eng.train_body
         overlap = grad_hook is not None and hasattr(grad_hook, "start_bucket")
-        if overlap:
+        if overlap and getattr(grad_hook, "one_graph", False) and x.is_cuda and eng.g.left.n_enc > 1:
+            # data parallel, one launch sequence: both all-reduces are issued from inside backward (captured into the step
+            # graph), the first one waits only for the streams that feed its bucket
+            run(B, pos_weight, self.dropout_enabled, 0, grad_hook)
+        elif overlap:
             # data parallel: all-reduce the first gradient bucket (everything but the Gaussian encoding and left
             # encoder 0: ~3/4 of the bytes) on a side stream while the rest of the left stream's backward runs
             (lo1, hi1), (lo2, hi2) = eng.buckets
