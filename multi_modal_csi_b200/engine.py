@@ -462,7 +462,14 @@ class THATEngine(StepCounters):
         nm = f"layer_{sg.name}_norm."
         ops.layernorm_fwd(x_in.t, self.P(nm + "weight"), self.P(nm + "bias"), st["hn"].t, st["meanf"],
                           st["rstdf"], B, L, d, HALO, LN_EPS)
-        for j, k in enumerate(sg.head_k):
+        if self.fused_conv:
+            # the two head convs (k = 8 / 16 or 2 / 4 over the same normalised stream) as one banded GEMM
+            segs, bands = sg.head_bands()
+            self._alg(sum(2 * B * (L - k + 1) * d * sg.head_n * k for k in sg.head_k))
+            ops.gemm_nt_banded(st["hn"].t, self.W(f"f:layer_{sg.name}_cnn"), st["p"].t, rows, len(sg.head_k) * sg.head_np,
+                               segs, bands, self.PB(f"layer_{sg.name}_cnn.bias"), None, 0.0, 0, self.rng)
+        else:
+          for j, k in enumerate(sg.head_k):
             w = f"layer_{sg.name}_cnn_{j}"
             segs = [(t, 0, t * Dp, Dp) for t in range(k)]
             self._alg(2 * B * (L - k + 1) * d * sg.head_n * k)          # valid convolution: L - k + 1 outputs per sample

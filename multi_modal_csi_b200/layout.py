@@ -87,6 +87,17 @@ class StreamGeom:
         kernel reads row m + t - (k-1)//2, PyTorch's padding="same")."""
         return sorted({t - (k - 1) // 2 for k in self.kernels for t in range(k)})
 
+    def head_bands(self):
+        """(segments, bands) of the fused head convs: tap t (shift t) contributes to the columns of the convs with k > t."""
+        Dp, Np, segs, bands = self.Dp, self.head_np, [], []
+        ks = list(self.head_k)
+        assert ks == sorted(ks), "head convs are stacked by ascending kernel size"
+        for t in range(max(ks)):
+            first = min(j for j, k in enumerate(ks) if k > t)
+            segs.append((t, 0, t * Dp, Dp))
+            bands.append((first * Np, len(ks) * Np))
+        return segs, bands
+
     def conv_bands(self):
         """(segments, bands) of csi_gemm_nt_banded for the fused forward conv: segment t = shift conv_shifts[t], contributing to
         the columns of the branches that have that tap."""
@@ -312,11 +323,19 @@ def build_pack_plan(g: ModelGeom, arena: Arena, fused_conv: bool = True) -> Pack
         Np = s.head_np
         bmat = alloc(f"b:layer_{s.name}_cnn", d, sum(s.head_k) * Np)
         seg = 0
+        # fused forward operand of the two head convs (csi_gemm_nt_banded): rows j*Np.. = head conv j, column block t = tap t
+        # (valid convolutions: both start at shift 0); + their biases side by side at the same pitch
+        hfused = alloc(f"f:layer_{s.name}_cnn", len(s.head_k) * Np, max(s.head_k) * Dp)
+        bias_mats[f"layer_{s.name}_cnn.bias"] = PackedMat(boff, len(s.head_k) * Np, 1)
         for j, k in enumerate(s.head_k):
             w = f"layer_{s.name}_cnn_{j}.weight"
-            add(w, s.head_n, d, k, alloc("f:" + w, s.head_n, k * Dp), 0, Dp, 0)
+            if not fused_conv:
+                add(w, s.head_n, d, k, alloc("f:" + w, s.head_n, k * Dp), 0, Dp, 0)
+            add(w, s.head_n, d, k, PackedMat(hfused.off + j * Np * hfused.ld, s.head_n, hfused.ld), 0, Dp, 0)
+            bias_entries.append((arena.offsets[f"layer_{s.name}_cnn_{j}.bias"], boff + j * Np, s.head_n, 1, 1, 1, 0, 1, 0, NOG, NOG))
             add(w, s.head_n, d, k, bmat, 1, Np, seg)
             seg += k
+        boff += ru(len(s.head_k) * Np, 64)
     # output layer(s): one forward operand [heads*cp, 288] (head h = rows h*cp..), one data-gradient operand [288, heads*cp]
     # (head h = segment h of width cp) and -- for several heads -- one packed bias vector with the same pitch
     fmat = alloc("f:layer_output.weight", g.ld_out if g.heads > 1 else g.out, FEAT)
