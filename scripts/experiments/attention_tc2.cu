@@ -1,3 +1,6 @@
+// EXPERIMENT, not part of libcsi_that.so (moved out of multi_modal_csi_b200/csrc at the end of round 2): build it by adding this file
+// to SRCS in multi_modal_csi_b200/csrc/Makefile (it includes "tc_common.cuh" from there); scripts/test_attn_tc.py picks up
+// csi_attn_fwd_tc2 when the library exports it.  Measured 71 us at B=256, L=150, d=270 against 51 us for the mma.sync forward.
 // tcgen05 / TMEM attention forward, second generation (that.py:113-115,149; sequences of up to 160 tokens: the temporal stream).
 //
 // attention_tc.cu runs a (head, query tile) job end to end inside one team of warps: S MMA -> wait -> softmax -> PV MMA ->

@@ -17,7 +17,7 @@ def mk(nsec, scale):
 qkv, do, o, dqkv = mk(3, 0.5), mk(1, 0.5), mk(1, 0.0), mk(3, 0.0)
 lse = torch.zeros(B * H * L, device="cuda"); dbias = torch.zeros(3 * d, device="cuda")
 st = C.c_void_p(torch.cuda.current_stream().cuda_stream)
-fwd = {"tc": lib.csi_attn_fwd_tc, "tc2": lib.csi_attn_fwd_tc2, "mma": lib.csi_attn_fwd_mma}
+fwd = {"tc": lib.csi_attn_fwd_tc, "mma": lib.csi_attn_fwd_mma}
 lib.csi_attn_fwd_mma(_p(qkv), _ld(qkv), _p(o), _ld(o), _p(lse), B, L, d, H, hp, HALO, st)
 for _ in range(reps):
     if kind in fwd:

@@ -42,7 +42,7 @@ def rel(a, b):
 
 
 def run_fwd(kind, qkv, o, lse, B, L, d, H, hp):
-    fn = {"tc": lib.csi_attn_fwd_tc, "tc2": lib.csi_attn_fwd_tc2, "mma": lib.csi_attn_fwd_mma}[kind]
+    fn = lib.csi_attn_fwd_tc2 if kind == "tc2" else {"tc": lib.csi_attn_fwd_tc, "mma": lib.csi_attn_fwd_mma}[kind]
     rc = fn(_p(qkv), _ld(qkv), _p(o), _ld(o), _p(lse), B, L, d, H, hp, HALO, st())
     if rc:
         raise RuntimeError(lib.csi_last_error().decode())
@@ -71,7 +71,7 @@ def check(B, L, d, H=10, bwd=True):
     ref_o = ref.transpose(1, 2)
     ref_lse = torch.logsumexp((q @ k.transpose(-1, -2)) / hd ** 0.5, dim=-1)       # [B,H,L]
     out = {}
-    for kind in ("mma", "tc", "tc2"):
+    for kind in ("mma", "tc") + (("tc2",) if hasattr(lib, "csi_attn_fwd_tc2") else ()):
         if kind == "tc2" and not lib.csi_attn_tc2_ok(L, d, H, hp):
             continue
         fo, o = mk(B, L, H, hd, hp, 1, 0, 0.0)
@@ -116,7 +116,7 @@ def timeit(B, L, d, H=10):
     lse = torch.zeros(B * H * L, device="cuda")
     dbias = torch.zeros(3 * d, device="cuda")
     line = f"time B={B} L={L} d={d} hp={hp}:"
-    for kind in ("mma", "tc", "tc2"):
+    for kind in ("mma", "tc") + (("tc2",) if hasattr(lib, "csi_attn_fwd_tc2") else ()):
         for name, fn in (("fwd", lambda: run_fwd(kind, qkv, o, lse, B, L, d, H, hp)),
                          ("bwd", lambda: run_bwd(kind, qkv, o, do, dqkv, lse, B, L, d, H, hp, dbias))):
             try:
