@@ -13,7 +13,7 @@ void csi_set_error(const char* fmt, ...) {
     va_list ap; va_start(ap, fmt); vsnprintf(g_err, sizeof(g_err), fmt, ap); va_end(ap);
 }
 extern "C" const char* csi_last_error(void) { return g_err; }
-extern "C" int csi_abi_version(void) { return 4; }
+extern "C" int csi_abi_version(void) { return 5; }      // 5: csi_gemm_nt_banded, csi_gemm_tn_workspace
 extern "C" int csi_device_arch(int device) {
     cudaDeviceProp p;
     CSI_CUDA(cudaGetDeviceProperties(&p, device));

@@ -13,7 +13,7 @@ import torch
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.path.join(_HERE, "libcsi_that.so")
-ABI_VERSION = 4
+ABI_VERSION = 5
 
 
 class Seg(C.Structure):
