@@ -605,6 +605,29 @@ __global__ void __launch_bounds__(LNB2_WARPS * 32, 2) ln_bwd2_kernel(
                 }
             }
             s1 = warp_sum(s1) * inv_d; s2 = warp_sum(s2) * inv_d;
+            // Dropout decisions of the masked copy: an 8-channel Philox group serves the float4 column groups of TWO
+            // neighbouring lanes, and a lane meets two groups in two consecutive j.  The even lane of a pair generates the
+            // group of iteration j, the odd lane the one of j+1, and they swap the halves they need (two shuffles): one
+            // Philox call per lane and pair of iterations instead of two, same decisions bit for bit.
+            uint2 kw[NQ];
+            if (drop) {
+                const bool odd = (lane & 1) != 0;
+                const unsigned long long g0 = (unsigned long long)row * ld8 + (lane >> 1);
+#pragma unroll
+                for (int j = 0; j < NQ; j += 2) {
+                    if (j + 1 < NQ) {
+                        const uint4 g = rng_group(dc.k, drop_site, g0 + 16 * (odd ? j + 1 : j));
+                        const uint32_t t0 = __shfl_xor_sync(0xffffffffu, odd ? g.x : g.z, 1);
+                        const uint32_t t1 = __shfl_xor_sync(0xffffffffu, odd ? g.y : g.w, 1);
+                        const uint2 own = odd ? make_uint2(g.z, g.w) : make_uint2(g.x, g.y), got = make_uint2(t0, t1);
+                        kw[j] = odd ? got : own;
+                        kw[j + 1] = odd ? own : got;
+                    } else {
+                        const uint4 g = rng_group(dc.k, drop_site, g0 + 16 * j);
+                        kw[j] = odd ? make_uint2(g.z, g.w) : make_uint2(g.x, g.y);
+                    }
+                }
+            }
 #pragma unroll
             for (int j = 0; j < NQ; ++j) {
                 const int qd = lane + 32 * j, c = 4 * qd;
@@ -625,12 +648,10 @@ __global__ void __launch_bounds__(LNB2_WARPS * 32, 2) ln_bwd2_kernel(
                     stg4f<float>(dx + row * ld + c, o);
                     if (dxm) {
                         if (drop) {
-                            const uint4 gq = rng_group(dc.k, drop_site, (unsigned long long)row * ld8 + (qd >> 1));
-                            const int j0 = c & 7;
-                            o.x *= field16(gq, j0) >= dc.thr ? dc.inv_keep : 0.f;
-                            o.y *= field16(gq, j0 + 1) >= dc.thr ? dc.inv_keep : 0.f;
-                            o.z *= field16(gq, j0 + 2) >= dc.thr ? dc.inv_keep : 0.f;
-                            o.w *= field16(gq, j0 + 3) >= dc.thr ? dc.inv_keep : 0.f;
+                            o.x *= (kw[j].x & 0xFFFFu) >= dc.thr ? dc.inv_keep : 0.f;
+                            o.y *= (kw[j].x >> 16) >= dc.thr ? dc.inv_keep : 0.f;
+                            o.z *= (kw[j].y & 0xFFFFu) >= dc.thr ? dc.inv_keep : 0.f;
+                            o.w *= (kw[j].y >> 16) >= dc.thr ? dc.inv_keep : 0.f;
                         }
                         stg4f<TM>(dxm + row * ld + c, o);
                     }
