@@ -1257,11 +1257,52 @@ __global__ void __launch_bounds__(256) head_reduce_fwd_kernel(const T* __restric
     }
 }
 
+// eight consecutive channels per thread (16-byte loads): block = one sample, thread = (8-channel chunk, row lane)
+template <typename T>
+__global__ void __launch_bounds__(256) head_reduce_fwd8_kernel(const T* __restrict__ p, int ldp, int L, int halo, int N,
+                                                               int n0, int k0, int k1, float* __restrict__ feat, int ldf,
+                                                               int NC, int RL) {
+    extern __shared__ float hr_part[];                              // [RL][N]
+    const int b = blockIdx.x, c = threadIdx.x % NC, rl = threadIdx.x / NC, n = c * 8;
+    const int Lp = L + 2 * halo;
+    float a[8] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
+    if (rl < RL) {
+        const int tmax = L - (n < n0 ? k0 : k1);
+        const T* src = p + ((size_t)b * Lp + halo + rl) * ldp + n;
+        for (int t = rl; t <= tmax; t += RL, src += (size_t)RL * ldp) {
+            float v[8];
+            load8f<T>(src, v);
+#pragma unroll
+            for (int j = 0; j < 8; ++j) a[j] += leaky(v[j]);
+        }
+#pragma unroll
+        for (int j = 0; j < 8; ++j) hr_part[rl * N + n + j] = a[j];
+    }
+    __syncthreads();
+    for (int i = threadIdx.x; i < N; i += blockDim.x) {
+        float s = 0.f;
+        for (int r = 0; r < RL; ++r) s += hr_part[r * N + i];
+        feat[(size_t)b * ldf + i] = s;
+    }
+}
+
 extern "C" int csi_head_reduce_fwd(const void* p, int ldp, int dtype, int B, int L, int halo, int N, int n0, int k0,
                                    int k1, float* feat, int ldf, void* stream) {
     CSI_CHECK_ARG(p && feat, "null pointer");
     CSI_CHECK_ARG(k0 <= L && k1 <= L, "kernel longer than the sequence");
     if (B == 0) return CSI_OK;
+    {
+        const int es = dtype == CSI_BF16 ? 2 : 4, NC = N / 8;
+        if (N % 8 == 0 && n0 % 8 == 0 && NC >= 1 && NC <= 256 && (ldp * es) % 16 == 0 && (reinterpret_cast<uintptr_t>(p) % 16) == 0) {
+            int RL = 256 / NC;
+            if (RL > 32) RL = 32;
+            const size_t smem = (size_t)RL * N * sizeof(float);
+            if (dtype == CSI_BF16) head_reduce_fwd8_kernel<bf16><<<B, 256, smem, ST(stream)>>>((const bf16*)p, ldp, L, halo, N, n0, k0, k1, feat, ldf, NC, RL);
+            else head_reduce_fwd8_kernel<float><<<B, 256, smem, ST(stream)>>>((const float*)p, ldp, L, halo, N, n0, k0, k1, feat, ldf, NC, RL);
+            CSI_LAUNCH_CHECK();
+            return CSI_OK;
+        }
+    }
     dim3 grid(B, cdiv(N, 32));
     if (dtype == CSI_BF16) head_reduce_fwd_kernel<bf16><<<grid, 256, 0, ST(stream)>>>((const bf16*)p, ldp, L, halo, N, n0, k0, k1, feat, ldf);
     else head_reduce_fwd_kernel<float><<<grid, 256, 0, ST(stream)>>>((const float*)p, ldp, L, halo, N, n0, k0, k1, feat, ldf);
