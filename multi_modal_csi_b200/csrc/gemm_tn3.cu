@@ -8,10 +8,13 @@
 // chunk of the token range.  Per 64-token block it fetches the A tile once and ONE Bv tile with a halo of `span` rows;
 // tap t's UMMA reads the Bv tile through a descriptor advanced by (shift_t - min_shift) rows of 128 B, and accumulates
 // into its own TMEM slot.  So a k=5 conv issues 20 UMMAs per (A, Bv) stage instead of 4, and the operand traffic per
-// FLOP drops 5x.  Partial sums of the token chunks are reduced with fp32 atomics into the reference [N, C, k] layout.
+// FLOP drops 5x.  The partial sums of the token chunks go to a workspace registered for the stream (csi_gemm_tn_workspace) and
+// are added to the reference [N, C, k] layout by tn3_reduce_kernel in a fixed order (bit-reproducible); without a workspace
+// they are reduced with fp32 atomics from every CTA (round-1 path, kept for callers that own no scratch memory).
 //
 //   warp 0      TMA producer          warp 1      tcgen05.mma issuer (one elected lane, warp-uniform loop)
-//   warps 2-9   epilogue: tcgen05.ld -> red.global.add.f32 (two warps per TMEM lane quarter, alternate 16-column groups)
+//   warps 2-9   epilogue: tcgen05.ld -> workspace slab (column-major, one 128-byte line per store) | red.global.add.f32
+//               (two warps per TMEM lane quarter, alternate column groups)
 #include "tc_common.cuh"
 #include <stdlib.h>
 
