@@ -10,6 +10,10 @@
 // shared-memory address (TMA writes and UMMA reads agree), so a row-shifted view of the same stage is a valid K-major
 // operand.  B (weights) tiles stream through their own ring, one per (tap, channel block).
 //
+// Banded calls (csi_gemm_nt_banded): every segment carries the band of output columns it contributes to (its weights are zero
+// elsewhere), column tiles are cut at the band boundaries (T3Params::tab_n0 / tab_bn) and the producer and issue loops skip the
+// taps whose band does not meet the tile -- the three Conv1d branches of an encoder run as one GEMM with N = 3*Dp.
+//
 //   warp 0      TMA producer: A ring (box rows = 128 + span) and B ring (BN x 64), mbarrier tx-count
 //   warp 1      tcgen05.mma issuer (UMMA 128 x BN x 16, bf16 -> fp32), two TMEM accumulators
 //   warps 2-5   epilogue: tcgen05.ld -> bias / Philox dropout / fp32 residual -> swizzled smem panel -> TMA store
