@@ -623,3 +623,48 @@ def LY_numel(shape):
     for s in shape:
         n *= s
     return n
+
+
+def test_conv_and_head_bands_of_the_fused_gemms():
+    """layout.StreamGeom.conv_bands / head_bands: the segments and output-column bands csi_gemm_nt_banded gets for the fused conv
+    trio (that.py:122-135: kernel sizes 1/3/5 left, 1/2/3 right, padding="same") and the fused head convs (valid convolutions),
+    and the stacked operand of build_pack_plan: every tap of every branch lands in the column block of its row shift, rows of a
+    branch outside the taps it has stay zero."""
+    import numpy as np
+    from multi_modal_csi_b200 import layout as LY
+    g = LY.ModelGeom(3000, 270, 54)
+    for sg in g.streams:
+        Dp = sg.Dp
+        segs, bands = sg.conv_bands()
+        shifts = [s[0] for s in segs]
+        assert shifts == sorted({t - (k - 1) // 2 for k in sg.kernels for t in range(k)})
+        for (sh, aoff, boff, klen), (lo, hi) in zip(segs, bands):
+            assert aoff == 0 and klen == Dp and boff == shifts.index(sh) * Dp
+            has = [j for j, k in enumerate(sg.kernels) if -((k - 1) // 2) <= sh <= k - 1 - (k - 1) // 2]
+            assert (lo, hi) == (has[0] * Dp, (has[-1] + 1) * Dp) and lo % 16 == 0 and hi % 16 == 0
+        hsegs, hbands = sg.head_bands()
+        assert [s[0] for s in hsegs] == list(range(max(sg.head_k)))
+        for t, (lo, hi) in enumerate(hbands):
+            first = min(j for j, k in enumerate(sg.head_k) if k > t)
+            assert (lo, hi) == (first * sg.head_np, len(sg.head_k) * sg.head_np)
+    # the stacked forward operand against a direct construction
+    arena = LY.build_arena(LY.parameter_specs(g))
+    plan = LY.build_pack_plan(g, arena)
+    from mirror_ops import MirrorOps
+    ops = MirrorOps()
+    params = torch.randn(arena.size)
+    packed = torch.zeros(plan.size)
+    ops.pack_weights(params, packed, ops.make_pack_table(plan.entries, "cpu"), len(plan.entries), plan.max_elems)
+    sg, e = g.left, 2
+    p, Dp, d = sg.prefix(e), sg.Dp, sg.d
+    m = plan.mats["f:" + p + "layer_cnn"]
+    W = packed[m.off:m.off + m.rows * m.ld].view(m.rows, m.ld)
+    shifts = sg.conv_shifts
+    want = torch.zeros_like(W)
+    for j, k in enumerate(sg.kernels):
+        name = f"{p}layer_cnn.{j}.0.weight"
+        w = params[arena.offsets[name]:arena.offsets[name] + d * d * k].view(d, d, k)
+        for t in range(k):
+            c = shifts.index(t - (k - 1) // 2)
+            want[j * Dp:j * Dp + d, c * Dp:c * Dp + d] = w[:, :, t]
+    assert torch.equal(W, want)
